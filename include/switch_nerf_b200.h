@@ -1,0 +1,208 @@
+/*
+ * switch_nerf_b200 -- C ABI of the B200-native Switch-NeRF forward/render hot path.
+ *
+ * Every entry point takes plain device pointers + sizes + a CUDA stream
+ * (`void*` == cudaStream_t), enqueues work on that stream, never synchronises
+ * the host, never allocates or frees caller memory (scratch comes from a
+ * caller-provided workspace sized by snb_workspace_bytes), and returns an int
+ * status: 0 = ok, otherwise an SNB_E* code whose text is available through
+ * snb_last_error() (thread-local).  There are NO torch types here: the Python
+ * mirror (switch_nerf_b200/*.py) binds these symbols with ctypes exactly as a
+ * maintainer of the reference would.
+ *
+ * Each function cites the reference interface it replaces; paths are relative
+ * to /root/reference/switch_nerf/.
+ */
+#ifndef SWITCH_NERF_B200_H_
+#define SWITCH_NERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNB_OK 0
+#define SNB_EINVAL 1      /* bad argument (shape, NULL pointer, unsupported topology) */
+#define SNB_ECUDA 2       /* a CUDA runtime call or launch failed */
+#define SNB_EWORKSPACE 3  /* workspace too small */
+#define SNB_EUNSUPPORTED 4 /* precision / topology not supported by the selected path */
+
+/* Compute precision of the model forward.
+ *  SNB_PREC_FP32 : every GEMM in fp32 on the CUDA cores (what the reference does
+ *                  without autocast; used for BASELINE.json configs[0] parity).
+ *  SNB_PREC_BF16 : the autocast(bf16) map of the reference (README.md:77
+ *                  --amp_use_bfloat16): bf16 operands, fp32 accumulation in TMEM
+ *                  (tcgen05), fp32 LayerNorm / gate / softmax / softplus /
+ *                  compositing. */
+#define SNB_PREC_FP32 0
+#define SNB_PREC_BF16 1
+
+typedef struct snb_model snb_model_t; /* opaque: packed weights + tile tables (library-owned) */
+
+/* Topology of one NeRFMoE / MipNeRFMoE network: the `model:` block of
+ * configs/switch_nerf/{building,mission_bay}.yaml + opts.py defaults. */
+typedef struct snb_model_desc {
+  int32_t num_experts;      /* E: layers."0" local_expert_num (opts.py moe_local_expert_num)   */
+  int32_t width;            /* M: layers."0".in_ch (256 Building, 512 Mission Bay)             */
+  int32_t expert_layers;    /* layers."0".num (7)                                              */
+  int32_t skip_layer;       /* layers."0".skips[0] (3), -1 = none                              */
+  int32_t gate_layers;      /* layers.moe_external_gate.num (2)                                */
+  int32_t pos_xyz_freqs;    /* hparams.pos_xyz_dim (12)                                        */
+  int32_t pos_dir_freqs;    /* hparams.pos_dir_dim (4)                                         */
+  int32_t appearance_dim;   /* hparams.appearance_dim (48)                                     */
+  int32_t appearance_count; /* rows of embedding_a                                             */
+  int32_t hidden2;          /* layers."2".out_ch (128)                                         */
+  int32_t mip;              /* 0: NeRFMoE (x = [xyz3,dir3,idx1]); 1: MipNeRFMoE (x = [mean3,cov3,dir3,idx1]) */
+} snb_model_desc;
+
+/* Device pointers to fp32 weights in the reference's state_dict layout
+ * (names from a live models/nerf_moe.py:103-310 instance). */
+typedef struct snb_weights {
+  const float* xyz_w;        /* layers.xyz.fcs.0.weight              [M, 3+6*pos_xyz_freqs]    */
+  const float* xyz_b;        /* layers.xyz.fcs.0.bias                [M]                       */
+  const float* gate_w[4];    /* layers.moe_external_gate.fcs.{i}.weight [M, M]                 */
+  const float* gate_b[4];    /* layers.moe_external_gate.fcs.{i}.bias   [M]                    */
+  const float* ln_w;         /* layers.gate_input_norm.weight        [M]                       */
+  const float* ln_b;         /* layers.gate_input_norm.bias          [M]                       */
+  const float* wg;           /* layers.0.gates.0.wg.weight           [E, M] (no bias)          */
+  const float* expert_w[16]; /* layers.0.experts.0.weights.{j}       [E, M(in), M(out)]        */
+  const float* expert_b[16]; /* layers.0.experts.0.bias.{j}          [E, 1, M]                 */
+  const float* l1_w;         /* layers.1.fcs.0.weight                [M, M]                    */
+  const float* l1_b;         /* layers.1.fcs.0.bias                  [M]                       */
+  const float* l2_w;         /* layers.2.fcs.0.weight                [H2, M+3+6*pos_dir_freqs+appearance_dim] */
+  const float* l2_b;         /* layers.2.fcs.0.bias                  [H2]                      */
+  const float* sigma_w;      /* layers.sigma.fcs.0.weight            [1, M]                    */
+  const float* sigma_b;      /* layers.sigma.fcs.0.bias              [1]                       */
+  const float* color_w;      /* layers.color.fcs.0.weight            [3, H2]                   */
+  const float* color_b;      /* layers.color.fcs.0.bias              [3]                       */
+  const float* emb_a;        /* embedding_a.weight                   [appearance_count, appearance_dim] */
+} snb_weights;
+
+/* Routing options of one MoE forward: TopKGate ctor args
+ * (modules/tutel_moe_ext/tutel_moe_layer_nobatch.py:33-96). */
+typedef struct snb_route_opts {
+  double capacity_factor; /* hparams.moe_capacity_factor (>0); double like the Python float it mirrors */
+  int32_t bpr;            /* batch_prioritized_routing                                          */
+  int32_t no_batch;       /* MOELayer.moe_no_batch: 1 = capacity-free eval mode (nothing dropped) */
+} snb_route_opts;
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* snb_last_error(void);
+int snb_version(void);
+
+/* ---- model object ----------------------------------------------------------------------- */
+/* Replaces models/nerf_moe.py:1004-1041 get_nerf_moe_inner + load_state_dict: copies/packs the
+ * caller's fp32 weights into kernel-native layouts (fp32 [N,K] for the CUDA-core path; bf16
+ * UMMA canonical K-major core-matrix tiles for the tcgen05 path).  Call again after an
+ * optimizer step (snb_model_update) -- packing is one pass over ~16 MB. */
+int snb_model_create(const snb_model_desc* desc, const snb_weights* w, void* stream, snb_model_t** out);
+int snb_model_update(snb_model_t* m, const snb_weights* w, void* stream);
+void snb_model_destroy(snb_model_t* m);
+
+/* Scratch bytes needed by snb_moe_forward / snb_render_rays for chunks of up to
+ * `max_chunk_samples` rows and capacity factors up to `max_capacity_factor`. */
+size_t snb_workspace_bytes(const snb_model_t* m, int64_t max_chunk_samples, double max_capacity_factor);
+
+/* ---- a9: routing ------------------------------------------------------------------------ */
+/* Replaces extract_critical (tutel_fast_dispatch.py:176-217, k=1) incl. one_hot (131-134),
+ * compute_sorted_location (136-139), load_balance (141-150) and Tutel's fast_cumsum_sub_one:
+ *   idx[s]  = argmax_e gates[s,e]  (lowest e wins exact ties)
+ *   gate[s] = gates[s, idx[s]]
+ *   loc[s]  = #{s' : idx[s']==idx[s], s' before s}  where "before" is ascending s (bpr=0) or
+ *             descending max-gate with ties by ascending s (bpr=1)
+ *   counts[e] = #{s : idx[s]==e};  *capacity = int(cf * ceil(S/E));  *l_aux = E/S^2 * sum_e me_e*ce_e
+ * gates fp32 [S,E] row-major; idx/loc int32 [S]; gate fp32 [S]; counts int32 [E];
+ * capacity int32 [1] and l_aux fp32 [1] are DEVICE scalars (no host round trip).
+ * workspace: snb_route_workspace_bytes(S, E). */
+size_t snb_route_workspace_bytes(int64_t S, int32_t E);
+int snb_route_top1(const float* gates, int64_t S, int32_t E, double capacity_factor, int32_t bpr,
+                   int32_t* idx, int32_t* loc, float* gate, int32_t* counts, int32_t* capacity,
+                   float* l_aux, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a10/a12/a13: dispatch + combine (Tutel K4/K5, in-tree K1/K2) ----------------------- */
+/* Replaces GatingEncoder.forward (tutel_fast_dispatch.py:15-28; _nobatch.py:16-37):
+ *   out = zeros[rows_out, H];  out[row(s)] = x[s]  for kept samples
+ *   row(s) = idx[s]*capacity + loc[s], kept iff loc[s] < capacity          (begin == NULL)
+ *   row(s) = begin[idx[s]] + loc[s],  always kept                           (begin != NULL)
+ * and GatingDecoder.forward (48-63): y[s] = gate[s]*buf[row(s)] if kept else 0. */
+int snb_dispatch_fwd(const float* x, const int32_t* idx, const int32_t* loc, const int32_t* begin,
+                     int64_t S, int32_t H, int32_t capacity, int64_t rows_out, float* out, void* stream);
+int snb_combine(const float* buf, const int32_t* idx, const int32_t* loc, const int32_t* begin,
+                const float* gate, int64_t S, int32_t H, int32_t capacity, int64_t rows_buf,
+                float* y, void* stream);
+
+/* ---- a4..a14: one model_chunk of NeRFMoE.forward / MipNeRFMoE.forward -------------------- */
+/* Replaces `nerf(x, sigma_noise=...)` (models/nerf_moe.py:320-455 / 675-810) for the
+ * Building / Mission-Bay topology:
+ *   x [S, 7] (mip: [S,10]) fp32 = [xyz(3) (cov_diag(3)), dir(3), image_index(1 as float)]
+ *   out [S,4] fp32 = [sigmoid(rgb)(3), softplus(sigma-1)(1)]
+ *   moe_idx (nullable) int32 [S] = extras["moe_gates"][0][:,0]; l_aux fp32 device scalar =
+ *   extras["moe_loss"][0].  dbg_* are optional taps for parity tests (may be NULL):
+ *   dbg_gates fp32 [S,E], dbg_loc int32 [S]. */
+int snb_moe_forward(snb_model_t* m, const float* x, int64_t S, const float* sigma_noise,
+                    const snb_route_opts* opts, int32_t precision, float* out, int32_t* moe_idx,
+                    float* l_aux, float* dbg_gates, int32_t* dbg_loc, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ---- a1..a3: rendering.render_rays ------------------------------------------------------- */
+typedef struct snb_render_opts {
+  int32_t coarse_samples;   /* hparams.coarse_samples                                          */
+  int32_t fine_samples;     /* hparams.fine_samples (0 = coarse only)                          */
+  int64_t model_chunk_size; /* hparams.model_chunk_size: routing/capacity are per chunk (F7)   */
+  float perturb;            /* hparams.perturb if nerf.training else 0                         */
+  uint64_t seed;            /* Philox seed for perturb / stochastic pdf sampling               */
+  int32_t white_bkgd;       /* hparams.white_bkgd                                              */
+  int32_t precision;        /* SNB_PREC_*                                                      */
+  snb_route_opts route;
+} snb_render_opts;
+
+/* Per-ray outputs (all nullable; device pointers). Keys of the reference `results` dict
+ * (rendering.py:466-494; runner.py:1089-1121). */
+typedef struct snb_render_out {
+  float* rgb;            /* rgb_{fine|coarse}            [N,3] */
+  float* depth;          /* depth_*                      [N]   */
+  float* depth_variance; /* depth_variance_*             [N]   */
+  float* bg_lambda;      /* bg_lambda_* = T[...,-1]      [N]   */
+  float* gate_loss_coarse; /* [ceil(N*coarse/chunk)]           */
+  float* gate_loss_fine;   /* [ceil(N*fine/chunk)]             */
+  int32_t* moe_gates_coarse; /* [N, coarse] expert ids          */
+  int32_t* moe_gates_fine;   /* [N, fine]                       */
+  float* z_fine;         /* tap: fine z values           [N, fine]      */
+  float* raw_coarse;     /* tap: per-sample [rgb,sigma]  [N, coarse, 4] */
+  float* raw_fine;       /* tap: per-sample [rgb,sigma]  [N, fine, 4]   */
+} snb_render_out;
+
+size_t snb_render_workspace_bytes(const snb_model_t* m, int64_t n_rays, const snb_render_opts* o);
+
+/* Replaces rendering.render_rays (rendering.py:15-196) with bg_nerf=None, use_cascade=False:
+ * coarse z (linspace + perturb, :85-88, 573-584), points o+d*z (:90), chunked model calls
+ * (:354-383), alpha/transmittance/weights (:436-461), _sample_pdf (:587-637), fine pass,
+ * sorted merge of coarse+fine (:419-429) and the composite (:466-494).
+ * rays [N,8] fp32 = (o3,d3,near,far); image_indices int32 [N]; last_delta nullable [N]
+ * (defaults to 1e10, rendering.py:33). */
+int snb_render_rays(snb_model_t* m, const float* rays, const int32_t* image_indices,
+                    const float* last_delta, int64_t n_rays, const snb_render_opts* opts,
+                    const snb_render_out* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stand-alone composite (rendering.py:436-494, flip=False): z [N,S] ascending, raw [N,S,4]. */
+int snb_composite(const float* z, const float* raw, const float* last_delta, int64_t n_rays,
+                  int32_t n_samples, int32_t white_bkgd, float* rgb, float* depth,
+                  float* depth_variance, float* bg_lambda, float* weights, void* stream);
+
+/* Stand-alone inverse-CDF sampling (rendering.py:587-637); u nullable => det linspace. */
+int snb_sample_pdf(const float* bins, const float* weights, const float* u, int64_t n_rays,
+                   int32_t n_bins_minus1, int32_t n_fine, float* z_fine, void* stream);
+
+/* ---- self-test of the tcgen05 building block (used by tests/ and smoke) ------------------ */
+/* D[128,N] = A[128,K] * B[N,K]^T with bf16 operands / fp32 accumulate through the same UMMA
+ * descriptor + TMEM + bulk-copy machinery the fused kernels use.  A,B bf16 row-major (K
+ * contiguous) device pointers, D fp32 row-major. K%16==0, N%16==0, N<=256. */
+int snb_umma_selftest(const void* a_bf16, const void* b_bf16, int32_t N, int32_t K, float* d,
+                      int32_t variant, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWITCH_NERF_B200_H_ */

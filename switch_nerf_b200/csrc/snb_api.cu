@@ -1,0 +1,349 @@
+// C-ABI entry points (include/switch_nerf_b200.h): argument checking, model object, workspace
+// carving and the host-side orchestration of render_rays.  No host synchronisation anywhere.
+#include <stdarg.h>
+#include <new>
+
+#include "snb_common.cuh"
+
+namespace snb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// implemented in snb_fp32.cu / snb_render.cu / snb_route.cu
+int snb_dispatch_impl(const float* x, const int* idx, const int* loc, const int* begin, const int* cap_dev,
+                      int cap_host, int64_t S, int H, int64_t rows_out, float* out, bool zero, cudaStream_t st);
+int snb_combine_impl(const float* buf, const int* idx, const int* loc, const int* begin, const float* gate,
+                     const int* cap_dev, int cap_host, int64_t S, int H, int64_t rows_buf, float* y, bool relu,
+                     cudaStream_t st);
+int route_top1_generic(const float* gates, int64_t S, int32_t E, double cf, int32_t bpr, int32_t* idx,
+                       int32_t* loc, float* gate, int32_t* counts, int32_t* capacity, float* l_aux, void* ws,
+                       size_t ws_bytes, cudaStream_t st);
+int composite_launch(const float* z, const float* raw, const float* last_delta, int64_t N, int S, int white_bkgd,
+                     float* rgb, float* depth, float* var, float* lam, float* weights, cudaStream_t st);
+int sample_pdf_launch(const float* bins, int ld_bins, const float* weights, int ld_w, int w_off, const float* u,
+                      int64_t N, int nb, int nf, uint64_t seed, int det, float* zf, cudaStream_t st);
+int coarse_z_launch(const float* rays, int64_t N, int Sc, float perturb, uint64_t seed, float* z, cudaStream_t st);
+int fill_x_launch(const float* rays, const int* image_indices, const float* z, int64_t N, int Sn, float* x,
+                  cudaStream_t st);
+int zmid_launch(const float* z, int64_t N, int S, float* mid, cudaStream_t st);
+int merge_composite_launch(const float* zf, const float* zc, const float* raw_f, const float* raw_c,
+                           const float* last_delta, int64_t N, int Sf, int Sc, int white_bkgd, float* rgb,
+                           float* depth, float* var, float* lam, cudaStream_t st);
+int umma_selftest(const void* a, const void* b, int N, int K, float* d, int variant, cudaStream_t st);
+
+// [E][K][N] -> [E][N][K]
+__global__ void k_transpose_expert(const float* __restrict__ in, float* __restrict__ out, int E, int K, int N) {
+  __shared__ float t[32][33];
+  const int e = blockIdx.z;
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const float* src = in + (size_t)e * K * N;
+  float* dst = out + (size_t)e * K * N;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int k = k0 + i, n = n0 + threadIdx.x;
+    if (k < K && n < N) t[i][threadIdx.x] = src[(size_t)k * N + n];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int n = n0 + i, k = k0 + threadIdx.x;
+    if (k < K && n < N) dst[(size_t)n * K + k] = t[threadIdx.x][i];
+  }
+}
+
+static int check_desc(const snb_model_desc* d) {
+  SNB_REQUIRE(d, "desc is NULL");
+  SNB_REQUIRE(d->num_experts >= 1 && d->num_experts <= 64, "num_experts=%d unsupported (1..64)", d->num_experts);
+  SNB_REQUIRE(d->width >= 16 && d->width <= 1024 && d->width % 16 == 0, "width=%d unsupported", d->width);
+  SNB_REQUIRE(d->expert_layers >= 1 && d->expert_layers <= 16, "expert_layers=%d unsupported", d->expert_layers);
+  SNB_REQUIRE(d->skip_layer < d->expert_layers, "skip_layer=%d out of range", d->skip_layer);
+  SNB_REQUIRE(d->gate_layers >= 1 && d->gate_layers <= 4, "gate_layers=%d unsupported", d->gate_layers);
+  SNB_REQUIRE(d->pos_xyz_freqs >= 0 && d->pos_xyz_freqs <= 16, "pos_xyz_freqs=%d unsupported", d->pos_xyz_freqs);
+  SNB_REQUIRE(d->pos_dir_freqs >= 0 && d->pos_dir_freqs <= 16, "pos_dir_freqs=%d unsupported", d->pos_dir_freqs);
+  SNB_REQUIRE(d->appearance_dim >= 0 && d->appearance_dim <= 256, "appearance_dim=%d unsupported", d->appearance_dim);
+  SNB_REQUIRE(d->appearance_count >= 1, "appearance_count must be >= 1");
+  SNB_REQUIRE(d->hidden2 >= 1 && d->hidden2 <= 1024, "hidden2=%d unsupported", d->hidden2);
+  return SNB_OK;
+}
+
+static int upload(Model* m, const snb_weights* w, cudaStream_t st) {
+  const snb_model_desc& d = m->d;
+  const int M = d.width, E = d.num_experts;
+  auto cp = [&](float* dst, const float* src, size_t n) -> int {
+    SNB_REQUIRE(src, "a weight pointer is NULL");
+    SNB_CHECK_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return SNB_OK;
+  };
+  int rc;
+  if ((rc = cp(m->xyz_w, w->xyz_w, (size_t)M * m->xyz_in))) return rc;
+  if ((rc = cp(m->xyz_b, w->xyz_b, M))) return rc;
+  for (int i = 0; i < d.gate_layers; ++i) {
+    if ((rc = cp(m->gate_w[i], w->gate_w[i], (size_t)M * M))) return rc;
+    if ((rc = cp(m->gate_b[i], w->gate_b[i], M))) return rc;
+  }
+  if ((rc = cp(m->ln_w, w->ln_w, M))) return rc;
+  if ((rc = cp(m->ln_b, w->ln_b, M))) return rc;
+  if ((rc = cp(m->wg, w->wg, (size_t)E * M))) return rc;
+  for (int j = 0; j < d.expert_layers; ++j) {
+    SNB_REQUIRE(w->expert_w[j] && w->expert_b[j], "expert weight pointer %d is NULL", j);
+    dim3 grid((unsigned)cdiv(M, 32), (unsigned)cdiv(M, 32), (unsigned)E), blk(32, 8);
+    k_transpose_expert<<<grid, blk, 0, st>>>(w->expert_w[j], m->exp_w[j], E, M, M);
+    SNB_CHECK_LAUNCH("k_transpose_expert");
+    if ((rc = cp(m->exp_b[j], w->expert_b[j], (size_t)E * M))) return rc;
+  }
+  if ((rc = cp(m->l1_w, w->l1_w, (size_t)M * M))) return rc;
+  if ((rc = cp(m->l1_b, w->l1_b, M))) return rc;
+  if ((rc = cp(m->l2_w, w->l2_w, (size_t)d.hidden2 * m->cat_in))) return rc;
+  if ((rc = cp(m->l2_b, w->l2_b, d.hidden2))) return rc;
+  if ((rc = cp(m->sigma_w, w->sigma_w, M))) return rc;
+  if ((rc = cp(m->sigma_b, w->sigma_b, 1))) return rc;
+  if ((rc = cp(m->color_w, w->color_w, (size_t)3 * d.hidden2))) return rc;
+  if ((rc = cp(m->color_b, w->color_b, 3))) return rc;
+  if (d.appearance_dim > 0)
+    if ((rc = cp(m->emb_a, w->emb_a, (size_t)d.appearance_count * d.appearance_dim))) return rc;
+  if (tc_supported(m)) return tc_pack_weights(m, w, st);
+  return SNB_OK;
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+extern "C" {
+
+const char* snb_last_error(void) { return g_err; }
+int snb_version(void) { return 100; }
+
+int snb_model_create(const snb_model_desc* desc, const snb_weights* w, void* stream, snb_model_t** out) {
+  SNB_REQUIRE(out && w, "snb_model_create: NULL argument");
+  int rc = check_desc(desc);
+  if (rc) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("snb_model_create: no CUDA device -- switch_nerf_b200 has no CPU path");
+    return SNB_ECUDA;
+  }
+  Model* m = new (std::nothrow) Model();
+  SNB_REQUIRE(m, "out of host memory");
+  m->d = *desc;
+  m->xyz_in = 3 + 6 * desc->pos_xyz_freqs;
+  m->dir_in = 3 + 6 * desc->pos_dir_freqs;
+  m->cat_in = desc->width + m->dir_in + desc->appearance_dim;
+  m->x_cols = (desc->mip ? 6 : 3) + 3 + 1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  const int M = desc->width, E = desc->num_experts, L = desc->expert_layers;
+  size_t n = 0;
+  auto cnt = [&](size_t k) { size_t o = n; n += (k + 63) / 64 * 64; return o; };
+  size_t o_xyz_w = cnt((size_t)M * m->xyz_in), o_xyz_b = cnt(M);
+  size_t o_gw[4], o_gb[4];
+  for (int i = 0; i < desc->gate_layers; ++i) { o_gw[i] = cnt((size_t)M * M); o_gb[i] = cnt(M); }
+  size_t o_lnw = cnt(M), o_lnb = cnt(M), o_wg = cnt((size_t)E * M);
+  size_t o_ew[16], o_eb[16];
+  for (int j = 0; j < L; ++j) { o_ew[j] = cnt((size_t)E * M * M); o_eb[j] = cnt((size_t)E * M); }
+  size_t o_l1w = cnt((size_t)M * M), o_l1b = cnt(M), o_l2w = cnt((size_t)desc->hidden2 * m->cat_in), o_l2b = cnt(desc->hidden2);
+  size_t o_sw = cnt(M), o_sb = cnt(1), o_cw = cnt((size_t)3 * desc->hidden2), o_cb = cnt(3);
+  size_t o_emb = cnt((size_t)desc->appearance_count * (desc->appearance_dim > 0 ? desc->appearance_dim : 1));
+  m->f32_bytes = n * sizeof(float);
+  cudaError_t e = cudaMalloc(&m->f32_blob, m->f32_bytes);
+  if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", m->f32_bytes, cudaGetErrorString(e)); delete m; return SNB_ECUDA; }
+  float* b = m->f32_blob;
+  m->xyz_w = b + o_xyz_w; m->xyz_b = b + o_xyz_b;
+  for (int i = 0; i < desc->gate_layers; ++i) { m->gate_w[i] = b + o_gw[i]; m->gate_b[i] = b + o_gb[i]; }
+  m->ln_w = b + o_lnw; m->ln_b = b + o_lnb; m->wg = b + o_wg;
+  for (int j = 0; j < L; ++j) { m->exp_w[j] = b + o_ew[j]; m->exp_b[j] = b + o_eb[j]; }
+  m->l1_w = b + o_l1w; m->l1_b = b + o_l1b; m->l2_w = b + o_l2w; m->l2_b = b + o_l2b;
+  m->sigma_w = b + o_sw; m->sigma_b = b + o_sb; m->color_w = b + o_cw; m->color_b = b + o_cb; m->emb_a = b + o_emb;
+  rc = upload(m, w, (cudaStream_t)stream);
+  if (rc) { snb_model_destroy((snb_model_t*)m); return rc; }
+  *out = (snb_model_t*)m;
+  return SNB_OK;
+}
+
+int snb_model_update(snb_model_t* mm, const snb_weights* w, void* stream) {
+  SNB_REQUIRE(mm && w, "snb_model_update: NULL argument");
+  return upload((Model*)mm, w, (cudaStream_t)stream);
+}
+
+void snb_model_destroy(snb_model_t* mm) {
+  Model* m = (Model*)mm;
+  if (!m) return;
+  if (m->f32_blob) cudaFree(m->f32_blob);
+  if (m->tc_blob) cudaFree(m->tc_blob);
+  delete m;
+}
+
+size_t snb_workspace_bytes(const snb_model_t* mm, int64_t max_chunk_samples, double max_cf) {
+  const Model* m = (const Model*)mm;
+  if (!m) return 0;
+  size_t a = fp32_workspace_bytes(m, max_chunk_samples, max_cf);
+  size_t b = tc_supported(m) ? tc_workspace_bytes(m, max_chunk_samples, max_cf) : 0;
+  return (a > b ? a : b) + 4096;
+}
+
+size_t snb_route_workspace_bytes(int64_t S, int32_t E) { return route_workspace_bytes(S, E); }
+
+int snb_route_top1(const float* gates, int64_t S, int32_t E, double capacity_factor, int32_t bpr, int32_t* idx,
+                   int32_t* loc, float* gate, int32_t* counts, int32_t* capacity, float* l_aux, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  SNB_REQUIRE(capacity_factor > 0, "capacity_factor must be > 0 (dynamic capacity is not part of the hot path)");
+  return route_top1_generic(gates, S, E, capacity_factor, bpr, idx, loc, gate, counts, capacity, l_aux, workspace,
+                            workspace_bytes, (cudaStream_t)stream);
+}
+
+int snb_dispatch_fwd(const float* x, const int32_t* idx, const int32_t* loc, const int32_t* begin, int64_t S,
+                     int32_t H, int32_t capacity, int64_t rows_out, float* out, void* stream) {
+  SNB_REQUIRE(out && (S == 0 || (x && idx && loc)), "snb_dispatch_fwd: NULL pointer");
+  return snb_dispatch_impl(x, idx, loc, begin, nullptr, capacity, S, H, rows_out, out, true, (cudaStream_t)stream);
+}
+
+int snb_combine(const float* buf, const int32_t* idx, const int32_t* loc, const int32_t* begin, const float* gate,
+                int64_t S, int32_t H, int32_t capacity, int64_t rows_buf, float* y, void* stream) {
+  SNB_REQUIRE(S == 0 || (buf && idx && loc && y), "snb_combine: NULL pointer");
+  return snb_combine_impl(buf, idx, loc, begin, gate, nullptr, capacity, S, H, rows_buf, y, false, (cudaStream_t)stream);
+}
+
+int snb_moe_forward(snb_model_t* mm, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* opts,
+                    int32_t precision, float* out, int32_t* moe_idx, float* l_aux, float* dbg_gates,
+                    int32_t* dbg_loc, void* workspace, size_t workspace_bytes, void* stream) {
+  Model* m = (Model*)mm;
+  SNB_REQUIRE(m && opts, "snb_moe_forward: NULL model/opts");
+  SNB_REQUIRE(S >= 0, "snb_moe_forward: negative S");
+  SNB_REQUIRE(S == 0 || (x && out), "snb_moe_forward: NULL x/out");
+  SNB_REQUIRE(opts->capacity_factor > 0, "capacity_factor must be > 0");
+  SNB_REQUIRE(S < (1ll << 31) / 16, "snb_moe_forward: S too large for one chunk");
+  Arena ws(workspace, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S == 0) {
+    if (l_aux) SNB_CHECK_CUDA(cudaMemsetAsync(l_aux, 0, sizeof(float), st));
+    return SNB_OK;
+  }
+  if (precision == SNB_PREC_FP32)
+    return fp32_forward(m, x, S, sigma_noise, opts, out, moe_idx, l_aux, dbg_gates, dbg_loc, ws, st);
+  if (precision == SNB_PREC_BF16) {
+    if (!tc_supported(m)) {
+      set_error("SNB_PREC_BF16 (tcgen05) supports width 256/512 topologies only (got width=%d, hidden2=%d)",
+                m->d.width, m->d.hidden2);
+      return SNB_EUNSUPPORTED;
+    }
+    return tc_forward(m, x, S, sigma_noise, opts, out, moe_idx, l_aux, dbg_gates, dbg_loc, ws, st);
+  }
+  set_error("unknown precision %d", precision);
+  return SNB_EINVAL;
+}
+
+int snb_composite(const float* z, const float* raw, const float* last_delta, int64_t n_rays, int32_t n_samples,
+                  int32_t white_bkgd, float* rgb, float* depth, float* depth_variance, float* bg_lambda,
+                  float* weights, void* stream) {
+  SNB_REQUIRE(n_rays == 0 || (z && raw), "snb_composite: NULL pointer");
+  return composite_launch(z, raw, last_delta, n_rays, n_samples, white_bkgd, rgb, depth, depth_variance, bg_lambda,
+                          weights, (cudaStream_t)stream);
+}
+
+int snb_sample_pdf(const float* bins, const float* weights, const float* u, int64_t n_rays, int32_t n_bins_minus1,
+                   int32_t n_fine, float* z_fine, void* stream) {
+  SNB_REQUIRE(n_rays == 0 || (bins && weights && z_fine), "snb_sample_pdf: NULL pointer");
+  return sample_pdf_launch(bins, n_bins_minus1 + 1, weights, n_bins_minus1, 0, u, n_rays, n_bins_minus1, n_fine, 0,
+                           u == nullptr, z_fine, (cudaStream_t)stream);
+}
+
+static size_t render_ws_layout(const Model* m, int64_t N, const snb_render_opts* o, size_t* model_ws) {
+  const int Sc = o->coarse_samples, Sf = o->fine_samples;
+  const int64_t Smax = (int64_t)N * (Sc > Sf ? Sc : Sf);
+  int64_t chunk = o->model_chunk_size < Smax ? o->model_chunk_size : Smax;
+  if (chunk < 1) chunk = 1;
+  size_t mw = snb_workspace_bytes((const snb_model_t*)m, chunk, o->route.capacity_factor);
+  if (model_ws) *model_ws = mw;
+  size_t b = mw;
+  auto add = [&](size_t n) { b += align_up(n * sizeof(float), 256); };
+  add((size_t)N * Sc);            // zc
+  add((size_t)N * Sc);            // weights_c
+  add((size_t)N * (Sc > 1 ? Sc - 1 : 1));  // zmid
+  add((size_t)N * (Sf > 0 ? Sf : 1));      // zf
+  add((size_t)Smax * m->x_cols);  // x
+  add((size_t)N * Sc * 4);        // raw_c
+  add((size_t)N * (Sf > 0 ? Sf : 1) * 4);  // raw_f
+  add((size_t)N * (Sc > Sf ? Sc : Sf));    // moe idx scratch (int)
+  return b + 4096;
+}
+
+size_t snb_render_workspace_bytes(const snb_model_t* mm, int64_t n_rays, const snb_render_opts* o) {
+  if (!mm || !o) return 0;
+  return render_ws_layout((const Model*)mm, n_rays, o, nullptr);
+}
+
+int snb_render_rays(snb_model_t* mm, const float* rays, const int32_t* image_indices, const float* last_delta,
+                    int64_t N, const snb_render_opts* o, const snb_render_out* out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  Model* m = (Model*)mm;
+  SNB_REQUIRE(m && o && out, "snb_render_rays: NULL argument");
+  SNB_REQUIRE(!m->d.mip, "snb_render_rays: this entry point renders NeRFMoE; mip models use snb_render_rays_mip");
+  SNB_REQUIRE(N >= 0 && (N == 0 || rays), "snb_render_rays: bad rays");
+  SNB_REQUIRE(o->coarse_samples >= 2 && o->fine_samples >= 0, "snb_render_rays: bad sample counts");
+  SNB_REQUIRE(o->model_chunk_size >= 1, "snb_render_rays: bad model_chunk_size");
+  SNB_REQUIRE(o->fine_samples == 0 || o->coarse_samples >= 3, "fine sampling needs >= 3 coarse samples");
+  if (N == 0) return SNB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Sc = o->coarse_samples, Sf = o->fine_samples;
+  size_t model_ws = 0;
+  size_t need = render_ws_layout(m, N, o, &model_ws);
+  if (workspace_bytes < need) { set_error("snb_render_rays: workspace %zu < required %zu", workspace_bytes, need); return SNB_EWORKSPACE; }
+  Arena a(workspace, workspace_bytes);
+  char* mws = a.take<char>(model_ws);
+  float* zc = a.take<float>((size_t)N * Sc);
+  float* wc = a.take<float>((size_t)N * Sc);
+  float* zmid = a.take<float>((size_t)N * (Sc - 1));
+  float* zf = a.take<float>((size_t)N * (Sf > 0 ? Sf : 1));
+  const int64_t Smax = (int64_t)N * (Sc > Sf ? Sc : Sf);
+  float* x = a.take<float>((size_t)Smax * m->x_cols);
+  float* raw_c = a.take<float>((size_t)N * Sc * 4);
+  float* raw_f = a.take<float>((size_t)N * (Sf > 0 ? Sf : 1) * 4);
+  if (!a.ok) { set_error("snb_render_rays: workspace carve failed"); return SNB_EWORKSPACE; }
+  if (out->raw_coarse) raw_c = out->raw_coarse;
+  if (out->raw_fine && Sf > 0) raw_f = out->raw_fine;
+  if (out->z_fine && Sf > 0) zf = out->z_fine;
+
+  auto run_pass = [&](const float* z, int Sn, float* raw, int32_t* gates_out, float* loss_out) -> int {
+    int rc = fill_x_launch(rays, image_indices, z, N, Sn, x, st);
+    if (rc) return rc;
+    const int64_t B = N * Sn;
+    int ci = 0;
+    for (int64_t i = 0; i < B; i += o->model_chunk_size, ++ci) {       // rendering.py:354
+      const int64_t rows = (B - i < o->model_chunk_size) ? (B - i) : o->model_chunk_size;
+      rc = snb_moe_forward(mm, x + i * m->x_cols, rows, nullptr, &o->route, o->precision, raw + i * 4,
+                           gates_out ? gates_out + i : nullptr, loss_out ? loss_out + ci : nullptr, nullptr, nullptr,
+                           mws, model_ws, st);
+      if (rc) return rc;
+    }
+    return SNB_OK;
+  };
+
+  int rc;
+  if ((rc = coarse_z_launch(rays, N, Sc, o->perturb, o->seed, zc, st))) return rc;
+  if ((rc = run_pass(zc, Sc, raw_c, out->moe_gates_coarse, out->gate_loss_coarse))) return rc;
+  if (Sf == 0) {
+    return composite_launch(zc, raw_c, last_delta, N, Sc, o->white_bkgd, out->rgb, out->depth, out->depth_variance,
+                            out->bg_lambda, nullptr, st);
+  }
+  // coarse weights -> pdf over the interior bins (rendering.py:237-241)
+  if ((rc = composite_launch(zc, raw_c, last_delta, N, Sc, 0, nullptr, nullptr, nullptr, nullptr, wc, st))) return rc;
+  if ((rc = zmid_launch(zc, N, Sc, zmid, st))) return rc;
+  if ((rc = sample_pdf_launch(zmid, Sc - 1, wc, Sc, 1, nullptr, N, Sc - 2, Sf, o->seed, o->perturb == 0.f, zf, st))) return rc;
+  if ((rc = run_pass(zf, Sf, raw_f, out->moe_gates_fine, out->gate_loss_fine))) return rc;
+  return merge_composite_launch(zf, zc, raw_f, raw_c, last_delta, N, Sf, Sc, o->white_bkgd, out->rgb, out->depth,
+                                out->depth_variance, out->bg_lambda, st);
+}
+
+int snb_umma_selftest(const void* a_bf16, const void* b_bf16, int32_t N, int32_t K, float* d, int32_t variant,
+                      void* stream) {
+  SNB_REQUIRE(a_bf16 && b_bf16 && d, "snb_umma_selftest: NULL pointer");
+  return umma_selftest(a_bf16, b_bf16, N, K, d, variant, (cudaStream_t)stream);
+}
+
+}  // extern "C"

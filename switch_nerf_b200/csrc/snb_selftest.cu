@@ -1,0 +1,119 @@
+// snb_umma_selftest: one 128 x N x K bf16 GEMM tile through exactly the machinery the fused
+// kernels rely on -- canonical no-swizzle K-major core-matrix operands in shared memory, UMMA
+// shared-memory + instruction descriptors, single-thread tcgen05.mma issue, tcgen05.commit ->
+// mbarrier, TMEM allocation and tcgen05.ld epilogue, and (variant bit 1) a 1-D bulk async copy
+// of a pre-packed B image.  tests/test_umma_selftest.py checks it against a float reference,
+// which pins the descriptor encodings on real hardware before the large kernels depend on them.
+#include "snb_common.cuh"
+#include "snb_umma.cuh"
+
+namespace snb {
+using namespace ptx;
+
+// canonical offset of element (r, k) (bf16) for a tile whose 8-row groups are `sbo` bytes apart and whose
+// K-adjacent core matrices are `lbo` bytes apart
+__device__ __forceinline__ uint32_t canon_off(int r, int k, uint32_t lbo, uint32_t sbo) {
+  return (uint32_t)(r >> 3) * sbo + (uint32_t)(k >> 3) * lbo + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 7) * 2u;
+}
+
+__global__ void k_pack_canonical(const __nv_bfloat16* __restrict__ src, int R, int K, uint32_t lbo, uint32_t sbo,
+                                 __nv_bfloat16* __restrict__ dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R * K; i += gridDim.x * blockDim.x) {
+    int r = i / K, k = i % K;
+    dst[canon_off(r, k, lbo, sbo) / 2] = src[i];
+  }
+}
+
+__global__ void __launch_bounds__(128) k_umma_selftest(const __nv_bfloat16* __restrict__ A,
+                                                       const __nv_bfloat16* __restrict__ B,
+                                                       const __nv_bfloat16* __restrict__ B_packed, int N, int K,
+                                                       float* __restrict__ D, int variant) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_mma, bar_copy;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lbo = 128, sboA = (uint32_t)(K / 8) * 128, sboB = (uint32_t)(K / 8) * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)128 * K * 2;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_mma, 1);
+    mbar_init(&bar_copy, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+  // A: generic-proxy stores into the canonical layout (what the epilogue warps do in the fused kernels)
+  for (int i = threadIdx.x; i < 128 * (K / 8); i += blockDim.x) {
+    int r = i / (K / 8), kc = i % (K / 8);
+    uint4 v = *reinterpret_cast<const uint4*>(A + (size_t)r * K + kc * 8);
+    *reinterpret_cast<uint4*>(sA + canon_off(r, kc * 8, lbo, sboA)) = v;
+  }
+  const bool use_bulk = (variant & 2) != 0;
+  if (!use_bulk) {
+    for (int i = threadIdx.x; i < N * (K / 8); i += blockDim.x) {
+      int r = i / (K / 8), kc = i % (K / 8);
+      uint4 v = *reinterpret_cast<const uint4*>(B + (size_t)r * K + kc * 8);
+      *reinterpret_cast<uint4*>(sB + canon_off(r, kc * 8, lbo, sboB)) = v;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 1 && lane == 0) {
+    if (use_bulk) {
+      const uint32_t bytes = (uint32_t)N * K * 2;
+      mbar_arrive_expect_tx(&bar_copy, bytes);
+      bulk_g2s(sB, B_packed, bytes, &bar_copy);
+      mbar_wait(&bar_copy, 0);
+    }
+    const uint32_t idesc = umma_idesc_bf16(128, N);
+    const bool swap = (variant & 1) != 0;
+    for (int k = 0; k < K / 16; ++k) {
+      // one MMA consumes K=16 = two core matrices along K
+      uint32_t a_addr = smem_u32(sA) + (uint32_t)k * 2 * lbo;
+      uint32_t b_addr = smem_u32(sB) + (uint32_t)k * 2 * lbo;
+      uint64_t da = swap ? umma_smem_desc(a_addr, sboA, lbo) : umma_smem_desc(a_addr, lbo, sboA);
+      uint64_t db = swap ? umma_smem_desc(b_addr, sboB, lbo) : umma_smem_desc(b_addr, lbo, sboB);
+      umma_bf16(tmem_base, da, db, idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  // epilogue: warp w reads TMEM lanes [32w, 32w+32)
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < N) D[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem_base);
+}
+
+int umma_selftest(const void* a, const void* b, int N, int K, float* d, int variant, cudaStream_t st) {
+  SNB_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "selftest: N=%d must be a multiple of 16 in [16,256]", N);
+  SNB_REQUIRE(K >= 16 && K <= 512 && K % 16 == 0, "selftest: K=%d must be a multiple of 16 in [16,512]", K);
+  size_t smem = (size_t)(128 + N) * K * 2 + 1024;
+  SNB_REQUIRE(smem <= 227 * 1024, "selftest: tile does not fit shared memory");
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  __nv_bfloat16* packed = nullptr;
+  if (variant & 2) {
+    SNB_CHECK_CUDA(cudaMallocAsync((void**)&packed, (size_t)N * K * 2, st));
+    k_pack_canonical<<<64, 256, 0, st>>>((const __nv_bfloat16*)b, N, K, 128, (uint32_t)(K / 8) * 128, packed);
+    SNB_CHECK_LAUNCH("k_pack_canonical");
+  }
+  k_umma_selftest<<<1, 128, smem, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, packed, N, K, d, variant);
+  SNB_CHECK_LAUNCH("k_umma_selftest");
+  if (packed) SNB_CHECK_CUDA(cudaFreeAsync(packed, st));
+  return SNB_OK;
+}
+
+}  // namespace snb

@@ -1,0 +1,85 @@
+"""CPU: the oracle restatement reproduces the committed golden fixtures, which were written by the
+UNMODIFIED reference (oracle/make_golden.py).  Bit-exact in fp32."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import switch_nerf_oracle as O
+from oracle.make_golden import ROUTE_CASES, make_gates, model_inputs
+from tests.util import golden_sd, load_golden
+
+
+def _sha(t):
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("case", ROUTE_CASES, ids=[c[0] for c in ROUTE_CASES])
+def test_route_golden(case):
+    name, S, E, cf, bpr, seed, temp, tie, sat = case
+    g = load_golden("route_cases.npz")
+    gates = make_gates(S, E, seed, temp, tie, sat)
+    assert _sha(gates) == str(g[f"{name}/sha"][3]), "gate generator drifted"
+    idx, loc, gv, cap, l_aux = O.route_top1(gates, cf, bpr)
+    assert cap == int(g[f"{name}/cap"][0])
+    assert _sha(idx) == str(g[f"{name}/sha"][0])
+    assert _sha(loc) == str(g[f"{name}/sha"][1])
+    assert _sha(gv) == str(g[f"{name}/sha"][2])
+    assert float(l_aux) == float(g[f"{name}/l_aux"][0])
+    if S <= 8192:
+        assert np.array_equal(idx.numpy(), g[f"{name}/idx"]) and np.array_equal(loc.numpy(), g[f"{name}/loc"])
+
+
+def test_capacity_formula():
+    # tutel_fast_dispatch.py:210-211 ; Python int() truncation of a double product
+    assert O.capacity_of(131072, 8, 1.0) == 16384
+    assert O.capacity_of(131072, 8, 0.5) == 8192
+    assert O.capacity_of(131072, 8, 2.0) == 32768
+    assert O.capacity_of(5000, 8, 0.5) == 312
+    assert O.capacity_of(7, 8, 1.0) == 1
+    assert O.capacity_of(10, 1, 0.7) == int(0.7 * 10)
+
+
+@pytest.mark.parametrize("tag", ["e4_cf1_bpr_fp32", "e8_cf05_nobpr_fp32", "e8_cf1_bpr_fp32_s777", "e4_nobatch_fp32"])
+def test_model_golden_fp32(tag):
+    g = load_golden(f"model_{tag}.npz")
+    E, cf, bpr, S, seed, gs, count, nobatch, _ = g["params"]
+    sd = golden_sd(g)
+    x = torch.from_numpy(g["x"])
+    assert torch.equal(x, model_inputs(int(S), int(count), int(seed) + 100))
+    cfg = O.default_cfg(sd, float(cf), bool(bpr), moe_no_batch=bool(nobatch))
+    out, ex = O.nerf_moe_forward(x, sd, cfg, mode="fp32")
+    assert np.array_equal(out.numpy(), g["outputs"])
+    assert np.array_equal(ex["idx"].numpy(), g["idx"])
+    assert np.array_equal(ex["loc"].numpy(), g["loc"])
+    assert float(ex["l_aux"]) == float(g["l_aux"][0])
+
+
+def test_model_golden_bf16():
+    """The bf16 rounding map of the oracle vs the reference under torch.autocast('cpu', bf16):
+    outputs are bf16 (ulp 2^-8 near 1), so agreement is 'within one output ulp, almost always exact'."""
+    g = load_golden("model_e8_cf1_bpr_bf16cpu.npz")
+    sd = golden_sd(g)
+    cfg = O.default_cfg(sd, 1.0, True)
+    out, ex = O.nerf_moe_forward(torch.from_numpy(g["x"]), sd, cfg, mode="bf16", flavor="cpu")
+    d = np.abs(out.numpy() - g["outputs"])
+    same_route = ex["idx"].numpy() == g["idx"]
+    assert same_route.mean() > 0.995
+    assert d[same_route].max() <= 2 ** -7 + 1e-6      # <= 2 bf16 ulps of a value in [0.5, 1)
+    assert (d > 1e-3).mean() < 0.03
+    assert d.mean() < 1e-4
+
+
+@pytest.mark.parametrize("tag", ["config1", "config1_coarse_only", "ragged_chunks"])
+def test_render_golden(tag):
+    g = load_golden(f"render_{tag}.npz")
+    E, cf, bpr, n_rays, cs, fs, chunk, seed, gs, count = g["params"]
+    sd = golden_sd(g)
+    cfg = O.default_cfg(sd, float(cf), bool(bpr))
+    res = O.render_rays(sd, cfg, torch.from_numpy(g["rays"]), torch.from_numpy(g["image_indices"]),
+                        coarse_samples=int(cs), fine_samples=int(fs), model_chunk_size=int(chunk))
+    typ = "fine" if fs > 0 else "coarse"
+    for k in (f"rgb_{typ}", f"depth_{typ}", f"depth_variance_{typ}", "gate_loss_coarse"):
+        assert np.array_equal(res[k].numpy(), g[k]), k
+    assert np.array_equal(res["moe_gates_coarse"].numpy().astype(np.int32), g["moe_gates_coarse"])
