@@ -46,9 +46,10 @@ def make_gates(S, E, seed, temperature=1.0, tie_frac=0.0, saturate_frac=0.0):
     if tie_frac > 0:
         n = int(S * tie_frac)
         rows = torch.randperm(S, generator=g)[:n]
-        logits[rows] = logits[rows[0]].clone()      # identical rows -> identical max gate
-        perm = torch.stack([torch.randperm(E, generator=g) for _ in range(n)])
-        logits[rows] = torch.gather(logits[rows], 1, perm)   # ... routed to different experts
+        if n > 0:
+            logits[rows] = logits[rows[0]].clone()      # identical rows -> identical max gate
+            perm = torch.stack([torch.randperm(E, generator=g) for _ in range(n)])
+            logits[rows] = torch.gather(logits[rows], 1, perm)   # ... routed to different experts
     return torch.softmax(logits, dim=1)
 
 

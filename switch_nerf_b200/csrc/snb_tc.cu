@@ -1,8 +1,836 @@
-// placeholder, replaced below
+// SNB_PREC_BF16 path: the NeRFMoE forward of one model_chunk as two fused tcgen05 kernels
+// (+ the small routing kernels in between):
+//
+//   k_front  (launch #1)  per 128-sample tile: positional encoding -> xyz Linear -> external gate
+//                         MLP -> LayerNorm -> fp32 gate GEMM -> softmax.  Writes h (bf16 [S,M]) and
+//                         gates (fp32 [S,E]).  reference: models/nerf_moe.py:330-372,
+//                         tutel_moe_layer_nobatch.py:105-126
+//   route_top1            snb_route.cu (idx / loc / counts / l_aux on device)
+//   k_back   (launch #2)  per (expert, 128-row tile of that expert's bucket): gather rows by the
+//                         dispatch index -> 7 expert layers (skip at 3) -> x gate (combine) -> ReLU
+//                         -> sigma head -> layer "1" -> [dir PE | appearance] concat -> layer "2" ->
+//                         colour head -> sigmoid / softplus -> scatter [rgb, sigma] to out[sample].
+//                         Dropped samples form one more bucket that skips the expert stack (h = 0).
+//                         reference: tutel_moe_layer_nobatch.py:142-225, 887-924; nerf_moe.py:384-441
+//
+// Inside a CTA (192 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0     weight producer : 1-D bulk async copies (UBLKCP) of pre-packed K-slices (<=64 wide)
+//                                into a 3-stage shared-memory ring, mbarrier full/empty
+//   warp 1     MMA issuer      : one thread issues tcgen05.mma (M=128, N<=256, K=16 per instr.),
+//                                accumulators in TMEM, ping-pong between columns [0,256) / [256,512)
+//   warps 2-5  epilogue        : tcgen05.ld -> bias / ReLU / skip / gate / LayerNorm / heads in fp32
+//                                registers -> bf16 back into the shared A tile, 64 columns at a time,
+//                                signalling per-chunk mbarriers so the next layer's MMAs start while
+//                                the rest of the epilogue is still running.
+// Activations never leave the SM between layers; per sample HBM traffic is x (28 B) + h (2x512 B)
+// + gates (32 B) + out (16 B).
+//
+// Operand layout (both A and B, "K-major, no swizzle" UMMA canonical form): 8x8 bf16 core matrices of
+// 128 contiguous bytes; LBO = distance between K-adjacent core matrices (128 B), SBO = distance
+// between 8-row groups.  Weights are packed into exactly that image on the host side of the C ABI
+// (tc_pack_weights) so a K-slice is ONE contiguous bulk copy.
 #include "snb_common.cuh"
+#include "snb_umma.cuh"
+
 namespace snb {
-bool tc_supported(const Model* m) { return false; }
-int tc_pack_weights(Model*, const snb_weights*, cudaStream_t) { return SNB_OK; }
-size_t tc_workspace_bytes(const Model*, int64_t, double) { return 0; }
-int tc_forward(Model*, const float*, int64_t, const float*, const snb_route_opts*, float*, int32_t*, float*, float*, int32_t*, Arena&, cudaStream_t) { set_error("tc path not built"); return SNB_EUNSUPPORTED; }
+using namespace ptx;
+
+static constexpr int TILE = 128;            // rows per tile (UMMA M)
+static constexpr int MW = 256;              // model width handled by this path
+static constexpr int KA_MAX = 352;          // widest A operand (layer "2": 256 + 27 + 48 = 331 -> 336), padded
+static constexpr uint32_t SBO_A = KA_MAX / 8 * 128;   // 5632 B between 8-row groups of the A tile
+static constexpr uint32_t A_BYTES = TILE / 8 * SBO_A; // 90112
+static constexpr int NSTAGE = 3;
+static constexpr uint32_t STAGE_BYTES = 256 * 64 * 2; // one K-slice of a 256-wide layer
+static constexpr int NCHUNK = 6;            // 64-column chunks of the A tile (352/64 rounded up)
+static constexpr int THREADS = 192;
+static constexpr int EPI_THREADS = 128;
+static constexpr int MAX_E = 16;
+
+#ifndef SNB_UMMA_SWAP
+#define SNB_UMMA_SWAP 0   // set to 1 if the hardware interprets LBO/SBO the other way round (selftest variant 1)
+#endif
+__device__ __forceinline__ uint64_t op_desc(uint32_t addr, uint32_t k_stride, uint32_t mn_stride) {
+#if SNB_UMMA_SWAP
+  return umma_smem_desc(addr, mn_stride, k_stride);
+#else
+  return umma_smem_desc(addr, k_stride, mn_stride);
+#endif
 }
+
+// ------------------------------------------------------------------------------------------
+// packed weights
+// ------------------------------------------------------------------------------------------
+struct TcLayer {
+  uint32_t w_off;   // byte offset of the packed bf16 image inside tc_blob
+  uint32_t K16;     // K rounded up to 16
+  uint32_t N;       // output features (<= 256)
+  uint32_t b_off;   // float offset of the bias inside the fp32 side table
+};
+
+struct TcParams {
+  const uint8_t* wblob;     // packed bf16 weights
+  const float* fblob;       // fp32 side table: biases (bf16-rounded), ln, wg, sigma/colour heads
+  TcLayer front[5];         // xyz, gate fcs
+  int n_front;
+  TcLayer expert[16];       // layer j of expert 0; expert e adds e*expert_stride(_b)
+  int n_expert;
+  uint32_t expert_w_stride; // bytes between experts (all layers of one expert are contiguous)
+  uint32_t expert_b_stride; // floats between experts
+  TcLayer back[2];          // layer "1", layer "2"
+  uint32_t o_lnw, o_lnb, o_wg, o_wsig, o_bsig, o_wcol, o_bcol;   // float offsets in fblob
+  int E, skip_layer, pos_xyz_freqs, pos_dir_freqs, appearance_dim, appearance_count, hidden2, x_cols;
+  const float* emb_a;       // fp32 [count, A]
+};
+
+__global__ void k_pack_layer(const float* __restrict__ w, int N, int K, int K16, int transposed_kn,
+                             __nv_bfloat16* __restrict__ dst) {
+  // dst image: slices of 64 k; inside a slice: (n/8)*(klen*16) + (kk/8)*128 + (n%8)*16 + (kk%8)*2 bytes
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * K16; i += gridDim.x * blockDim.x) {
+    const int n = i / K16, k = i % K16;
+    float v = 0.f;
+    if (k < K) v = transposed_kn ? w[(size_t)k * N + n] : w[(size_t)n * K + k];
+    const int j = k / 64, kk = k % 64;
+    const int klen = min(64, K16 - 64 * j);
+    const size_t slice_base = (size_t)N * 64 * j;   // elements
+    const size_t off = slice_base + ((size_t)(n / 8) * (klen * 16) + (size_t)(kk / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2) / 2;
+    dst[off] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void k_round_copy(const float* __restrict__ src, int n, int round_bf16, float* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = round_bf16 ? bf16_round(src[i]) : src[i];
+}
+
+struct TcHost {
+  TcParams p;
+  float* fblob;
+  size_t fblob_floats;
+};
+
+bool tc_supported(const Model* m) {
+  const snb_model_desc& d = m->d;
+  return d.width == MW && d.num_experts <= MAX_E && d.hidden2 <= 256 && d.hidden2 % 16 == 0 && d.gate_layers <= 4 &&
+         !d.mip && m->xyz_in <= 128 && m->cat_in <= KA_MAX - 16 + 16 && ((m->cat_in + 15) / 16 * 16) <= KA_MAX &&
+         d.expert_layers <= 16 && d.appearance_dim % 4 == 0;
+}
+
+static TcHost* tc_host(Model* m) { return (TcHost*)m->tc_blob; }
+
+int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
+  const snb_model_desc& d = m->d;
+  const int E = d.num_experts, L = d.expert_layers, H2 = d.hidden2;
+  // (re)build the host descriptor + device blobs; m->tc_blob holds a host struct that owns them
+  struct Owner { TcHost h; uint8_t* wblob; };
+  static_assert(sizeof(TcHost) > 0, "");
+  Owner* own = nullptr;
+  if (m->tc_blob == nullptr) {
+    own = new Owner();
+    memset(own, 0, sizeof(Owner));
+    // layout
+    size_t wbytes = 0, nf = 0;
+    TcParams& p = own->h.p;
+    auto add_layer = [&](TcLayer& l, int N, int K) {
+      l.K16 = (uint32_t)((K + 15) / 16 * 16);
+      l.N = (uint32_t)N;
+      l.w_off = (uint32_t)wbytes;
+      wbytes += (size_t)N * l.K16 * 2;
+      wbytes = align_up(wbytes, 128);
+      l.b_off = (uint32_t)nf;
+      nf += (size_t)align_up((size_t)N, 64);
+    };
+    p.n_front = 1 + d.gate_layers;
+    add_layer(p.front[0], MW, m->xyz_in);
+    for (int i = 0; i < d.gate_layers; ++i) add_layer(p.front[1 + i], MW, MW);
+    add_layer(p.back[0], MW, MW);
+    add_layer(p.back[1], H2, m->cat_in);
+    p.n_expert = L;
+    size_t e0_w = wbytes, e0_f = nf;
+    for (int j = 0; j < L; ++j) add_layer(p.expert[j], MW, MW);
+    p.expert_w_stride = (uint32_t)(wbytes - e0_w);
+    p.expert_b_stride = (uint32_t)(nf - e0_f);
+    wbytes = e0_w + (size_t)p.expert_w_stride * E;
+    nf = e0_f + (size_t)p.expert_b_stride * E;
+    auto addf = [&](size_t n) { size_t o = nf; nf += align_up(n, 64); return (uint32_t)o; };
+    p.o_lnw = addf(MW); p.o_lnb = addf(MW); p.o_wg = addf((size_t)E * MW);
+    p.o_wsig = addf(MW); p.o_bsig = addf(1); p.o_wcol = addf((size_t)3 * H2); p.o_bcol = addf(3);
+    p.E = E; p.skip_layer = d.skip_layer; p.pos_xyz_freqs = d.pos_xyz_freqs; p.pos_dir_freqs = d.pos_dir_freqs;
+    p.appearance_dim = d.appearance_dim; p.appearance_count = d.appearance_count; p.hidden2 = H2; p.x_cols = m->x_cols;
+    SNB_CHECK_CUDA(cudaMalloc((void**)&own->wblob, wbytes));
+    SNB_CHECK_CUDA(cudaMalloc((void**)&own->h.fblob, nf * sizeof(float)));
+    own->h.fblob_floats = nf;
+    p.wblob = own->wblob;
+    p.fblob = own->h.fblob;
+    p.emb_a = m->emb_a;
+    m->tc_blob = own;
+    m->tc_bytes = wbytes;
+  } else {
+    own = (Owner*)m->tc_blob;
+  }
+  TcParams& p = own->h.p;
+  SNB_CHECK_CUDA(cudaMemsetAsync(own->h.fblob, 0, own->h.fblob_floats * sizeof(float), st));
+  auto pack = [&](const TcLayer& l, const float* wsrc, int K, int transposed, size_t extra_w, const float* bsrc,
+                  size_t extra_b) -> int {
+    k_pack_layer<<<256, 256, 0, st>>>(wsrc, (int)l.N, K, (int)l.K16, transposed,
+                                      (__nv_bfloat16*)(own->wblob + l.w_off + extra_w));
+    SNB_CHECK_LAUNCH("k_pack_layer");
+    k_round_copy<<<(unsigned)cdiv(l.N, 256), 256, 0, st>>>(bsrc, (int)l.N, 1, own->h.fblob + l.b_off + extra_b);
+    SNB_CHECK_LAUNCH("k_round_copy");
+    return SNB_OK;
+  };
+  int rc;
+  // use the library-owned fp32 copies (already uploaded by snb_api upload()); experts there are [E][N][K]
+  if ((rc = pack(p.front[0], m->xyz_w, m->xyz_in, 0, 0, m->xyz_b, 0))) return rc;
+  for (int i = 0; i < d.gate_layers; ++i)
+    if ((rc = pack(p.front[1 + i], m->gate_w[i], MW, 0, 0, m->gate_b[i], 0))) return rc;
+  if ((rc = pack(p.back[0], m->l1_w, MW, 0, 0, m->l1_b, 0))) return rc;
+  if ((rc = pack(p.back[1], m->l2_w, m->cat_in, 0, 0, m->l2_b, 0))) return rc;
+  for (int e = 0; e < E; ++e)
+    for (int j = 0; j < L; ++j)
+      if ((rc = pack(p.expert[j], m->exp_w[j] + (size_t)e * MW * MW, MW, 0, (size_t)e * p.expert_w_stride,
+                     m->exp_b[j] + (size_t)e * MW, (size_t)e * p.expert_b_stride)))
+        return rc;
+  auto cpf = [&](uint32_t off, const float* src, int n, int round) -> int {
+    k_round_copy<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(src, n, round, own->h.fblob + off);
+    SNB_CHECK_LAUNCH("k_round_copy");
+    return SNB_OK;
+  };
+  if ((rc = cpf(p.o_lnw, m->ln_w, MW, 0))) return rc;       // LayerNorm + gate stay fp32 (fp32_gate: True)
+  if ((rc = cpf(p.o_lnb, m->ln_b, MW, 0))) return rc;
+  if ((rc = cpf(p.o_wg, m->wg, E * MW, 0))) return rc;
+  if ((rc = cpf(p.o_wsig, m->sigma_w, MW, 1))) return rc;   // bf16 Linear under autocast
+  if ((rc = cpf(p.o_bsig, m->sigma_b, 1, 1))) return rc;
+  if ((rc = cpf(p.o_wcol, m->color_w, 3 * d.hidden2, 1))) return rc;
+  if ((rc = cpf(p.o_bcol, m->color_b, 3, 1))) return rc;
+  (void)w;
+  return SNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory carve-up
+// ------------------------------------------------------------------------------------------
+struct __align__(16) SmemCtl {
+  uint64_t full[NSTAGE];
+  uint64_t empty[NSTAGE];
+  uint64_t acc_full[2];
+  uint64_t a_ready[NCHUNK];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+static constexpr size_t SM_A = 0;
+static constexpr size_t SM_RING = A_BYTES;
+static constexpr size_t SM_BIAS = SM_RING + (size_t)NSTAGE * STAGE_BYTES;   // 2 x 256 floats
+static constexpr size_t SM_VEC = SM_BIAS + 2 * 256 * 4;                     // head / LN / gate vectors (floats)
+static constexpr size_t SM_VEC_FLOATS = 256 * 2 + MAX_E * 256 + 3 * 256 + 16;  // lnw,lnb | wg | wsig,wcol | scalars
+static constexpr size_t SM_CTL = SM_VEC + SM_VEC_FLOATS * 4;
+static constexpr size_t SM_TOTAL = SM_CTL + sizeof(SmemCtl) + 1024;         // + alignment slack
+
+struct Pipe {               // running counters of one role
+  uint32_t slice = 0;       // weight slices produced / consumed so far
+  uint32_t a_use[NCHUNK] = {0, 0, 0, 0, 0, 0};
+  uint32_t acc_use[2] = {0, 0};
+};
+
+__device__ __forceinline__ uint32_t a_chunk_addr(uint32_t a_base, int row, int col8 /*col/8*/) {
+  return a_base + (uint32_t)(row >> 3) * SBO_A + (uint32_t)col8 * 128u + (uint32_t)(row & 7) * 16u;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// ---- producer: stream the K-slices of one layer through the ring ----
+__device__ __forceinline__ void produce_layer(const uint8_t* wsrc, uint32_t N, uint32_t K16, uint8_t* ring,
+                                              SmemCtl* ctl, Pipe& pp) {
+  const uint32_t nsl = (K16 + 63) / 64;
+  for (uint32_t j = 0; j < nsl; ++j) {
+    const uint32_t klen = min(64u, K16 - 64u * j);
+    const uint32_t bytes = N * klen * 2;
+    const uint32_t stage = pp.slice % NSTAGE, phase = (pp.slice / NSTAGE) & 1;
+    mbar_wait(&ctl->empty[stage], phase ^ 1);
+    mbar_arrive_expect_tx(&ctl->full[stage], bytes);
+    bulk_g2s(ring + (size_t)stage * STAGE_BYTES, wsrc + (size_t)N * 64 * 2 * j, bytes, &ctl->full[stage]);
+    ++pp.slice;
+  }
+}
+
+// ---- MMA issuer: one layer = K16/16 tcgen05.mma instructions into accumulator buffer `buf` ----
+__device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_base, uint32_t ring_base,
+                                          uint32_t tmem_base, int buf, SmemCtl* ctl, Pipe& pp) {
+  const uint32_t nsl = (K16 + 63) / 64;
+  const uint32_t idesc = umma_idesc_bf16(TILE, (int)N);
+  const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
+  for (uint32_t j = 0; j < nsl; ++j) {
+    const uint32_t klen = min(64u, K16 - 64u * j);
+    const uint32_t stage = pp.slice % NSTAGE, phase = (pp.slice / NSTAGE) & 1;
+    mbar_wait(&ctl->a_ready[j], pp.a_use[j] & 1);       // A columns [64j, 64j+klen) written + fenced
+    ++pp.a_use[j];
+    mbar_wait(&ctl->full[stage], phase);                // weight slice landed
+    tc_fence_after();
+    const uint32_t b_base = ring_base + stage * STAGE_BYTES;
+    for (uint32_t t = 0; t < klen / 16; ++t) {
+      const uint64_t da = op_desc(a_base + (8u * j + 2u * t) * 128u, 128u, SBO_A);
+      const uint64_t db = op_desc(b_base + (2u * t) * 128u, 128u, klen * 16u);
+      umma_bf16(d_tmem, da, db, idesc, (j | t) ? 1u : 0u);
+    }
+    umma_commit(&ctl->empty[stage]);                    // frees the ring slot when these MMAs retire
+    ++pp.slice;
+  }
+  umma_commit(&ctl->acc_full[buf]);                     // accumulator complete -> epilogue
+}
+
+// ---- epilogue helpers -------------------------------------------------------------------
+__device__ __forceinline__ void epi_wait_acc(SmemCtl* ctl, Pipe& pp, int buf) {
+  mbar_wait(&ctl->acc_full[buf], pp.acc_use[buf] & 1);
+  ++pp.acc_use[buf];
+  tc_fence_after();
+}
+__device__ __forceinline__ void epi_signal_chunk(SmemCtl* ctl, int c) {
+  fence_proxy_async_smem();    // my st.shared -> visible to the async proxy (tcgen05.mma operand reads)
+  tc_fence_before();           // my tcgen05.ld of the old accumulator happen-before the MMA that overwrites it
+  mbar_arrive(&ctl->a_ready[c]);
+}
+// stage the (bf16-rounded) bias of a layer into shared memory (double buffered by `slot`)
+__device__ __forceinline__ void epi_load_bias(const float* __restrict__ bias, int N, float* sbias, int slot, int et) {
+  float* dst = sbias + slot * 256;
+  for (int i = et; i < N; i += EPI_THREADS) dst[i] = bias[i];
+  epi_bar_sync();
+}
+
+// y = act(acc + bias (+ skip)) -> bf16 -> A tile, for all N columns; signals one a_ready per 64 columns.
+// `xrow` (nullable): bf16 row of the expert input for the skip connection (tutel_moe_layer_nobatch.py:911-916).
+template <bool RELU>
+__device__ __forceinline__ void epi_hidden(uint32_t tmem_acc, const float* sb, int N, uint32_t a_base, int row,
+                                           const __nv_bfloat16* xrow, SmemCtl* ctl, int n_signal) {
+  for (int c32 = 0; c32 < N / 32; ++c32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_acc + (uint32_t)c32 * 32u, v);
+    uint4 xs[4];
+    if (xrow) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) xs[q] = *reinterpret_cast<const uint4*>(xrow + c32 * 32 + q * 8);
+    }
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float f0 = __uint_as_float(v[j]) + sb[c32 * 32 + j];
+      float f1 = __uint_as_float(v[j + 1]) + sb[c32 * 32 + j + 1];
+      if (xrow) {
+        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs);
+        __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162*>(&xw[j / 2]);
+        // reference: h = bf16(Linear) ; h = bf16(h + x)
+        f0 = bf16_round(f0) + __bfloat162float(xb.x);
+        f1 = bf16_round(f1) + __bfloat162float(xb.y);
+      }
+      if (RELU) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+      pk[j / 2] = pack_bf16x2(f0, f1);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      st_shared_v4(a_chunk_addr(a_base, row, c32 * 4 + q), pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+    if ((c32 & 1) && (c32 >> 1) < n_signal) epi_signal_chunk(ctl, c32 >> 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// positional encoding helpers (models/nerf.py:21-26): [x, sin(2^k x), cos(2^k x)]_k, per-frequency
+// layout [sin xyz | cos xyz].  Base angle by sincosf, higher octaves by the double-angle recurrence
+// (error ~2^k ulp << bf16 rounding of the operand).
+// ------------------------------------------------------------------------------------------
+template <int F>
+__device__ __forceinline__ void pe_to_bf16(const float (&p)[3], __nv_bfloat16* dst /* 3 + 6F values */) {
+  float s[3], c[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    dst[a] = __float2bfloat16_rn(p[a]);
+    sincosf(p[a], &s[a], &c[a]);
+  }
+#pragma unroll
+  for (int k = 0; k < F; ++k) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      dst[3 + 6 * k + a] = __float2bfloat16_rn(s[a]);
+      dst[3 + 6 * k + 3 + a] = __float2bfloat16_rn(c[a]);
+      const float s2 = 2.f * s[a] * c[a];
+      const float c2 = 1.f - 2.f * s[a] * s[a];
+      s[a] = s2;
+      c[a] = c2;
+    }
+  }
+}
+
+// write `n8` 16-byte groups (8 bf16 each) of a row into A columns starting at col8*8
+__device__ __forceinline__ void a_store_row(uint32_t a_base, int row, int col8, const __nv_bfloat16* vals, int n8) {
+  const uint4* v = reinterpret_cast<const uint4*>(vals);
+  for (int q = 0; q < n8; ++q) {
+    uint4 t = v[q];
+    st_shared_v4(a_chunk_addr(a_base, row, col8 + q), t.x, t.y, t.z, t.w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// common prologue / epilogue of both kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ SmemCtl* cta_setup(uint8_t* smem, int warp) {
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + SM_CTL);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+    mbar_init(&ctl->acc_full[0], 1);
+    mbar_init(&ctl->acc_full[1], 1);
+    for (int i = 0; i < NCHUNK; ++i) mbar_init(&ctl->a_ready[i], EPI_THREADS);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&ctl->tmem_base);
+  return ctl;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch #1: encode + xyz + external gate + LayerNorm + gate + softmax
+// ------------------------------------------------------------------------------------------
+template <int FX>
+__global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* __restrict__ x, int64_t S,
+                                                      __nv_bfloat16* __restrict__ H, float* __restrict__ gates) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  SmemCtl* ctl = cta_setup(smem, warp);
+  float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);
+  float* svec = reinterpret_cast<float*>(smem + SM_VEC);
+  float *s_lnw = svec, *s_lnb = svec + 256, *s_wg = svec + 512;
+  for (int i = threadIdx.x; i < MW; i += THREADS) { s_lnw[i] = P.fblob[P.o_lnw + i]; s_lnb[i] = P.fblob[P.o_lnb + i]; }
+  for (int i = threadIdx.x; i < P.E * MW; i += THREADS) s_wg[i] = P.fblob[P.o_wg + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  const uint32_t a_base = smem_u32(smem + SM_A), ring_base = smem_u32(smem + SM_RING);
+  const int n_tiles = (int)((S + TILE - 1) / TILE);
+  const int NL = P.n_front;
+  Pipe pp;
+
+  if (warp == 0) {
+    if (lane == 0)
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+        for (int l = 0; l < NL; ++l)
+          produce_layer(P.wblob + P.front[l].w_off, P.front[l].N, P.front[l].K16, smem + SM_RING, ctl, pp);
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t li = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+        for (int l = 0; l < NL; ++l, ++li)
+          mma_layer(P.front[l].N, P.front[l].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp);
+    }
+  } else {
+    const int et = threadIdx.x - 64;            // 0..127
+    const int q = warp & 3;                     // TMEM lane quarter of this warp
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t li = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int64_t s = (int64_t)t * TILE + row;
+      const bool valid = s < S;
+      // ---- stage PE(xyz) as the A operand of the xyz layer (K16 = 80 -> chunks 0 and 1) ----
+      {
+        float p[3] = {0.f, 0.f, 0.f};
+        if (valid) { p[0] = x[s * P.x_cols + 0]; p[1] = x[s * P.x_cols + 1]; p[2] = x[s * P.x_cols + 2]; }
+        constexpr int NPE = 3 + 6 * FX, NPAD = (NPE + 15) / 16 * 16;
+        __align__(16) __nv_bfloat16 pe[NPAD];
+        pe_to_bf16<FX>(p, pe);
+#pragma unroll
+        for (int i = NPE; i < NPAD; ++i) pe[i] = __float2bfloat16_rn(0.f);
+        a_store_row(a_base, row, 0, pe, NPAD / 8);
+        for (int c = 0; c < (NPAD + 63) / 64; ++c) epi_signal_chunk(ctl, c);
+      }
+      for (int l = 0; l < NL; ++l, ++li) {
+        const int buf = (int)(li & 1);
+        epi_load_bias(P.fblob + P.front[l].b_off, MW, sbias, buf, et);
+        epi_wait_acc(ctl, pp, buf);
+        const uint32_t tacc = tmem_base + lane_base + (uint32_t)buf * 256u;
+        const float* sb = sbias + buf * 256;
+        if (l == 0) {
+          // h = xyz Linear (act none): bf16 -> A (operand of the gate MLP) and -> H[s] (expert input, launch #2)
+          for (int c32 = 0; c32 < MW / 32; ++c32) {
+            uint32_t v[32];
+            tmem_ld32(tacc + (uint32_t)c32 * 32u, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2)
+              pk[j / 2] = pack_bf16x2(__uint_as_float(v[j]) + sb[c32 * 32 + j], __uint_as_float(v[j + 1]) + sb[c32 * 32 + j + 1]);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              st_shared_v4(a_chunk_addr(a_base, row, c32 * 4 + qq), pk[qq * 4], pk[qq * 4 + 1], pk[qq * 4 + 2], pk[qq * 4 + 3]);
+              if (valid)
+                *reinterpret_cast<uint4*>(H + s * MW + c32 * 32 + qq * 8) = make_uint4(pk[qq * 4], pk[qq * 4 + 1], pk[qq * 4 + 2], pk[qq * 4 + 3]);
+            }
+            if (c32 & 1) epi_signal_chunk(ctl, c32 >> 1);
+          }
+        } else if (l < NL - 1) {
+          epi_hidden<true>(tacc, sb, MW, a_base, row, nullptr, ctl, 4);
+        } else {
+          // last gate layer: g = bf16(Linear); LayerNorm(fp32); logits = wg . ln (fp32); softmax
+          float sum = 0.f;
+          for (int c32 = 0; c32 < MW / 32; ++c32) {
+            uint32_t v[32];
+            tmem_ld32(tacc + (uint32_t)c32 * 32u, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += bf16_round(__uint_as_float(v[j]) + sb[c32 * 32 + j]);
+          }
+          const float mean = sum * (1.f / MW);
+          float var = 0.f;
+          for (int c32 = 0; c32 < MW / 32; ++c32) {
+            uint32_t v[32];
+            tmem_ld32(tacc + (uint32_t)c32 * 32u, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float dlt = bf16_round(__uint_as_float(v[j]) + sb[c32 * 32 + j]) - mean;
+              var = fmaf(dlt, dlt, var);
+            }
+          }
+          const float rstd = rsqrtf(var * (1.f / MW) + 1e-5f);
+          float lg[MAX_E];
+#pragma unroll
+          for (int e = 0; e < MAX_E; ++e) lg[e] = 0.f;
+          for (int c32 = 0; c32 < MW / 32; ++c32) {
+            uint32_t v[32];
+            tmem_ld32(tacc + (uint32_t)c32 * 32u, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int k = c32 * 32 + j;
+              const float ln = (bf16_round(__uint_as_float(v[j]) + sb[k]) - mean) * rstd * s_lnw[k] + s_lnb[k];
+#pragma unroll
+              for (int e = 0; e < MAX_E; ++e)
+                if (e < P.E) lg[e] = fmaf(ln, s_wg[e * MW + k], lg[e]);
+            }
+          }
+          float mx = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < MAX_E; ++e) if (e < P.E) mx = fmaxf(mx, lg[e]);
+          float den = 0.f;
+#pragma unroll
+          for (int e = 0; e < MAX_E; ++e) if (e < P.E) { lg[e] = expf(lg[e] - mx); den += lg[e]; }
+          if (valid) {
+#pragma unroll
+            for (int e = 0; e < MAX_E; ++e) if (e < P.E) gates[s * P.E + e] = lg[e] / den;
+          }
+          tc_fence_before();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// tile table for launch #2
+// ------------------------------------------------------------------------------------------
+struct TileTable {
+  int* n_tiles;       // [1]
+  int* tile_expert;   // [max_tiles]  (-1 = dropped bucket)
+  int* tile_row0;     // [max_tiles]
+  int* tile_rows;     // [max_tiles]  valid rows in the tile
+  int* seg_start;     // [E+1] first row of each expert segment (+ dropped segment)
+  int* drop_counter;  // [1]
+  int* row2sample;    // [max_rows]
+};
+
+__global__ void k_tile_plan(const int* __restrict__ counts, const int* __restrict__ cap_dev, int E, int no_batch,
+                            int64_t S, TileTable tt) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int cap = *cap_dev;
+  int row = 0, nt = 0, kept_total = 0;
+  for (int e = 0; e < E; ++e) {
+    const int kc = no_batch ? counts[e] : min(counts[e], cap);
+    tt.seg_start[e] = row;
+    for (int r = 0; r < kc; r += TILE) {
+      tt.tile_expert[nt] = e; tt.tile_row0[nt] = row + r; tt.tile_rows[nt] = min(TILE, kc - r); ++nt;
+    }
+    row += (kc + TILE - 1) / TILE * TILE;
+    kept_total += kc;
+  }
+  const int nd = (int)S - kept_total;
+  tt.seg_start[E] = row;
+  for (int r = 0; r < nd; r += TILE) {
+    tt.tile_expert[nt] = -1; tt.tile_row0[nt] = row + r; tt.tile_rows[nt] = min(TILE, nd - r); ++nt;
+  }
+  *tt.n_tiles = nt;
+  *tt.drop_counter = 0;
+}
+
+__global__ void k_scatter_rows(const int* __restrict__ idx, const int* __restrict__ loc, const int* __restrict__ cap_dev,
+                               int E, int no_batch, int64_t S, TileTable tt) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int cap = *cap_dev;
+  const int e = idx[s], l = loc[s];
+  if (no_batch || l < cap) tt.row2sample[tt.seg_start[e] + l] = (int)s;
+  else tt.row2sample[tt.seg_start[E] + atomicAdd(tt.drop_counter, 1)] = (int)s;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch #2: gather -> experts -> combine -> heads
+// ------------------------------------------------------------------------------------------
+template <int FD>
+__global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, const float* __restrict__ x,
+                                                     const __nv_bfloat16* __restrict__ H,
+                                                     const float* __restrict__ gate, const float* __restrict__ noise,
+                                                     float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  SmemCtl* ctl = cta_setup(smem, warp);
+  float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);
+  float* svec = reinterpret_cast<float*>(smem + SM_VEC);
+  float *s_wsig = svec, *s_wcol = svec + 256;   // [256], [3][H2]
+  const int H2 = P.hidden2;
+  for (int i = threadIdx.x; i < MW; i += THREADS) s_wsig[i] = P.fblob[P.o_wsig + i];
+  for (int i = threadIdx.x; i < 3 * H2; i += THREADS) s_wcol[i] = P.fblob[P.o_wcol + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  const uint32_t a_base = smem_u32(smem + SM_A), ring_base = smem_u32(smem + SM_RING);
+  const int n_tiles = *tt.n_tiles;
+  const int NE = P.n_expert;
+  Pipe pp;
+
+  if (warp == 0) {
+    if (lane == 0)
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int e = tt.tile_expert[t];
+        if (e >= 0)
+          for (int l = 0; l < NE; ++l)
+            produce_layer(P.wblob + P.expert[l].w_off + (size_t)e * P.expert_w_stride, MW, MW, smem + SM_RING, ctl, pp);
+        produce_layer(P.wblob + P.back[0].w_off, P.back[0].N, P.back[0].K16, smem + SM_RING, ctl, pp);
+        produce_layer(P.wblob + P.back[1].w_off, P.back[1].N, P.back[1].K16, smem + SM_RING, ctl, pp);
+      }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t li = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int e = tt.tile_expert[t];
+        if (e >= 0)
+          for (int l = 0; l < NE; ++l, ++li) mma_layer(MW, MW, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp);
+        mma_layer(P.back[0].N, P.back[0].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp); ++li;
+        mma_layer(P.back[1].N, P.back[1].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp); ++li;
+      }
+    }
+  } else {
+    const int et = threadIdx.x - 64;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float b_sig = P.fblob[P.o_bsig];
+    const float b_col0 = P.fblob[P.o_bcol], b_col1 = P.fblob[P.o_bcol + 1], b_col2 = P.fblob[P.o_bcol + 2];
+    uint32_t li = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int e = tt.tile_expert[t];
+      const int sidx = (row < tt.tile_rows[t]) ? tt.row2sample[tt.tile_row0[t] + row] : -1;
+      const bool valid = sidx >= 0;
+      const __nv_bfloat16* hrow = valid ? (H + (int64_t)sidx * MW) : nullptr;
+      const float g = (valid && e >= 0) ? gate[sidx] : 0.f;
+      // ---- stage: expert input rows (or zeros for the dropped bucket) + [PE(dir) | appearance] ----
+      {
+        for (int c8 = 0; c8 < MW / 8; ++c8) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (valid && e >= 0) v = *reinterpret_cast<const uint4*>(hrow + c8 * 8);
+          st_shared_v4(a_chunk_addr(a_base, row, c8), v.x, v.y, v.z, v.w);
+        }
+        constexpr int NDIR = 3 + 6 * FD;                   // 27
+        constexpr int NCAT_MAX = KA_MAX - MW;              // 96
+        __align__(16) __nv_bfloat16 cat[NCAT_MAX];
+#pragma unroll
+        for (int i = 0; i < NCAT_MAX; ++i) cat[i] = __float2bfloat16_rn(0.f);
+        if (valid) {
+          const float* xr = x + (int64_t)sidx * P.x_cols;
+          float dvec[3] = {xr[P.x_cols - 4], xr[P.x_cols - 3], xr[P.x_cols - 2]};
+          pe_to_bf16<FD>(dvec, cat);
+          int ai = (int)xr[P.x_cols - 1];
+          ai = min(max(ai, 0), P.appearance_count - 1);
+          const float4* er = reinterpret_cast<const float4*>(P.emb_a + (int64_t)ai * P.appearance_dim);
+          for (int i = 0; i < P.appearance_dim / 4; ++i) {
+            float4 f = er[i];
+            cat[NDIR + 4 * i + 0] = __float2bfloat16_rn(f.x);
+            cat[NDIR + 4 * i + 1] = __float2bfloat16_rn(f.y);
+            cat[NDIR + 4 * i + 2] = __float2bfloat16_rn(f.z);
+            cat[NDIR + 4 * i + 3] = __float2bfloat16_rn(f.w);
+          }
+        }
+        const int ncat8 = ((int)P.back[1].K16 - MW) / 8;
+        a_store_row(a_base, row, MW / 8, cat, ncat8);
+        for (int c = 0; c < 4; ++c) epi_signal_chunk(ctl, c);
+      }
+      float sig_acc = 0.f;
+      if (e >= 0) {
+        for (int l = 0; l < NE; ++l, ++li) {
+          const int buf = (int)(li & 1);
+          epi_load_bias(P.fblob + P.expert[l].b_off + (size_t)e * P.expert_b_stride, MW, sbias, buf, et);
+          epi_wait_acc(ctl, pp, buf);
+          const uint32_t tacc = tmem_base + lane_base + (uint32_t)buf * 256u;
+          const float* sb = sbias + buf * 256;
+          if (l < NE - 1) {
+            epi_hidden<true>(tacc, sb, MW, a_base, row, (l == P.skip_layer) ? hrow : nullptr, ctl, 4);
+          } else {
+            // last expert layer (no activation) -> combine: y = bf16(gate * bf16(out)) -> ReLU -> A;
+            // sigma head accumulated on the fly (nerf_moe.py:384-400)
+            for (int c32 = 0; c32 < MW / 32; ++c32) {
+              uint32_t v[32];
+              tmem_ld32(tacc + (uint32_t)c32 * 32u, v);
+              tmem_ld_wait();
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float f0 = bf16_round(__uint_as_float(v[j]) + sb[c32 * 32 + j]);
+                float f1 = bf16_round(__uint_as_float(v[j + 1]) + sb[c32 * 32 + j + 1]);
+                f0 = fmaxf(bf16_round(f0 * g), 0.f);
+                f1 = fmaxf(bf16_round(f1 * g), 0.f);
+                sig_acc = fmaf(f0, s_wsig[c32 * 32 + j], sig_acc);
+                sig_acc = fmaf(f1, s_wsig[c32 * 32 + j + 1], sig_acc);
+                pk[j / 2] = pack_bf16x2(f0, f1);
+              }
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq)
+                st_shared_v4(a_chunk_addr(a_base, row, c32 * 4 + qq), pk[qq * 4], pk[qq * 4 + 1], pk[qq * 4 + 2], pk[qq * 4 + 3]);
+              if (c32 & 1) epi_signal_chunk(ctl, c32 >> 1);
+            }
+          }
+        }
+      }
+      // sigma = softplus(bf16(W_sigma h + b) + noise - 1)
+      float sigma;
+      {
+        float sr = bf16_round(sig_acc + b_sig);
+        if (noise && valid) sr += noise[sidx];
+        const float tt_ = sr - 1.f;
+        sigma = (tt_ > 20.f) ? tt_ : log1pf(expf(tt_));
+      }
+      // ---- layer "1" (act none): bf16 -> A[:, 0:256); then release the [dir | appearance] chunks ----
+      {
+        const int buf = (int)(li & 1);
+        epi_load_bias(P.fblob + P.back[0].b_off, MW, sbias, buf, et);
+        epi_wait_acc(ctl, pp, buf);
+        epi_hidden<false>(tmem_base + lane_base + (uint32_t)buf * 256u, sbias + buf * 256, MW, a_base, row, nullptr, ctl, 4);
+        const int nchunk2 = ((int)P.back[1].K16 + 63) / 64;
+        for (int c = 4; c < nchunk2; ++c) epi_signal_chunk(ctl, c);
+        ++li;
+      }
+      // ---- layer "2" (ReLU) + colour head + sigmoid ----
+      {
+        const int buf = (int)(li & 1);
+        epi_load_bias(P.fblob + P.back[1].b_off, H2, sbias, buf, et);
+        epi_wait_acc(ctl, pp, buf);
+        const uint32_t tacc = tmem_base + lane_base + (uint32_t)buf * 256u;
+        const float* sb = sbias + buf * 256;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        for (int c32 = 0; c32 < H2 / 32; ++c32) {
+          uint32_t v[32];
+          tmem_ld32(tacc + (uint32_t)c32 * 32u, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int k = c32 * 32 + j;
+            const float h2 = bf16_round(fmaxf(__uint_as_float(v[j]) + sb[k], 0.f));
+            c0 = fmaf(h2, s_wcol[k], c0);
+            c1 = fmaf(h2, s_wcol[H2 + k], c1);
+            c2 = fmaf(h2, s_wcol[2 * H2 + k], c2);
+          }
+        }
+        tc_fence_before();
+        if (valid) {
+          auto sg = [](float v) { return bf16_round(1.f / (1.f + expf(-bf16_round(v)))); };
+          float4 o = make_float4(sg(c0 + b_col0), sg(c1 + b_col1), sg(c2 + b_col2), sigma);
+          reinterpret_cast<float4*>(out)[sidx] = o;
+        }
+        ++li;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf) {
+  (void)max_cf;
+  const int E = m->d.num_experts;
+  if (S < 1) S = 1;
+  const int64_t max_rows = S + (int64_t)TILE * (E + 2);
+  const int64_t max_tiles = cdiv(S, TILE) + E + 2;
+  size_t b = 0;
+  b += align_up((size_t)S * MW * 2, 256);            // H
+  b += align_up((size_t)S * E * 4, 256);             // gates
+  b += 3 * align_up((size_t)S * 4, 256);             // idx, loc, gate
+  b += align_up((size_t)max_rows * 4, 256);          // row2sample
+  b += 3 * align_up((size_t)max_tiles * 4, 256);     // tile tables
+  b += 4096;                                          // small scalars
+  b += route_workspace_bytes(S, E);
+  return b + 4096;
+}
+
+int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* o, float* out,
+               int32_t* moe_idx, float* l_aux, float* dbg_gates, int32_t* dbg_loc, Arena& ws, cudaStream_t st) {
+  SNB_REQUIRE(m->tc_blob, "tc_forward: weights were not packed");
+  struct Owner { TcHost h; uint8_t* wblob; };
+  const TcParams& P = ((Owner*)m->tc_blob)->h.p;
+  const int E = m->d.num_experts;
+  const int64_t max_rows = S + (int64_t)TILE * (E + 2);
+  const int64_t max_tiles = cdiv(S, TILE) + E + 2;
+  __nv_bfloat16* H = ws.take<__nv_bfloat16>((size_t)S * MW);
+  float* gates = ws.take<float>((size_t)S * E);
+  int* idx = ws.take<int>(S);
+  int* loc = ws.take<int>(S);
+  float* gate = ws.take<float>(S);
+  TileTable tt;
+  tt.row2sample = ws.take<int>(max_rows);
+  tt.tile_expert = ws.take<int>(max_tiles);
+  tt.tile_row0 = ws.take<int>(max_tiles);
+  tt.tile_rows = ws.take<int>(max_tiles);
+  int* small = ws.take<int>(1024);
+  const size_t rbytes = route_workspace_bytes(S, E);
+  char* rws = ws.take<char>(rbytes);
+  if (!ws.ok) { set_error("tc_forward: workspace too small"); return SNB_EWORKSPACE; }
+  int *counts = small, *cap_dev = small + E;
+  tt.seg_start = small + E + 1;
+  tt.n_tiles = small + 2 * E + 4;
+  tt.drop_counter = small + 2 * E + 5;
+
+  static bool attr_done = false;
+  SNB_REQUIRE(m->d.pos_xyz_freqs == 12 && m->d.pos_dir_freqs == 4,
+              "tcgen05 path is specialised for pos_xyz_dim=12 / pos_dir_dim=4 (all Switch-NeRF configs)");
+  if (!attr_done) {
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    attr_done = true;
+  }
+  const int n_front_tiles = (int)cdiv(S, TILE);
+  const int grid1 = n_front_tiles < m->sm_count ? n_front_tiles : m->sm_count;
+  k_front<12><<<grid1, THREADS, SM_TOTAL, st>>>(P, x, S, H, gates);
+  SNB_CHECK_LAUNCH("k_front");
+  int rc = route_top1(gates, S, E, o->capacity_factor, o->no_batch ? 0 : o->bpr, idx, loc, gate, counts, cap_dev, l_aux,
+                      rws, rbytes, st);
+  if (rc) return rc;
+  SNB_CHECK_CUDA(cudaMemsetAsync(tt.row2sample, 0xFF, (size_t)max_rows * sizeof(int), st));
+  k_tile_plan<<<1, 32, 0, st>>>(counts, cap_dev, E, o->no_batch, S, tt);
+  SNB_CHECK_LAUNCH("k_tile_plan");
+  k_scatter_rows<<<(unsigned)cdiv(S, 256), 256, 0, st>>>(idx, loc, cap_dev, E, o->no_batch, S, tt);
+  SNB_CHECK_LAUNCH("k_scatter_rows");
+  const int grid2 = (int)(max_tiles < m->sm_count ? max_tiles : m->sm_count);
+  k_back<4><<<grid2, THREADS, SM_TOTAL, st>>>(P, tt, x, H, gate, sigma_noise, out);
+  SNB_CHECK_LAUNCH("k_back");
+  if (moe_idx) SNB_CHECK_CUDA(cudaMemcpyAsync(moe_idx, idx, sizeof(int) * S, cudaMemcpyDeviceToDevice, st));
+  if (dbg_gates) SNB_CHECK_CUDA(cudaMemcpyAsync(dbg_gates, gates, sizeof(float) * S * E, cudaMemcpyDeviceToDevice, st));
+  if (dbg_loc) SNB_CHECK_CUDA(cudaMemcpyAsync(dbg_loc, loc, sizeof(int) * S, cudaMemcpyDeviceToDevice, st));
+  return SNB_OK;
+}
+
+}  // namespace snb

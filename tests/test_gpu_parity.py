@@ -229,3 +229,92 @@ def test_render_perturb_is_stratified(built_lib):
                          hp, None, None, True, True, False, seed=123)
     assert all(torch.isfinite(v.float()).all() for v in res.values())
     assert (res["rgb_fine"] >= 0).all() and (res["rgb_fine"] <= 1.0 + 1e-5).all()
+
+
+# ----------------------------------------------------------------------------- bf16 tcgen05 path
+def _bf16_stats(out, ref, ok):
+    d = np.abs(out - ref)[ok]
+    return float(d.max()), float(d.mean()), float((d > TOL).mean())
+
+
+@pytest.mark.parametrize("tag,cf,bpr", [("e8_cf1_bpr_bf16cpu", 1.0, True), ("e8_cf05_nobpr_fp32", 0.5, False),
+                                        ("e4_cf1_bpr_fp32", 1.0, True), ("e8_cf1_bpr_fp32_s777", 1.0, True)])
+def test_model_bf16_tcgen05(built_lib, tag, cf, bpr):
+    """Fused tcgen05 path (SNB_PREC_BF16) on the golden inputs.
+
+    bf16 operands cannot reproduce an fp32 result to 1e-3 per sample (the reference's own autocast
+    path differs from its fp32 path by ~3e-3 max / 8e-4 mean on these inputs, and its rgb output is
+    itself quantised to bf16, ulp 2^-8).  The gates therefore are:
+      (1) vs the oracle's bf16 rounding map (pinned against the reference under autocast): same-route
+          samples agree to <= 2 output ulps (2^-7) max, <= 1e-3 for >= 97%, mean <= 2e-4;
+      (2) vs the fp32 reference golden: error no larger than 1.25x the reference-autocast map's own
+          error (mean) -- i.e. the fused path is as accurate as what it replaces;
+      (3) routing: expert ids agree with the fp32 reference for >= 99% of samples (near-tie flips).
+    """
+    g = load_golden(f"model_{tag}.npz")
+    sd = golden_sd(g)
+    x = torch.from_numpy(g["x"])
+    cfg = O.default_cfg(sd, cf, bpr)
+    o_bf, ex_bf = O.nerf_moe_forward(x, sd, cfg, mode="bf16", flavor="cuda")
+    o_32, ex_32 = O.nerf_moe_forward(x, sd, cfg, mode="fp32")
+    model, _ = make_model(sd, cf, bpr, False, "bf16")
+    r = model(x.cuda(), return_debug=True)
+    torch.cuda.synchronize()
+    out = r["outputs"].cpu().numpy()
+    idx = r["extras"]["moe_gates"][0].view(-1).cpu().numpy()
+    loc = r["extras"]["debug_loc"].cpu().numpy()
+    cap = ex_bf["capacity"]
+    assert np.isfinite(out).all()
+    assert (idx == ex_32["idx"].numpy()).mean() >= 0.99
+    ok = (idx == ex_bf["idx"].numpy()) & ((loc < cap) == (ex_bf["loc"].numpy() < cap))
+    assert ok.mean() >= 0.98
+    mx, mean, frac = _bf16_stats(out, o_bf.numpy(), ok)
+    assert mx <= 2 ** -7 * max(1.0, float(o_bf.abs().max())) + 1e-6, f"max abs err vs bf16 map {mx}"
+    assert frac <= 0.03 and mean <= 2e-4, (mx, mean, frac)
+    ok32 = (idx == ex_32["idx"].numpy()) & ((loc < cap) == (ex_32["loc"].numpy() < cap))
+    _, mean32, _ = _bf16_stats(out, o_32.numpy(), ok32)
+    ok_ref = (ex_bf["idx"] == ex_32["idx"]).numpy() & ((ex_bf["loc"] < cap) == (ex_32["loc"] < cap)).numpy()
+    _, mean_ref, _ = _bf16_stats(o_bf.numpy(), o_32.numpy(), ok_ref)
+    assert mean32 <= 1.25 * mean_ref + 1e-5, (mean32, mean_ref)
+    assert abs(float(r["extras"]["moe_loss"][0]) - float(ex_32["l_aux"])) < 5e-3
+
+
+def test_model_bf16_vs_fp32_path_full_chunk(built_lib):
+    """Building chunk size (S=131072, E=8, cf=1, BPR): fused tcgen05 path vs the fp32 CUDA path on device."""
+    sd = O.synthetic_state_dict(num_experts=8, appearance_count=64, seed=11, gate_scale=4.0)
+    S = 131072
+    g = torch.Generator().manual_seed(5)
+    x = torch.cat([(torch.rand(S, 3, generator=g) - 0.5) * 1.6,
+                   torch.nn.functional.normalize(torch.randn(S, 3, generator=g), dim=-1),
+                   torch.randint(0, 64, (S, 1), generator=g).float()], 1).cuda()
+    m32, _ = make_model(sd, 1.0, True, False, "fp32")
+    m16, _ = make_model(sd, 1.0, True, False, "bf16")
+    r32 = m32(x, return_debug=True)
+    r16 = m16(x, return_debug=True)
+    torch.cuda.synchronize()
+    i32, i16 = r32["extras"]["moe_gates"][0].view(-1), r16["extras"]["moe_gates"][0].view(-1)
+    cap = 16384
+    k32, k16 = r32["extras"]["debug_loc"] < cap, r16["extras"]["debug_loc"] < cap
+    ok = (i32 == i16) & (k32 == k16)
+    assert ok.float().mean().item() >= 0.97
+    d = (r32["outputs"] - r16["outputs"]).abs()[ok]
+    assert torch.isfinite(r16["outputs"]).all()
+    assert d.mean().item() < 2e-3 and d.max().item() < 0.25
+    mse = ((r32["outputs"][ok][:, :3] - r16["outputs"][ok][:, :3]) ** 2).mean().item()
+    assert -10 * np.log10(mse) > 45.0          # PSNR of per-sample rgb, bf16 path vs fp32 path
+
+
+def test_render_bf16_config1(built_lib):
+    from switch_nerf_b200.rendering import render_rays
+    g = load_golden("render_config1.npz")
+    sd = golden_sd(g)
+    model, hp = make_model(sd, 1.0, True, False, "bf16")
+    hp.coarse_samples, hp.fine_samples, hp.model_chunk_size = 32, 32, 4096
+    res, _ = render_rays(model, None, torch.from_numpy(g["rays"]).cuda(), torch.from_numpy(g["image_indices"]).cuda(),
+                         hp, None, None, True, True, False)
+    torch.cuda.synchronize()
+    rgb = res["rgb_fine"].cpu().numpy()
+    err = np.abs(rgb - g["rgb_fine"])
+    # per-ray composite averages the per-sample bf16 error; routing flips near capacity move single samples
+    assert np.median(err) < 2e-3 and err.mean() < 4e-3
+    assert O.psnr(torch.from_numpy(rgb), torch.from_numpy(g["rgb_fine"])) > 40.0
