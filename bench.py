@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Switch-NeRF forward/render hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): point-samples/sec (rays x network evaluations per ray) per box.
+Workload at every N (BASELINE.json configs[1], per GPU): Building topology, 8 experts, width 256,
+8192 rays x (257 coarse + 257 fine) samples = 4 210 688 point-samples per step, model_chunk_size
+131072, capacity_factor 1.0, batch-prioritised routing, bf16 tensor-core compute, synthetic rays and
+random-init weights (no datasets/checkpoints offline).  One "step" = one rendering.render_rays forward
+over the ray batch.  Rays are independent units: ranks shard them with no data-path collective (the
+reference ships with --no_expert_parallel), so scaling is "weak" (8192 rays per GPU).
+
+`value`  : device-timed (CUDA events, max over ranks) with the ray batch already resident in HBM.
+`e2e`    : the same step through the public API (switch_nerf_b200.rendering.render_rays) with HOST
+           pinned rays: the H2D copy of rays/indices and the D2H read of the per-ray result are inside
+           the timed region.
+`--impl reference`: the reference's own CPU implementation of the path (the oracle port, pinned
+           bit-exact against the unmodified reference) on the host cores, bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RAYS, COARSE, FINE, CHUNK, EXPERTS = 8192, 257, 257, 131072, 8
+FLOPS_PER_SAMPLE = 1_439_232            # SURVEY.md 8d, Building, forward, useful work only
+FLOPS_BACK_KEPT = 917_504 + 512 + 131_072 + 84_736 + 768      # launch #2, sample that reaches an expert
+FLOPS_BACK_DROPPED = 512 + 131_072 + 84_736 + 768             # launch #2, dropped sample (no expert stack)
+WORKLOAD = "building: 8192 rays x (257+257) samples, 8 experts, width 256, chunk 131072, cf=1.0, BPR"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1419.2), d.get("hbm_gbs", 6570.6), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(rank, device):
+    from switch_nerf_b200 import synthetic as O
+    from switch_nerf_b200.configs import make_hparams
+    from switch_nerf_b200.nerf_moe import get_nerf_moe_inner
+    sd = O.synthetic_state_dict(num_experts=EXPERTS, appearance_count=2048, seed=0, gate_scale=4.0)
+    hp = make_hparams(num_experts=EXPERTS, capacity_factor=1.0, bpr=True, model_chunk_size=CHUNK,
+                      coarse_samples=COARSE, fine_samples=FINE, amp_bf16=True, moe_return_gates=False)
+    model = get_nerf_moe_inner(hp, 2048, 3)
+    model.load_state_dict(sd)
+    model = model.to(device).eval()
+    rays, idx = O.synthetic_rays(N_RAYS, 2048, seed=100 + rank)
+    return model, hp, rays, idx, sd
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    from oracle import switch_nerf_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.synthetic_state_dict(num_experts=EXPERTS, appearance_count=2048, seed=0, gate_scale=4.0)
+    cfg = O.default_cfg(sd, 1.0, True)
+    n = 256                                  # bounded sample of the workload: 256 of the 8192 rays per step
+    rays, idx = O.synthetic_rays(N_RAYS, 2048, seed=100)
+    rays, idx = rays[:n], idx[:n]
+    samples = n * (COARSE + FINE)
+
+    def step():
+        with torch.no_grad():
+            O.render_rays(sd, cfg, rays, idx, coarse_samples=COARSE, fine_samples=FINE, model_chunk_size=CHUNK)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = samples * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "point-samples/sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{n} of {N_RAYS} rays per step ({samples} point-samples)"},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} rays x {COARSE + FINE} samples per step, fp32, torch CPU ops, {cores} threads"},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def cpu_baseline():
+    from oracle import switch_nerf_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.synthetic_state_dict(num_experts=EXPERTS, appearance_count=2048, seed=0, gate_scale=4.0)
+    cfg = O.default_cfg(sd, 1.0, True)
+    n = 512
+    rays, idx = O.synthetic_rays(N_RAYS, 2048, seed=100)
+    rays, idx = rays[:n], idx[:n]
+    with torch.no_grad():
+        O.render_rays(sd, cfg, rays[:64], idx[:64], coarse_samples=COARSE, fine_samples=FINE, model_chunk_size=CHUNK)
+        t0 = time.perf_counter()
+        O.render_rays(sd, cfg, rays, idx, coarse_samples=COARSE, fine_samples=FINE, model_chunk_size=CHUNK)
+        dt = time.perf_counter() - t0
+    return {"value": n * (COARSE + FINE) / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{n} of {N_RAYS} rays x {COARSE + FINE} samples, one pass, fp32 oracle port, {cores} threads"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: switch_nerf_b200 has no CPU path")
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    from switch_nerf_b200 import _lib as L
+    from switch_nerf_b200.rendering import render_rays
+    import ctypes as C
+
+    model, hp, rays_h, idx_h, sd = build_inputs(rank, device)
+    model.precision = args.precision
+    lib = L.lib()
+    rays_pin, idx_pin = rays_h.pin_memory(), idx_h.to(torch.int32).pin_memory()
+    rays_d, idx_d = rays_pin.to(device), idx_pin.to(device)
+    samples_per_step = N_RAYS * (COARSE + FINE)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)      # > 126 MB L2
+
+    def step_resident():
+        return render_rays(model, None, rays_d, idx_d, hp, None, None, True, True, False)[0]
+
+    def step_e2e():
+        r = rays_pin.to(device, non_blocking=True)
+        i = idx_pin.to(device, non_blocking=True)
+        res = render_rays(model, None, r, i, hp, None, None, True, True, False)[0]
+        return res["rgb_fine"].cpu(), res["depth_fine"].cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, with_events=True):
+        evs = []
+        barrier()
+        for _ in range(steps):
+            flush.zero_()                                  # L2 flush between timed iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    step_e2e()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.snb_profile_enable(1)
+    launches0 = lib.snb_launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = lib.snb_launch_count() - launches0
+    prof = (C.c_double * 4)()
+    L.check(lib.snb_profile_collect(prof))
+    lib.snb_profile_enable(0)
+    # e2e: host wall clock around H2D + step + D2H, max over ranks
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        ms_per_step = ms_total / args.steps
+        value = world * samples_per_step / (ms_per_step * 1e-3)
+        peak_tf, peak_hbm, which = measured_peaks()
+        front_ms, route_ms, back_ms, n_chunks = prof[0], prof[1], prof[2], prof[3]
+        roof = None
+        if n_chunks > 0 and back_ms > 0:
+            # dominant kernel = launch #2 (k_back).  Algorithmic FLOPs per launch = samples of the chunk x the
+            # back-end figure (upper bound uses every sample as kept; dropped samples skip the expert stack).
+            per_launch_samples = samples_per_step * args.steps / n_chunks
+            avg_ms = back_ms / n_chunks
+            tf = per_launch_samples * FLOPS_BACK_KEPT / (avg_ms * 1e-3) / 1e12
+            roof = {"kernel": "k_back (gather+experts+combine+heads)", "bound": "tensor", "achieved": tf,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "peak_source": f"{which}, sustained bf16",
+                    "avg_launch_ms": avg_ms, "traffic": None,
+                    "phase_ms_per_step": {"front": front_ms / args.steps, "route": route_ms / args.steps,
+                                          "back": back_ms / args.steps},
+                    "step_tflops": world * samples_per_step * FLOPS_PER_SAMPLE / (ms_per_step * 1e-3) / 1e12 / world}
+        out = {
+            "metric": "point-samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "l2": "256 MiB buffer written between timed steps",
+                       "parallelism": f"dp{world} over rays, no data-path collective"},
+            "clocks": clocks,
+            "e2e": {"value": world * samples_per_step * args.steps / e2e_s, "unit": "samples/s",
+                    "h2d_bytes_per_step": int(rays_pin.numel() * 4 + idx_pin.numel() * 4),
+                    "d2h_bytes_per_step": int(N_RAYS * 3 * 4 + N_RAYS * 4)},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -91,6 +91,15 @@ typedef struct snb_route_opts {
 /* ---- library ---------------------------------------------------------------------------- */
 const char* snb_last_error(void);
 int snb_version(void);
+/* Number of kernels this library has launched in this process (all streams); bench.py reports the
+ * delta over its timed region as `gpu_launches`. */
+int64_t snb_launch_count(void);
+/* Phase timing of snb_moe_forward (SNB_PREC_BF16): when enabled, CUDA events are recorded on the
+ * caller's stream around launch #1 (front), the routing kernels and launch #2 (back); no host sync.
+ * snb_profile_collect synchronises the device and returns the sums since the last enable/collect:
+ * out[0..3] = {front_ms, route_ms, back_ms, n_chunks}.  Used by bench.py for the roofline line. */
+int snb_profile_enable(int32_t on);
+int snb_profile_collect(double* out4);
 
 /* ---- model object ----------------------------------------------------------------------- */
 /* Replaces models/nerf_moe.py:1004-1041 get_nerf_moe_inner + load_state_dict: copies/packs the

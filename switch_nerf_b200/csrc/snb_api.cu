@@ -1,13 +1,33 @@
 // C-ABI entry points (include/switch_nerf_b200.h): argument checking, model object, workspace
 // carving and the host-side orchestration of render_rays.  No host synchronisation anywhere.
 #include <stdarg.h>
+#include <atomic>
 #include <new>
+#include <vector>
 
 #include "snb_common.cuh"
 
 namespace snb {
 
 static thread_local char g_err[1024] = "";
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static bool g_prof_on = false;
+static std::vector<PhaseEvents> g_prof_pool;
+static size_t g_prof_used = 0;
+PhaseEvents* profile_next() {
+  if (!g_prof_on) return nullptr;
+  if (g_prof_used >= g_prof_pool.size()) {
+    if (g_prof_pool.size() >= 65536) return nullptr;
+    PhaseEvents pe;
+    for (int i = 0; i < 4; ++i)
+      if (cudaEventCreate(&pe.e[i]) != cudaSuccess) return nullptr;
+    g_prof_pool.push_back(pe);
+  }
+  return &g_prof_pool[g_prof_used++];
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -118,6 +138,29 @@ extern "C" {
 
 const char* snb_last_error(void) { return g_err; }
 int snb_version(void) { return 100; }
+int64_t snb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int snb_profile_enable(int32_t on) {
+  g_prof_on = on != 0;
+  g_prof_used = 0;
+  return SNB_OK;
+}
+
+int snb_profile_collect(double* out4) {
+  SNB_REQUIRE(out4, "snb_profile_collect: NULL");
+  SNB_CHECK_CUDA(cudaDeviceSynchronize());
+  double f = 0, r = 0, b = 0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    float t;
+    PhaseEvents& pe = g_prof_pool[i];
+    SNB_CHECK_CUDA(cudaEventElapsedTime(&t, pe.e[0], pe.e[1])); f += t;
+    SNB_CHECK_CUDA(cudaEventElapsedTime(&t, pe.e[1], pe.e[2])); r += t;
+    SNB_CHECK_CUDA(cudaEventElapsedTime(&t, pe.e[2], pe.e[3])); b += t;
+  }
+  out4[0] = f; out4[1] = r; out4[2] = b; out4[3] = (double)g_prof_used;
+  g_prof_used = 0;
+  return SNB_OK;
+}
 
 int snb_model_create(const snb_model_desc* desc, const snb_weights* w, void* stream, snb_model_t** out) {
   SNB_REQUIRE(out && w, "snb_model_create: NULL argument");
@@ -175,7 +218,7 @@ void snb_model_destroy(snb_model_t* mm) {
   Model* m = (Model*)mm;
   if (!m) return;
   if (m->f32_blob) cudaFree(m->f32_blob);
-  if (m->tc_blob) cudaFree(m->tc_blob);
+  tc_release(m);
   delete m;
 }
 

@@ -11,6 +11,10 @@
 namespace snb {
 
 void set_error(const char* fmt, ...);
+void count_launch();
+struct PhaseEvents { cudaEvent_t e[4]; };
+// returns nullptr when profiling is off (or the event pool is exhausted)
+PhaseEvents* profile_next();
 
 #define SNB_CHECK_CUDA(expr)                                                        \
   do {                                                                              \
@@ -23,6 +27,7 @@ void set_error(const char* fmt, ...);
 
 #define SNB_CHECK_LAUNCH(name)                                                      \
   do {                                                                              \
+    snb::count_launch();                                                            \
     cudaError_t _e = cudaGetLastError();                                            \
     if (_e != cudaSuccess) {                                                        \
       snb::set_error("launch of %s failed: %s (%s:%d)", name, cudaGetErrorString(_e), __FILE__, __LINE__); \
@@ -93,6 +98,7 @@ int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, co
                Arena& ws, cudaStream_t st);
 size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf);
 bool tc_supported(const Model* m);
+void tc_release(Model* m);
 
 size_t route_workspace_bytes(int64_t S, int32_t E);
 // Routing on device: see snb_route_top1 in the public header.  `ebase/erows` (nullable, [E]):

@@ -116,14 +116,22 @@ bool tc_supported(const Model* m) {
          d.expert_layers <= 16 && d.appearance_dim % 4 == 0;
 }
 
-static TcHost* tc_host(Model* m) { return (TcHost*)m->tc_blob; }
+struct TcOwner { TcHost h; uint8_t* wblob; };
+
+void tc_release(Model* m) {
+  TcOwner* own = (TcOwner*)m->tc_blob;
+  if (!own) return;
+  if (own->wblob) cudaFree(own->wblob);
+  if (own->h.fblob) cudaFree(own->h.fblob);
+  delete own;
+  m->tc_blob = nullptr;
+}
 
 int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
   const snb_model_desc& d = m->d;
   const int E = d.num_experts, L = d.expert_layers, H2 = d.hidden2;
   // (re)build the host descriptor + device blobs; m->tc_blob holds a host struct that owns them
-  struct Owner { TcHost h; uint8_t* wblob; };
-  static_assert(sizeof(TcHost) > 0, "");
+  using Owner = TcOwner;
   Owner* own = nullptr;
   if (m->tc_blob == nullptr) {
     own = new Owner();
@@ -780,8 +788,7 @@ size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf) {
 int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* o, float* out,
                int32_t* moe_idx, float* l_aux, float* dbg_gates, int32_t* dbg_loc, Arena& ws, cudaStream_t st) {
   SNB_REQUIRE(m->tc_blob, "tc_forward: weights were not packed");
-  struct Owner { TcHost h; uint8_t* wblob; };
-  const TcParams& P = ((Owner*)m->tc_blob)->h.p;
+  const TcParams& P = ((TcOwner*)m->tc_blob)->h.p;
   const int E = m->d.num_experts;
   const int64_t max_rows = S + (int64_t)TILE * (E + 2);
   const int64_t max_tiles = cdiv(S, TILE) + E + 2;
@@ -814,8 +821,11 @@ int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, co
   }
   const int n_front_tiles = (int)cdiv(S, TILE);
   const int grid1 = n_front_tiles < m->sm_count ? n_front_tiles : m->sm_count;
+  PhaseEvents* pe = profile_next();
+  if (pe) cudaEventRecord(pe->e[0], st);
   k_front<12><<<grid1, THREADS, SM_TOTAL, st>>>(P, x, S, H, gates);
   SNB_CHECK_LAUNCH("k_front");
+  if (pe) cudaEventRecord(pe->e[1], st);
   int rc = route_top1(gates, S, E, o->capacity_factor, o->no_batch ? 0 : o->bpr, idx, loc, gate, counts, cap_dev, l_aux,
                       rws, rbytes, st);
   if (rc) return rc;
@@ -825,8 +835,10 @@ int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, co
   k_scatter_rows<<<(unsigned)cdiv(S, 256), 256, 0, st>>>(idx, loc, cap_dev, E, o->no_batch, S, tt);
   SNB_CHECK_LAUNCH("k_scatter_rows");
   const int grid2 = (int)(max_tiles < m->sm_count ? max_tiles : m->sm_count);
+  if (pe) cudaEventRecord(pe->e[2], st);
   k_back<4><<<grid2, THREADS, SM_TOTAL, st>>>(P, tt, x, H, gate, sigma_noise, out);
   SNB_CHECK_LAUNCH("k_back");
+  if (pe) cudaEventRecord(pe->e[3], st);
   if (moe_idx) SNB_CHECK_CUDA(cudaMemcpyAsync(moe_idx, idx, sizeof(int) * S, cudaMemcpyDeviceToDevice, st));
   if (dbg_gates) SNB_CHECK_CUDA(cudaMemcpyAsync(dbg_gates, gates, sizeof(float) * S * E, cudaMemcpyDeviceToDevice, st));
   if (dbg_loc) SNB_CHECK_CUDA(cudaMemcpyAsync(dbg_loc, loc, sizeof(int) * S, cudaMemcpyDeviceToDevice, st));

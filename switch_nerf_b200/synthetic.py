@@ -1,0 +1,49 @@
+"""Deterministic synthetic inputs and random-init weights of the Building topology:
+seeded ray batches and state_dicts with the reference's keys/shapes.  Used by bench.py, smoke() and
+the tests; there are no datasets or checkpoints offline."""
+import math
+from typing import Dict, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+def synthetic_rays(n_rays: int, appearance_count: int, seed: int = 0) -> Tuple[Tensor, Tensor]:
+    """o ~ U(-0.2,0.2)^3, d = normalised N(0,I), near=0.05, far=1.0."""
+    g = torch.Generator().manual_seed(seed)
+    o = (torch.rand(n_rays, 3, generator=g) - 0.5) * 0.4
+    d = F.normalize(torch.randn(n_rays, 3, generator=g), dim=-1)
+    rays = torch.cat([o, d, torch.full((n_rays, 1), 0.05), torch.full((n_rays, 1), 1.0)], 1)
+    idx = torch.randint(0, appearance_count, (n_rays,), generator=g)
+    return rays, idx
+
+
+def synthetic_state_dict(num_experts=8, width=256, expert_layers=7, appearance_count=2048,
+                         appearance_dim=48, hidden2=128, xyz_in=75, dir_in=27, seed=0,
+                         gate_scale: float = 1.0) -> Dict[str, Tensor]:
+    """Random-init weights with the reference's state_dict keys/shapes and
+    nn.Linear-style U(-1/sqrt(in), 1/sqrt(in)) scaling.  `gate_scale` multiplies wg
+    (logit temperature, config 5)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def lin(out_f, in_f):
+        k = 1.0 / math.sqrt(in_f)
+        return ((torch.rand(out_f, in_f, generator=g) * 2 - 1) * k, (torch.rand(out_f, generator=g) * 2 - 1) * k)
+
+    sd = {}
+    for j in range(expert_layers):
+        k = 1.0 / math.sqrt(width)
+        sd[f"layers.0.experts.0.weights.{j}"] = (torch.rand(num_experts, width, width, generator=g) * 2 - 1) * k
+        sd[f"layers.0.experts.0.bias.{j}"] = (torch.rand(num_experts, 1, width, generator=g) * 2 - 1) * k
+    sd["layers.0.gates.0.wg.weight"] = lin(num_experts, width)[0] * gate_scale
+    for name, (o, i) in {"layers.1": (width, width), "layers.2": (hidden2, width + dir_in + appearance_dim),
+                         "layers.xyz": (width, xyz_in), "layers.sigma": (1, width), "layers.color": (3, hidden2)}.items():
+        sd[f"{name}.fcs.0.weight"], sd[f"{name}.fcs.0.bias"] = lin(o, i)
+    for i in range(2):
+        sd[f"layers.moe_external_gate.fcs.{i}.weight"], sd[f"layers.moe_external_gate.fcs.{i}.bias"] = lin(width, width)
+    sd["layers.gate_input_norm.weight"] = torch.ones(width) + 0.1 * torch.randn(width, generator=g)
+    sd["layers.gate_input_norm.bias"] = 0.1 * torch.randn(width, generator=g)
+    sd["embedding_a.weight"] = torch.randn(appearance_count, appearance_dim, generator=g)
+    return sd
