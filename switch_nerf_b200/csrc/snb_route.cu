@@ -6,7 +6,7 @@
 //
 // Everything is integer / ballot work bound by HBM and launch latency, not by math:
 //   k_top1        1 thread / sample, coalesced [S,E] fp32 read (4E B/sample), writes idx/gate/key
-//   radix passes  stable LSD radix sort of (key, sample) pairs, 8-bit digits, only for BPR
+//   radix passes  stable LSD radix sort of (key, sample) pairs, 9-bit digits, only for BPR
 //   k_loc         warp-ballot (match_any) rank inside a 256-sample block + scanned block offsets
 // No host round trip: capacity / counts / l_aux stay in device memory.
 #include "snb_common.cuh"
@@ -16,6 +16,8 @@ namespace snb {
 static constexpr int RB = 256;      // samples per block in top1 / hist / loc kernels
 static constexpr int ST = 2048;     // sort tile (elements per block)
 static constexpr int SORT_THREADS = 256;
+static constexpr int DBITS = 9;            // radix digit width
+static constexpr int NBINS = 1 << DBITS;
 
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RB) k_top1(const float* __restrict__ gates, int64_t S, int E,
@@ -93,28 +95,42 @@ __global__ void __launch_bounds__(RB) k_expert_hist(const int* __restrict__ idx,
 }
 
 // One block: exclusive scan of the per-block expert counts (-> blockoff), totals, capacity, l_aux.
-__global__ void k_finalize(const float* __restrict__ pm, const int* __restrict__ pc, int nblk, int E, int64_t S,
-                           double cf, int* __restrict__ counts, int* __restrict__ capacity,
-                           float* __restrict__ l_aux, int* __restrict__ blockoff, int write_stats) {
+// Warp w scans the blocks of expert e = w, w+nwarps, ... with shuffle prefix sums (coalesced in b).
+__global__ void __launch_bounds__(1024) k_finalize(const float* __restrict__ pm, const int* __restrict__ pc, int nblk,
+                                                   int E, int64_t S, double cf, int* __restrict__ counts,
+                                                   int* __restrict__ capacity, float* __restrict__ l_aux,
+                                                   int* __restrict__ blockoff, int write_stats) {
   __shared__ float s_prod[1024];
-  const int e = threadIdx.x;
-  float prod = 0.f;
-  if (e < E) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_prod[i] = 0.f;
+  __syncthreads();
+  for (int e = w; e < E; e += nw) {
     int run = 0;
     double me = 0.0;
-    for (int b = 0; b < nblk; ++b) {
-      int c = pc[(int64_t)b * E + e];
-      blockoff[(int64_t)b * E + e] = run;
-      run += c;
-      if (write_stats) me += (double)pm[(int64_t)b * E + e];
+    for (int b0 = 0; b0 < nblk; b0 += 32) {
+      const int b = b0 + lane;
+      int c = (b < nblk) ? pc[(int64_t)b * E + e] : 0;
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (b < nblk) blockoff[(int64_t)b * E + e] = run + inc - c;
+      run += __shfl_sync(0xffffffffu, inc, 31);
+      if (write_stats) {
+        double m = (b < nblk) ? (double)pm[(int64_t)b * E + e] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+        me += m;
+      }
     }
-    if (write_stats) {
+    if (write_stats && lane == 0) {
       counts[e] = run;
-      prod = (float)me * (float)run;   // me * ce in fp32 (tutel_fast_dispatch.py:143-145)
+      s_prod[e] = (float)me * (float)run;   // me * ce in fp32 (tutel_fast_dispatch.py:143-145)
     }
   }
   if (!write_stats) return;
-  s_prod[threadIdx.x] = prod;
   __syncthreads();
   if (threadIdx.x == 0) {
     float acc = 0.f;
@@ -150,34 +166,46 @@ __global__ void __launch_bounds__(RB) k_loc(const int* __restrict__ idx, const u
 
 // ------------------------------- stable LSD radix sort ---------------------------------
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint32_t* __restrict__ keys, int64_t S, int shift,
-                                                            int nblk, int* __restrict__ hist /*[256][nblk]*/) {
-  __shared__ int h[256];
-  h[threadIdx.x] = 0;
+                                                            int nblk, int* __restrict__ hist /*[NBINS][nblk]*/) {
+  __shared__ int h[NBINS];
+  for (int i = threadIdx.x; i < NBINS; i += SORT_THREADS) h[i] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * ST;
   for (int j = 0; j < ST / SORT_THREADS; ++j) {
     int64_t i = base + j * SORT_THREADS + threadIdx.x;
-    if (i < S) atomicAdd(&h[(keys[i] >> shift) & 255], 1);
+    if (i < S) atomicAdd(&h[(keys[i] >> shift) & (NBINS - 1)], 1);
   }
   __syncthreads();
-  hist[(int64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+  for (int i = threadIdx.x; i < NBINS; i += SORT_THREADS) hist[(int64_t)i * nblk + blockIdx.x] = h[i];
 }
 
-// exclusive scan of hist[256*nblk] in place (single block, sequential chunks per thread)
+// exclusive scan of hist[NBINS*nblk] in place (single block: per-thread runs + shuffle block scan)
 __global__ void __launch_bounds__(1024) k_sort_scan(int* __restrict__ hist, int n) {
-  __shared__ int part[1024];
+  __shared__ int wsum[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int per = (n + 1023) / 1024;
   const int lo = threadIdx.x * per, hi = min(n, lo + per);
   int sum = 0;
   for (int i = lo; i < hi; ++i) sum += hist[i];
-  part[threadIdx.x] = sum;
+  int inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[w] = inc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int i = 0; i < 1024; ++i) { int t = part[i]; part[i] = run; run += t; }
+  if (w == 0) {
+    int v = wsum[lane], vi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, vi, o);
+      if (lane >= o) vi += t;
+    }
+    wsum[lane] = vi - v;
   }
   __syncthreads();
-  int run = part[threadIdx.x];
+  int run = wsum[w] + inc - sum;
   for (int i = lo; i < hi; ++i) { int t = hist[i]; hist[i] = run; run += t; }
 }
 
@@ -186,18 +214,18 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint32_t* _
                                                                int shift, int nblk, const int* __restrict__ hist,
                                                                uint32_t* __restrict__ keys_out,
                                                                uint32_t* __restrict__ vals_out) {
-  __shared__ int run[256];                       // elements of each digit already placed by this block
-  __shared__ int wcnt[SORT_THREADS / 32][256];   // per-warp digit counts of the current round
+  __shared__ int run[NBINS];                       // elements of each digit already placed by this block
+  __shared__ int wcnt[SORT_THREADS / 32][NBINS];   // per-warp digit counts of the current round
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  run[threadIdx.x] = 0;
-  for (int k = threadIdx.x; k < (SORT_THREADS / 32) * 256; k += SORT_THREADS) (&wcnt[0][0])[k] = 0;
+  for (int k = threadIdx.x; k < NBINS; k += SORT_THREADS) run[k] = 0;
+  for (int k = threadIdx.x; k < (SORT_THREADS / 32) * NBINS; k += SORT_THREADS) (&wcnt[0][0])[k] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * ST;
   for (int j = 0; j < ST / SORT_THREADS; ++j) {
     const int64_t i = base + j * SORT_THREADS + threadIdx.x;
     const bool valid = i < S;
     uint32_t key = valid ? keys_in[i] : 0u;
-    int d = valid ? (int)((key >> shift) & 255) : -1;
+    int d = valid ? (int)((key >> shift) & (NBINS - 1)) : -1;
     unsigned m = __match_any_sync(0xffffffffu, d);
     int r = __popc(m & ((1u << lane) - 1));
     if (valid && r == 0) wcnt[w][d] = __popc(m);
@@ -210,8 +238,8 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint32_t* _
       vals_out[dst] = vals_in ? vals_in[i] : (uint32_t)i;
     }
     __syncthreads();
-    {
-      int d2 = threadIdx.x, c = 0;
+    for (int d2 = threadIdx.x; d2 < NBINS; d2 += SORT_THREADS) {
+      int c = 0;
 #pragma unroll
       for (int ww = 0; ww < SORT_THREADS / 32; ++ww) { c += wcnt[ww][d2]; wcnt[ww][d2] = 0; }
       run[d2] += c;
@@ -228,7 +256,7 @@ size_t route_workspace_bytes(int64_t S, int32_t E) {
   b += align_up((size_t)nblk * E * sizeof(int), 256);     // pc
   b += align_up((size_t)nblk * E * sizeof(int), 256);     // blockoff
   b += 4 * align_up((size_t)(S > 0 ? S : 1) * sizeof(uint32_t), 256);  // keys x2, vals x2
-  b += align_up((size_t)256 * nsort * sizeof(int), 256);  // sort hist
+  b += align_up((size_t)NBINS * nsort * sizeof(int), 256);  // sort hist
   return b + 1024;
 }
 
@@ -253,13 +281,13 @@ static int route_impl(const float* gates, int64_t S, int32_t E, double cf, int32
   uint32_t* k1 = a.take<uint32_t>(S);
   uint32_t* v0 = a.take<uint32_t>(S);
   uint32_t* v1 = a.take<uint32_t>(S);
-  int* shist = a.take<int>((size_t)256 * nsort);
+  int* shist = a.take<int>((size_t)NBINS * nsort);
   if (!a.ok) { set_error("route: workspace too small (%zu bytes given)", ws_bytes); return SNB_EWORKSPACE; }
 
   const size_t smem = (size_t)(RB / 32) * E * (sizeof(float) + sizeof(int));
   k_top1<<<nblk, RB, smem, st>>>(gates, S, E, idx, gate, bpr ? k0 : nullptr, softmax_keys, pm, pc);
   SNB_CHECK_LAUNCH("k_top1");
-  const int fin_threads = (int)align_up((size_t)E, 32);
+  const int fin_threads = (E >= 32) ? 1024 : 32 * E;
   k_finalize<<<1, fin_threads, 0, st>>>(pm, pc, nblk, E, S, cf, counts, capacity, l_aux, blockoff, 1);
   SNB_CHECK_LAUNCH("k_finalize");
   const uint32_t* order = nullptr;
@@ -267,20 +295,20 @@ static int route_impl(const float* gates, int64_t S, int32_t E, double cf, int32
     // number of significant key bits: softmax keys are < bits(1.0f) - bits(tiny) ; generic keys use 32
     int nbits = 32;
     if (softmax_keys) {
-      // max gate >= 1/E  =>  key <= bits(1.0) - bits(1/(2E))  (factor 2 of slack)
-      float lo = 1.0f / (2.0f * (float)E);
+      // max gate >= 1/E (up to rounding of the softmax)  =>  key <= bits(1.0) - bits(0.99/E)
+      float lo = 0.99f / (float)E;
       uint32_t lob;
       memcpy(&lob, &lo, 4);
       uint32_t maxk = 0x3F800000u - lob;
       nbits = 32 - __builtin_clz(maxk | 1u);
     }
-    const int passes = (nbits + 7) / 8;
+    const int passes = (nbits + DBITS - 1) / DBITS;
     uint32_t *kin = k0, *kout = k1, *vin = nullptr, *vout = v0;
     for (int p = 0; p < passes; ++p) {
-      const int shift = 8 * p;
+      const int shift = DBITS * p;
       k_sort_hist<<<nsort, SORT_THREADS, 0, st>>>(kin, S, shift, nsort, shist);
       SNB_CHECK_LAUNCH("k_sort_hist");
-      k_sort_scan<<<1, 1024, 0, st>>>(shist, 256 * nsort);
+      k_sort_scan<<<1, 1024, 0, st>>>(shist, NBINS * nsort);
       SNB_CHECK_LAUNCH("k_sort_scan");
       k_sort_scatter<<<nsort, SORT_THREADS, 0, st>>>(kin, vin, S, shift, nsort, shist, kout, vout);
       SNB_CHECK_LAUNCH("k_sort_scatter");

@@ -13,15 +13,22 @@
 //                         Dropped samples form one more bucket that skips the expert stack (h = 0).
 //                         reference: tutel_moe_layer_nobatch.py:142-225, 887-924; nerf_moe.py:384-441
 //
-// Inside a CTA (192 threads, 1 CTA / SM, persistent over tiles):
+// Inside a CTA (576 threads = 18 warps, 1 CTA / SM, persistent over tiles):
 //   warp 0     weight producer : 1-D bulk async copies (UBLKCP) of pre-packed K-slices (<=64 wide)
 //                                into a 3-stage shared-memory ring, mbarrier full/empty
 //   warp 1     MMA issuer      : one thread issues tcgen05.mma (M=128, N<=256, K=16 per instr.),
 //                                accumulators in TMEM, ping-pong between columns [0,256) / [256,512)
-//   warps 2-5  epilogue        : tcgen05.ld -> bias / ReLU / skip / gate / LayerNorm / heads in fp32
-//                                registers -> bf16 back into the shared A tile, 64 columns at a time,
-//                                signalling per-chunk mbarriers so the next layer's MMAs start while
-//                                the rest of the epilogue is still running.
+//   warps 2-17 epilogue        : 16 warps = 4 TMEM lane quarters x 4 column sub-slices.  tcgen05.ld ->
+//                                bias / ReLU / skip / gate / heads in fp32 registers -> bf16 back into
+//                                the shared A tile, one 64-column chunk at a time (each warp owns 16 of
+//                                the 64 columns), signalling a per-chunk mbarrier so the next layer's
+//                                MMAs start while the rest of the epilogue is still running.  Row-wise
+//                                reductions (LayerNorm statistics, sigma / colour dot products) are
+//                                finished through a small shared-memory exchange.
+// The fp32 gate GEMM (fp32_gate: True) runs on the tensor cores too: LayerNorm is folded into the
+// weights, logits = rstd * (g . (gamma*wg)^T - mean * c1) + c0, g is exactly representable in bf16
+// (it is the bf16 output of the gate MLP) and gamma*wg is split into bf16 hi + lo parts (N = 2x16),
+// which reproduces the fp32 product to ~2^-17 relative.
 // Activations never leave the SM between layers; per sample HBM traffic is x (28 B) + h (2x512 B)
 // + gates (32 B) + out (16 B).
 //
@@ -43,8 +50,10 @@ static constexpr uint32_t A_BYTES = TILE / 8 * SBO_A; // 90112
 static constexpr int NSTAGE = 3;
 static constexpr uint32_t STAGE_BYTES = 256 * 64 * 2; // one K-slice of a 256-wide layer
 static constexpr int NCHUNK = 6;            // 64-column chunks of the A tile (352/64 rounded up)
-static constexpr int THREADS = 192;
-static constexpr int EPI_THREADS = 128;
+static constexpr int EPI_WARPS = 16;
+static constexpr int EPI_THREADS = EPI_WARPS * 32;   // 512
+static constexpr int THREADS = 64 + EPI_THREADS;      // 576
+static constexpr int GATE_N = 32;                     // gate GEMM: 16 "hi" + 16 "lo" output columns
 static constexpr int MAX_E = 16;
 
 #ifndef SNB_UMMA_SWAP
@@ -70,32 +79,68 @@ struct TcLayer {
 
 struct TcParams {
   const uint8_t* wblob;     // packed bf16 weights
-  const float* fblob;       // fp32 side table: biases (bf16-rounded), ln, wg, sigma/colour heads
+  const float* fblob;       // fp32 side table: biases (bf16-rounded), gate constants, sigma/colour heads
   TcLayer front[5];         // xyz, gate fcs
   int n_front;
+  TcLayer gate;             // folded LayerNorm+gate GEMM: rows [0,16) = hi(gamma*wg), rows [16,32) = lo
   TcLayer expert[16];       // layer j of expert 0; expert e adds e*expert_stride(_b)
   int n_expert;
   uint32_t expert_w_stride; // bytes between experts (all layers of one expert are contiguous)
   uint32_t expert_b_stride; // floats between experts
   TcLayer back[2];          // layer "1", layer "2"
-  uint32_t o_lnw, o_lnb, o_wg, o_wsig, o_bsig, o_wcol, o_bcol;   // float offsets in fblob
+  uint32_t o_c0, o_c1, o_wsig, o_bsig, o_wcol, o_bcol;   // float offsets in fblob
   int E, skip_layer, pos_xyz_freqs, pos_dir_freqs, appearance_dim, appearance_count, hidden2, x_cols;
   const float* emb_a;       // fp32 [count, A]
 };
 
-__global__ void k_pack_layer(const float* __restrict__ w, int N, int K, int K16, int transposed_kn,
-                             __nv_bfloat16* __restrict__ dst) {
-  // dst image: slices of 64 k; inside a slice: (n/8)*(klen*16) + (kk/8)*128 + (n%8)*16 + (kk%8)*2 bytes
+// canonical image: slices of 64 k; inside a slice (n/8)*(klen*16) + (kk/8)*128 + (n%8)*16 + (kk%8)*2 bytes
+__device__ __forceinline__ size_t packed_index(int n, int k, int N, int K16) {
+  const int j = k / 64, kk = k % 64;
+  const int klen = min(64, K16 - 64 * j);
+  return (size_t)N * 64 * j + ((size_t)(n / 8) * (klen * 16) + (size_t)(kk / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2) / 2;
+}
+
+__global__ void k_pack_layer(const float* __restrict__ w, int N, int K, int K16, __nv_bfloat16* __restrict__ dst) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * K16; i += gridDim.x * blockDim.x) {
     const int n = i / K16, k = i % K16;
-    float v = 0.f;
-    if (k < K) v = transposed_kn ? w[(size_t)k * N + n] : w[(size_t)n * K + k];
-    const int j = k / 64, kk = k % 64;
-    const int klen = min(64, K16 - 64 * j);
-    const size_t slice_base = (size_t)N * 64 * j;   // elements
-    const size_t off = slice_base + ((size_t)(n / 8) * (klen * 16) + (size_t)(kk / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2) / 2;
-    dst[off] = __float2bfloat16_rn(v);
+    const float v = (k < K) ? w[(size_t)n * K + k] : 0.f;
+    dst[packed_index(n, k, N, K16)] = __float2bfloat16_rn(v);
   }
+}
+
+// gate GEMM operand: W'[e,k] = ln_w[k] * wg[e,k]; row e = bf16 hi part, row 16+e = bf16 lo part
+__global__ void k_pack_gate(const float* __restrict__ ln_w, const float* __restrict__ wg, int E, int K,
+                            __nv_bfloat16* __restrict__ dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < GATE_N * K; i += gridDim.x * blockDim.x) {
+    const int n = i / K, k = i % K;
+    const int e = n % 16;
+    float v = 0.f;
+    if (e < E) {
+      const float wv = ln_w[k] * wg[(size_t)e * K + k];
+      const float hi = bf16_round(wv);
+      v = (n < 16) ? hi : (wv - hi);
+    }
+    dst[packed_index(n, k, GATE_N, K)] = __float2bfloat16_rn(v);
+  }
+}
+
+// c1[e] = sum_k ln_w[k]*wg[e,k] ; c0[e] = sum_k ln_b[k]*wg[e,k]   (one warp per expert)
+__global__ void k_gate_consts(const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                              const float* __restrict__ wg, int E, int K, float* __restrict__ c0,
+                              float* __restrict__ c1) {
+  const int e = blockIdx.x, lane = threadIdx.x;
+  if (e >= E) return;
+  double a0 = 0.0, a1 = 0.0;
+  for (int k = lane; k < K; k += 32) {
+    a1 += (double)ln_w[k] * (double)wg[(size_t)e * K + k];
+    a0 += (double)ln_b[k] * (double)wg[(size_t)e * K + k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if (lane == 0) { c0[e] = (float)a0; c1[e] = (float)a1; }
 }
 
 __global__ void k_round_copy(const float* __restrict__ src, int n, int round_bf16, float* __restrict__ dst) {
@@ -111,9 +156,9 @@ struct TcHost {
 
 bool tc_supported(const Model* m) {
   const snb_model_desc& d = m->d;
-  return d.width == MW && d.num_experts <= MAX_E && d.hidden2 <= 256 && d.hidden2 % 16 == 0 && d.gate_layers <= 4 &&
-         !d.mip && m->xyz_in <= 128 && m->cat_in <= KA_MAX - 16 + 16 && ((m->cat_in + 15) / 16 * 16) <= KA_MAX &&
-         d.expert_layers <= 16 && d.appearance_dim % 4 == 0;
+  return d.width == MW && d.num_experts <= MAX_E && d.hidden2 <= 256 && d.hidden2 % 64 == 0 && d.gate_layers <= 4 &&
+         !d.mip && m->xyz_in <= 128 && ((m->cat_in + 15) / 16 * 16) <= KA_MAX && d.expert_layers <= 16 &&
+         d.appearance_dim % 4 == 0 && d.pos_xyz_freqs == 12 && d.pos_dir_freqs == 4;
 }
 
 struct TcOwner { TcHost h; uint8_t* wblob; };
@@ -130,13 +175,10 @@ void tc_release(Model* m) {
 int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
   const snb_model_desc& d = m->d;
   const int E = d.num_experts, L = d.expert_layers, H2 = d.hidden2;
-  // (re)build the host descriptor + device blobs; m->tc_blob holds a host struct that owns them
-  using Owner = TcOwner;
-  Owner* own = nullptr;
+  TcOwner* own = nullptr;
   if (m->tc_blob == nullptr) {
-    own = new Owner();
-    memset(own, 0, sizeof(Owner));
-    // layout
+    own = new TcOwner();
+    memset(own, 0, sizeof(TcOwner));
     size_t wbytes = 0, nf = 0;
     TcParams& p = own->h.p;
     auto add_layer = [&](TcLayer& l, int N, int K) {
@@ -151,6 +193,7 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
     p.n_front = 1 + d.gate_layers;
     add_layer(p.front[0], MW, m->xyz_in);
     for (int i = 0; i < d.gate_layers; ++i) add_layer(p.front[1 + i], MW, MW);
+    add_layer(p.gate, GATE_N, MW);
     add_layer(p.back[0], MW, MW);
     add_layer(p.back[1], H2, m->cat_in);
     p.n_expert = L;
@@ -161,7 +204,7 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
     wbytes = e0_w + (size_t)p.expert_w_stride * E;
     nf = e0_f + (size_t)p.expert_b_stride * E;
     auto addf = [&](size_t n) { size_t o = nf; nf += align_up(n, 64); return (uint32_t)o; };
-    p.o_lnw = addf(MW); p.o_lnb = addf(MW); p.o_wg = addf((size_t)E * MW);
+    p.o_c0 = addf(MAX_E); p.o_c1 = addf(MAX_E);
     p.o_wsig = addf(MW); p.o_bsig = addf(1); p.o_wcol = addf((size_t)3 * H2); p.o_bcol = addf(3);
     p.E = E; p.skip_layer = d.skip_layer; p.pos_xyz_freqs = d.pos_xyz_freqs; p.pos_dir_freqs = d.pos_dir_freqs;
     p.appearance_dim = d.appearance_dim; p.appearance_count = d.appearance_count; p.hidden2 = H2; p.x_cols = m->x_cols;
@@ -174,39 +217,38 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
     m->tc_blob = own;
     m->tc_bytes = wbytes;
   } else {
-    own = (Owner*)m->tc_blob;
+    own = (TcOwner*)m->tc_blob;
   }
   TcParams& p = own->h.p;
   SNB_CHECK_CUDA(cudaMemsetAsync(own->h.fblob, 0, own->h.fblob_floats * sizeof(float), st));
-  auto pack = [&](const TcLayer& l, const float* wsrc, int K, int transposed, size_t extra_w, const float* bsrc,
-                  size_t extra_b) -> int {
-    k_pack_layer<<<256, 256, 0, st>>>(wsrc, (int)l.N, K, (int)l.K16, transposed,
-                                      (__nv_bfloat16*)(own->wblob + l.w_off + extra_w));
+  auto pack = [&](const TcLayer& l, const float* wsrc, int K, size_t extra_w, const float* bsrc, size_t extra_b) -> int {
+    k_pack_layer<<<256, 256, 0, st>>>(wsrc, (int)l.N, K, (int)l.K16, (__nv_bfloat16*)(own->wblob + l.w_off + extra_w));
     SNB_CHECK_LAUNCH("k_pack_layer");
     k_round_copy<<<(unsigned)cdiv(l.N, 256), 256, 0, st>>>(bsrc, (int)l.N, 1, own->h.fblob + l.b_off + extra_b);
     SNB_CHECK_LAUNCH("k_round_copy");
     return SNB_OK;
   };
   int rc;
-  // use the library-owned fp32 copies (already uploaded by snb_api upload()); experts there are [E][N][K]
-  if ((rc = pack(p.front[0], m->xyz_w, m->xyz_in, 0, 0, m->xyz_b, 0))) return rc;
+  // sources are the library-owned fp32 copies uploaded by snb_api upload(); experts there are [E][N][K]
+  if ((rc = pack(p.front[0], m->xyz_w, m->xyz_in, 0, m->xyz_b, 0))) return rc;
   for (int i = 0; i < d.gate_layers; ++i)
-    if ((rc = pack(p.front[1 + i], m->gate_w[i], MW, 0, 0, m->gate_b[i], 0))) return rc;
-  if ((rc = pack(p.back[0], m->l1_w, MW, 0, 0, m->l1_b, 0))) return rc;
-  if ((rc = pack(p.back[1], m->l2_w, m->cat_in, 0, 0, m->l2_b, 0))) return rc;
+    if ((rc = pack(p.front[1 + i], m->gate_w[i], MW, 0, m->gate_b[i], 0))) return rc;
+  if ((rc = pack(p.back[0], m->l1_w, MW, 0, m->l1_b, 0))) return rc;
+  if ((rc = pack(p.back[1], m->l2_w, m->cat_in, 0, m->l2_b, 0))) return rc;
   for (int e = 0; e < E; ++e)
     for (int j = 0; j < L; ++j)
-      if ((rc = pack(p.expert[j], m->exp_w[j] + (size_t)e * MW * MW, MW, 0, (size_t)e * p.expert_w_stride,
+      if ((rc = pack(p.expert[j], m->exp_w[j] + (size_t)e * MW * MW, MW, (size_t)e * p.expert_w_stride,
                      m->exp_b[j] + (size_t)e * MW, (size_t)e * p.expert_b_stride)))
         return rc;
+  k_pack_gate<<<32, 256, 0, st>>>(m->ln_w, m->wg, E, MW, (__nv_bfloat16*)(own->wblob + p.gate.w_off));
+  SNB_CHECK_LAUNCH("k_pack_gate");
+  k_gate_consts<<<E, 32, 0, st>>>(m->ln_w, m->ln_b, m->wg, E, MW, own->h.fblob + p.o_c0, own->h.fblob + p.o_c1);
+  SNB_CHECK_LAUNCH("k_gate_consts");
   auto cpf = [&](uint32_t off, const float* src, int n, int round) -> int {
     k_round_copy<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(src, n, round, own->h.fblob + off);
     SNB_CHECK_LAUNCH("k_round_copy");
     return SNB_OK;
   };
-  if ((rc = cpf(p.o_lnw, m->ln_w, MW, 0))) return rc;       // LayerNorm + gate stay fp32 (fp32_gate: True)
-  if ((rc = cpf(p.o_lnb, m->ln_b, MW, 0))) return rc;
-  if ((rc = cpf(p.o_wg, m->wg, E * MW, 0))) return rc;
   if ((rc = cpf(p.o_wsig, m->sigma_w, MW, 1))) return rc;   // bf16 Linear under autocast
   if ((rc = cpf(p.o_bsig, m->sigma_b, 1, 1))) return rc;
   if ((rc = cpf(p.o_wcol, m->color_w, 3 * d.hidden2, 1))) return rc;
@@ -229,10 +271,13 @@ struct __align__(16) SmemCtl {
 static constexpr size_t SM_A = 0;
 static constexpr size_t SM_RING = A_BYTES;
 static constexpr size_t SM_BIAS = SM_RING + (size_t)NSTAGE * STAGE_BYTES;   // 2 x 256 floats
-static constexpr size_t SM_VEC = SM_BIAS + 2 * 256 * 4;                     // head / LN / gate vectors (floats)
-static constexpr size_t SM_VEC_FLOATS = 256 * 2 + MAX_E * 256 + 3 * 256 + 16;  // lnw,lnb | wg | wsig,wcol | scalars
-static constexpr size_t SM_CTL = SM_VEC + SM_VEC_FLOATS * 4;
+static constexpr size_t SM_VEC = SM_BIAS + 2 * 256 * 4;                     // head vectors: wsig[256], wcol[3*256]
+static constexpr size_t SM_VEC_FLOATS = 256 + 3 * 256 + 64;
+static constexpr size_t SM_RED = SM_VEC + SM_VEC_FLOATS * 4;                // row-reduction scratch [4][4][128] floats
+static constexpr size_t SM_RED_FLOATS = 4 * 4 * 128;
+static constexpr size_t SM_CTL = SM_RED + SM_RED_FLOATS * 4;
 static constexpr size_t SM_TOTAL = SM_CTL + sizeof(SmemCtl) + 1024;         // + alignment slack
+static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 
 struct Pipe {               // running counters of one role
   uint32_t slice = 0;       // weight slices produced / consumed so far
@@ -246,7 +291,18 @@ __device__ __forceinline__ uint32_t a_chunk_addr(uint32_t a_base, int row, int c
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+// 32 lanes x 16 columns: thread t of the warp gets TMEM lane (base_lane + t), columns c..c+15
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 
 // ---- producer: stream the K-slices of one layer through the ring ----
 __device__ __forceinline__ void produce_layer(const uint8_t* wsrc, uint32_t N, uint32_t K16, uint8_t* ring,
@@ -289,42 +345,53 @@ __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_b
 }
 
 // ---- epilogue helpers -------------------------------------------------------------------
+struct EpiCtx {
+  int lane, q, cs, row;     // TMEM lane quarter, column sub-slice (16 of every 64 columns), tile row
+  int et;                   // 0..511
+  uint32_t lane_base;       // (q*32) << 16
+};
+
 __device__ __forceinline__ void epi_wait_acc(SmemCtl* ctl, Pipe& pp, int buf) {
   mbar_wait(&ctl->acc_full[buf], pp.acc_use[buf] & 1);
   ++pp.acc_use[buf];
   tc_fence_after();
 }
-__device__ __forceinline__ void epi_signal_chunk(SmemCtl* ctl, int c) {
+// every epilogue warp arrives once per chunk (a_ready count = 16): all lanes fence, lane 0 arrives
+__device__ __forceinline__ void epi_signal_chunk(SmemCtl* ctl, int c, int lane) {
   fence_proxy_async_smem();    // my st.shared -> visible to the async proxy (tcgen05.mma operand reads)
   tc_fence_before();           // my tcgen05.ld of the old accumulator happen-before the MMA that overwrites it
-  mbar_arrive(&ctl->a_ready[c]);
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&ctl->a_ready[c]);
 }
 // stage the (bf16-rounded) bias of a layer into shared memory (double buffered by `slot`)
 __device__ __forceinline__ void epi_load_bias(const float* __restrict__ bias, int N, float* sbias, int slot, int et) {
   float* dst = sbias + slot * 256;
-  for (int i = et; i < N; i += EPI_THREADS) dst[i] = bias[i];
+  if (et < N) dst[et] = bias[et];
   epi_bar_sync();
 }
 
-// y = act(acc + bias (+ skip)) -> bf16 -> A tile, for all N columns; signals one a_ready per 64 columns.
+// y = act(acc + bias (+ skip)) -> bf16 -> A tile; this thread owns columns [64c + 16cs, +16) of every chunk c.
 // `xrow` (nullable): bf16 row of the expert input for the skip connection (tutel_moe_layer_nobatch.py:911-916).
+// `hdst` (nullable): also store the bf16 row to global memory (h for launch #2).
 template <bool RELU>
-__device__ __forceinline__ void epi_hidden(uint32_t tmem_acc, const float* sb, int N, uint32_t a_base, int row,
-                                           const __nv_bfloat16* xrow, SmemCtl* ctl, int n_signal) {
-  for (int c32 = 0; c32 < N / 32; ++c32) {
-    uint32_t v[32];
-    tmem_ld32(tmem_acc + (uint32_t)c32 * 32u, v);
-    uint4 xs[4];
+__device__ __forceinline__ void epi_hidden(uint32_t tmem_acc, const float* sb, int nchunks, uint32_t a_base,
+                                           const EpiCtx& ec, const __nv_bfloat16* xrow, __nv_bfloat16* hdst,
+                                           SmemCtl* ctl) {
+  for (int c = 0; c < nchunks; ++c) {
+    const int col0 = c * 64 + ec.cs * 16;
+    uint32_t v[16];
+    tmem_ld16(tmem_acc + (uint32_t)col0, v);
+    uint4 xs[2];
     if (xrow) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) xs[q] = *reinterpret_cast<const uint4*>(xrow + c32 * 32 + q * 8);
+      xs[0] = *reinterpret_cast<const uint4*>(xrow + col0);
+      xs[1] = *reinterpret_cast<const uint4*>(xrow + col0 + 8);
     }
     tmem_ld_wait();
-    uint32_t pk[16];
+    uint32_t pk[8];
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float f0 = __uint_as_float(v[j]) + sb[c32 * 32 + j];
-      float f1 = __uint_as_float(v[j + 1]) + sb[c32 * 32 + j + 1];
+    for (int j = 0; j < 16; j += 2) {
+      float f0 = __uint_as_float(v[j]) + sb[col0 + j];
+      float f1 = __uint_as_float(v[j + 1]) + sb[col0 + j + 1];
       if (xrow) {
         const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs);
         __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162*>(&xw[j / 2]);
@@ -335,10 +402,13 @@ __device__ __forceinline__ void epi_hidden(uint32_t tmem_acc, const float* sb, i
       if (RELU) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
       pk[j / 2] = pack_bf16x2(f0, f1);
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      st_shared_v4(a_chunk_addr(a_base, row, c32 * 4 + q), pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-    if ((c32 & 1) && (c32 >> 1) < n_signal) epi_signal_chunk(ctl, c32 >> 1);
+    st_shared_v4(a_chunk_addr(a_base, ec.row, col0 / 8), pk[0], pk[1], pk[2], pk[3]);
+    st_shared_v4(a_chunk_addr(a_base, ec.row, col0 / 8 + 1), pk[4], pk[5], pk[6], pk[7]);
+    if (hdst) {
+      *reinterpret_cast<uint4*>(hdst + col0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(hdst + col0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+    epi_signal_chunk(ctl, c, ec.lane);
   }
 }
 
@@ -379,7 +449,7 @@ __device__ __forceinline__ void a_store_row(uint32_t a_base, int row, int col8, 
 }
 
 // ------------------------------------------------------------------------------------------
-// common prologue / epilogue of both kernels
+// common prologue of both kernels
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ SmemCtl* cta_setup(uint8_t* smem, int warp) {
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + SM_CTL);
@@ -387,15 +457,25 @@ __device__ __forceinline__ SmemCtl* cta_setup(uint8_t* smem, int warp) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
     mbar_init(&ctl->acc_full[0], 1);
     mbar_init(&ctl->acc_full[1], 1);
-    for (int i = 0; i < NCHUNK; ++i) mbar_init(&ctl->a_ready[i], EPI_THREADS);
+    for (int i = 0; i < NCHUNK; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&ctl->tmem_base);
   return ctl;
 }
+__device__ __forceinline__ EpiCtx epi_ctx(int warp, int lane) {
+  EpiCtx ec;
+  ec.lane = lane;
+  ec.q = warp & 3;                 // hardware rule: a warp reads the TMEM lanes 32*(warp_id % 4) ...
+  ec.cs = (warp - 2) >> 2;         // ... so warps {2..5}, {6..9}, {10..13}, {14..17} cover all 4 quarters each
+  ec.row = ec.q * 32 + lane;
+  ec.et = (int)threadIdx.x - 64;
+  ec.lane_base = (uint32_t)(ec.q * 32) << 16;
+  return ec;
+}
 
 // ------------------------------------------------------------------------------------------
-// launch #1: encode + xyz + external gate + LayerNorm + gate + softmax
+// launch #1: encode + xyz + external gate MLP + folded LayerNorm/gate GEMM + softmax
 // ------------------------------------------------------------------------------------------
 template <int FX>
 __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* __restrict__ x, int64_t S,
@@ -405,10 +485,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   SmemCtl* ctl = cta_setup(smem, warp);
   float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);
-  float* svec = reinterpret_cast<float*>(smem + SM_VEC);
-  float *s_lnw = svec, *s_lnb = svec + 256, *s_wg = svec + 512;
-  for (int i = threadIdx.x; i < MW; i += THREADS) { s_lnw[i] = P.fblob[P.o_lnw + i]; s_lnb[i] = P.fblob[P.o_lnb + i]; }
-  for (int i = threadIdx.x; i < P.E * MW; i += THREADS) s_wg[i] = P.fblob[P.o_wg + i];
+  float* sred = reinterpret_cast<float*>(smem + SM_RED);      // [2][4][128]: sum / sumsq partials per cs
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -420,114 +497,112 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
 
   if (warp == 0) {
     if (lane == 0)
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         for (int l = 0; l < NL; ++l)
           produce_layer(P.wblob + P.front[l].w_off, P.front[l].N, P.front[l].K16, smem + SM_RING, ctl, pp);
+        produce_layer(P.wblob + P.gate.w_off, GATE_N, MW, smem + SM_RING, ctl, pp);
+      }
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t li = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         for (int l = 0; l < NL; ++l, ++li)
           mma_layer(P.front[l].N, P.front[l].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp);
+        mma_layer(GATE_N, MW, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp);
+        ++li;
+      }
     }
   } else {
-    const int et = threadIdx.x - 64;            // 0..127
-    const int q = warp & 3;                     // TMEM lane quarter of this warp
-    const int row = q * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const EpiCtx ec = epi_ctx(warp, lane);
+    const int row = ec.row;
     uint32_t li = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int64_t s = (int64_t)t * TILE + row;
       const bool valid = s < S;
       // ---- stage PE(xyz) as the A operand of the xyz layer (K16 = 80 -> chunks 0 and 1) ----
-      {
+      constexpr int NPE = 3 + 6 * FX, NPAD = (NPE + 15) / 16 * 16;
+      if (ec.cs == 0) {
         float p[3] = {0.f, 0.f, 0.f};
         if (valid) { p[0] = x[s * P.x_cols + 0]; p[1] = x[s * P.x_cols + 1]; p[2] = x[s * P.x_cols + 2]; }
-        constexpr int NPE = 3 + 6 * FX, NPAD = (NPE + 15) / 16 * 16;
         __align__(16) __nv_bfloat16 pe[NPAD];
         pe_to_bf16<FX>(p, pe);
 #pragma unroll
         for (int i = NPE; i < NPAD; ++i) pe[i] = __float2bfloat16_rn(0.f);
         a_store_row(a_base, row, 0, pe, NPAD / 8);
-        for (int c = 0; c < (NPAD + 63) / 64; ++c) epi_signal_chunk(ctl, c);
       }
+      for (int c = 0; c < (NPAD + 63) / 64; ++c) epi_signal_chunk(ctl, c, lane);
       for (int l = 0; l < NL; ++l, ++li) {
         const int buf = (int)(li & 1);
-        epi_load_bias(P.fblob + P.front[l].b_off, MW, sbias, buf, et);
+        epi_load_bias(P.fblob + P.front[l].b_off, MW, sbias, buf, ec.et);
         epi_wait_acc(ctl, pp, buf);
-        const uint32_t tacc = tmem_base + lane_base + (uint32_t)buf * 256u;
+        const uint32_t tacc = tmem_base + ec.lane_base + (uint32_t)buf * 256u;
         const float* sb = sbias + buf * 256;
         if (l == 0) {
-          // h = xyz Linear (act none): bf16 -> A (operand of the gate MLP) and -> H[s] (expert input, launch #2)
-          for (int c32 = 0; c32 < MW / 32; ++c32) {
-            uint32_t v[32];
-            tmem_ld32(tacc + (uint32_t)c32 * 32u, v);
-            tmem_ld_wait();
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2)
-              pk[j / 2] = pack_bf16x2(__uint_as_float(v[j]) + sb[c32 * 32 + j], __uint_as_float(v[j + 1]) + sb[c32 * 32 + j + 1]);
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-              st_shared_v4(a_chunk_addr(a_base, row, c32 * 4 + qq), pk[qq * 4], pk[qq * 4 + 1], pk[qq * 4 + 2], pk[qq * 4 + 3]);
-              if (valid)
-                *reinterpret_cast<uint4*>(H + s * MW + c32 * 32 + qq * 8) = make_uint4(pk[qq * 4], pk[qq * 4 + 1], pk[qq * 4 + 2], pk[qq * 4 + 3]);
-            }
-            if (c32 & 1) epi_signal_chunk(ctl, c32 >> 1);
-          }
+          // h = xyz Linear (act none): bf16 -> A (operand of the gate MLP) and -> H[s] (expert input of launch #2)
+          epi_hidden<false>(tacc, sb, 4, a_base, ec, nullptr, valid ? (H + s * MW) : nullptr, ctl);
         } else if (l < NL - 1) {
-          epi_hidden<true>(tacc, sb, MW, a_base, row, nullptr, ctl, 4);
+          epi_hidden<true>(tacc, sb, 4, a_base, ec, nullptr, nullptr, ctl);
         } else {
-          // last gate layer: g = bf16(Linear); LayerNorm(fp32); logits = wg . ln (fp32); softmax
-          float sum = 0.f;
-          for (int c32 = 0; c32 < MW / 32; ++c32) {
-            uint32_t v[32];
-            tmem_ld32(tacc + (uint32_t)c32 * 32u, v);
+          // last gate-MLP layer: g = bf16(Linear) -> A (operand of the folded gate GEMM) + LayerNorm statistics
+          float sum = 0.f, sq = 0.f;
+          for (int c = 0; c < 4; ++c) {
+            const int col0 = c * 64 + ec.cs * 16;
+            uint32_t v[16];
+            tmem_ld16(tacc + (uint32_t)col0, v);
             tmem_ld_wait();
+            uint32_t pk[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum += bf16_round(__uint_as_float(v[j]) + sb[c32 * 32 + j]);
+            for (int j = 0; j < 16; j += 2) {
+              const float g0 = bf16_round(__uint_as_float(v[j]) + sb[col0 + j]);
+              const float g1 = bf16_round(__uint_as_float(v[j + 1]) + sb[col0 + j + 1]);
+              sum += g0 + g1;
+              sq = fmaf(g0, g0, fmaf(g1, g1, sq));
+              pk[j / 2] = pack_bf16x2(g0, g1);
+            }
+            st_shared_v4(a_chunk_addr(a_base, row, col0 / 8), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(a_chunk_addr(a_base, row, col0 / 8 + 1), pk[4], pk[5], pk[6], pk[7]);
+            epi_signal_chunk(ctl, c, lane);
           }
+          sred[(0 * 4 + ec.cs) * 128 + row] = sum;
+          sred[(1 * 4 + ec.cs) * 128 + row] = sq;
+        }
+      }
+      // ---- folded LayerNorm + gate GEMM epilogue: logits = rstd*(G_hi + G_lo - mean*c1) + c0 ; softmax ----
+      {
+        const int buf = (int)(li & 1);
+        epi_bar_sync();                       // LayerNorm partial sums of all 4 column sub-slices are in sred
+        epi_wait_acc(ctl, pp, buf);
+        if (ec.cs == 0) {
+          const float sum = sred[0 * 128 + row] + sred[1 * 128 + row] + sred[2 * 128 + row] + sred[3 * 128 + row];
+          const float sq = sred[4 * 128 + row] + sred[5 * 128 + row] + sred[6 * 128 + row] + sred[7 * 128 + row];
           const float mean = sum * (1.f / MW);
-          float var = 0.f;
-          for (int c32 = 0; c32 < MW / 32; ++c32) {
-            uint32_t v[32];
-            tmem_ld32(tacc + (uint32_t)c32 * 32u, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float dlt = bf16_round(__uint_as_float(v[j]) + sb[c32 * 32 + j]) - mean;
-              var = fmaf(dlt, dlt, var);
-            }
-          }
-          const float rstd = rsqrtf(var * (1.f / MW) + 1e-5f);
+          const float var = fmaxf(sq * (1.f / MW) - mean * mean, 0.f);
+          const float rstd = rsqrtf(var + 1e-5f);
+          const uint32_t tacc = tmem_base + ec.lane_base + (uint32_t)buf * 256u;
+          uint32_t hi[16], lo[16];
+          tmem_ld16(tacc, hi);
+          tmem_ld16(tacc + 16u, lo);
+          tmem_ld_wait();
           float lg[MAX_E];
-#pragma unroll
-          for (int e = 0; e < MAX_E; ++e) lg[e] = 0.f;
-          for (int c32 = 0; c32 < MW / 32; ++c32) {
-            uint32_t v[32];
-            tmem_ld32(tacc + (uint32_t)c32 * 32u, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int k = c32 * 32 + j;
-              const float ln = (bf16_round(__uint_as_float(v[j]) + sb[k]) - mean) * rstd * s_lnw[k] + s_lnb[k];
-#pragma unroll
-              for (int e = 0; e < MAX_E; ++e)
-                if (e < P.E) lg[e] = fmaf(ln, s_wg[e * MW + k], lg[e]);
-            }
-          }
           float mx = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < MAX_E; ++e) if (e < P.E) mx = fmaxf(mx, lg[e]);
+          for (int e = 0; e < MAX_E; ++e) {
+            lg[e] = rstd * (__uint_as_float(hi[e]) + __uint_as_float(lo[e]) - mean * P.fblob[P.o_c1 + e]) + P.fblob[P.o_c0 + e];
+            if (e < P.E) mx = fmaxf(mx, lg[e]);
+          }
           float den = 0.f;
 #pragma unroll
-          for (int e = 0; e < MAX_E; ++e) if (e < P.E) { lg[e] = expf(lg[e] - mx); den += lg[e]; }
+          for (int e = 0; e < MAX_E; ++e)
+            if (e < P.E) { lg[e] = expf(lg[e] - mx); den += lg[e]; }
           if (valid) {
 #pragma unroll
-            for (int e = 0; e < MAX_E; ++e) if (e < P.E) gates[s * P.E + e] = lg[e] / den;
+            for (int e = 0; e < MAX_E; ++e)
+              if (e < P.E) gates[s * P.E + e] = lg[e] / den;
           }
-          tc_fence_before();
         }
+        tc_fence_before();
+        epi_bar_sync();                       // sred is reused by the next tile
+        ++li;
       }
     }
   }
@@ -549,27 +624,37 @@ struct TileTable {
   int* row2sample;    // [max_rows]
 };
 
-__global__ void k_tile_plan(const int* __restrict__ counts, const int* __restrict__ cap_dev, int E, int no_batch,
-                            int64_t S, TileTable tt) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(256) k_tile_plan(const int* __restrict__ counts, const int* __restrict__ cap_dev, int E,
+                                                   int no_batch, int64_t S, TileTable tt) {
+  __shared__ int s_row[MAX_E + 2], s_tile[MAX_E + 2], s_kc[MAX_E + 1];
   const int cap = *cap_dev;
-  int row = 0, nt = 0, kept_total = 0;
-  for (int e = 0; e < E; ++e) {
-    const int kc = no_batch ? counts[e] : min(counts[e], cap);
-    tt.seg_start[e] = row;
-    for (int r = 0; r < kc; r += TILE) {
-      tt.tile_expert[nt] = e; tt.tile_row0[nt] = row + r; tt.tile_rows[nt] = min(TILE, kc - r); ++nt;
+  if (threadIdx.x == 0) {
+    int row = 0, nt = 0, kept_total = 0;
+    for (int e = 0; e < E; ++e) {
+      const int kc = no_batch ? counts[e] : min(counts[e], cap);
+      s_row[e] = row; s_tile[e] = nt; s_kc[e] = kc;
+      tt.seg_start[e] = row;
+      row += (kc + TILE - 1) / TILE * TILE;
+      nt += (kc + TILE - 1) / TILE;
+      kept_total += kc;
     }
-    row += (kc + TILE - 1) / TILE * TILE;
-    kept_total += kc;
+    const int nd = (int)S - kept_total;
+    s_row[E] = row; s_tile[E] = nt; s_kc[E] = nd;
+    tt.seg_start[E] = row;
+    nt += (nd + TILE - 1) / TILE;
+    s_tile[E + 1] = nt;
+    *tt.n_tiles = nt;
+    *tt.drop_counter = 0;
   }
-  const int nd = (int)S - kept_total;
-  tt.seg_start[E] = row;
-  for (int r = 0; r < nd; r += TILE) {
-    tt.tile_expert[nt] = -1; tt.tile_row0[nt] = row + r; tt.tile_rows[nt] = min(TILE, nd - r); ++nt;
+  __syncthreads();
+  for (int e = 0; e <= E; ++e) {
+    const int t0 = s_tile[e], nt = (s_kc[e] + TILE - 1) / TILE;
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+      tt.tile_expert[t0 + i] = (e < E) ? e : -1;
+      tt.tile_row0[t0 + i] = s_row[e] + i * TILE;
+      tt.tile_rows[t0 + i] = min(TILE, s_kc[e] - i * TILE);
+    }
   }
-  *tt.n_tiles = nt;
-  *tt.drop_counter = 0;
 }
 
 __global__ void k_scatter_rows(const int* __restrict__ idx, const int* __restrict__ loc, const int* __restrict__ cap_dev,
@@ -596,7 +681,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
   SmemCtl* ctl = cta_setup(smem, warp);
   float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);
   float* svec = reinterpret_cast<float*>(smem + SM_VEC);
-  float *s_wsig = svec, *s_wcol = svec + 256;   // [256], [3][H2]
+  float* sred = reinterpret_cast<float*>(smem + SM_RED);      // [4 values][4 cs][128 rows]
+  float *s_wsig = svec, *s_wcol = svec + 256;                 // [256], [3][H2]
   const int H2 = P.hidden2;
   for (int i = threadIdx.x; i < MW; i += THREADS) s_wsig[i] = P.fblob[P.o_wsig + i];
   for (int i = threadIdx.x; i < 3 * H2; i += THREADS) s_wcol[i] = P.fblob[P.o_wcol + i];
@@ -631,10 +717,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
       }
     }
   } else {
-    const int et = threadIdx.x - 64;
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const EpiCtx ec = epi_ctx(warp, lane);
+    const int row = ec.row;
     const float b_sig = P.fblob[P.o_bsig];
     const float b_col0 = P.fblob[P.o_bcol], b_col1 = P.fblob[P.o_bcol + 1], b_col2 = P.fblob[P.o_bcol + 2];
     uint32_t li = 0;
@@ -644,106 +728,104 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
       const bool valid = sidx >= 0;
       const __nv_bfloat16* hrow = valid ? (H + (int64_t)sidx * MW) : nullptr;
       const float g = (valid && e >= 0) ? gate[sidx] : 0.f;
-      // ---- stage: expert input rows (or zeros for the dropped bucket) + [PE(dir) | appearance] ----
+      // ---- stage: expert input rows (or zeros for the dropped bucket); thread cs copies A chunk cs (128 B) ----
       {
-        for (int c8 = 0; c8 < MW / 8; ++c8) {
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (valid && e >= 0) v = *reinterpret_cast<const uint4*>(hrow + c8 * 8);
-          st_shared_v4(a_chunk_addr(a_base, row, c8), v.x, v.y, v.z, v.w);
-        }
-        constexpr int NDIR = 3 + 6 * FD;                   // 27
-        constexpr int NCAT_MAX = KA_MAX - MW;              // 96
-        __align__(16) __nv_bfloat16 cat[NCAT_MAX];
 #pragma unroll
-        for (int i = 0; i < NCAT_MAX; ++i) cat[i] = __float2bfloat16_rn(0.f);
-        if (valid) {
-          const float* xr = x + (int64_t)sidx * P.x_cols;
-          float dvec[3] = {xr[P.x_cols - 4], xr[P.x_cols - 3], xr[P.x_cols - 2]};
-          pe_to_bf16<FD>(dvec, cat);
-          int ai = (int)xr[P.x_cols - 1];
-          ai = min(max(ai, 0), P.appearance_count - 1);
-          const float4* er = reinterpret_cast<const float4*>(P.emb_a + (int64_t)ai * P.appearance_dim);
-          for (int i = 0; i < P.appearance_dim / 4; ++i) {
-            float4 f = er[i];
-            cat[NDIR + 4 * i + 0] = __float2bfloat16_rn(f.x);
-            cat[NDIR + 4 * i + 1] = __float2bfloat16_rn(f.y);
-            cat[NDIR + 4 * i + 2] = __float2bfloat16_rn(f.z);
-            cat[NDIR + 4 * i + 3] = __float2bfloat16_rn(f.w);
-          }
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (valid && e >= 0) v = *reinterpret_cast<const uint4*>(hrow + ec.cs * 64 + c8 * 8);
+          st_shared_v4(a_chunk_addr(a_base, row, ec.cs * 8 + c8), v.x, v.y, v.z, v.w);
         }
-        const int ncat8 = ((int)P.back[1].K16 - MW) / 8;
-        a_store_row(a_base, row, MW / 8, cat, ncat8);
-        for (int c = 0; c < 4; ++c) epi_signal_chunk(ctl, c);
+        // ---- [PE(dir) | appearance | 0-pad] -> A columns [256, K16 of layer "2")  (cs == 1 threads) ----
+        if (ec.cs == 1) {
+          constexpr int NDIR = 3 + 6 * FD;                   // 27
+          constexpr int NCAT_MAX = KA_MAX - MW;              // 96
+          __align__(16) __nv_bfloat16 cat[NCAT_MAX];
+#pragma unroll
+          for (int i = 0; i < NCAT_MAX; ++i) cat[i] = __float2bfloat16_rn(0.f);
+          if (valid) {
+            const float* xr = x + (int64_t)sidx * P.x_cols;
+            float dvec[3] = {xr[P.x_cols - 4], xr[P.x_cols - 3], xr[P.x_cols - 2]};
+            pe_to_bf16<FD>(dvec, cat);
+            int ai = (int)xr[P.x_cols - 1];
+            ai = min(max(ai, 0), P.appearance_count - 1);
+            const float4* er = reinterpret_cast<const float4*>(P.emb_a + (int64_t)ai * P.appearance_dim);
+            for (int i = 0; i < P.appearance_dim / 4; ++i) {
+              float4 f = er[i];
+              cat[NDIR + 4 * i + 0] = __float2bfloat16_rn(f.x);
+              cat[NDIR + 4 * i + 1] = __float2bfloat16_rn(f.y);
+              cat[NDIR + 4 * i + 2] = __float2bfloat16_rn(f.z);
+              cat[NDIR + 4 * i + 3] = __float2bfloat16_rn(f.w);
+            }
+          }
+          a_store_row(a_base, row, MW / 8, cat, ((int)P.back[1].K16 - MW) / 8);
+        }
+        for (int c = 0; c < 4; ++c) epi_signal_chunk(ctl, c, lane);
       }
       float sig_acc = 0.f;
       if (e >= 0) {
         for (int l = 0; l < NE; ++l, ++li) {
           const int buf = (int)(li & 1);
-          epi_load_bias(P.fblob + P.expert[l].b_off + (size_t)e * P.expert_b_stride, MW, sbias, buf, et);
+          epi_load_bias(P.fblob + P.expert[l].b_off + (size_t)e * P.expert_b_stride, MW, sbias, buf, ec.et);
           epi_wait_acc(ctl, pp, buf);
-          const uint32_t tacc = tmem_base + lane_base + (uint32_t)buf * 256u;
+          const uint32_t tacc = tmem_base + ec.lane_base + (uint32_t)buf * 256u;
           const float* sb = sbias + buf * 256;
           if (l < NE - 1) {
-            epi_hidden<true>(tacc, sb, MW, a_base, row, (l == P.skip_layer) ? hrow : nullptr, ctl, 4);
+            epi_hidden<true>(tacc, sb, 4, a_base, ec, (l == P.skip_layer) ? hrow : nullptr, nullptr, ctl);
           } else {
             // last expert layer (no activation) -> combine: y = bf16(gate * bf16(out)) -> ReLU -> A;
             // sigma head accumulated on the fly (nerf_moe.py:384-400)
-            for (int c32 = 0; c32 < MW / 32; ++c32) {
-              uint32_t v[32];
-              tmem_ld32(tacc + (uint32_t)c32 * 32u, v);
+            for (int c = 0; c < 4; ++c) {
+              const int col0 = c * 64 + ec.cs * 16;
+              uint32_t v[16];
+              tmem_ld16(tacc + (uint32_t)col0, v);
               tmem_ld_wait();
-              uint32_t pk[16];
+              uint32_t pk[8];
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                float f0 = bf16_round(__uint_as_float(v[j]) + sb[c32 * 32 + j]);
-                float f1 = bf16_round(__uint_as_float(v[j + 1]) + sb[c32 * 32 + j + 1]);
+              for (int j = 0; j < 16; j += 2) {
+                float f0 = bf16_round(__uint_as_float(v[j]) + sb[col0 + j]);
+                float f1 = bf16_round(__uint_as_float(v[j + 1]) + sb[col0 + j + 1]);
                 f0 = fmaxf(bf16_round(f0 * g), 0.f);
                 f1 = fmaxf(bf16_round(f1 * g), 0.f);
-                sig_acc = fmaf(f0, s_wsig[c32 * 32 + j], sig_acc);
-                sig_acc = fmaf(f1, s_wsig[c32 * 32 + j + 1], sig_acc);
+                sig_acc = fmaf(f0, s_wsig[col0 + j], sig_acc);
+                sig_acc = fmaf(f1, s_wsig[col0 + j + 1], sig_acc);
                 pk[j / 2] = pack_bf16x2(f0, f1);
               }
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq)
-                st_shared_v4(a_chunk_addr(a_base, row, c32 * 4 + qq), pk[qq * 4], pk[qq * 4 + 1], pk[qq * 4 + 2], pk[qq * 4 + 3]);
-              if (c32 & 1) epi_signal_chunk(ctl, c32 >> 1);
+              st_shared_v4(a_chunk_addr(a_base, row, col0 / 8), pk[0], pk[1], pk[2], pk[3]);
+              st_shared_v4(a_chunk_addr(a_base, row, col0 / 8 + 1), pk[4], pk[5], pk[6], pk[7]);
+              epi_signal_chunk(ctl, c, lane);
             }
           }
         }
       }
-      // sigma = softplus(bf16(W_sigma h + b) + noise - 1)
-      float sigma;
-      {
-        float sr = bf16_round(sig_acc + b_sig);
-        if (noise && valid) sr += noise[sidx];
-        const float tt_ = sr - 1.f;
-        sigma = (tt_ > 20.f) ? tt_ : log1pf(expf(tt_));
-      }
+      sred[(0 * 4 + ec.cs) * 128 + row] = sig_acc;          // sigma partial of this column sub-slice
       // ---- layer "1" (act none): bf16 -> A[:, 0:256); then release the [dir | appearance] chunks ----
       {
         const int buf = (int)(li & 1);
-        epi_load_bias(P.fblob + P.back[0].b_off, MW, sbias, buf, et);
+        epi_load_bias(P.fblob + P.back[0].b_off, MW, sbias, buf, ec.et);
         epi_wait_acc(ctl, pp, buf);
-        epi_hidden<false>(tmem_base + lane_base + (uint32_t)buf * 256u, sbias + buf * 256, MW, a_base, row, nullptr, ctl, 4);
+        epi_hidden<false>(tmem_base + ec.lane_base + (uint32_t)buf * 256u, sbias + buf * 256, 4, a_base, ec, nullptr,
+                          nullptr, ctl);
         const int nchunk2 = ((int)P.back[1].K16 + 63) / 64;
-        for (int c = 4; c < nchunk2; ++c) epi_signal_chunk(ctl, c);
+        for (int c = 4; c < nchunk2; ++c) epi_signal_chunk(ctl, c, lane);
         ++li;
       }
-      // ---- layer "2" (ReLU) + colour head + sigmoid ----
+      // ---- layer "2" (ReLU) + colour head partial dot products ----
       {
         const int buf = (int)(li & 1);
-        epi_load_bias(P.fblob + P.back[1].b_off, H2, sbias, buf, et);
+        epi_load_bias(P.fblob + P.back[1].b_off, H2, sbias, buf, ec.et);
         epi_wait_acc(ctl, pp, buf);
-        const uint32_t tacc = tmem_base + lane_base + (uint32_t)buf * 256u;
+        const uint32_t tacc = tmem_base + ec.lane_base + (uint32_t)buf * 256u;
         const float* sb = sbias + buf * 256;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-        for (int c32 = 0; c32 < H2 / 32; ++c32) {
-          uint32_t v[32];
-          tmem_ld32(tacc + (uint32_t)c32 * 32u, v);
+        for (int c = 0; c < H2 / 64; ++c) {
+          const int col0 = c * 64 + ec.cs * 16;
+          uint32_t v[16];
+          tmem_ld16(tacc + (uint32_t)col0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int k = c32 * 32 + j;
+          for (int j = 0; j < 16; ++j) {
+            const int k = col0 + j;
             const float h2 = bf16_round(fmaxf(__uint_as_float(v[j]) + sb[k], 0.f));
             c0 = fmaf(h2, s_wcol[k], c0);
             c1 = fmaf(h2, s_wcol[H2 + k], c1);
@@ -751,11 +833,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
           }
         }
         tc_fence_before();
-        if (valid) {
+        sred[(1 * 4 + ec.cs) * 128 + row] = c0;
+        sred[(2 * 4 + ec.cs) * 128 + row] = c1;
+        sred[(3 * 4 + ec.cs) * 128 + row] = c2;
+        epi_bar_sync();
+        if (ec.cs == 0 && valid) {
+          auto rsum = [&](int v) { return sred[(v * 4 + 0) * 128 + row] + sred[(v * 4 + 1) * 128 + row] +
+                                          sred[(v * 4 + 2) * 128 + row] + sred[(v * 4 + 3) * 128 + row]; };
+          // sigma = softplus(bf16(W_sigma h + b) + noise - 1)
+          float sr = bf16_round(rsum(0) + b_sig);
+          if (noise) sr += noise[sidx];
+          const float tt_ = sr - 1.f;
+          const float sigma = (tt_ > 20.f) ? tt_ : log1pf(expf(tt_));
           auto sg = [](float v) { return bf16_round(1.f / (1.f + expf(-bf16_round(v)))); };
-          float4 o = make_float4(sg(c0 + b_col0), sg(c1 + b_col1), sg(c2 + b_col2), sigma);
+          float4 o = make_float4(sg(rsum(1) + b_col0), sg(rsum(2) + b_col1), sg(rsum(3) + b_col2), sigma);
           reinterpret_cast<float4*>(out)[sidx] = o;
         }
+        epi_bar_sync();                       // sred is reused by the next tile
         ++li;
       }
     }
@@ -830,7 +924,7 @@ int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, co
                       rws, rbytes, st);
   if (rc) return rc;
   SNB_CHECK_CUDA(cudaMemsetAsync(tt.row2sample, 0xFF, (size_t)max_rows * sizeof(int), st));
-  k_tile_plan<<<1, 32, 0, st>>>(counts, cap_dev, E, o->no_batch, S, tt);
+  k_tile_plan<<<1, 256, 0, st>>>(counts, cap_dev, E, o->no_batch, S, tt);
   SNB_CHECK_LAUNCH("k_tile_plan");
   k_scatter_rows<<<(unsigned)cdiv(S, 256), 256, 0, st>>>(idx, loc, cap_dev, E, o->no_batch, S, tt);
   SNB_CHECK_LAUNCH("k_scatter_rows");
