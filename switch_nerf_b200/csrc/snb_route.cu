@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const uint32_t* __re
     int base0 = wbase + inc - (v0 + v1);
     int p0 = 0, p1 = 0;
     const int2* th = reinterpret_cast<const int2*>(thist);
+#pragma unroll 8
     for (int b = 0; b < (int)blockIdx.x; ++b) {
       int2 t = th[(int64_t)b * (NBINS / 2) + threadIdx.x];
       p0 += t.x; p1 += t.y;
