@@ -100,6 +100,9 @@ int64_t snb_launch_count(void);
  * out[0..3] = {front_ms, route_ms, back_ms, n_chunks}.  Used by bench.py for the roofline line. */
 int snb_profile_enable(int32_t on);
 int snb_profile_collect(double* out4);
+/* Debug only (env SNB_TIMELINE=1): clock marks of CTA 0 of the last fused forward; returns the number of
+ * 64-bit words copied (0 when disabled).  Synchronises the device. */
+int snb_debug_timeline(uint64_t* host_out, int32_t n);
 
 /* ---- model object ----------------------------------------------------------------------- */
 /* Replaces models/nerf_moe.py:1004-1041 get_nerf_moe_inner + load_state_dict: copies/packs the

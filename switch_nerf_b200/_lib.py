@@ -62,6 +62,7 @@ _SIGNATURES = {
     "snb_launch_count": (C.c_int64, []),
     "snb_profile_enable": (C.c_int, [C.c_int32]),
     "snb_profile_collect": (C.c_int, [C.POINTER(C.c_double)]),
+    "snb_debug_timeline": (C.c_int, [C.POINTER(C.c_uint64), C.c_int32]),
     "snb_model_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(Weights), C.c_void_p, C.POINTER(C.c_void_p)]),
     "snb_model_update": (C.c_int, [C.c_void_p, C.POINTER(Weights), C.c_void_p]),
     "snb_model_destroy": (None, [C.c_void_p]),

@@ -57,6 +57,7 @@ int merge_composite_launch(const float* zf, const float* zc, const float* raw_f,
                            const float* last_delta, int64_t N, int Sf, int Sc, int white_bkgd, float* rgb,
                            float* depth, float* var, float* lam, cudaStream_t st);
 int umma_selftest(const void* a, const void* b, int N, int K, float* d, int variant, cudaStream_t st);
+int tc_timeline_read(unsigned long long* host, int n);
 
 // [E][K][N] -> [E][N][K]
 __global__ void k_transpose_expert(const float* __restrict__ in, float* __restrict__ out, int E, int K, int N) {
@@ -145,6 +146,8 @@ int snb_profile_enable(int32_t on) {
   g_prof_used = 0;
   return SNB_OK;
 }
+
+int snb_debug_timeline(uint64_t* host_out, int32_t n) { return tc_timeline_read((unsigned long long*)host_out, n); }
 
 int snb_profile_collect(double* out4) {
   SNB_REQUIRE(out4, "snb_profile_collect: NULL");

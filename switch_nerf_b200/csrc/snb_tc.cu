@@ -37,10 +37,13 @@
 // between 8-row groups.  Weights are packed into exactly that image on the host side of the C ABI
 // (tc_pack_weights) so a K-slice is ONE contiguous bulk copy.
 #include "snb_common.cuh"
+#include <stdlib.h>
+
 #include "snb_umma.cuh"
 
 namespace snb {
 using namespace ptx;
+extern unsigned long long* g_timeline;
 
 static constexpr int TILE = 128;            // rows per tile (UMMA M)
 static constexpr int MW = 256;              // model width handled by this path
@@ -91,6 +94,7 @@ struct TcParams {
   uint32_t o_c0, o_c1, o_wsig, o_bsig, o_wcol, o_bcol;   // float offsets in fblob
   int E, skip_layer, pos_xyz_freqs, pos_dir_freqs, appearance_dim, appearance_count, hidden2, x_cols;
   const float* emb_a;       // fp32 [count, A]
+  unsigned long long* tl;   // debug timeline (nullable): [role][TL_N] (tag<<48 | clock) marks of CTA 0
 };
 
 // canonical image: slices of 64 k; inside a slice (n/8)*(klen*16) + (kk/8)*128 + (n%8)*16 + (kk%8)*2 bytes
@@ -279,6 +283,11 @@ static constexpr size_t SM_CTL = SM_RED + SM_RED_FLOATS * 4;
 static constexpr size_t SM_TOTAL = SM_CTL + sizeof(SmemCtl) + 1024;         // + alignment slack
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 
+static constexpr int TL_N = 2048;
+__device__ __forceinline__ void tl_mark(unsigned long long* tl, int role, int& n, int tag) {
+  if (tl && blockIdx.x == 0 && n < TL_N) tl[role * TL_N + n++] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+}
+
 struct Pipe {               // running counters of one role
   uint32_t slice = 0;       // weight slices produced / consumed so far
   uint32_t a_use[NCHUNK] = {0, 0, 0, 0, 0, 0};
@@ -321,7 +330,8 @@ __device__ __forceinline__ void produce_layer(const uint8_t* wsrc, uint32_t N, u
 
 // ---- MMA issuer: one layer = K16/16 tcgen05.mma instructions into accumulator buffer `buf` ----
 __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_base, uint32_t ring_base,
-                                          uint32_t tmem_base, int buf, SmemCtl* ctl, Pipe& pp) {
+                                          uint32_t tmem_base, int buf, SmemCtl* ctl, Pipe& pp,
+                                          unsigned long long* tl = nullptr, int* tn = nullptr) {
   const uint32_t nsl = (K16 + 63) / 64;
   const uint32_t idesc = umma_idesc_bf16(TILE, (int)N);
   const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
@@ -330,7 +340,9 @@ __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_b
     const uint32_t stage = pp.slice % NSTAGE, phase = (pp.slice / NSTAGE) & 1;
     mbar_wait(&ctl->a_ready[j], pp.a_use[j] & 1);       // A columns [64j, 64j+klen) written + fenced
     ++pp.a_use[j];
+    if (tn) tl_mark(tl, 1, *tn, 100 + (int)j);
     mbar_wait(&ctl->full[stage], phase);                // weight slice landed
+    if (tn) tl_mark(tl, 1, *tn, 110 + (int)j);
     tc_fence_after();
     const uint32_t b_base = ring_base + stage * STAGE_BYTES;
     for (uint32_t t = 0; t < klen / 16; ++t) {
@@ -342,6 +354,7 @@ __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_b
     ++pp.slice;
   }
   umma_commit(&ctl->acc_full[buf]);                     // accumulator complete -> epilogue
+  if (tn) tl_mark(tl, 1, *tn, 120);
 }
 
 // ---- epilogue helpers -------------------------------------------------------------------
@@ -505,10 +518,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t li = 0;
+      int tn = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        tl_mark(P.tl, 1, tn, 1);
         for (int l = 0; l < NL; ++l, ++li)
-          mma_layer(P.front[l].N, P.front[l].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp);
-        mma_layer(GATE_N, MW, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp);
+          mma_layer(P.front[l].N, P.front[l].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, P.tl, &tn);
+        mma_layer(GATE_N, MW, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, P.tl, &tn);
         ++li;
       }
     }
@@ -516,9 +531,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
     const EpiCtx ec = epi_ctx(warp, lane);
     const int row = ec.row;
     uint32_t li = 0;
+    int tn = 0;
+    unsigned long long* tl = (warp == 2 && lane == 0) ? P.tl : nullptr;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int64_t s = (int64_t)t * TILE + row;
       const bool valid = s < S;
+      tl_mark(tl, 0, tn, 1);
       // ---- stage PE(xyz) as the A operand of the xyz layer (K16 = 80 -> chunks 0 and 1) ----
       constexpr int NPE = 3 + 6 * FX, NPAD = (NPE + 15) / 16 * 16;
       if (ec.cs == 0) {
@@ -531,10 +549,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
         a_store_row(a_base, row, 0, pe, NPAD / 8);
       }
       for (int c = 0; c < (NPAD + 63) / 64; ++c) epi_signal_chunk(ctl, c, lane);
+      tl_mark(tl, 0, tn, 2);
       for (int l = 0; l < NL; ++l, ++li) {
         const int buf = (int)(li & 1);
         epi_load_bias(P.fblob + P.front[l].b_off, MW, sbias, buf, ec.et);
+        tl_mark(tl, 0, tn, 10 + l);
         epi_wait_acc(ctl, pp, buf);
+        tl_mark(tl, 0, tn, 20 + l);
         const uint32_t tacc = tmem_base + ec.lane_base + (uint32_t)buf * 256u;
         const float* sb = sbias + buf * 256;
         if (l == 0) {
@@ -566,12 +587,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
           sred[(0 * 4 + ec.cs) * 128 + row] = sum;
           sred[(1 * 4 + ec.cs) * 128 + row] = sq;
         }
+        tl_mark(tl, 0, tn, 30 + l);
       }
       // ---- folded LayerNorm + gate GEMM epilogue: logits = rstd*(G_hi + G_lo - mean*c1) + c0 ; softmax ----
       {
         const int buf = (int)(li & 1);
         epi_bar_sync();                       // LayerNorm partial sums of all 4 column sub-slices are in sred
         epi_wait_acc(ctl, pp, buf);
+        tl_mark(tl, 0, tn, 40);
         if (ec.cs == 0) {
           const float sum = sred[0 * 128 + row] + sred[1 * 128 + row] + sred[2 * 128 + row] + sred[3 * 128 + row];
           const float sq = sred[4 * 128 + row] + sred[5 * 128 + row] + sred[6 * 128 + row] + sred[7 * 128 + row];
@@ -602,6 +625,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
         }
         tc_fence_before();
         epi_bar_sync();                       // sred is reused by the next tile
+        tl_mark(tl, 0, tn, 41);
         ++li;
       }
     }
@@ -708,12 +732,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t li = 0;
+      int tn = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int e = tt.tile_expert[t];
+        tl_mark(P.tl, 1, tn, 1);
         if (e >= 0)
-          for (int l = 0; l < NE; ++l, ++li) mma_layer(MW, MW, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp);
-        mma_layer(P.back[0].N, P.back[0].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp); ++li;
-        mma_layer(P.back[1].N, P.back[1].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp); ++li;
+          for (int l = 0; l < NE; ++l, ++li) mma_layer(MW, MW, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, P.tl, &tn);
+        mma_layer(P.back[0].N, P.back[0].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, P.tl, &tn); ++li;
+        mma_layer(P.back[1].N, P.back[1].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, P.tl, &tn); ++li;
       }
     }
   } else {
@@ -722,8 +748,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
     const float b_sig = P.fblob[P.o_bsig];
     const float b_col0 = P.fblob[P.o_bcol], b_col1 = P.fblob[P.o_bcol + 1], b_col2 = P.fblob[P.o_bcol + 2];
     uint32_t li = 0;
+    int tn = 0;
+    unsigned long long* tl = (warp == 2 && lane == 0) ? P.tl : nullptr;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int e = tt.tile_expert[t];
+      tl_mark(tl, 0, tn, 1);
       const int sidx = (row < tt.tile_rows[t]) ? tt.row2sample[tt.tile_row0[t] + row] : -1;
       const bool valid = sidx >= 0;
       const __nv_bfloat16* hrow = valid ? (H + (int64_t)sidx * MW) : nullptr;
@@ -762,12 +791,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
         }
         for (int c = 0; c < 4; ++c) epi_signal_chunk(ctl, c, lane);
       }
+      tl_mark(tl, 0, tn, 2);
       float sig_acc = 0.f;
       if (e >= 0) {
         for (int l = 0; l < NE; ++l, ++li) {
           const int buf = (int)(li & 1);
           epi_load_bias(P.fblob + P.expert[l].b_off + (size_t)e * P.expert_b_stride, MW, sbias, buf, ec.et);
+          tl_mark(tl, 0, tn, 10 + l);
           epi_wait_acc(ctl, pp, buf);
+          tl_mark(tl, 0, tn, 20 + l);
           const uint32_t tacc = tmem_base + ec.lane_base + (uint32_t)buf * 256u;
           const float* sb = sbias + buf * 256;
           if (l < NE - 1) {
@@ -796,6 +828,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
               epi_signal_chunk(ctl, c, lane);
             }
           }
+          tl_mark(tl, 0, tn, 30 + l);
         }
       }
       sred[(0 * 4 + ec.cs) * 128 + row] = sig_acc;          // sigma partial of this column sub-slice
@@ -808,6 +841,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
                           nullptr, ctl);
         const int nchunk2 = ((int)P.back[1].K16 + 63) / 64;
         for (int c = 4; c < nchunk2; ++c) epi_signal_chunk(ctl, c, lane);
+        tl_mark(tl, 0, tn, 50);
         ++li;
       }
       // ---- layer "2" (ReLU) + colour head partial dot products ----
@@ -850,6 +884,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
           reinterpret_cast<float4*>(out)[sidx] = o;
         }
         epi_bar_sync();                       // sred is reused by the next tile
+        tl_mark(tl, 0, tn, 51);
         ++li;
       }
     }
@@ -862,6 +897,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+unsigned long long* g_timeline = nullptr;
+int tc_timeline_read(unsigned long long* host, int n) {
+  if (!g_timeline) return 0;
+  if (n > 4 * TL_N) n = 4 * TL_N;
+  cudaDeviceSynchronize();
+  cudaMemcpy(host, g_timeline, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  return n;
+}
+
 size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf) {
   (void)max_cf;
   const int E = m->d.num_experts;
@@ -882,7 +926,22 @@ size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf) {
 int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* o, float* out,
                int32_t* moe_idx, float* l_aux, float* dbg_gates, int32_t* dbg_loc, Arena& ws, cudaStream_t st) {
   SNB_REQUIRE(m->tc_blob, "tc_forward: weights were not packed");
-  const TcParams& P = ((TcOwner*)m->tc_blob)->h.p;
+  TcParams P = ((TcOwner*)m->tc_blob)->h.p;
+  TcParams Pb = P;
+  {
+    // debug only: SNB_TIMELINE=1 records clock marks of CTA 0 (front: slots [0,2*TL_N), back: [2*TL_N, 4*TL_N))
+    static unsigned long long* tl_buf = nullptr;
+    static int tl_checked = 0;
+    if (!tl_checked) {
+      tl_checked = 1;
+      if (getenv("SNB_TIMELINE")) { cudaMalloc((void**)&tl_buf, 4 * TL_N * 8); g_timeline = tl_buf; }
+    }
+    if (tl_buf) {
+      cudaMemsetAsync(tl_buf, 0, 4 * TL_N * 8, st);
+      P.tl = tl_buf;
+      Pb.tl = tl_buf + 2 * TL_N;
+    }
+  }
   const int E = m->d.num_experts;
   const int64_t max_rows = S + (int64_t)TILE * (E + 2);
   const int64_t max_tiles = cdiv(S, TILE) + E + 2;
@@ -930,7 +989,7 @@ int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, co
   SNB_CHECK_LAUNCH("k_scatter_rows");
   const int grid2 = (int)(max_tiles < m->sm_count ? max_tiles : m->sm_count);
   if (pe) cudaEventRecord(pe->e[2], st);
-  k_back<4><<<grid2, THREADS, SM_TOTAL, st>>>(P, tt, x, H, gate, sigma_noise, out);
+  k_back<4><<<grid2, THREADS, SM_TOTAL, st>>>(Pb, tt, x, H, gate, sigma_noise, out);
   SNB_CHECK_LAUNCH("k_back");
   if (pe) cudaEventRecord(pe->e[3], st);
   if (moe_idx) SNB_CHECK_CUDA(cudaMemcpyAsync(moe_idx, idx, sizeof(int) * S, cudaMemcpyDeviceToDevice, st));
