@@ -22,7 +22,7 @@ PhaseEvents* profile_next() {
   if (g_prof_used >= g_prof_pool.size()) {
     if (g_prof_pool.size() >= 65536) return nullptr;
     PhaseEvents pe;
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 6; ++i)
       if (cudaEventCreate(&pe.e[i]) != cudaSuccess) return nullptr;
     g_prof_pool.push_back(pe);
   }
@@ -157,8 +157,8 @@ int snb_profile_collect(double* out4) {
     float t;
     PhaseEvents& pe = g_prof_pool[i];
     SNB_CHECK_CUDA(cudaEventElapsedTime(&t, pe.e[0], pe.e[1])); f += t;
-    SNB_CHECK_CUDA(cudaEventElapsedTime(&t, pe.e[1], pe.e[2])); r += t;
-    SNB_CHECK_CUDA(cudaEventElapsedTime(&t, pe.e[2], pe.e[3])); b += t;
+    SNB_CHECK_CUDA(cudaEventElapsedTime(&t, pe.e[2], pe.e[3])); r += t;
+    SNB_CHECK_CUDA(cudaEventElapsedTime(&t, pe.e[4], pe.e[5])); b += t;
   }
   out4[0] = f; out4[1] = r; out4[2] = b; out4[3] = (double)g_prof_used;
   g_prof_used = 0;
@@ -222,6 +222,10 @@ void snb_model_destroy(snb_model_t* mm) {
   if (!m) return;
   if (m->f32_blob) cudaFree(m->f32_blob);
   tc_release(m);
+  if (m->side_stream) {
+    cudaStreamDestroy(m->side_stream);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_front[i]); cudaEventDestroy(m->ev_route[i]); }
+  }
   delete m;
 }
 
@@ -304,9 +308,9 @@ static size_t render_ws_layout(const Model* m, int64_t N, const snb_render_opts*
   const int64_t Smax = (int64_t)N * (Sc > Sf ? Sc : Sf);
   int64_t chunk = o->model_chunk_size < Smax ? o->model_chunk_size : Smax;
   if (chunk < 1) chunk = 1;
-  size_t mw = snb_workspace_bytes((const snb_model_t*)m, chunk, o->route.capacity_factor);
+  size_t mw = align_up(snb_workspace_bytes((const snb_model_t*)m, chunk, o->route.capacity_factor), 256);
   if (model_ws) *model_ws = mw;
-  size_t b = mw;
+  size_t b = 2 * mw;            // two chunk workspaces: consecutive chunks are software-pipelined
   auto add = [&](size_t n) { b += align_up(n * sizeof(float), 256); };
   add((size_t)N * Sc);            // zc
   add((size_t)N * Sc);            // weights_c
@@ -342,6 +346,7 @@ int snb_render_rays(snb_model_t* mm, const float* rays, const int32_t* image_ind
   if (workspace_bytes < need) { set_error("snb_render_rays: workspace %zu < required %zu", workspace_bytes, need); return SNB_EWORKSPACE; }
   Arena a(workspace, workspace_bytes);
   char* mws = a.take<char>(model_ws);
+  char* mws1 = a.take<char>(model_ws);
   float* zc = a.take<float>((size_t)N * Sc);
   float* wc = a.take<float>((size_t)N * Sc);
   float* zmid = a.take<float>((size_t)N * (Sc - 1));
@@ -359,6 +364,8 @@ int snb_render_rays(snb_model_t* mm, const float* rays, const int32_t* image_ind
     int rc = fill_x_launch(rays, image_indices, z, N, Sn, x, st);
     if (rc) return rc;
     const int64_t B = N * Sn;
+    if (o->precision == SNB_PREC_BF16 && tc_supported(m))
+      return tc_forward_chunks(m, x, B, o->model_chunk_size, &o->route, raw, gates_out, loss_out, mws, mws1, model_ws, st);
     int ci = 0;
     for (int64_t i = 0; i < B; i += o->model_chunk_size, ++ci) {       // rendering.py:354
       const int64_t rows = (B - i < o->model_chunk_size) ? (B - i) : o->model_chunk_size;

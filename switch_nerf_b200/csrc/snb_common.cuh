@@ -12,7 +12,7 @@ namespace snb {
 
 void set_error(const char* fmt, ...);
 void count_launch();
-struct PhaseEvents { cudaEvent_t e[4]; };
+struct PhaseEvents { cudaEvent_t e[6]; };   // front [0,1] | route [2,3] | back [4,5]
 // returns nullptr when profiling is off (or the event pool is exhausted)
 PhaseEvents* profile_next();
 
@@ -84,6 +84,9 @@ struct Model {
   void* tc_blob = nullptr;
   size_t tc_bytes = 0;
   int sm_count = 148;
+  // software pipelining of render_rays: routing kernels run on this stream
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_route[2] = {nullptr, nullptr};
 };
 
 // ---- entry points implemented in the individual .cu files ----
@@ -97,6 +100,8 @@ int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, co
                float* out, int32_t* moe_idx, float* l_aux, float* dbg_gates, int32_t* dbg_loc,
                Arena& ws, cudaStream_t st);
 size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf);
+int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const snb_route_opts* o, float* out,
+                      int32_t* moe_idx, float* l_aux, void* ws0, void* ws1, size_t ws_bytes, cudaStream_t st);
 bool tc_supported(const Model* m);
 void tc_release(Model* m);
 

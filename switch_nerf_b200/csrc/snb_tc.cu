@@ -383,45 +383,78 @@ __device__ __forceinline__ void epi_load_bias(const float* __restrict__ bias, in
   epi_bar_sync();
 }
 
+// pack two fp32 into bf16x2 (lo = first argument) with optional ReLU fused into the conversion
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t d;
+  if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 // y = act(acc + bias (+ skip)) -> bf16 -> A tile; this thread owns columns [64c + 16cs, +16) of every chunk c.
+// TMEM loads are issued two chunks at a time (one wait per pair).
 // `xrow` (nullable): bf16 row of the expert input for the skip connection (tutel_moe_layer_nobatch.py:911-916).
-// `hdst` (nullable): also store the bf16 row to global memory (h for launch #2).
 template <bool RELU>
 __device__ __forceinline__ void epi_hidden(uint32_t tmem_acc, const float* sb, int nchunks, uint32_t a_base,
-                                           const EpiCtx& ec, const __nv_bfloat16* xrow, __nv_bfloat16* hdst,
-                                           SmemCtl* ctl) {
-  for (int c = 0; c < nchunks; ++c) {
-    const int col0 = c * 64 + ec.cs * 16;
-    uint32_t v[16];
-    tmem_ld16(tmem_acc + (uint32_t)col0, v);
-    uint4 xs[2];
+                                           const EpiCtx& ec, const __nv_bfloat16* xrow, SmemCtl* ctl) {
+  for (int c2 = 0; c2 < nchunks; c2 += 2) {
+    uint32_t v[2][16];
+    const int colA = c2 * 64 + ec.cs * 16;
+    tmem_ld16(tmem_acc + (uint32_t)colA, v[0]);
+    if (c2 + 1 < nchunks) tmem_ld16(tmem_acc + (uint32_t)(colA + 64), v[1]);
+    uint4 xs[2][2];
     if (xrow) {
-      xs[0] = *reinterpret_cast<const uint4*>(xrow + col0);
-      xs[1] = *reinterpret_cast<const uint4*>(xrow + col0 + 8);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        xs[h][0] = *reinterpret_cast<const uint4*>(xrow + colA + 64 * h);
+        xs[h][1] = *reinterpret_cast<const uint4*>(xrow + colA + 64 * h + 8);
+      }
     }
     tmem_ld_wait();
-    uint32_t pk[8];
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-      float f0 = __uint_as_float(v[j]) + sb[col0 + j];
-      float f1 = __uint_as_float(v[j + 1]) + sb[col0 + j + 1];
-      if (xrow) {
-        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs);
-        __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162*>(&xw[j / 2]);
-        // reference: h = bf16(Linear) ; h = bf16(h + x)
-        f0 = bf16_round(f0) + __bfloat162float(xb.x);
-        f1 = bf16_round(f1) + __bfloat162float(xb.y);
+    for (int h = 0; h < 2; ++h) {
+      if (c2 + h >= nchunks) break;
+      const int col0 = colA + 64 * h;
+      const float4* b4 = reinterpret_cast<const float4*>(sb + col0);
+      uint32_t pk[8];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b = b4[j4];
+        float f0 = __uint_as_float(v[h][4 * j4 + 0]) + b.x;
+        float f1 = __uint_as_float(v[h][4 * j4 + 1]) + b.y;
+        float f2 = __uint_as_float(v[h][4 * j4 + 2]) + b.z;
+        float f3 = __uint_as_float(v[h][4 * j4 + 3]) + b.w;
+        if (xrow) {
+          // reference: h = bf16(Linear) ; h = bf16(h + x)
+          const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xs[h][0]);
+          __nv_bfloat162 xa = *reinterpret_cast<const __nv_bfloat162*>(&xw[2 * j4]);
+          __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162*>(&xw[2 * j4 + 1]);
+          f0 = bf16_round(f0) + __bfloat162float(xa.x);
+          f1 = bf16_round(f1) + __bfloat162float(xa.y);
+          f2 = bf16_round(f2) + __bfloat162float(xb.x);
+          f3 = bf16_round(f3) + __bfloat162float(xb.y);
+        }
+        pk[2 * j4] = pack2<RELU>(f0, f1);
+        pk[2 * j4 + 1] = pack2<RELU>(f2, f3);
       }
-      if (RELU) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-      pk[j / 2] = pack_bf16x2(f0, f1);
+      st_shared_v4(a_chunk_addr(a_base, ec.row, col0 / 8), pk[0], pk[1], pk[2], pk[3]);
+      st_shared_v4(a_chunk_addr(a_base, ec.row, col0 / 8 + 1), pk[4], pk[5], pk[6], pk[7]);
+      epi_signal_chunk(ctl, c2 + h, ec.lane);
     }
-    st_shared_v4(a_chunk_addr(a_base, ec.row, col0 / 8), pk[0], pk[1], pk[2], pk[3]);
-    st_shared_v4(a_chunk_addr(a_base, ec.row, col0 / 8 + 1), pk[4], pk[5], pk[6], pk[7]);
-    if (hdst) {
-      *reinterpret_cast<uint4*>(hdst + col0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(hdst + col0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-    }
-    epi_signal_chunk(ctl, c, ec.lane);
+  }
+}
+
+// copy this thread's 4 x 16 columns of the (just written) A tile row to global memory -- off the critical path
+__device__ __forceinline__ void a_row_to_global(const uint8_t* smem_a, const EpiCtx& ec, __nv_bfloat16* dst) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int col0 = c * 64 + ec.cs * 16;
+    const uint8_t* src = smem_a + (size_t)(ec.row >> 3) * SBO_A + (size_t)(col0 / 8) * 128 + (size_t)(ec.row & 7) * 16;
+    const uint4 a = *reinterpret_cast<const uint4*>(src);
+    const uint4 b = *reinterpret_cast<const uint4*>(src + 128);
+    *reinterpret_cast<uint4*>(dst + col0) = a;
+    *reinterpret_cast<uint4*>(dst + col0 + 8) = b;
   }
 }
 
@@ -494,7 +527,7 @@ template <int FX>
 __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* __restrict__ x, int64_t S,
                                                       __nv_bfloat16* __restrict__ H, float* __restrict__ gates) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   SmemCtl* ctl = cta_setup(smem, warp);
   float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);
@@ -533,6 +566,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
     uint32_t li = 0;
     int tn = 0;
     unsigned long long* tl = (warp == 2 && lane == 0) ? P.tl : nullptr;
+    float pn[3] = {0.f, 0.f, 0.f};          // xyz of this thread's row in the NEXT tile (prefetched one tile ahead)
+    if (ec.cs == 0) {
+      const int64_t s0 = (int64_t)blockIdx.x * TILE + row;
+      if ((int)blockIdx.x < n_tiles && s0 < S) { pn[0] = x[s0 * P.x_cols]; pn[1] = x[s0 * P.x_cols + 1]; pn[2] = x[s0 * P.x_cols + 2]; }
+    }
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int64_t s = (int64_t)t * TILE + row;
       const bool valid = s < S;
@@ -540,8 +578,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
       // ---- stage PE(xyz) as the A operand of the xyz layer (K16 = 80 -> chunks 0 and 1) ----
       constexpr int NPE = 3 + 6 * FX, NPAD = (NPE + 15) / 16 * 16;
       if (ec.cs == 0) {
-        float p[3] = {0.f, 0.f, 0.f};
-        if (valid) { p[0] = x[s * P.x_cols + 0]; p[1] = x[s * P.x_cols + 1]; p[2] = x[s * P.x_cols + 2]; }
+        float p[3] = {pn[0], pn[1], pn[2]};
+        {
+          const int64_t sn = s + (int64_t)gridDim.x * TILE;
+          pn[0] = pn[1] = pn[2] = 0.f;
+          if (t + (int)gridDim.x < n_tiles && sn < S) { pn[0] = x[sn * P.x_cols]; pn[1] = x[sn * P.x_cols + 1]; pn[2] = x[sn * P.x_cols + 2]; }
+        }
         __align__(16) __nv_bfloat16 pe[NPAD];
         pe_to_bf16<FX>(p, pe);
 #pragma unroll
@@ -560,9 +602,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
         const float* sb = sbias + buf * 256;
         if (l == 0) {
           // h = xyz Linear (act none): bf16 -> A (operand of the gate MLP) and -> H[s] (expert input of launch #2)
-          epi_hidden<false>(tacc, sb, 4, a_base, ec, nullptr, valid ? (H + s * MW) : nullptr, ctl);
+          epi_hidden<false>(tacc, sb, 4, a_base, ec, nullptr, ctl);
+          if (valid) a_row_to_global(smem + SM_A, ec, H + s * MW);   // after the signals: off the MMA critical path
         } else if (l < NL - 1) {
-          epi_hidden<true>(tacc, sb, 4, a_base, ec, nullptr, nullptr, ctl);
+          epi_hidden<true>(tacc, sb, 4, a_base, ec, nullptr, ctl);
         } else {
           // last gate-MLP layer: g = bf16(Linear) -> A (operand of the folded gate GEMM) + LayerNorm statistics
           float sum = 0.f, sq = 0.f;
@@ -700,7 +743,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
                                                      const float* __restrict__ gate, const float* __restrict__ noise,
                                                      float* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   SmemCtl* ctl = cta_setup(smem, warp);
   float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);
@@ -750,20 +793,42 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
     uint32_t li = 0;
     int tn = 0;
     unsigned long long* tl = (warp == 2 && lane == 0) ? P.tl : nullptr;
+    // per-row inputs of the tile are fetched one tile ahead (dependent-load chain row2sample -> x/gate is
+    // hidden behind the previous tile); only the 512-byte h row is gathered at staging time
+    struct RowIn { int e, sidx; float g, d0, d1, d2; int ai; };
+    auto fetch_row = [&](int t) {
+      RowIn r;
+      r.e = -1; r.sidx = -1; r.g = 0.f; r.d0 = r.d1 = r.d2 = 0.f; r.ai = 0;
+      if (t < n_tiles) {
+        r.e = tt.tile_expert[t];
+        if (row < tt.tile_rows[t]) r.sidx = tt.row2sample[tt.tile_row0[t] + row];
+        if (r.sidx >= 0) {
+          if (r.e >= 0) r.g = gate[r.sidx];
+          if (ec.cs == 1) {
+            const float* xr = x + (int64_t)r.sidx * P.x_cols;
+            r.d0 = xr[P.x_cols - 4]; r.d1 = xr[P.x_cols - 3]; r.d2 = xr[P.x_cols - 2];
+            r.ai = min(max((int)xr[P.x_cols - 1], 0), P.appearance_count - 1);
+          }
+        }
+      }
+      return r;
+    };
+    RowIn nxt = fetch_row((int)blockIdx.x);
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int e = tt.tile_expert[t];
+      const RowIn cur = nxt;
+      const int e = cur.e;
       tl_mark(tl, 0, tn, 1);
-      const int sidx = (row < tt.tile_rows[t]) ? tt.row2sample[tt.tile_row0[t] + row] : -1;
+      const int sidx = cur.sidx;
       const bool valid = sidx >= 0;
       const __nv_bfloat16* hrow = valid ? (H + (int64_t)sidx * MW) : nullptr;
-      const float g = (valid && e >= 0) ? gate[sidx] : 0.f;
+      const float g = cur.g;
       // ---- stage: expert input rows (or zeros for the dropped bucket); thread cs copies A chunk cs (128 B) ----
       {
+        uint4 hv[8];
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8) {
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (valid && e >= 0) v = *reinterpret_cast<const uint4*>(hrow + ec.cs * 64 + c8 * 8);
-          st_shared_v4(a_chunk_addr(a_base, row, ec.cs * 8 + c8), v.x, v.y, v.z, v.w);
+          hv[c8] = make_uint4(0, 0, 0, 0);
+          if (valid && e >= 0) hv[c8] = *reinterpret_cast<const uint4*>(hrow + ec.cs * 64 + c8 * 8);
         }
         // ---- [PE(dir) | appearance | 0-pad] -> A columns [256, K16 of layer "2")  (cs == 1 threads) ----
         if (ec.cs == 1) {
@@ -773,12 +838,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
 #pragma unroll
           for (int i = 0; i < NCAT_MAX; ++i) cat[i] = __float2bfloat16_rn(0.f);
           if (valid) {
-            const float* xr = x + (int64_t)sidx * P.x_cols;
-            float dvec[3] = {xr[P.x_cols - 4], xr[P.x_cols - 3], xr[P.x_cols - 2]};
+            float dvec[3] = {cur.d0, cur.d1, cur.d2};
             pe_to_bf16<FD>(dvec, cat);
-            int ai = (int)xr[P.x_cols - 1];
-            ai = min(max(ai, 0), P.appearance_count - 1);
-            const float4* er = reinterpret_cast<const float4*>(P.emb_a + (int64_t)ai * P.appearance_dim);
+            const float4* er = reinterpret_cast<const float4*>(P.emb_a + (int64_t)cur.ai * P.appearance_dim);
             for (int i = 0; i < P.appearance_dim / 4; ++i) {
               float4 f = er[i];
               cat[NDIR + 4 * i + 0] = __float2bfloat16_rn(f.x);
@@ -789,8 +851,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
           }
           a_store_row(a_base, row, MW / 8, cat, ((int)P.back[1].K16 - MW) / 8);
         }
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8)
+          st_shared_v4(a_chunk_addr(a_base, row, ec.cs * 8 + c8), hv[c8].x, hv[c8].y, hv[c8].z, hv[c8].w);
         for (int c = 0; c < 4; ++c) epi_signal_chunk(ctl, c, lane);
       }
+      nxt = fetch_row(t + (int)gridDim.x);
       tl_mark(tl, 0, tn, 2);
       float sig_acc = 0.f;
       if (e >= 0) {
@@ -803,7 +869,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
           const uint32_t tacc = tmem_base + ec.lane_base + (uint32_t)buf * 256u;
           const float* sb = sbias + buf * 256;
           if (l < NE - 1) {
-            epi_hidden<true>(tacc, sb, 4, a_base, ec, (l == P.skip_layer) ? hrow : nullptr, nullptr, ctl);
+            epi_hidden<true>(tacc, sb, 4, a_base, ec, (l == P.skip_layer) ? hrow : nullptr, ctl);
           } else {
             // last expert layer (no activation) -> combine: y = bf16(gate * bf16(out)) -> ReLU -> A;
             // sigma head accumulated on the fly (nerf_moe.py:384-400)
@@ -837,8 +903,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
         const int buf = (int)(li & 1);
         epi_load_bias(P.fblob + P.back[0].b_off, MW, sbias, buf, ec.et);
         epi_wait_acc(ctl, pp, buf);
-        epi_hidden<false>(tmem_base + ec.lane_base + (uint32_t)buf * 256u, sbias + buf * 256, 4, a_base, ec, nullptr,
-                          nullptr, ctl);
+        epi_hidden<false>(tmem_base + ec.lane_base + (uint32_t)buf * 256u, sbias + buf * 256, 4, a_base, ec, nullptr, ctl);
         const int nchunk2 = ((int)P.back[1].K16 + 63) / 64;
         for (int c = 4; c < nchunk2; ++c) epi_signal_chunk(ctl, c, lane);
         tl_mark(tl, 0, tn, 50);
@@ -923,11 +988,37 @@ size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf) {
   return b + 4096;
 }
 
-int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* o, float* out,
-               int32_t* moe_idx, float* l_aux, float* dbg_gates, int32_t* dbg_loc, Arena& ws, cudaStream_t st) {
+// ---- one model_chunk as three separately enqueueable phases (so render_rays can software-pipeline
+// them: the routing kernels of chunk c run on a side stream underneath launch #1 of chunk c+1) ----
+struct TcChunk {
+  TcParams Pf, Pb;
+  const float* x;
+  int64_t S;
+  const float* noise;
+  snb_route_opts o;
+  float* out;
+  int32_t* moe_idx;
+  float* l_aux;
+  float* dbg_gates;
+  int32_t* dbg_loc;
+  __nv_bfloat16* H;
+  float* gates;
+  int *idx, *loc;
+  float* gate;
+  TileTable tt;
+  int *counts, *cap_dev;
+  char* rws;
+  size_t rbytes;
+  int64_t max_rows, max_tiles;
+  PhaseEvents* pe;
+};
+
+static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const float* sigma_noise,
+                         const snb_route_opts* o, float* out, int32_t* moe_idx, float* l_aux, float* dbg_gates,
+                         int32_t* dbg_loc, Arena& ws, cudaStream_t st) {
   SNB_REQUIRE(m->tc_blob, "tc_forward: weights were not packed");
-  TcParams P = ((TcOwner*)m->tc_blob)->h.p;
-  TcParams Pb = P;
+  c.Pf = ((TcOwner*)m->tc_blob)->h.p;
+  c.Pb = c.Pf;
   {
     // debug only: SNB_TIMELINE=1 records clock marks of CTA 0 (front: slots [0,2*TL_N), back: [2*TL_N, 4*TL_N))
     static unsigned long long* tl_buf = nullptr;
@@ -938,64 +1029,126 @@ int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, co
     }
     if (tl_buf) {
       cudaMemsetAsync(tl_buf, 0, 4 * TL_N * 8, st);
-      P.tl = tl_buf;
-      Pb.tl = tl_buf + 2 * TL_N;
+      c.Pf.tl = tl_buf;
+      c.Pb.tl = tl_buf + 2 * TL_N;
     }
   }
   const int E = m->d.num_experts;
-  const int64_t max_rows = S + (int64_t)TILE * (E + 2);
-  const int64_t max_tiles = cdiv(S, TILE) + E + 2;
-  __nv_bfloat16* H = ws.take<__nv_bfloat16>((size_t)S * MW);
-  float* gates = ws.take<float>((size_t)S * E);
-  int* idx = ws.take<int>(S);
-  int* loc = ws.take<int>(S);
-  float* gate = ws.take<float>(S);
-  TileTable tt;
-  tt.row2sample = ws.take<int>(max_rows);
-  tt.tile_expert = ws.take<int>(max_tiles);
-  tt.tile_row0 = ws.take<int>(max_tiles);
-  tt.tile_rows = ws.take<int>(max_tiles);
+  c.x = x; c.S = S; c.noise = sigma_noise; c.o = *o; c.out = out; c.moe_idx = moe_idx; c.l_aux = l_aux;
+  c.dbg_gates = dbg_gates; c.dbg_loc = dbg_loc;
+  c.max_rows = S + (int64_t)TILE * (E + 2);
+  c.max_tiles = cdiv(S, TILE) + E + 2;
+  c.H = ws.take<__nv_bfloat16>((size_t)S * MW);
+  c.gates = ws.take<float>((size_t)S * E);
+  c.idx = ws.take<int>(S);
+  c.loc = ws.take<int>(S);
+  c.gate = ws.take<float>(S);
+  c.tt.row2sample = ws.take<int>(c.max_rows);
+  c.tt.tile_expert = ws.take<int>(c.max_tiles);
+  c.tt.tile_row0 = ws.take<int>(c.max_tiles);
+  c.tt.tile_rows = ws.take<int>(c.max_tiles);
   int* small = ws.take<int>(1024);
-  const size_t rbytes = route_workspace_bytes(S, E);
-  char* rws = ws.take<char>(rbytes);
+  c.rbytes = route_workspace_bytes(S, E);
+  c.rws = ws.take<char>(c.rbytes);
   if (!ws.ok) { set_error("tc_forward: workspace too small"); return SNB_EWORKSPACE; }
-  int *counts = small, *cap_dev = small + E;
-  tt.seg_start = small + E + 1;
-  tt.n_tiles = small + 2 * E + 4;
-  tt.drop_counter = small + 2 * E + 5;
-
+  c.counts = small; c.cap_dev = small + E;
+  c.tt.seg_start = small + E + 1;
+  c.tt.n_tiles = small + 2 * E + 4;
+  c.tt.drop_counter = small + 2 * E + 5;
   static bool attr_done = false;
-  SNB_REQUIRE(m->d.pos_xyz_freqs == 12 && m->d.pos_dir_freqs == 4,
-              "tcgen05 path is specialised for pos_xyz_dim=12 / pos_dir_dim=4 (all Switch-NeRF configs)");
   if (!attr_done) {
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     attr_done = true;
   }
-  const int n_front_tiles = (int)cdiv(S, TILE);
-  const int grid1 = n_front_tiles < m->sm_count ? n_front_tiles : m->sm_count;
-  PhaseEvents* pe = profile_next();
-  if (pe) cudaEventRecord(pe->e[0], st);
-  k_front<12><<<grid1, THREADS, SM_TOTAL, st>>>(P, x, S, H, gates);
-  SNB_CHECK_LAUNCH("k_front");
-  if (pe) cudaEventRecord(pe->e[1], st);
-  int rc = route_top1(gates, S, E, o->capacity_factor, o->no_batch ? 0 : o->bpr, idx, loc, gate, counts, cap_dev, l_aux,
-                      rws, rbytes, st);
-  if (rc) return rc;
-  SNB_CHECK_CUDA(cudaMemsetAsync(tt.row2sample, 0xFF, (size_t)max_rows * sizeof(int), st));
-  k_tile_plan<<<1, 256, 0, st>>>(counts, cap_dev, E, o->no_batch, S, tt);
-  SNB_CHECK_LAUNCH("k_tile_plan");
-  k_scatter_rows<<<(unsigned)cdiv(S, 256), 256, 0, st>>>(idx, loc, cap_dev, E, o->no_batch, S, tt);
-  SNB_CHECK_LAUNCH("k_scatter_rows");
-  const int grid2 = (int)(max_tiles < m->sm_count ? max_tiles : m->sm_count);
-  if (pe) cudaEventRecord(pe->e[2], st);
-  k_back<4><<<grid2, THREADS, SM_TOTAL, st>>>(Pb, tt, x, H, gate, sigma_noise, out);
-  SNB_CHECK_LAUNCH("k_back");
-  if (pe) cudaEventRecord(pe->e[3], st);
-  if (moe_idx) SNB_CHECK_CUDA(cudaMemcpyAsync(moe_idx, idx, sizeof(int) * S, cudaMemcpyDeviceToDevice, st));
-  if (dbg_gates) SNB_CHECK_CUDA(cudaMemcpyAsync(dbg_gates, gates, sizeof(float) * S * E, cudaMemcpyDeviceToDevice, st));
-  if (dbg_loc) SNB_CHECK_CUDA(cudaMemcpyAsync(dbg_loc, loc, sizeof(int) * S, cudaMemcpyDeviceToDevice, st));
+  c.pe = profile_next();
   return SNB_OK;
+}
+
+static int tc_front(Model* m, TcChunk& c, cudaStream_t st) {
+  const int n_front_tiles = (int)cdiv(c.S, TILE);
+  const int grid1 = n_front_tiles < m->sm_count ? n_front_tiles : m->sm_count;
+  if (c.pe) cudaEventRecord(c.pe->e[0], st);
+  k_front<12><<<grid1, THREADS, SM_TOTAL, st>>>(c.Pf, c.x, c.S, c.H, c.gates);
+  SNB_CHECK_LAUNCH("k_front");
+  if (c.pe) cudaEventRecord(c.pe->e[1], st);
+  return SNB_OK;
+}
+
+static int tc_route(Model* m, TcChunk& c, cudaStream_t st) {
+  const int E = m->d.num_experts;
+  if (c.pe) cudaEventRecord(c.pe->e[2], st);
+  int rc = route_top1(c.gates, c.S, E, c.o.capacity_factor, c.o.no_batch ? 0 : c.o.bpr, c.idx, c.loc, c.gate, c.counts,
+                      c.cap_dev, c.l_aux, c.rws, c.rbytes, st);
+  if (rc) return rc;
+  SNB_CHECK_CUDA(cudaMemsetAsync(c.tt.row2sample, 0xFF, (size_t)c.max_rows * sizeof(int), st));
+  k_tile_plan<<<1, 256, 0, st>>>(c.counts, c.cap_dev, E, c.o.no_batch, c.S, c.tt);
+  SNB_CHECK_LAUNCH("k_tile_plan");
+  k_scatter_rows<<<(unsigned)cdiv(c.S, 256), 256, 0, st>>>(c.idx, c.loc, c.cap_dev, E, c.o.no_batch, c.S, c.tt);
+  SNB_CHECK_LAUNCH("k_scatter_rows");
+  if (c.moe_idx) SNB_CHECK_CUDA(cudaMemcpyAsync(c.moe_idx, c.idx, sizeof(int) * c.S, cudaMemcpyDeviceToDevice, st));
+  if (c.dbg_gates) SNB_CHECK_CUDA(cudaMemcpyAsync(c.dbg_gates, c.gates, sizeof(float) * c.S * E, cudaMemcpyDeviceToDevice, st));
+  if (c.dbg_loc) SNB_CHECK_CUDA(cudaMemcpyAsync(c.dbg_loc, c.loc, sizeof(int) * c.S, cudaMemcpyDeviceToDevice, st));
+  if (c.pe) cudaEventRecord(c.pe->e[3], st);
+  return SNB_OK;
+}
+
+static int tc_back(Model* m, TcChunk& c, cudaStream_t st) {
+  const int grid2 = (int)(c.max_tiles < m->sm_count ? c.max_tiles : m->sm_count);
+  if (c.pe) cudaEventRecord(c.pe->e[4], st);
+  k_back<4><<<grid2, THREADS, SM_TOTAL, st>>>(c.Pb, c.tt, c.x, c.H, c.gate, c.noise, c.out);
+  SNB_CHECK_LAUNCH("k_back");
+  if (c.pe) cudaEventRecord(c.pe->e[5], st);
+  return SNB_OK;
+}
+
+int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* o, float* out,
+               int32_t* moe_idx, float* l_aux, float* dbg_gates, int32_t* dbg_loc, Arena& ws, cudaStream_t st) {
+  TcChunk c;
+  int rc = tc_chunk_init(m, c, x, S, sigma_noise, o, out, moe_idx, l_aux, dbg_gates, dbg_loc, ws, st);
+  if (rc) return rc;
+  if ((rc = tc_front(m, c, st))) return rc;
+  if ((rc = tc_route(m, c, st))) return rc;
+  return tc_back(m, c, st);
+}
+
+// All model chunks of one render pass, software-pipelined over the caller's stream `st` and the model's
+// side stream: st = front(0) front(1) back(0) front(2) back(1) ... ; side = route(0) route(1) ...
+// Two workspace sets alternate between consecutive chunks.
+int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const snb_route_opts* o, float* out,
+                      int32_t* moe_idx, float* l_aux, void* ws0, void* ws1, size_t ws_bytes, cudaStream_t st) {
+  if (B <= 0) return SNB_OK;
+  if (!m->side_stream) {
+    SNB_CHECK_CUDA(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      SNB_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_front[i], cudaEventDisableTiming));
+      SNB_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_route[i], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t sr = m->side_stream;
+  TcChunk cc[2];
+  int ci = 0;
+  int rc;
+  for (int64_t i = 0; i < B; i += chunk, ++ci) {
+    const int64_t rows = (B - i < chunk) ? (B - i) : chunk;
+    const int k = ci & 1;
+    Arena a(k ? ws1 : ws0, ws_bytes);
+    if ((rc = tc_chunk_init(m, cc[k], x + i * m->x_cols, rows, nullptr, o, out + i * 4, moe_idx ? moe_idx + i : nullptr,
+                            l_aux ? l_aux + ci : nullptr, nullptr, nullptr, a, st)))
+      return rc;
+    if ((rc = tc_front(m, cc[k], st))) return rc;
+    SNB_CHECK_CUDA(cudaEventRecord(m->ev_front[k], st));
+    SNB_CHECK_CUDA(cudaStreamWaitEvent(sr, m->ev_front[k], 0));
+    if ((rc = tc_route(m, cc[k], sr))) return rc;
+    SNB_CHECK_CUDA(cudaEventRecord(m->ev_route[k], sr));
+    if (ci >= 1) {
+      SNB_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_route[k ^ 1], 0));
+      if ((rc = tc_back(m, cc[k ^ 1], st))) return rc;
+    }
+  }
+  const int k = (ci - 1) & 1;
+  SNB_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_route[k], 0));
+  return tc_back(m, cc[k], st);
 }
 
 }  // namespace snb
