@@ -112,17 +112,26 @@ __global__ void __launch_bounds__(1024) k_finalize(const float* __restrict__ pm,
   for (int e = w; e < E; e += nw) {
     int run = 0;
     double me = 0.0;
-    for (int b0 = 0; b0 < nblk; b0 += 32) {
-      const int b = b0 + lane;
-      int c = (b < nblk) ? pc[(int64_t)b * E + e] : 0;
-      int inc = c;
+    for (int bb = 0; bb < nblk; bb += 32 * 8) {
+      int cv[8];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
+      for (int u = 0; u < 8; ++u) {           // independent loads first (L2 latency paid once per batch)
+        const int b = bb + u * 32 + lane;
+        cv[u] = (b < nblk) ? pc[(int64_t)b * E + e] : 0;
       }
-      if (b < nblk) blockoff[(int64_t)b * E + e] = run + inc - c;
-      run += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int b = bb + u * 32 + lane;
+        const int c = cv[u];
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (b < nblk) blockoff[(int64_t)b * E + e] = run + inc - c;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
     }
     if (write_stats) {
       for (int b0 = 0; b0 < npm; b0 += 32) {
@@ -186,12 +195,13 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const uint32_t* __re
                                                             const int* __restrict__ idx, int E, int* __restrict__ pc2,
                                                             uint32_t* __restrict__ keys_out,
                                                             uint32_t* __restrict__ vals_out) {
-  __shared__ int off0[NBINS];                      // global offset of the first element of each digit from this tile
-  __shared__ int run[NBINS];                       // elements of each digit already placed by this tile
-  __shared__ int wcnt[SORT_THREADS / 32][NBINS];   // per-warp digit counts of the current round
-  __shared__ int wsum[SORT_THREADS / 32];
+  constexpr int NW = SORT_THREADS / 32, PER = ST / SORT_THREADS;   // 8 warps x 8 rounds: warp w owns elements [w*256, +256)
+  __shared__ int off0[NBINS];            // global offset of the first element of each digit from this tile
+  __shared__ int whist[NW][NBINS];       // per-warp digit counts -> exclusive prefix over the warps of the tile
+  __shared__ int wsum[NW];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int shift = DBITS * pass;
+  for (int k = threadIdx.x; k < NW * NBINS; k += SORT_THREADS) (&whist[0][0])[k] = 0;
   {
     const int d0 = 2 * threadIdx.x;                // NBINS == 2 * SORT_THREADS
     const int v0 = totals[pass * NBINS + d0], v1 = totals[pass * NBINS + d0 + 1];
@@ -205,7 +215,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const uint32_t* __re
     __syncthreads();
     int wbase = 0;
     for (int ww = 0; ww < w; ++ww) wbase += wsum[ww];
-    int base0 = wbase + inc - (v0 + v1);
+    const int base0 = wbase + inc - (v0 + v1);
     int p0 = 0, p1 = 0;
     const int2* th = reinterpret_cast<const int2*>(thist);
 #pragma unroll 8
@@ -215,42 +225,49 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const uint32_t* __re
     }
     off0[d0] = base0 + p0;
     off0[d0 + 1] = base0 + v0 + p1;
-    run[d0] = 0; run[d0 + 1] = 0;
-    for (int k = threadIdx.x; k < (SORT_THREADS / 32) * NBINS; k += SORT_THREADS) (&wcnt[0][0])[k] = 0;
   }
   __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * ST;
-  for (int j = 0; j < ST / SORT_THREADS; ++j) {
-    if (base + (int64_t)j * SORT_THREADS >= S) break;            // block-uniform
-    const int64_t i = base + j * SORT_THREADS + threadIdx.x;
-    const bool valid = i < S;
-    uint32_t key = valid ? keys_in[i] : 0u;
-    int d = valid ? (int)((key >> shift) & (NBINS - 1)) : -1;
-    unsigned m = __match_any_sync(0xffffffffu, d);
-    int r = __popc(m & ((1u << lane) - 1));
-    if (valid && r == 0) wcnt[w][d] = __popc(m);
-    __syncthreads();
-    if (valid) {
-      int off = off0[d] + run[d] + r;
-      for (int ww = 0; ww < w; ++ww) off += wcnt[ww][d];
-      const uint32_t val = vals_in ? vals_in[i] : (uint32_t)i;
-      keys_out[off] = key;
-      vals_out[off] = val;
-      if (!last) atomicAdd(&thist_next[(int64_t)(off / ST) * NBINS + ((key >> (shift + DBITS)) & (NBINS - 1))], 1);
-      else atomicAdd(&pc2[(int64_t)(off / RB) * E + idx[val]], 1);
-    }
-    __syncthreads();
-    for (int d2 = threadIdx.x; d2 < NBINS; d2 += SORT_THREADS) {
-      int c = 0;
+  // phase 1: ranks inside the warp's own 256 elements (warp-synchronous, no block barriers)
+  const int64_t wbase_i = (int64_t)blockIdx.x * ST + (int64_t)w * (PER * 32);
+  uint32_t key[PER], val[PER];
+  int rk[PER];                                    // rank among equal digits inside this warp, -1 = out of range
 #pragma unroll
-      for (int ww = 0; ww < SORT_THREADS / 32; ++ww) { c += wcnt[ww][d2]; wcnt[ww][d2] = 0; }
-      run[d2] += c;
-    }
-    __syncthreads();
+  for (int j = 0; j < PER; ++j) {
+    const int64_t i = wbase_i + j * 32 + lane;
+    const bool valid = i < S;
+    key[j] = valid ? keys_in[i] : 0u;
+    val[j] = valid ? (vals_in ? vals_in[i] : (uint32_t)i) : 0u;
+    const int d = valid ? (int)((key[j] >> shift) & (NBINS - 1)) : -1;
+    const unsigned m = __match_any_sync(0xffffffffu, d);
+    const int r = __popc(m & ((1u << lane) - 1));
+    int prev = 0;
+    if (valid) prev = whist[w][d];
+    __syncwarp();
+    if (valid && r == 0) whist[w][d] = prev + __popc(m);
+    __syncwarp();
+    rk[j] = valid ? prev + r : -1;
+  }
+  __syncthreads();
+  // phase 2: exclusive prefix over the warps, per digit (2 digits per thread)
+  for (int d = threadIdx.x; d < NBINS; d += SORT_THREADS) {
+    int run = off0[d];
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww) { const int c = whist[ww][d]; whist[ww][d] = run; run += c; }
+  }
+  __syncthreads();
+  // phase 3: scatter
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    if (rk[j] < 0) continue;
+    const int d = (int)((key[j] >> shift) & (NBINS - 1));
+    const int off = whist[w][d] + rk[j];
+    keys_out[off] = key[j];
+    vals_out[off] = val[j];
+    if (!last) atomicAdd(&thist_next[(int64_t)(off / ST) * NBINS + ((key[j] >> (shift + DBITS)) & (NBINS - 1))], 1);
+    else atomicAdd(&pc2[(int64_t)(off / RB) * E + idx[val[j]]], 1);
   }
 }
 
-// ---------------------------------------------------------------------------------------
 static constexpr int MAX_PASS = 4;
 static_assert(NBINS == 2 * SORT_THREADS, "k_sort_pass assumes two digits per thread");
 

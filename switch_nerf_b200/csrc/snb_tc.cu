@@ -1119,13 +1119,16 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
                       int32_t* moe_idx, float* l_aux, void* ws0, void* ws1, size_t ws_bytes, cudaStream_t st) {
   if (B <= 0) return SNB_OK;
   if (!m->side_stream) {
-    SNB_CHECK_CUDA(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    SNB_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    SNB_CHECK_CUDA(cudaStreamCreateWithPriority(&m->side_stream, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < 2; ++i) {
       SNB_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_front[i], cudaEventDisableTiming));
       SNB_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_route[i], cudaEventDisableTiming));
     }
   }
-  cudaStream_t sr = m->side_stream;
+  static const bool no_overlap = getenv("SNB_NO_OVERLAP") != nullptr;   // debug/A-B switch: route on the caller's stream
+  cudaStream_t sr = no_overlap ? st : m->side_stream;
   TcChunk cc[2];
   int ci = 0;
   int rc;
