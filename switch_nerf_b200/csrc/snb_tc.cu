@@ -397,7 +397,8 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 // `xrow` (nullable): bf16 row of the expert input for the skip connection (tutel_moe_layer_nobatch.py:911-916).
 template <bool RELU>
 __device__ __forceinline__ void epi_hidden(uint32_t tmem_acc, const float* sb, int nchunks, uint32_t a_base,
-                                           const EpiCtx& ec, const __nv_bfloat16* xrow, SmemCtl* ctl) {
+                                           const EpiCtx& ec, const __nv_bfloat16* xrow, SmemCtl* ctl,
+                                           unsigned long long* tl = nullptr, int* tn = nullptr) {
   for (int c2 = 0; c2 < nchunks; c2 += 2) {
     uint32_t v[2][16];
     const int colA = c2 * 64 + ec.cs * 16;
@@ -412,6 +413,7 @@ __device__ __forceinline__ void epi_hidden(uint32_t tmem_acc, const float* sb, i
       }
     }
     tmem_ld_wait();
+    if (tn) tl_mark(tl, 0, *tn, 70 + c2);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (c2 + h >= nchunks) break;
@@ -440,7 +442,9 @@ __device__ __forceinline__ void epi_hidden(uint32_t tmem_acc, const float* sb, i
       }
       st_shared_v4(a_chunk_addr(a_base, ec.row, col0 / 8), pk[0], pk[1], pk[2], pk[3]);
       st_shared_v4(a_chunk_addr(a_base, ec.row, col0 / 8 + 1), pk[4], pk[5], pk[6], pk[7]);
+      if (tn) tl_mark(tl, 0, *tn, 60 + c2 + h);
       epi_signal_chunk(ctl, c2 + h, ec.lane);
+      if (tn) tl_mark(tl, 0, *tn, 80 + c2 + h);
     }
   }
 }
@@ -602,10 +606,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
         const float* sb = sbias + buf * 256;
         if (l == 0) {
           // h = xyz Linear (act none): bf16 -> A (operand of the gate MLP) and -> H[s] (expert input of launch #2)
-          epi_hidden<false>(tacc, sb, 4, a_base, ec, nullptr, ctl);
+          epi_hidden<false>(tacc, sb, 4, a_base, ec, nullptr, ctl, tl, &tn);
+          tl_mark(tl, 0, tn, 90);
           if (valid) a_row_to_global(smem + SM_A, ec, H + s * MW);   // after the signals: off the MMA critical path
         } else if (l < NL - 1) {
-          epi_hidden<true>(tacc, sb, 4, a_base, ec, nullptr, ctl);
+          epi_hidden<true>(tacc, sb, 4, a_base, ec, nullptr, ctl, tl, &tn);
         } else {
           // last gate-MLP layer: g = bf16(Linear) -> A (operand of the folded gate GEMM) + LayerNorm statistics
           float sum = 0.f, sq = 0.f;
