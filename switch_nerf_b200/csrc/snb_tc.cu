@@ -449,16 +449,17 @@ __device__ __forceinline__ void epi_hidden(uint32_t tmem_acc, const float* sb, i
   }
 }
 
-// copy this thread's 4 x 16 columns of the (just written) A tile row to global memory -- off the critical path
-__device__ __forceinline__ void a_row_to_global(const uint8_t* smem_a, const EpiCtx& ec, __nv_bfloat16* dst) {
+// Store the 256-column bf16 A tile to global memory, one full 512-byte row per warp instruction
+// (lane l moves the 16-byte group l of the row): fully coalesced.  Warp (q, cs) moves rows
+// q*32 + cs*8 + i, i = 0..7.  `row_ptr(r)` returns the destination row pointer or nullptr.
+template <typename RowPtr>
+__device__ __forceinline__ void a_tile_to_global(const uint8_t* smem_a, const EpiCtx& ec, RowPtr row_ptr) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int col0 = c * 64 + ec.cs * 16;
-    const uint8_t* src = smem_a + (size_t)(ec.row >> 3) * SBO_A + (size_t)(col0 / 8) * 128 + (size_t)(ec.row & 7) * 16;
-    const uint4 a = *reinterpret_cast<const uint4*>(src);
-    const uint4 b = *reinterpret_cast<const uint4*>(src + 128);
-    *reinterpret_cast<uint4*>(dst + col0) = a;
-    *reinterpret_cast<uint4*>(dst + col0 + 8) = b;
+  for (int i = 0; i < 8; ++i) {
+    const int r = ec.q * 32 + ec.cs * 8 + i;
+    __nv_bfloat16* dst = row_ptr(r);
+    const uint8_t* src = smem_a + (size_t)(r >> 3) * SBO_A + (size_t)ec.lane * 128 + (size_t)(r & 7) * 16;
+    if (dst) *reinterpret_cast<uint4*>(dst + ec.lane * 8) = *reinterpret_cast<const uint4*>(src);
   }
 }
 
@@ -599,6 +600,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
       for (int l = 0; l < NL; ++l, ++li) {
         const int buf = (int)(li & 1);
         epi_load_bias(P.fblob + P.front[l].b_off, MW, sbias, buf, ec.et);
+        if (l == 1) {
+          // h (written into the A tile by the L0 epilogue of ALL warps, complete after the barrier above) -> H:
+          // coalesced 512-byte rows, overlapping the L1 MMAs; a second barrier fences the L1 epilogue's A writes
+          const int64_t s0 = (int64_t)t * TILE;
+          a_tile_to_global(smem + SM_A, ec, [&](int r) { return (s0 + r < S) ? (H + (s0 + r) * MW) : (__nv_bfloat16*)nullptr; });
+          epi_bar_sync();
+        }
         tl_mark(tl, 0, tn, 10 + l);
         epi_wait_acc(ctl, pp, buf);
         tl_mark(tl, 0, tn, 20 + l);
@@ -608,7 +616,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
           // h = xyz Linear (act none): bf16 -> A (operand of the gate MLP) and -> H[s] (expert input of launch #2)
           epi_hidden<false>(tacc, sb, 4, a_base, ec, nullptr, ctl, tl, &tn);
           tl_mark(tl, 0, tn, 90);
-          if (valid) a_row_to_global(smem + SM_A, ec, H + s * MW);   // after the signals: off the MMA critical path
         } else if (l < NL - 1) {
           epi_hidden<true>(tacc, sb, 4, a_base, ec, nullptr, ctl, tl, &tn);
         } else {
@@ -829,11 +836,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
       const float g = cur.g;
       // ---- stage: expert input rows (or zeros for the dropped bucket); thread cs copies A chunk cs (128 B) ----
       {
+        // warp (q, cs) gathers rows q*32 + cs*8 + i: one coalesced 512-byte row per instruction
         uint4 hv[8];
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          hv[c8] = make_uint4(0, 0, 0, 0);
-          if (valid && e >= 0) hv[c8] = *reinterpret_cast<const uint4*>(hrow + ec.cs * 64 + c8 * 8);
+        for (int i = 0; i < 8; ++i) {
+          const int sr = __shfl_sync(0xffffffffu, sidx, ec.cs * 8 + i);
+          hv[i] = make_uint4(0, 0, 0, 0);
+          if (sr >= 0 && e >= 0) hv[i] = *reinterpret_cast<const uint4*>(H + (int64_t)sr * MW + lane * 8);
         }
         // ---- [PE(dir) | appearance | 0-pad] -> A columns [256, K16 of layer "2")  (cs == 1 threads) ----
         if (ec.cs == 1) {
@@ -857,8 +866,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
           a_store_row(a_base, row, MW / 8, cat, ((int)P.back[1].K16 - MW) / 8);
         }
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8)
-          st_shared_v4(a_chunk_addr(a_base, row, ec.cs * 8 + c8), hv[c8].x, hv[c8].y, hv[c8].z, hv[c8].w);
+        for (int i = 0; i < 8; ++i)
+          st_shared_v4(a_chunk_addr(a_base, ec.q * 32 + ec.cs * 8 + i, lane), hv[i].x, hv[i].y, hv[i].z, hv[i].w);
         for (int c = 0; c < 4; ++c) epi_signal_chunk(ctl, c, lane);
       }
       nxt = fetch_row(t + (int)gridDim.x);
