@@ -54,8 +54,8 @@ int fill_x_launch(const float* rays, const int* image_indices, const float* z, i
                   cudaStream_t st);
 int zmid_launch(const float* z, int64_t N, int S, float* mid, cudaStream_t st);
 int merge_composite_launch(const float* zf, const float* zc, const float* raw_f, const float* raw_c,
-                           const float* last_delta, int64_t N, int Sf, int Sc, int white_bkgd, float* rgb,
-                           float* depth, float* var, float* lam, cudaStream_t st);
+                           const float* last_delta, int64_t N, int Sf, int Sc, int presorted, int white_bkgd,
+                           float* rgb, float* depth, float* var, float* lam, cudaStream_t st);
 int umma_selftest(const void* a, const void* b, int N, int K, float* d, int variant, cudaStream_t st);
 int tc_timeline_read(unsigned long long* host, int n);
 
@@ -389,7 +389,8 @@ int snb_render_rays(snb_model_t* mm, const float* rays, const int32_t* image_ind
   if ((rc = zmid_launch(zc, N, Sc, zmid, st))) return rc;
   if ((rc = sample_pdf_launch(zmid, Sc - 1, wc, Sc, 1, nullptr, N, Sc - 2, Sf, o->seed, o->perturb == 0.f, zf, st))) return rc;
   if ((rc = run_pass(zf, Sf, raw_f, out->moe_gates_fine, out->gate_loss_fine))) return rc;
-  return merge_composite_launch(zf, zc, raw_f, raw_c, last_delta, N, Sf, Sc, o->white_bkgd, out->rgb, out->depth,
+  // perturb == 0: z_fine comes from an ascending u through a monotone cdf, z_coarse is a linspace -> both sorted
+  return merge_composite_launch(zf, zc, raw_f, raw_c, last_delta, N, Sf, Sc, o->perturb == 0.f, o->white_bkgd, out->rgb, out->depth,
                                 out->depth_variance, out->bg_lambda, st);
 }
 

@@ -209,13 +209,63 @@ __global__ void k_zmid(const float* __restrict__ z, int64_t N, int S, float* __r
 __global__ void __launch_bounds__(256) k_merge_composite(const float* __restrict__ zf, const float* __restrict__ zc,
                                                          const float* __restrict__ raw_f, const float* __restrict__ raw_c,
                                                          const float* __restrict__ last_delta, int64_t N, int Sf, int Sc,
-                                                         int P2, int white_bkgd, float* __restrict__ rgb,
-                                                         float* __restrict__ depth, float* __restrict__ var,
-                                                         float* __restrict__ lam) {
+                                                         int P2, int presorted, int white_bkgd,
+                                                         float* __restrict__ rgb, float* __restrict__ depth,
+                                                         float* __restrict__ var, float* __restrict__ lam) {
   extern __shared__ unsigned long long keys[];  // [P2] keys, then 2*S floats
   const int64_t r = blockIdx.x;
   const int S = Sf + Sc;
   float* wsm = reinterpret_cast<float*>(keys + P2);
+  if (presorted) {
+    // both lists ascending (deterministic sampling): merged position by rank -- fine element i goes to
+    // i + #{coarse < zf[i]}, coarse element j to j + #{fine <= zc[j]} (ties: fine first == the stable sort)
+    float* szf = wsm;
+    float* szc = wsm + Sf;
+    for (int i = threadIdx.x; i < Sf; i += blockDim.x) szf[i] = zf[r * Sf + i];
+    for (int i = threadIdx.x; i < Sc; i += blockDim.x) szc[i] = zc[r * Sc + i];
+    __syncthreads();
+    // The rank formulas below need monotone lists.  Rounding in the lerp / linspace can leave a 1-ulp inversion
+    // between neighbours; a running maximum (warps 0 and 1) removes it (the reference's sort would have swapped
+    // the two samples instead -- a <= 1 ulp difference in one delta).
+    if (threadIdx.x < 64) {
+      float* lst = (threadIdx.x < 32) ? szf : szc;
+      const int n = (threadIdx.x < 32) ? Sf : Sc;
+      const int lane = threadIdx.x & 31;
+      float carry = -INFINITY;
+      for (int j0 = 0; j0 < n; j0 += 32) {
+        float v = (j0 + lane < n) ? lst[j0 + lane] : -INFINITY;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          float t = __shfl_up_sync(0xffffffffu, v, o);
+          if (lane >= o) v = fmaxf(v, t);
+        }
+        v = fmaxf(v, carry);
+        if (j0 + lane < n) lst[j0 + lane] = v;
+        carry = __shfl_sync(0xffffffffu, v, 31);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+      float z;
+      int pos;
+      if (i < Sf) {
+        z = szf[i];
+        int lo = 0, hi = Sc;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (szc[mid] < z) lo = mid + 1; else hi = mid; }
+        pos = i + lo;
+      } else {
+        const int j = i - Sf;
+        z = szc[j];
+        int lo = 0, hi = Sf;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (szf[mid] <= z) lo = mid + 1; else hi = mid; }
+        pos = j + lo;
+      }
+      uint32_t b = __float_as_uint(z);
+      uint32_t asc = b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+      keys[pos] = ((unsigned long long)asc << 32) | (unsigned)i;
+    }
+    __syncthreads();
+  } else
   for (int i = threadIdx.x; i < P2; i += blockDim.x) {
     unsigned long long k = ~0ull;
     if (i < S) {
@@ -227,7 +277,7 @@ __global__ void __launch_bounds__(256) k_merge_composite(const float* __restrict
     keys[i] = k;
   }
   __syncthreads();
-  for (int k = 2; k <= P2; k <<= 1) {
+  for (int k = 2; k <= (presorted ? 0 : P2); k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int i = threadIdx.x; i < P2; i += blockDim.x) {
         int ixj = i ^ j;
@@ -302,8 +352,8 @@ int zmid_launch(const float* z, int64_t N, int S, float* mid, cudaStream_t st) {
 }
 
 int merge_composite_launch(const float* zf, const float* zc, const float* raw_f, const float* raw_c,
-                           const float* last_delta, int64_t N, int Sf, int Sc, int white_bkgd, float* rgb,
-                           float* depth, float* var, float* lam, cudaStream_t st) {
+                           const float* last_delta, int64_t N, int Sf, int Sc, int presorted, int white_bkgd,
+                           float* rgb, float* depth, float* var, float* lam, cudaStream_t st) {
   if (N == 0) return SNB_OK;
   const int S = Sf + Sc;
   int P2 = 1;
@@ -311,7 +361,7 @@ int merge_composite_launch(const float* zf, const float* zc, const float* raw_f,
   SNB_REQUIRE(P2 <= 8192, "merge: %d samples per ray is too many", S);
   size_t smem = (size_t)P2 * 8 + (size_t)2 * S * sizeof(float);
   if (smem > 48 * 1024) SNB_CHECK_CUDA(cudaFuncSetAttribute(k_merge_composite, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_merge_composite<<<(unsigned)N, 256, smem, st>>>(zf, zc, raw_f, raw_c, last_delta, N, Sf, Sc, P2, white_bkgd, rgb, depth, var, lam);
+  k_merge_composite<<<(unsigned)N, presorted ? 128 : 256, smem, st>>>(zf, zc, raw_f, raw_c, last_delta, N, Sf, Sc, P2, presorted, white_bkgd, rgb, depth, var, lam);
   SNB_CHECK_LAUNCH("k_merge_composite");
   return SNB_OK;
 }
