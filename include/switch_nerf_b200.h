@@ -184,6 +184,7 @@ typedef struct snb_render_out {
   float* z_fine;         /* tap: fine z values           [N, fine]      */
   float* raw_coarse;     /* tap: per-sample [rgb,sigma]  [N, coarse, 4] */
   float* raw_fine;       /* tap: per-sample [rgb,sigma]  [N, fine, 4]   */
+  float* rgb_coarse;     /* mip renderer only: rgb_coarse [N,3] (rendering_mip.py composites both levels) */
 } snb_render_out;
 
 size_t snb_render_workspace_bytes(const snb_model_t* m, int64_t n_rays, const snb_render_opts* o);
@@ -197,6 +198,21 @@ size_t snb_render_workspace_bytes(const snb_model_t* m, int64_t n_rays, const sn
 int snb_render_rays(snb_model_t* m, const float* rays, const int32_t* image_indices,
                     const float* last_delta, int64_t n_rays, const snb_render_opts* opts,
                     const snb_render_out* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces rendering_mip.render_rays (rendering_mip.py:133-174, 177-261, 264-425) for MipNeRFMoE models
+ * (snb_model_desc.mip = 1), eval mode (perturb = 0 -> deterministic resampling):
+ * coarse edges linspace(near, far, coarse_samples) -> mip_cast_rays (15-25) per interval -> model chunks ->
+ * composite on interval mid points with rgb padding (382-425) -> blurred weights + padding (217-224) ->
+ * sorted_piecewise_constant_pdf1 (75-131; the O(N*S^2) mask replaced by a binary search over the same cdf) ->
+ * fine edges -> second model pass -> composite.  coarse_samples / fine_samples count EDGES (hparams values),
+ * i.e. coarse_samples-1 and fine_samples-1 network evaluations per ray.  radii [N] (or [N,1]).
+ * rgb_padding < 0 means hparams.rgb_padding = None.  out->rgb/depth/depth_variance are the fine level (coarse
+ * when fine_samples == 0), out->rgb_coarse the coarse composite; moe_gates_* are [N, samples-1]. */
+size_t snb_render_mip_workspace_bytes(const snb_model_t* m, int64_t n_rays, const snb_render_opts* o);
+int snb_render_rays_mip(snb_model_t* m, const float* rays, const float* radii, const int32_t* image_indices,
+                        const float* last_delta, int64_t n_rays, const snb_render_opts* opts,
+                        float weights_resample_padding, float rgb_padding, const snb_render_out* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Stand-alone composite (rendering.py:436-494, flip=False): z [N,S] ascending, raw [N,S,4]. */
 int snb_composite(const float* z, const float* raw, const float* last_delta, int64_t n_rays,

@@ -172,6 +172,37 @@ def golden_render(tag, E, cf, bpr, n_rays, cs, fs, chunk, gate_scale=4.0, seed=5
     print("render", tag, {k: tuple(v.shape) for k, v in res.items()})
 
 
+def golden_render_mip(tag, E, width, n_rays, cs, fs, chunk, gate_scale=3.0, seed=9):
+    """rendering_mip.render_rays + MipNeRFMoE (Mission Bay topology when width=512), eval mode."""
+    R.install_shims()
+    from switch_nerf import rendering_mip
+    appearance_count = 16
+    sd = O.synthetic_state_dict(num_experts=E, appearance_count=appearance_count, seed=seed, gate_scale=gate_scale, width=width)
+    hp = R.make_hparams(num_experts=E, model_chunk_size=chunk, coarse_samples=cs, fine_samples=fs, width=width,
+                        nerfmoe_class_name="MipNeRFMoE")
+    hp.perturb = 0
+    m = R.build_reference_model(hp, appearance_count=appearance_count).eval()
+    m.load_state_dict(sd)
+    rays, idx = O.synthetic_rays(n_rays, appearance_count, seed=seed + 1)
+    g = torch.Generator().manual_seed(seed + 2)
+    radii = torch.rand(n_rays, 1, generator=g) * 1.5e-3 + 5e-4          # SURVEY 8d: radii ~ U(5e-4, 2e-3)
+    with torch.no_grad(), R.stable_argsort():
+        res, _ = rendering_mip.render_rays(m, rays, radii, idx, hp, True, True)
+    mine = O.render_rays_mip(sd, O.default_cfg(sd, 1.0, True, mip=True), rays, radii, idx, coarse_samples=cs,
+                             fine_samples=fs, model_chunk_size=chunk)
+    for k in ("rgb_coarse", "rgb_fine", "depth_fine", "depth_variance_fine", "gate_loss_coarse", "gate_loss_fine"):
+        assert float((res[k] - mine[k]).abs().max()) == 0.0, k
+    save = {k: v.numpy() for k, v in res.items()}
+    save["moe_gates_coarse"] = save["moe_gates_coarse"].astype(np.int32)
+    save["moe_gates_fine"] = save["moe_gates_fine"].astype(np.int32)
+    save["z_fine"] = mine["_z_fine"].numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"render_{tag}.npz"),
+                        params=np.array([E, width, n_rays, cs, fs, chunk, seed, gate_scale, appearance_count], dtype=np.float64),
+                        sd_checksum=np.array([sd_checksum(sd)]), rays=rays.numpy(), radii=radii.numpy(),
+                        image_indices=idx.numpy(), **save)
+    print("render", tag, {k: tuple(v.shape) for k, v in res.items()})
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(8)
@@ -185,6 +216,8 @@ def main():
     golden_render("config1", 4, 1.0, True, 256, 32, 32, 4096)
     golden_render("config1_coarse_only", 4, 1.0, True, 256, 64, 0, 4096)
     golden_render("ragged_chunks", 8, 1.0, True, 100, 17, 9, 1000)
+    golden_render_mip("mip_w256", 4, 256, 128, 33, 33, 3000)
+    golden_render_mip("mip_mission_bay_w512", 8, 512, 64, 33, 33, 1500)
 
 
 if __name__ == "__main__":

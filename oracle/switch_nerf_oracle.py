@@ -369,6 +369,107 @@ def render_rays(sd: Dict[str, Tensor], cfg: dict, rays: Tensor, image_indices: T
     return res
 
 
+
+# --------------------------------------------------------------------------- #
+# mip renderer (rendering_mip.py) -- Mission Bay / Bungee configs              #
+# --------------------------------------------------------------------------- #
+def mip_cast_rays(origin: Tensor, direction: Tensor, radius: Tensor, t: Tensor):
+    """rendering_mip.py:15-25: conical-frustum mean / diagonal covariance per interval."""
+    t0, t1 = t[..., :-1], t[..., 1:]
+    c, d = (t0 + t1) / 2, (t1 - t0) / 2
+    t_mean = c + (2 * c * d ** 2) / (3 * c ** 2 + d ** 2)
+    t_var = (d ** 2) / 3 - (4 / 15) * ((d ** 4 * (12 * c ** 2 - d ** 2)) / (3 * c ** 2 + d ** 2) ** 2)
+    r_var = radius ** 2 * ((c ** 2) / 4 + (5 / 12) * d ** 2 - (4 / 15) * (d ** 4) / (3 * c ** 2 + d ** 2))
+    mean = origin[..., None, :] + direction[..., None, :] * t_mean[..., None]
+    null_outer_diag = 1 - (direction ** 2) / torch.sum(direction ** 2, -1, keepdims=True)
+    cov_diag = t_var[..., None] * (direction ** 2)[..., None, :] + r_var[..., None] * null_outer_diag[..., None, :]
+    return mean, cov_diag
+
+
+def sorted_piecewise_constant_pdf(bins: Tensor, weights: Tensor, num_samples: int, u: Optional[Tensor] = None) -> Tensor:
+    """rendering_mip.py:75-131 (sorted_piecewise_constant_pdf1), deterministic branch unless `u` is given.
+    The O(N*S^2) boolean mask of the reference is restated with searchsorted (same selected edges)."""
+    eps = 1e-5
+    weights = weights.clone()
+    weight_sum = torch.sum(weights, dim=-1, keepdim=True)
+    padding = torch.clamp_min(eps - weight_sum, 0)
+    weights = weights + padding / weights.shape[-1]
+    weight_sum = weight_sum + padding
+    pdf = weights / weight_sum
+    cdf = torch.clamp_max(torch.cumsum(pdf[..., :-1], dim=-1), 1.0)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf, torch.ones_like(cdf[..., :1])], -1)
+    if u is None:
+        u = torch.linspace(0., 1. - torch.finfo(torch.float32).eps, num_samples)
+        u = u.expand(list(cdf.shape[:-1]) + [num_samples])
+    u = u.contiguous()
+    n = cdf.shape[-1]
+    hi = torch.searchsorted(cdf, u, right=True)          # first index with cdf > u
+    i0 = torch.clamp(hi - 1, 0, n - 1)                   # last index with cdf <= u (cdf[0] = 0 <= u always)
+    i1 = torch.clamp(hi, 0, n - 1)                       # no such index -> last edge (x[..., -1:])
+    b0, b1 = torch.gather(bins, -1, i0), torch.gather(bins, -1, i1)
+    c0, c1 = torch.gather(cdf, -1, i0), torch.gather(cdf, -1, i1)
+    t = torch.clip(torch.nan_to_num((u - c0) / (c1 - c0), 0), 0, 1)
+    return b0 + t * (b1 - b0)
+
+
+def mip_composite(z_edges: Tensor, rgbs: Tensor, sigmas: Tensor, last_delta: Tensor, rgb_padding: Optional[float]):
+    """rendering_mip.py:382-425: composite on interval mid points with rgb padding."""
+    if rgb_padding is not None:
+        rgbs = rgbs * (1 + 2 * rgb_padding) - rgb_padding
+    z = .5 * (z_edges[..., 1:] + z_edges[..., :-1])
+    return composite(z, rgbs, sigmas, last_delta)
+
+
+def _run_mip_chunks(mean, cov, rays_d, image_indices, sd, cfg, mode, chunk, flavor):
+    n_rays, n_s = mean.shape[:2]
+    x = torch.cat([mean.reshape(-1, 3), cov.reshape(-1, 3),
+                   rays_d.view(n_rays, 1, 3).expand(n_rays, n_s, 3).reshape(-1, 3),
+                   image_indices.view(n_rays, 1, 1).expand(n_rays, n_s, 1).reshape(-1, 1).to(mean.dtype)], 1)
+    outs, l_aux, idxs = [], [], []
+    for i in range(0, x.shape[0], chunk):
+        o, ex = nerf_moe_forward(x[i:i + chunk], sd, cfg, mode, flavor=flavor)
+        outs.append(o)
+        l_aux.append(ex["l_aux"].reshape(1))
+        idxs.append(ex["idx"].long().view(-1, 1, 1))
+    return torch.cat(outs, 0).view(n_rays, n_s, 4), torch.cat(l_aux, 0), torch.cat(idxs, 0).view(n_rays, n_s, 1, 1)
+
+
+def render_rays_mip(sd: Dict[str, Tensor], cfg: dict, rays: Tensor, radii: Tensor, image_indices: Tensor, *,
+                    coarse_samples: int, fine_samples: int, model_chunk_size: int, mode: str = "fp32",
+                    weights_resample_padding: float = 0.01, rgb_padding: Optional[float] = 0.001,
+                    flavor: str = "cuda") -> Dict[str, Tensor]:
+    """rendering_mip.render_rays (133-174) + _get_results (177-261) + _inference (264-425), eval mode
+    (perturb = 0, deterministic resampling)."""
+    n_rays = rays.shape[0]
+    rays_o, rays_d = rays[:, 0:3], rays[:, 3:6]
+    near, far = rays[:, 6:7], rays[:, 7:8]
+    last_delta = 1e10 * torch.ones(n_rays, 1)
+    z_steps = torch.linspace(0, 1, coarse_samples)
+    z_vals = (near * (1 - z_steps) + far * z_steps).expand(n_rays, coarse_samples)
+    res = {}
+    mean, cov = mip_cast_rays(rays_o, rays_d, radii, z_vals)
+    out_c, l_c, g_c = _run_mip_chunks(mean, cov, rays_d, image_indices, sd, cfg, mode, model_chunk_size, flavor)
+    res["gate_loss_coarse"], res["moe_gates_coarse"] = l_c, g_c
+    comp_c = mip_composite(z_vals, out_c[..., :3], out_c[..., 3], last_delta, rgb_padding)
+    res["rgb_coarse"] = comp_c["rgb"]
+    res["_raw_coarse"] = out_c
+    if fine_samples == 0:
+        res["depth_coarse"], res["depth_variance_coarse"] = comp_c["depth"], comp_c["depth_variance"]
+        return res
+    w = comp_c["weights"]
+    w_pad = torch.cat([w[..., :1], w, w[..., -1:]], -1)                       # :218-222
+    w_max = torch.maximum(w_pad[..., :-1], w_pad[..., 1:])
+    w_blur = 0.5 * (w_max[..., :-1] + w_max[..., 1:])
+    z_samples = sorted_piecewise_constant_pdf(z_vals, w_blur + weights_resample_padding, fine_samples)
+    z_fine, _ = torch.sort(z_samples, -1)
+    mean, cov = mip_cast_rays(rays_o, rays_d, radii, z_fine)
+    out_f, l_f, g_f = _run_mip_chunks(mean, cov, rays_d, image_indices, sd, cfg, mode, model_chunk_size, flavor)
+    res["gate_loss_fine"], res["moe_gates_fine"] = l_f, g_f
+    comp = mip_composite(z_fine, out_f[..., :3], out_f[..., 3], last_delta, rgb_padding)
+    res["rgb_fine"], res["depth_fine"], res["depth_variance_fine"] = comp["rgb"], comp["depth"], comp["depth_variance"]
+    res["_z_fine"], res["_raw_fine"] = z_fine, out_f
+    return res
+
 def psnr(a: Tensor, b: Tensor) -> float:
     """metrics.py:8-10."""
     return float(-10.0 * torch.log10(torch.mean((a - b) ** 2)))

@@ -52,7 +52,7 @@ class RenderOpts(C.Structure):
 class RenderOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "rgb", "depth", "depth_variance", "bg_lambda", "gate_loss_coarse", "gate_loss_fine",
-        "moe_gates_coarse", "moe_gates_fine", "z_fine", "raw_coarse", "raw_fine")]
+        "moe_gates_coarse", "moe_gates_fine", "z_fine", "raw_coarse", "raw_fine", "rgb_coarse")]
 
 
 # name -> (restype, argtypes); mirrors include/switch_nerf_b200.h one to one
@@ -80,6 +80,10 @@ _SIGNATURES = {
     "snb_render_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.POINTER(RenderOpts)]),
     "snb_render_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(RenderOpts),
                                   C.POINTER(RenderOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snb_render_mip_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.POINTER(RenderOpts)]),
+    "snb_render_rays_mip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.POINTER(RenderOpts), C.c_float, C.c_float, C.POINTER(RenderOut), C.c_void_p,
+                                      C.c_size_t, C.c_void_p]),
     "snb_composite": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snb_sample_pdf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,

@@ -57,6 +57,13 @@ int merge_composite_launch(const float* zf, const float* zc, const float* raw_f,
                            const float* last_delta, int64_t N, int Sf, int Sc, int presorted, int white_bkgd,
                            float* rgb, float* depth, float* var, float* lam, cudaStream_t st);
 int umma_selftest(const void* a, const void* b, int N, int K, float* d, int variant, cudaStream_t st);
+int mip_fill_x_launch(const float* rays, const float* radii, const int* image_indices, const float* ze, int64_t N,
+                      int Se, float* x, cudaStream_t st);
+int mip_composite_launch(const float* ze, const float* raw, const float* last_delta, int64_t N, int Se,
+                         float rgb_padding, int white_bkgd, float* rgb, float* depth, float* var, float* weights,
+                         cudaStream_t st);
+int mip_resample_launch(const float* ze, const float* weights, int64_t N, int Se, int nf, float resample_padding,
+                        float* zf, cudaStream_t st);
 int tc_timeline_read(unsigned long long* host, int n);
 
 // [E][K][N] -> [E][N][K]
@@ -392,6 +399,93 @@ int snb_render_rays(snb_model_t* mm, const float* rays, const int32_t* image_ind
   // perturb == 0: z_fine comes from an ascending u through a monotone cdf, z_coarse is a linspace -> both sorted
   return merge_composite_launch(zf, zc, raw_f, raw_c, last_delta, N, Sf, Sc, o->perturb == 0.f, o->white_bkgd, out->rgb, out->depth,
                                 out->depth_variance, out->bg_lambda, st);
+}
+
+
+static size_t render_mip_ws_layout(const Model* m, int64_t N, const snb_render_opts* o, size_t* model_ws) {
+  const int Sc = o->coarse_samples, Sf = o->fine_samples;
+  const int Smax = (Sc > Sf ? Sc : Sf) - 1;
+  const int64_t Bmax = (int64_t)N * Smax;
+  int64_t chunk = o->model_chunk_size < Bmax ? o->model_chunk_size : Bmax;
+  if (chunk < 1) chunk = 1;
+  size_t mw = align_up(snb_workspace_bytes((const snb_model_t*)m, chunk, o->route.capacity_factor), 256);
+  if (model_ws) *model_ws = mw;
+  size_t b = mw;
+  auto add = [&](size_t n) { b += align_up(n * sizeof(float), 256); };
+  add((size_t)N * Sc);                       // coarse edges
+  add((size_t)N * (Sf > 0 ? Sf : 1));        // fine edges
+  add((size_t)N * (Sc - 1));                 // coarse weights
+  add((size_t)Bmax * m->x_cols);             // x
+  add((size_t)N * (Sc - 1) * 4);             // raw coarse
+  add((size_t)N * (Sf > 1 ? Sf - 1 : 1) * 4);  // raw fine
+  return b + 4096;
+}
+
+size_t snb_render_mip_workspace_bytes(const snb_model_t* mm, int64_t n_rays, const snb_render_opts* o) {
+  if (!mm || !o) return 0;
+  return render_mip_ws_layout((const Model*)mm, n_rays, o, nullptr);
+}
+
+int snb_render_rays_mip(snb_model_t* mm, const float* rays, const float* radii, const int32_t* image_indices,
+                        const float* last_delta, int64_t N, const snb_render_opts* o, float weights_resample_padding,
+                        float rgb_padding, const snb_render_out* out, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  Model* m = (Model*)mm;
+  SNB_REQUIRE(m && o && out, "snb_render_rays_mip: NULL argument");
+  SNB_REQUIRE(m->d.mip, "snb_render_rays_mip needs a MipNeRFMoE model (desc.mip = 1)");
+  SNB_REQUIRE(N >= 0 && (N == 0 || (rays && radii)), "snb_render_rays_mip: bad rays/radii");
+  SNB_REQUIRE(o->coarse_samples >= 3 && (o->fine_samples == 0 || o->fine_samples >= 2), "snb_render_rays_mip: bad sample counts");
+  SNB_REQUIRE(o->model_chunk_size >= 1, "snb_render_rays_mip: bad model_chunk_size");
+  SNB_REQUIRE(o->perturb == 0.f, "snb_render_rays_mip: only the deterministic (eval) sampling is implemented");
+  if (N == 0) return SNB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Sc = o->coarse_samples, Sf = o->fine_samples;
+  size_t model_ws = 0;
+  size_t need = render_mip_ws_layout(m, N, o, &model_ws);
+  if (workspace_bytes < need) { set_error("snb_render_rays_mip: workspace %zu < required %zu", workspace_bytes, need); return SNB_EWORKSPACE; }
+  Arena a(workspace, workspace_bytes);
+  char* mws = a.take<char>(model_ws);
+  float* zc = a.take<float>((size_t)N * Sc);
+  float* zf = a.take<float>((size_t)N * (Sf > 0 ? Sf : 1));
+  float* wc = a.take<float>((size_t)N * (Sc - 1));
+  const int Smax = (Sc > Sf ? Sc : Sf) - 1;
+  float* x = a.take<float>((size_t)N * Smax * m->x_cols);
+  float* raw_c = a.take<float>((size_t)N * (Sc - 1) * 4);
+  float* raw_f = a.take<float>((size_t)N * (Sf > 1 ? Sf - 1 : 1) * 4);
+  if (!a.ok) { set_error("snb_render_rays_mip: workspace carve failed"); return SNB_EWORKSPACE; }
+  if (out->raw_coarse) raw_c = out->raw_coarse;
+  if (out->raw_fine && Sf > 0) raw_f = out->raw_fine;
+  if (out->z_fine && Sf > 0) zf = out->z_fine;
+  const float pad = rgb_padding < 0.f ? 0.f : rgb_padding;
+
+  auto run_pass = [&](const float* ze, int Se, float* raw, int32_t* gates_out, float* loss_out) -> int {
+    int rc = mip_fill_x_launch(rays, radii, image_indices, ze, N, Se, x, st);
+    if (rc) return rc;
+    const int64_t B = N * (Se - 1);
+    int ci = 0;
+    for (int64_t i = 0; i < B; i += o->model_chunk_size, ++ci) {       // rendering_mip.py:327
+      const int64_t rows = (B - i < o->model_chunk_size) ? (B - i) : o->model_chunk_size;
+      rc = snb_moe_forward(mm, x + i * m->x_cols, rows, nullptr, &o->route, o->precision, raw + i * 4,
+                           gates_out ? gates_out + i : nullptr, loss_out ? loss_out + ci : nullptr, nullptr, nullptr,
+                           mws, model_ws, st);
+      if (rc) return rc;
+    }
+    return SNB_OK;
+  };
+  int rc;
+  if ((rc = coarse_z_launch(rays, N, Sc, 0.f, 0, zc, st))) return rc;
+  if ((rc = run_pass(zc, Sc, raw_c, out->moe_gates_coarse, out->gate_loss_coarse))) return rc;
+  const bool only_coarse = (Sf == 0);
+  if ((rc = mip_composite_launch(zc, raw_c, last_delta, N, Sc, pad, o->white_bkgd,
+                                 only_coarse ? (out->rgb ? out->rgb : out->rgb_coarse) : out->rgb_coarse,
+                                 only_coarse ? out->depth : nullptr, only_coarse ? out->depth_variance : nullptr,
+                                 only_coarse ? nullptr : wc, st)))
+    return rc;
+  if (only_coarse) return SNB_OK;
+  if ((rc = mip_resample_launch(zc, wc, N, Sc, Sf, weights_resample_padding, zf, st))) return rc;
+  if ((rc = run_pass(zf, Sf, raw_f, out->moe_gates_fine, out->gate_loss_fine))) return rc;
+  return mip_composite_launch(zf, raw_f, last_delta, N, Sf, pad, o->white_bkgd, out->rgb, out->depth,
+                              out->depth_variance, nullptr, st);
 }
 
 int snb_umma_selftest(const void* a_bf16, const void* b_bf16, int32_t N, int32_t K, float* d, int32_t variant,

@@ -367,3 +367,165 @@ int merge_composite_launch(const float* zf, const float* zc, const float* raw_f,
 }
 
 }  // namespace snb
+
+// ==========================================================================================
+// mip renderer (reference rendering_mip.py): conical-frustum samples, composite on interval
+// mid points with rgb padding, blurred-weight piecewise-constant resampling.
+// ==========================================================================================
+namespace snb {
+
+__device__ __forceinline__ float linspace_to(int i, int n, float end) {   // ATen linspace(0, end, n)
+  if (n <= 1) return 0.f;
+  const float step = __fdiv_rn(end, (float)(n - 1));
+  return (i < n / 2) ? __fmul_rn(step, (float)i) : __fsub_rn(end, __fmul_rn(step, (float)(n - 1 - i)));
+}
+
+// x[r*(Se-1) + j] = [mean(3), cov_diag(3), dir(3), image_index]   rendering_mip.py:15-25, 287, 333-338
+__global__ void k_mip_fill_x(const float* __restrict__ rays, const float* __restrict__ radii,
+                             const int* __restrict__ image_indices, const float* __restrict__ ze, int64_t N, int Se,
+                             float* __restrict__ x) {
+  const int Sn = Se - 1;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * Sn) return;
+  const int64_t r = i / Sn;
+  const int j = (int)(i % Sn);
+  const float* ray = rays + r * 8;
+  const float t0 = ze[r * Se + j], t1 = ze[r * Se + j + 1];
+  const float radius = radii[r];
+  // same operation order as the reference expressions (no FMA contraction)
+  const float c = __fdiv_rn(__fadd_rn(t0, t1), 2.f), d = __fdiv_rn(__fsub_rn(t1, t0), 2.f);
+  const float c2 = __fmul_rn(c, c), d2 = __fmul_rn(d, d), d4 = __fmul_rn(d2, d2);
+  const float den = __fadd_rn(__fmul_rn(3.f, c2), d2);
+  const float t_mean = __fadd_rn(c, __fdiv_rn(__fmul_rn(__fmul_rn(2.f, c), d2), den));
+  const float t_var = __fsub_rn(__fdiv_rn(d2, 3.f),
+                                __fmul_rn(4.f / 15.f, __fdiv_rn(__fmul_rn(d4, __fsub_rn(__fmul_rn(12.f, c2), d2)), __fmul_rn(den, den))));
+  const float r_var = __fmul_rn(__fmul_rn(radius, radius),
+                                __fsub_rn(__fadd_rn(__fdiv_rn(c2, 4.f), __fmul_rn(5.f / 12.f, d2)),
+                                          __fdiv_rn(__fmul_rn(4.f / 15.f, d4), den)));
+  const float dx = ray[3], dy = ray[4], dz = ray[5];
+  const float dd[3] = {__fmul_rn(dx, dx), __fmul_rn(dy, dy), __fmul_rn(dz, dz)};
+  const float dn = __fadd_rn(__fadd_rn(dd[0], dd[1]), dd[2]);
+  float* xr = x + i * 10;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    xr[a] = __fadd_rn(ray[a], __fmul_rn(ray[3 + a], t_mean));
+    const float nod = __fsub_rn(1.f, __fdiv_rn(dd[a], dn));
+    xr[3 + a] = __fadd_rn(__fmul_rn(t_var, dd[a]), __fmul_rn(r_var, nod));
+    xr[6 + a] = ray[3 + a];
+  }
+  xr[9] = image_indices ? (float)image_indices[r] : 0.f;
+}
+
+// composite on mid points of the Se edges; raw [N, Se-1, 4]; rgb' = rgb*(1+2p) - p   rendering_mip.py:382-425
+__global__ void __launch_bounds__(128) k_mip_composite(const float* __restrict__ ze, const float* __restrict__ raw,
+                                                       const float* __restrict__ last_delta, int64_t N, int Se,
+                                                       float rgb_padding, int white_bkgd, float* __restrict__ rgb,
+                                                       float* __restrict__ depth, float* __restrict__ var,
+                                                       float* __restrict__ weights) {
+  extern __shared__ float sm[];  // [4 warps][2][Se-1]
+  const int S = Se - 1;
+  const int w = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * 4 + w;
+  if (r >= N) return;
+  float* ws = sm + (size_t)w * 2 * S;
+  const float* zr = ze + r * Se;
+  const float4* rr = reinterpret_cast<const float4*>(raw) + r * S;
+  const float a = 1.f + 2.f * rgb_padding;
+  auto fetch = [&](int j, float& zz, float& cr, float& cg, float& cb, float& sg) {
+    zz = __fmul_rn(0.5f, __fadd_rn(zr[j + 1], zr[j]));
+    float4 v = rr[j];
+    cr = __fsub_rn(__fmul_rn(v.x, a), rgb_padding);
+    cg = __fsub_rn(__fmul_rn(v.y, a), rgb_padding);
+    cb = __fsub_rn(__fmul_rn(v.z, a), rgb_padding);
+    sg = v.w;
+  };
+  warp_composite(S, last_delta ? last_delta[r] : 1e10f, white_bkgd, fetch, ws, ws + S, rgb ? rgb + r * 3 : nullptr,
+                 depth ? depth + r : nullptr, var ? var + r : nullptr, (float*)nullptr,
+                 weights ? weights + r * S : nullptr);
+}
+
+// weights [N, n] (n = Se-1 intervals of the Se edges) -> blurred + padded pdf -> nf sorted samples
+// rendering_mip.py:217-226 + sorted_piecewise_constant_pdf1 (75-131), deterministic u.  One warp per ray.
+__global__ void __launch_bounds__(128) k_mip_resample(const float* __restrict__ ze, const float* __restrict__ weights,
+                                                      int64_t N, int Se, int nf, float resample_padding,
+                                                      float* __restrict__ zf) {
+  extern __shared__ float sm[];  // [4 warps][(n) wprime + (n+1) cdf + (n+1) edges]
+  const int n = Se - 1;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 4 + w;
+  if (r >= N) return;
+  float* wp = sm + (size_t)w * (3 * n + 2);
+  float* cdf = wp + n;
+  float* eb = cdf + n + 1;
+  const float* wr = weights + r * n;
+  for (int j = lane; j <= n; j += 32) eb[j] = ze[r * Se + j];
+  float sum = 0.f;
+  for (int j = lane; j < n; j += 32) {
+    // weights_pad = [w0, w, w_last]; max of neighbours; blur = mean of consecutive maxima
+    const float wm1 = wr[max(j - 1, 0)], w0 = wr[j], wp1 = wr[min(j + 1, n - 1)];
+    const float m0 = fmaxf(wm1, w0), m1 = fmaxf(w0, wp1);
+    const float v = __fadd_rn(__fmul_rn(0.5f, __fadd_rn(m0, m1)), resample_padding);
+    wp[j] = v;
+    sum += v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float pad = fmaxf(0.f, 1e-5f - sum);
+  const float wsum = sum + pad;
+  __syncwarp();
+  if (lane == 0) {
+    double run = 0.0;                       // torch CPU cumsum: sequential, double accumulator
+    cdf[0] = 0.f;
+    for (int j = 0; j < n - 1; ++j) {
+      const float pdf = __fdiv_rn(__fadd_rn(wp[j], __fdiv_rn(pad, (float)n)), wsum);
+      run += (double)pdf;
+      cdf[j + 1] = fminf(1.f, (float)run);
+    }
+    cdf[n] = 1.f;
+  }
+  __syncwarp();
+  const float end = 1.f - 1.1920928955078125e-07f;   // 1 - finfo(float32).eps
+  for (int j = lane; j < nf; j += 32) {
+    const float u = linspace_to(j, nf, end);
+    int lo = 0, hi = n + 1;                  // first index with cdf > u
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+    const int i0 = min(max(lo - 1, 0), n), i1 = min(lo, n);
+    const float c0 = cdf[i0], c1 = cdf[i1];
+    float t = __fdiv_rn(u - c0, c1 - c0);
+    if (!(t == t) ) t = 0.f;                 // nan_to_num(nan -> 0); +-inf are clipped below
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    zf[r * nf + j] = __fadd_rn(eb[i0], __fmul_rn(t, eb[i1] - eb[i0]));
+  }
+}
+
+int mip_fill_x_launch(const float* rays, const float* radii, const int* image_indices, const float* ze, int64_t N,
+                      int Se, float* x, cudaStream_t st) {
+  if (N == 0 || Se < 2) return SNB_OK;
+  k_mip_fill_x<<<(unsigned)cdiv(N * (Se - 1), 256), 256, 0, st>>>(rays, radii, image_indices, ze, N, Se, x);
+  SNB_CHECK_LAUNCH("k_mip_fill_x");
+  return SNB_OK;
+}
+
+int mip_composite_launch(const float* ze, const float* raw, const float* last_delta, int64_t N, int Se,
+                         float rgb_padding, int white_bkgd, float* rgb, float* depth, float* var, float* weights,
+                         cudaStream_t st) {
+  if (N == 0) return SNB_OK;
+  SNB_REQUIRE(Se >= 2 && Se <= 4097, "mip composite: %d edges out of range", Se);
+  size_t smem = (size_t)4 * 2 * (Se - 1) * sizeof(float);
+  if (smem > 48 * 1024) SNB_CHECK_CUDA(cudaFuncSetAttribute(k_mip_composite, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_mip_composite<<<(unsigned)cdiv(N, 4), 128, smem, st>>>(ze, raw, last_delta, N, Se, rgb_padding, white_bkgd, rgb, depth, var, weights);
+  SNB_CHECK_LAUNCH("k_mip_composite");
+  return SNB_OK;
+}
+
+int mip_resample_launch(const float* ze, const float* weights, int64_t N, int Se, int nf, float resample_padding,
+                        float* zf, cudaStream_t st) {
+  if (N == 0 || nf == 0) return SNB_OK;
+  size_t smem = (size_t)4 * (3 * (Se - 1) + 2) * sizeof(float);
+  if (smem > 48 * 1024) SNB_CHECK_CUDA(cudaFuncSetAttribute(k_mip_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_mip_resample<<<(unsigned)cdiv(N, 4), 128, smem, st>>>(ze, weights, N, Se, nf, resample_padding, zf);
+  SNB_CHECK_LAUNCH("k_mip_resample");
+  return SNB_OK;
+}
+
+}  // namespace snb

@@ -319,3 +319,45 @@ def test_render_bf16_config1(built_lib):
     # per-ray composite averages the per-sample bf16 error; routing flips near capacity move single samples
     assert np.median(err) < 2e-3 and err.mean() < 4e-3
     assert O.psnr(torch.from_numpy(rgb), torch.from_numpy(g["rgb_fine"])) > 40.0
+
+
+# ----------------------------------------------------------------------------- a15 mip renderer (Mission Bay)
+@pytest.mark.parametrize("tag", ["mip_w256", "mip_mission_bay_w512"])
+def test_render_mip_fp32_vs_reference_golden(built_lib, tag):
+    """rendering_mip.render_rays + MipNeRFMoE (width 512 = mission_bay.yaml topology) vs the reference golden."""
+    from switch_nerf_b200.nerf_moe import get_nerf_moe_inner
+    from switch_nerf_b200.rendering_mip import render_rays as render_rays_mip
+    from oracle import ref_shims as R
+    g = load_golden(f"render_{tag}.npz")
+    E, width, n_rays, cs, fs, chunk, seed, gs, count = g["params"]
+    sd = O.synthetic_state_dict(num_experts=int(E), appearance_count=int(count), seed=int(seed), gate_scale=float(gs), width=int(width))
+    hp = R.make_hparams(num_experts=int(E), model_chunk_size=int(chunk), coarse_samples=int(cs), fine_samples=int(fs),
+                        width=int(width), nerfmoe_class_name="MipNeRFMoE")
+    hp.perturb = 0
+    model = get_nerf_moe_inner(hp, int(count), 3)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    res, _ = render_rays_mip(model, torch.from_numpy(g["rays"]).cuda(), torch.from_numpy(g["radii"]).cuda(),
+                             torch.from_numpy(g["image_indices"]).cuda(), hp, True, True, debug_taps=True)
+    torch.cuda.synchronize()
+    assert np.abs(res["_z_fine"].cpu().numpy() - g["z_fine"]).max() <= 1e-5
+    same = (res["moe_gates_coarse"].cpu().numpy().astype(np.int32) == g["moe_gates_coarse"]).mean()
+    assert same >= 0.999
+    for k in ("rgb_coarse", "rgb_fine", "depth_fine", "depth_variance_fine", "gate_loss_coarse", "gate_loss_fine"):
+        err = np.abs(res[k].cpu().numpy() - g[k]).max()
+        assert err <= TOL, f"{k}: max abs err {err}"
+
+
+def test_model_bf16_no_batch_mode(built_lib):
+    """moe_no_batch (capacity-free eval routing, tutel_moe_layer_nobatch.py:237-352) through the fused path."""
+    g = load_golden("model_e4_nobatch_fp32.npz")
+    sd = golden_sd(g)
+    x = torch.from_numpy(g["x"])
+    model, _ = make_model(sd, 1.0, False, True, "bf16")
+    r = model(x.cuda(), return_debug=True)
+    torch.cuda.synchronize()
+    idx = r["extras"]["moe_gates"][0].view(-1).cpu().numpy()
+    ok = idx == g["idx"]
+    assert ok.mean() >= 0.97
+    d = np.abs(r["outputs"].cpu().numpy() - g["outputs"])[ok]
+    assert d.mean() < 2e-3 and np.isfinite(d).all()

@@ -83,3 +83,15 @@ def test_render_golden(tag):
     for k in (f"rgb_{typ}", f"depth_{typ}", f"depth_variance_{typ}", "gate_loss_coarse"):
         assert np.array_equal(res[k].numpy(), g[k]), k
     assert np.array_equal(res["moe_gates_coarse"].numpy().astype(np.int32), g["moe_gates_coarse"])
+
+
+@pytest.mark.parametrize("tag", ["mip_w256", "mip_mission_bay_w512"])
+def test_render_mip_golden(tag):
+    """oracle restatement of rendering_mip.py + MipNeRFMoE vs the reference-written fixture (bit-exact)."""
+    g = load_golden(f"render_{tag}.npz")
+    E, width, n_rays, cs, fs, chunk, seed, gs, count = g["params"]
+    sd = O.synthetic_state_dict(num_experts=int(E), appearance_count=int(count), seed=int(seed), gate_scale=float(gs), width=int(width))
+    res = O.render_rays_mip(sd, O.default_cfg(sd, 1.0, True, mip=True), torch.from_numpy(g["rays"]), torch.from_numpy(g["radii"]),
+                            torch.from_numpy(g["image_indices"]), coarse_samples=int(cs), fine_samples=int(fs), model_chunk_size=int(chunk))
+    for k in ("rgb_coarse", "rgb_fine", "depth_fine", "depth_variance_fine", "gate_loss_coarse", "gate_loss_fine"):
+        assert np.array_equal(res[k].numpy(), g[k]), k
