@@ -365,7 +365,7 @@ struct EpiCtx {
 };
 
 __device__ __forceinline__ void epi_wait_acc(SmemCtl* ctl, Pipe& pp, int buf) {
-  mbar_wait(&ctl->acc_full[buf], pp.acc_use[buf] & 1);
+  mbar_wait_backoff(&ctl->acc_full[buf], pp.acc_use[buf] & 1);
   ++pp.acc_use[buf];
   tc_fence_after();
 }

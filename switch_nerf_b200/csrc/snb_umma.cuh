@@ -52,6 +52,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Waiting flavour for the many epilogue threads: back off with nanosleep between probes so that 512 polling
+// threads do not eat the issue slots of the MMA / producer warps (and of co-resident routing kernels).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (true) {
+    __nanosleep(40);
+    if (mbar_try_wait(bar, parity)) return;
+    if ((++spins & 0xFFFFu) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        printf("snb: mbarrier wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, parity);
+        __trap();
+      }
+    }
+  }
+}
+
 // ---- proxies / fences -----------------------------------------------------------------
 // generic-proxy st.shared -> visible to the async proxy (tcgen05.mma / bulk copies read smem through it)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
