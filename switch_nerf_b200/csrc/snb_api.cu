@@ -231,7 +231,7 @@ void snb_model_destroy(snb_model_t* mm) {
   tc_release(m);
   if (m->side_stream) {
     cudaStreamDestroy(m->side_stream);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_front[i]); cudaEventDestroy(m->ev_route[i]); }
+    for (int i = 0; i < 4; ++i) { cudaEventDestroy(m->ev_front[i]); cudaEventDestroy(m->ev_route[i]); }
   }
   delete m;
 }
@@ -317,7 +317,7 @@ static size_t render_ws_layout(const Model* m, int64_t N, const snb_render_opts*
   if (chunk < 1) chunk = 1;
   size_t mw = align_up(snb_workspace_bytes((const snb_model_t*)m, chunk, o->route.capacity_factor), 256);
   if (model_ws) *model_ws = mw;
-  size_t b = 2 * mw;            // two chunk workspaces: consecutive chunks are software-pipelined
+  size_t b = 4 * mw;            // four chunk workspaces: consecutive chunks are software-pipelined
   auto add = [&](size_t n) { b += align_up(n * sizeof(float), 256); };
   add((size_t)N * Sc);            // zc
   add((size_t)N * Sc);            // weights_c
@@ -352,8 +352,7 @@ int snb_render_rays(snb_model_t* mm, const float* rays, const int32_t* image_ind
   size_t need = render_ws_layout(m, N, o, &model_ws);
   if (workspace_bytes < need) { set_error("snb_render_rays: workspace %zu < required %zu", workspace_bytes, need); return SNB_EWORKSPACE; }
   Arena a(workspace, workspace_bytes);
-  char* mws = a.take<char>(model_ws);
-  char* mws1 = a.take<char>(model_ws);
+  char* mws = a.take<char>(4 * model_ws);
   float* zc = a.take<float>((size_t)N * Sc);
   float* wc = a.take<float>((size_t)N * Sc);
   float* zmid = a.take<float>((size_t)N * (Sc - 1));
@@ -372,7 +371,7 @@ int snb_render_rays(snb_model_t* mm, const float* rays, const int32_t* image_ind
     if (rc) return rc;
     const int64_t B = N * Sn;
     if (o->precision == SNB_PREC_BF16 && tc_supported(m))
-      return tc_forward_chunks(m, x, B, o->model_chunk_size, &o->route, raw, gates_out, loss_out, mws, mws1, model_ws, st);
+      return tc_forward_chunks(m, x, B, o->model_chunk_size, &o->route, raw, gates_out, loss_out, mws, model_ws, 4, st);
     int ci = 0;
     for (int64_t i = 0; i < B; i += o->model_chunk_size, ++ci) {       // rendering.py:354
       const int64_t rows = (B - i < o->model_chunk_size) ? (B - i) : o->model_chunk_size;

@@ -86,7 +86,7 @@ struct Model {
   int sm_count = 148;
   // software pipelining of render_rays: routing kernels run on this stream
   cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_route[2] = {nullptr, nullptr};
+  cudaEvent_t ev_front[4] = {nullptr, nullptr, nullptr, nullptr}, ev_route[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 // ---- entry points implemented in the individual .cu files ----
@@ -101,7 +101,7 @@ int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, co
                Arena& ws, cudaStream_t st);
 size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf);
 int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const snb_route_opts* o, float* out,
-                      int32_t* moe_idx, float* l_aux, void* ws0, void* ws1, size_t ws_bytes, cudaStream_t st);
+                      int32_t* moe_idx, float* l_aux, void* ws_base, size_t ws_stride, int nsets, cudaStream_t st);
 bool tc_supported(const Model* m);
 void tc_release(Model* m);
 

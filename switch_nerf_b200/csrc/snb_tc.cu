@@ -1025,6 +1025,7 @@ struct TcChunk {
   size_t rbytes;
   int64_t max_rows, max_tiles;
   PhaseEvents* pe;
+  int grid_cap;             // CTAs of the persistent kernels (<= SM count)
 };
 
 static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const float* sigma_noise,
@@ -1076,12 +1077,13 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
     attr_done = true;
   }
   c.pe = profile_next();
+  c.grid_cap = m->sm_count;
   return SNB_OK;
 }
 
 static int tc_front(Model* m, TcChunk& c, cudaStream_t st) {
   const int n_front_tiles = (int)cdiv(c.S, TILE);
-  const int grid1 = n_front_tiles < m->sm_count ? n_front_tiles : m->sm_count;
+  const int grid1 = n_front_tiles < c.grid_cap ? n_front_tiles : c.grid_cap;
   if (c.pe) cudaEventRecord(c.pe->e[0], st);
   k_front<12><<<grid1, THREADS, SM_TOTAL, st>>>(c.Pf, c.x, c.S, c.H, c.gates);
   SNB_CHECK_LAUNCH("k_front");
@@ -1108,7 +1110,7 @@ static int tc_route(Model* m, TcChunk& c, cudaStream_t st) {
 }
 
 static int tc_back(Model* m, TcChunk& c, cudaStream_t st) {
-  const int grid2 = (int)(c.max_tiles < m->sm_count ? c.max_tiles : m->sm_count);
+  const int grid2 = (int)(c.max_tiles < c.grid_cap ? c.max_tiles : c.grid_cap);
   if (c.pe) cudaEventRecord(c.pe->e[4], st);
   k_back<4><<<grid2, THREADS, SM_TOTAL, st>>>(c.Pb, c.tt, c.x, c.H, c.gate, c.noise, c.out);
   SNB_CHECK_LAUNCH("k_back");
@@ -1130,42 +1132,57 @@ int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, co
 // side stream: st = front(0) front(1) back(0) front(2) back(1) ... ; side = route(0) route(1) ...
 // Two workspace sets alternate between consecutive chunks.
 int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const snb_route_opts* o, float* out,
-                      int32_t* moe_idx, float* l_aux, void* ws0, void* ws1, size_t ws_bytes, cudaStream_t st) {
+                      int32_t* moe_idx, float* l_aux, void* ws_base, size_t ws_stride, int nsets, cudaStream_t st) {
   if (B <= 0) return SNB_OK;
+  constexpr int MAXSETS = 4;
   if (!m->side_stream) {
     int prio_lo = 0, prio_hi = 0;
     SNB_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     SNB_CHECK_CUDA(cudaStreamCreateWithPriority(&m->side_stream, cudaStreamNonBlocking, prio_hi));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < MAXSETS; ++i) {
       SNB_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_front[i], cudaEventDisableTiming));
       SNB_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_route[i], cudaEventDisableTiming));
     }
   }
-  static const bool no_overlap = getenv("SNB_NO_OVERLAP") != nullptr;   // debug/A-B switch: route on the caller's stream
+  // tuning / A-B switches (read once): SNB_NO_OVERLAP routes on the caller's stream; SNB_PIPE_DEPTH = how many
+  // launch #1 run ahead of launch #2 (1..3); SNB_ROUTE_SMS = SMs left free for the routing kernels
+  static const bool no_overlap = getenv("SNB_NO_OVERLAP") != nullptr;
+  static const int depth_env = getenv("SNB_PIPE_DEPTH") ? atoi(getenv("SNB_PIPE_DEPTH")) : 2;
+  static const int route_sms = getenv("SNB_ROUTE_SMS") ? atoi(getenv("SNB_ROUTE_SMS")) : 8;
+  int D = depth_env < 1 ? 1 : depth_env;
+  if (D > nsets - 1) D = nsets - 1;
+  if (D > MAXSETS - 1) D = MAXSETS - 1;
+  const int NS = D + 1;
   cudaStream_t sr = no_overlap ? st : m->side_stream;
-  TcChunk cc[2];
+  const int grid_cap = (!no_overlap && route_sms > 0 && route_sms < m->sm_count / 2) ? (m->sm_count - route_sms) & ~1 : m->sm_count;
+  TcChunk cc[MAXSETS];
   int ci = 0;
   int rc;
   for (int64_t i = 0; i < B; i += chunk, ++ci) {
     const int64_t rows = (B - i < chunk) ? (B - i) : chunk;
-    const int k = ci & 1;
-    Arena a(k ? ws1 : ws0, ws_bytes);
+    const int k = ci % NS;
+    Arena a((char*)ws_base + (size_t)k * ws_stride, ws_stride);
     if ((rc = tc_chunk_init(m, cc[k], x + i * m->x_cols, rows, nullptr, o, out + i * 4, moe_idx ? moe_idx + i : nullptr,
                             l_aux ? l_aux + ci : nullptr, nullptr, nullptr, a, st)))
       return rc;
+    cc[k].grid_cap = grid_cap;
     if ((rc = tc_front(m, cc[k], st))) return rc;
     SNB_CHECK_CUDA(cudaEventRecord(m->ev_front[k], st));
     SNB_CHECK_CUDA(cudaStreamWaitEvent(sr, m->ev_front[k], 0));
     if ((rc = tc_route(m, cc[k], sr))) return rc;
     SNB_CHECK_CUDA(cudaEventRecord(m->ev_route[k], sr));
-    if (ci >= 1) {
-      SNB_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_route[k ^ 1], 0));
-      if ((rc = tc_back(m, cc[k ^ 1], st))) return rc;
+    if (ci >= D) {
+      const int kb = (ci - D) % NS;
+      SNB_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_route[kb], 0));
+      if ((rc = tc_back(m, cc[kb], st))) return rc;
     }
   }
-  const int k = (ci - 1) & 1;
-  SNB_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_route[k], 0));
-  return tc_back(m, cc[k], st);
+  for (int j = (ci - D > 0 ? ci - D : 0); j < ci; ++j) {
+    const int kb = j % NS;
+    SNB_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_route[kb], 0));
+    if ((rc = tc_back(m, cc[kb], st))) return rc;
+  }
+  return SNB_OK;
 }
 
 }  // namespace snb
