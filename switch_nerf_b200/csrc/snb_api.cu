@@ -19,6 +19,7 @@ static std::vector<PhaseEvents> g_prof_pool;
 static size_t g_prof_used = 0;
 PhaseEvents* profile_next() {
   if (!g_prof_on) return nullptr;
+  if (g_prof_pool.capacity() < 65536) g_prof_pool.reserve(65536);   // callers keep pointers: never reallocate
   if (g_prof_used >= g_prof_pool.size()) {
     if (g_prof_pool.size() >= 65536) return nullptr;
     PhaseEvents pe;

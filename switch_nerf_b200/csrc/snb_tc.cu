@@ -1149,6 +1149,7 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
   static const bool no_overlap = getenv("SNB_NO_OVERLAP") != nullptr;
   static const int depth_env = getenv("SNB_PIPE_DEPTH") ? atoi(getenv("SNB_PIPE_DEPTH")) : 2;
   static const int route_sms = getenv("SNB_ROUTE_SMS") ? atoi(getenv("SNB_ROUTE_SMS")) : 8;
+  static const bool back_full = getenv("SNB_BACK_PART") == nullptr;   // launch #2 keeps every SM (tile rounds!)
   int D = depth_env < 1 ? 1 : depth_env;
   if (D > nsets - 1) D = nsets - 1;
   if (D > MAXSETS - 1) D = MAXSETS - 1;
@@ -1167,6 +1168,7 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
       return rc;
     cc[k].grid_cap = grid_cap;
     if ((rc = tc_front(m, cc[k], st))) return rc;
+    if (back_full) cc[k].grid_cap = m->sm_count;
     SNB_CHECK_CUDA(cudaEventRecord(m->ev_front[k], st));
     SNB_CHECK_CUDA(cudaStreamWaitEvent(sr, m->ev_front[k], 0));
     if ((rc = tc_route(m, cc[k], sr))) return rc;
