@@ -269,6 +269,7 @@ struct __align__(16) SmemCtl {
   uint64_t empty[NSTAGE];
   uint64_t acc_full[2];
   uint64_t a_ready[NCHUNK];
+  uint64_t peer_ok[NSTAGE];   // CTA pairs: "the peer CTA's A chunk + weight half for this ring slot are ready" (leader only)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -314,26 +315,33 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 
 // ---- producer: stream the K-slices of one layer through the ring ----
+// CG = 2 (CTA pair): each CTA streams its own half of the slice (rows [rank*N/2, +N/2) of the image are the
+// contiguous half of the bytes) -- half the L2 traffic and half the shared-memory landing traffic per SM.
+template <int CG>
 __device__ __forceinline__ void produce_layer(const uint8_t* wsrc, uint32_t N, uint32_t K16, uint8_t* ring,
-                                              SmemCtl* ctl, Pipe& pp) {
+                                              SmemCtl* ctl, Pipe& pp, uint32_t rank) {
   const uint32_t nsl = (K16 + 63) / 64;
   for (uint32_t j = 0; j < nsl; ++j) {
     const uint32_t klen = min(64u, K16 - 64u * j);
-    const uint32_t bytes = N * klen * 2;
+    const uint32_t bytes = N * klen * 2 / CG;
     const uint32_t stage = pp.slice % NSTAGE, phase = (pp.slice / NSTAGE) & 1;
     mbar_wait(&ctl->empty[stage], phase ^ 1);
     mbar_arrive_expect_tx(&ctl->full[stage], bytes);
-    bulk_g2s(ring + (size_t)stage * STAGE_BYTES, wsrc + (size_t)N * 64 * 2 * j, bytes, &ctl->full[stage]);
+    bulk_g2s(ring + (size_t)stage * STAGE_BYTES, wsrc + (size_t)N * 64 * 2 * j + (size_t)rank * bytes, bytes, &ctl->full[stage]);
     ++pp.slice;
   }
 }
 
 // ---- MMA issuer: one layer = K16/16 tcgen05.mma instructions into accumulator buffer `buf` ----
+// CG = 1: this CTA's 128 x N tile.  CG = 2: the leader CTA (rank 0) issues M = 256 instructions for the pair
+// (rows 0-127 = its own A tile / TMEM, rows 128-255 = the peer's); the peer CTA's warp 1 only forwards
+// "my A chunk and my weight half are in place" to the leader's peer_ok barrier of the ring slot.
+template <int CG>
 __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_base, uint32_t ring_base,
-                                          uint32_t tmem_base, int buf, SmemCtl* ctl, Pipe& pp,
+                                          uint32_t tmem_base, int buf, SmemCtl* ctl, Pipe& pp, uint32_t rank,
                                           unsigned long long* tl = nullptr, int* tn = nullptr) {
   const uint32_t nsl = (K16 + 63) / 64;
-  const uint32_t idesc = umma_idesc_bf16(TILE, (int)N);
+  const uint32_t idesc = umma_idesc_bf16(TILE * CG, (int)N);
   const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
   for (uint32_t j = 0; j < nsl; ++j) {
     const uint32_t klen = min(64u, K16 - 64u * j);
@@ -341,19 +349,35 @@ __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_b
     mbar_wait(&ctl->a_ready[j], pp.a_use[j] & 1);       // A columns [64j, 64j+klen) written + fenced
     ++pp.a_use[j];
     if (tn) tl_mark(tl, 1, *tn, 100 + (int)j);
-    mbar_wait(&ctl->full[stage], phase);                // weight slice landed
+    mbar_wait(&ctl->full[stage], phase);                // weight slice (or this CTA's half of it) landed
     if (tn) tl_mark(tl, 1, *tn, 110 + (int)j);
+    if (CG == 2 && rank != 0) {
+      // peer: tell the leader; the slot is recycled through the multicast commit on empty[stage]
+      mbar_arrive_remote(mapa_shared(smem_u32(&ctl->peer_ok[stage]), 0));
+      ++pp.slice;
+      continue;
+    }
+    if (CG == 2) {
+      mbar_wait(&ctl->peer_ok[stage], phase);
+      fence_acq_rel_cluster();
+    }
     tc_fence_after();
     const uint32_t b_base = ring_base + stage * STAGE_BYTES;
     for (uint32_t t = 0; t < klen / 16; ++t) {
       const uint64_t da = op_desc(a_base + (8u * j + 2u * t) * 128u, 128u, SBO_A);
       const uint64_t db = op_desc(b_base + (2u * t) * 128u, 128u, klen * 16u);
-      umma_bf16(d_tmem, da, db, idesc, (j | t) ? 1u : 0u);
+      if (CG == 2) umma_bf16_pair(d_tmem, da, db, idesc, (j | t) ? 1u : 0u);
+      else umma_bf16(d_tmem, da, db, idesc, (j | t) ? 1u : 0u);
     }
-    umma_commit(&ctl->empty[stage]);                    // frees the ring slot when these MMAs retire
+    if (CG == 2) umma_commit_pair(&ctl->empty[stage], 3);   // frees the ring slot in BOTH CTAs
+    else umma_commit(&ctl->empty[stage]);
     ++pp.slice;
   }
-  umma_commit(&ctl->acc_full[buf]);                     // accumulator complete -> epilogue
+  if (CG == 2) {
+    if (rank == 0) umma_commit_pair(&ctl->acc_full[buf], 3);  // accumulators complete -> both epilogues
+  } else {
+    umma_commit(&ctl->acc_full[buf]);
+  }
   if (tn) tl_mark(tl, 1, *tn, 120);
 }
 
@@ -502,17 +526,43 @@ __device__ __forceinline__ void a_store_row(uint32_t a_base, int row, int col8, 
 // ------------------------------------------------------------------------------------------
 // common prologue of both kernels
 // ------------------------------------------------------------------------------------------
+template <int CG>
 __device__ __forceinline__ SmemCtl* cta_setup(uint8_t* smem, int warp) {
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + SM_CTL);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&ctl->full[i], 1);
+      mbar_init(&ctl->empty[i], 1);
+      mbar_init(&ctl->peer_ok[i], 1);
+    }
     mbar_init(&ctl->acc_full[0], 1);
     mbar_init(&ctl->acc_full[1], 1);
     for (int i = 0; i < NCHUNK; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(&ctl->tmem_base);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_pair<512>(&ctl->tmem_base);
+    else tmem_alloc<512>(&ctl->tmem_base);
+  }
   return ctl;
+}
+// all threads: make the barrier inits / TMEM address visible (cluster-wide for CTA pairs)
+template <int CG>
+__device__ __forceinline__ void cta_setup_sync() {
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
+  tc_fence_after();
+}
+template <int CG>
+__device__ __forceinline__ void cta_teardown(uint32_t tmem_base, int warp) {
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all();     // the peer may still read this CTA's shared memory / arrive on its barriers
+  else __syncthreads();
+  if (warp == 1) {
+    if (CG == 2) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 __device__ __forceinline__ EpiCtx epi_ctx(int warp, int lane) {
   EpiCtx ec;
@@ -528,18 +578,18 @@ __device__ __forceinline__ EpiCtx epi_ctx(int warp, int lane) {
 // ------------------------------------------------------------------------------------------
 // launch #1: encode + xyz + external gate MLP + folded LayerNorm/gate GEMM + softmax
 // ------------------------------------------------------------------------------------------
-template <int FX>
+template <int FX, int CG>
 __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* __restrict__ x, int64_t S,
                                                       __nv_bfloat16* __restrict__ H, float* __restrict__ gates) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  SmemCtl* ctl = cta_setup(smem, warp);
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int t_first0 = CG * ((int)blockIdx.x / CG), t_stride = (int)gridDim.x;   // the CG CTAs of a cluster take CG consecutive tiles
+  SmemCtl* ctl = cta_setup<CG>(smem, warp);
   float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);
   float* sred = reinterpret_cast<float*>(smem + SM_RED);      // [2][4][128]: sum / sumsq partials per cs
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+  cta_setup_sync<CG>();
   const uint32_t tmem_base = ctl->tmem_base;
   const uint32_t a_base = smem_u32(smem + SM_A), ring_base = smem_u32(smem + SM_RING);
   const int n_tiles = (int)((S + TILE - 1) / TILE);
@@ -548,20 +598,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
 
   if (warp == 0) {
     if (lane == 0)
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int tb = t_first0; tb < n_tiles; tb += t_stride) {
+      const int t = tb + (int)rank;
         for (int l = 0; l < NL; ++l)
-          produce_layer(P.wblob + P.front[l].w_off, P.front[l].N, P.front[l].K16, smem + SM_RING, ctl, pp);
-        produce_layer(P.wblob + P.gate.w_off, GATE_N, MW, smem + SM_RING, ctl, pp);
+          produce_layer<CG>(P.wblob + P.front[l].w_off, P.front[l].N, P.front[l].K16, smem + SM_RING, ctl, pp, rank);
+        produce_layer<CG>(P.wblob + P.gate.w_off, GATE_N, MW, smem + SM_RING, ctl, pp, rank);
       }
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t li = 0;
       int tn = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int tb = t_first0; tb < n_tiles; tb += t_stride) {
+      const int t = tb + (int)rank;
         tl_mark(P.tl, 1, tn, 1);
         for (int l = 0; l < NL; ++l, ++li)
-          mma_layer(P.front[l].N, P.front[l].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, P.tl, &tn);
-        mma_layer(GATE_N, MW, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, P.tl, &tn);
+          mma_layer<CG>(P.front[l].N, P.front[l].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, rank, P.tl, &tn);
+        mma_layer<CG>(GATE_N, MW, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, rank, P.tl, &tn);
         ++li;
       }
     }
@@ -573,10 +625,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
     unsigned long long* tl = (warp == 2 && lane == 0) ? P.tl : nullptr;
     float pn[3] = {0.f, 0.f, 0.f};          // xyz of this thread's row in the NEXT tile (prefetched one tile ahead)
     if (ec.cs == 0) {
-      const int64_t s0 = (int64_t)blockIdx.x * TILE + row;
-      if ((int)blockIdx.x < n_tiles && s0 < S) { pn[0] = x[s0 * P.x_cols]; pn[1] = x[s0 * P.x_cols + 1]; pn[2] = x[s0 * P.x_cols + 2]; }
+      const int64_t s0 = (int64_t)(t_first0 + (int)rank) * TILE + row;
+      if (t_first0 < n_tiles && s0 < S) { pn[0] = x[s0 * P.x_cols]; pn[1] = x[s0 * P.x_cols + 1]; pn[2] = x[s0 * P.x_cols + 2]; }
     }
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    for (int tb = t_first0; tb < n_tiles; tb += t_stride) {
+      const int t = tb + (int)rank;
       const int64_t s = (int64_t)t * TILE + row;
       const bool valid = s < S;
       tl_mark(tl, 0, tn, 1);
@@ -585,9 +638,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
       if (ec.cs == 0) {
         float p[3] = {pn[0], pn[1], pn[2]};
         {
-          const int64_t sn = s + (int64_t)gridDim.x * TILE;
+          const int64_t sn = s + (int64_t)t_stride * TILE;
           pn[0] = pn[1] = pn[2] = 0.f;
-          if (t + (int)gridDim.x < n_tiles && sn < S) { pn[0] = x[sn * P.x_cols]; pn[1] = x[sn * P.x_cols + 1]; pn[2] = x[sn * P.x_cols + 2]; }
+          if (tb + t_stride < n_tiles && sn < S) { pn[0] = x[sn * P.x_cols]; pn[1] = x[sn * P.x_cols + 1]; pn[2] = x[sn * P.x_cols + 2]; }
         }
         __align__(16) __nv_bfloat16 pe[NPAD];
         pe_to_bf16<FX>(p, pe);
@@ -685,9 +738,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
       }
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  cta_teardown<CG>(tmem_base, warp);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -704,34 +755,34 @@ struct TileTable {
 };
 
 __global__ void __launch_bounds__(256) k_tile_plan(const int* __restrict__ counts, const int* __restrict__ cap_dev, int E,
-                                                   int no_batch, int64_t S, TileTable tt) {
-  __shared__ int s_row[MAX_E + 2], s_tile[MAX_E + 2], s_kc[MAX_E + 1];
+                                                   int no_batch, int64_t S, int pair, TileTable tt) {
+  // pair = 1 (CTA pairs): every bucket gets an even number of tiles (the second CTA of a pair must run the same
+  // expert's weights); the padding tile has 0 rows.
+  __shared__ int s_row[MAX_E + 2], s_tile[MAX_E + 2], s_kc[MAX_E + 1], s_nt[MAX_E + 1];
   const int cap = *cap_dev;
   if (threadIdx.x == 0) {
     int row = 0, nt = 0, kept_total = 0;
-    for (int e = 0; e < E; ++e) {
-      const int kc = no_batch ? counts[e] : min(counts[e], cap);
-      s_row[e] = row; s_tile[e] = nt; s_kc[e] = kc;
+    for (int e = 0; e <= E; ++e) {
+      int kc;
+      if (e < E) { kc = no_batch ? counts[e] : min(counts[e], cap); kept_total += kc; }
+      else kc = (int)S - kept_total;                       // dropped bucket
+      int n = (kc + TILE - 1) / TILE;
+      if (pair) n = (n + 1) & ~1;
+      s_row[e] = row; s_tile[e] = nt; s_kc[e] = kc; s_nt[e] = n;
       tt.seg_start[e] = row;
       row += (kc + TILE - 1) / TILE * TILE;
-      nt += (kc + TILE - 1) / TILE;
-      kept_total += kc;
+      nt += n;
     }
-    const int nd = (int)S - kept_total;
-    s_row[E] = row; s_tile[E] = nt; s_kc[E] = nd;
-    tt.seg_start[E] = row;
-    nt += (nd + TILE - 1) / TILE;
-    s_tile[E + 1] = nt;
     *tt.n_tiles = nt;
     *tt.drop_counter = 0;
   }
   __syncthreads();
   for (int e = 0; e <= E; ++e) {
-    const int t0 = s_tile[e], nt = (s_kc[e] + TILE - 1) / TILE;
+    const int t0 = s_tile[e], nt = s_nt[e];
     for (int i = threadIdx.x; i < nt; i += blockDim.x) {
       tt.tile_expert[t0 + i] = (e < E) ? e : -1;
       tt.tile_row0[t0 + i] = s_row[e] + i * TILE;
-      tt.tile_rows[t0 + i] = min(TILE, s_kc[e] - i * TILE);
+      tt.tile_rows[t0 + i] = max(0, min(TILE, s_kc[e] - i * TILE));
     }
   }
 }
@@ -749,7 +800,7 @@ __global__ void k_scatter_rows(const int* __restrict__ idx, const int* __restric
 // ------------------------------------------------------------------------------------------
 // launch #2: gather -> experts -> combine -> heads
 // ------------------------------------------------------------------------------------------
-template <int FD>
+template <int FD, int CG>
 __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, const float* __restrict__ x,
                                                      const __nv_bfloat16* __restrict__ H,
                                                      const float* __restrict__ gate, const float* __restrict__ noise,
@@ -757,7 +808,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  SmemCtl* ctl = cta_setup(smem, warp);
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int t_first0 = CG * ((int)blockIdx.x / CG), t_stride = (int)gridDim.x;   // pairs of tiles share the expert (k_tile_plan)
+  SmemCtl* ctl = cta_setup<CG>(smem, warp);
   float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);
   float* svec = reinterpret_cast<float*>(smem + SM_VEC);
   float* sred = reinterpret_cast<float*>(smem + SM_RED);      // [4 values][4 cs][128 rows]
@@ -765,9 +818,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
   const int H2 = P.hidden2;
   for (int i = threadIdx.x; i < MW; i += THREADS) s_wsig[i] = P.fblob[P.o_wsig + i];
   for (int i = threadIdx.x; i < 3 * H2; i += THREADS) s_wcol[i] = P.fblob[P.o_wcol + i];
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+  cta_setup_sync<CG>();
   const uint32_t tmem_base = ctl->tmem_base;
   const uint32_t a_base = smem_u32(smem + SM_A), ring_base = smem_u32(smem + SM_RING);
   const int n_tiles = *tt.n_tiles;
@@ -776,25 +827,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
 
   if (warp == 0) {
     if (lane == 0)
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int tb = t_first0; tb < n_tiles; tb += t_stride) {
+      const int t = tb + (int)rank;
         const int e = tt.tile_expert[t];
         if (e >= 0)
           for (int l = 0; l < NE; ++l)
-            produce_layer(P.wblob + P.expert[l].w_off + (size_t)e * P.expert_w_stride, MW, MW, smem + SM_RING, ctl, pp);
-        produce_layer(P.wblob + P.back[0].w_off, P.back[0].N, P.back[0].K16, smem + SM_RING, ctl, pp);
-        produce_layer(P.wblob + P.back[1].w_off, P.back[1].N, P.back[1].K16, smem + SM_RING, ctl, pp);
+            produce_layer<CG>(P.wblob + P.expert[l].w_off + (size_t)e * P.expert_w_stride, MW, MW, smem + SM_RING, ctl, pp, rank);
+        produce_layer<CG>(P.wblob + P.back[0].w_off, P.back[0].N, P.back[0].K16, smem + SM_RING, ctl, pp, rank);
+        produce_layer<CG>(P.wblob + P.back[1].w_off, P.back[1].N, P.back[1].K16, smem + SM_RING, ctl, pp, rank);
       }
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t li = 0;
       int tn = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int tb = t_first0; tb < n_tiles; tb += t_stride) {
+      const int t = tb + (int)rank;
         const int e = tt.tile_expert[t];
         tl_mark(P.tl, 1, tn, 1);
         if (e >= 0)
-          for (int l = 0; l < NE; ++l, ++li) mma_layer(MW, MW, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, P.tl, &tn);
-        mma_layer(P.back[0].N, P.back[0].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, P.tl, &tn); ++li;
-        mma_layer(P.back[1].N, P.back[1].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, P.tl, &tn); ++li;
+          for (int l = 0; l < NE; ++l, ++li) mma_layer<CG>(MW, MW, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, rank, P.tl, &tn);
+        mma_layer<CG>(P.back[0].N, P.back[0].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, rank, P.tl, &tn); ++li;
+        mma_layer<CG>(P.back[1].N, P.back[1].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, rank, P.tl, &tn); ++li;
       }
     }
   } else {
@@ -825,8 +878,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
       }
       return r;
     };
-    RowIn nxt = fetch_row((int)blockIdx.x);
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    RowIn nxt = fetch_row(t_first0 + (int)rank);
+    for (int tb = t_first0; tb < n_tiles; tb += t_stride) {
+      const int t = tb + (int)rank;
       const RowIn cur = nxt;
       const int e = cur.e;
       tl_mark(tl, 0, tn, 1);
@@ -870,7 +924,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
           st_shared_v4(a_chunk_addr(a_base, ec.q * 32 + ec.cs * 8 + i, lane), hv[i].x, hv[i].y, hv[i].z, hv[i].w);
         for (int c = 0; c < 4; ++c) epi_signal_chunk(ctl, c, lane);
       }
-      nxt = fetch_row(t + (int)gridDim.x);
+      nxt = fetch_row(t + t_stride);
       tl_mark(tl, 0, tn, 2);
       float sig_acc = 0.f;
       if (e >= 0) {
@@ -968,9 +1022,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
       }
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  cta_teardown<CG>(tmem_base, warp);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -990,7 +1042,7 @@ size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf) {
   const int E = m->d.num_experts;
   if (S < 1) S = 1;
   const int64_t max_rows = S + (int64_t)TILE * (E + 2);
-  const int64_t max_tiles = cdiv(S, TILE) + E + 2;
+  const int64_t max_tiles = cdiv(S, TILE) + 2 * (E + 2);
   size_t b = 0;
   b += align_up((size_t)S * MW * 2, 256);            // H
   b += align_up((size_t)S * E * 4, 256);             // gates
@@ -1026,6 +1078,7 @@ struct TcChunk {
   int64_t max_rows, max_tiles;
   PhaseEvents* pe;
   int grid_cap;             // CTAs of the persistent kernels (<= SM count)
+  int cg;                   // 1 = independent CTAs, 2 = CTA pairs (tcgen05 cta_group::2)
 };
 
 static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const float* sigma_noise,
@@ -1052,7 +1105,7 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
   c.x = x; c.S = S; c.noise = sigma_noise; c.o = *o; c.out = out; c.moe_idx = moe_idx; c.l_aux = l_aux;
   c.dbg_gates = dbg_gates; c.dbg_loc = dbg_loc;
   c.max_rows = S + (int64_t)TILE * (E + 2);
-  c.max_tiles = cdiv(S, TILE) + E + 2;
+  c.max_tiles = cdiv(S, TILE) + 2 * (E + 2);
   c.H = ws.take<__nv_bfloat16>((size_t)S * MW);
   c.gates = ws.take<float>((size_t)S * E);
   c.idx = ws.take<int>(S);
@@ -1072,10 +1125,14 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
   c.tt.drop_counter = small + 2 * E + 5;
   static bool attr_done = false;
   if (!attr_done) {
-    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
-    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     attr_done = true;
   }
+  static const int cg_env = getenv("SNB_CG") ? atoi(getenv("SNB_CG")) : 1;
+  c.cg = (cg_env == 2) ? 2 : 1;
   c.pe = profile_next();
   c.grid_cap = m->sm_count;
   return SNB_OK;
@@ -1083,9 +1140,21 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
 
 static int tc_front(Model* m, TcChunk& c, cudaStream_t st) {
   const int n_front_tiles = (int)cdiv(c.S, TILE);
-  const int grid1 = n_front_tiles < c.grid_cap ? n_front_tiles : c.grid_cap;
+  int grid1 = n_front_tiles < c.grid_cap ? n_front_tiles : c.grid_cap;
   if (c.pe) cudaEventRecord(c.pe->e[0], st);
-  k_front<12><<<grid1, THREADS, SM_TOTAL, st>>>(c.Pf, c.x, c.S, c.H, c.gates);
+  if (c.cg == 2) {
+    grid1 = (grid1 + 1) & ~1;
+    if (grid1 > (c.grid_cap & ~1)) grid1 = c.grid_cap & ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid1); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SM_TOTAL; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_front<12, 2>, c.Pf, c.x, c.S, c.H, c.gates));
+  } else {
+    k_front<12, 1><<<grid1, THREADS, SM_TOTAL, st>>>(c.Pf, c.x, c.S, c.H, c.gates);
+  }
   SNB_CHECK_LAUNCH("k_front");
   if (c.pe) cudaEventRecord(c.pe->e[1], st);
   return SNB_OK;
@@ -1098,7 +1167,7 @@ static int tc_route(Model* m, TcChunk& c, cudaStream_t st) {
                       c.cap_dev, c.l_aux, c.rws, c.rbytes, st);
   if (rc) return rc;
   SNB_CHECK_CUDA(cudaMemsetAsync(c.tt.row2sample, 0xFF, (size_t)c.max_rows * sizeof(int), st));
-  k_tile_plan<<<1, 256, 0, st>>>(c.counts, c.cap_dev, E, c.o.no_batch, c.S, c.tt);
+  k_tile_plan<<<1, 256, 0, st>>>(c.counts, c.cap_dev, E, c.o.no_batch, c.S, c.cg == 2, c.tt);
   SNB_CHECK_LAUNCH("k_tile_plan");
   k_scatter_rows<<<(unsigned)cdiv(c.S, 256), 256, 0, st>>>(c.idx, c.loc, c.cap_dev, E, c.o.no_batch, c.S, c.tt);
   SNB_CHECK_LAUNCH("k_scatter_rows");
@@ -1110,9 +1179,20 @@ static int tc_route(Model* m, TcChunk& c, cudaStream_t st) {
 }
 
 static int tc_back(Model* m, TcChunk& c, cudaStream_t st) {
-  const int grid2 = (int)(c.max_tiles < c.grid_cap ? c.max_tiles : c.grid_cap);
+  int grid2 = (int)(c.max_tiles < c.grid_cap ? c.max_tiles : c.grid_cap);
   if (c.pe) cudaEventRecord(c.pe->e[4], st);
-  k_back<4><<<grid2, THREADS, SM_TOTAL, st>>>(c.Pb, c.tt, c.x, c.H, c.gate, c.noise, c.out);
+  if (c.cg == 2) {
+    grid2 &= ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid2); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SM_TOTAL; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_back<4, 2>, c.Pb, c.tt, c.x, (const __nv_bfloat16*)c.H, (const float*)c.gate, c.noise, c.out));
+  } else {
+    k_back<4, 1><<<grid2, THREADS, SM_TOTAL, st>>>(c.Pb, c.tt, c.x, c.H, c.gate, c.noise, c.out);
+  }
   SNB_CHECK_LAUNCH("k_back");
   if (c.pe) cudaEventRecord(c.pe->e[5], st);
   return SNB_OK;
@@ -1148,7 +1228,7 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
   // launch #1 run ahead of launch #2 (1..3); SNB_ROUTE_SMS = SMs left free for the routing kernels
   static const bool no_overlap = getenv("SNB_NO_OVERLAP") != nullptr;
   static const int depth_env = getenv("SNB_PIPE_DEPTH") ? atoi(getenv("SNB_PIPE_DEPTH")) : 2;
-  static const int route_sms = getenv("SNB_ROUTE_SMS") ? atoi(getenv("SNB_ROUTE_SMS")) : 8;
+  static const int route_sms = getenv("SNB_ROUTE_SMS") ? atoi(getenv("SNB_ROUTE_SMS")) : 20;
   static const bool back_full = getenv("SNB_BACK_PART") == nullptr;   // launch #2 keeps every SM (tile rounds!)
   int D = depth_env < 1 ? 1 : depth_env;
   if (D > nsets - 1) D = nsets - 1;
