@@ -265,11 +265,11 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
 // shared-memory carve-up
 // ------------------------------------------------------------------------------------------
 struct __align__(16) SmemCtl {
-  uint64_t full[NSTAGE];
-  uint64_t empty[NSTAGE];
+  uint64_t full[2 * NSTAGE];      // CTA pairs use 2*NSTAGE half-size ring slots
+  uint64_t empty[2 * NSTAGE];
   uint64_t acc_full[2];
   uint64_t a_ready[NCHUNK];
-  uint64_t peer_ok[NSTAGE];   // CTA pairs: "the peer CTA's A chunk + weight half for this ring slot are ready" (leader only)
+  uint64_t peer_ok[2 * NSTAGE];   // CTA pairs: "the peer CTA's A chunk + weight half for this ring slot are ready" (leader only)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -324,10 +324,11 @@ __device__ __forceinline__ void produce_layer(const uint8_t* wsrc, uint32_t N, u
   for (uint32_t j = 0; j < nsl; ++j) {
     const uint32_t klen = min(64u, K16 - 64u * j);
     const uint32_t bytes = N * klen * 2 / CG;
-    const uint32_t stage = pp.slice % NSTAGE, phase = (pp.slice / NSTAGE) & 1;
+    constexpr uint32_t NS = NSTAGE * CG, SB = STAGE_BYTES / CG;
+    const uint32_t stage = pp.slice % NS, phase = (pp.slice / NS) & 1;
     mbar_wait(&ctl->empty[stage], phase ^ 1);
     mbar_arrive_expect_tx(&ctl->full[stage], bytes);
-    bulk_g2s(ring + (size_t)stage * STAGE_BYTES, wsrc + (size_t)N * 64 * 2 * j + (size_t)rank * bytes, bytes, &ctl->full[stage]);
+    bulk_g2s(ring + (size_t)stage * SB, wsrc + (size_t)N * 64 * 2 * j + (size_t)rank * bytes, bytes, &ctl->full[stage]);
     ++pp.slice;
   }
 }
@@ -345,7 +346,8 @@ __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_b
   const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
   for (uint32_t j = 0; j < nsl; ++j) {
     const uint32_t klen = min(64u, K16 - 64u * j);
-    const uint32_t stage = pp.slice % NSTAGE, phase = (pp.slice / NSTAGE) & 1;
+    constexpr uint32_t NS = NSTAGE * CG, SB = STAGE_BYTES / CG;
+    const uint32_t stage = pp.slice % NS, phase = (pp.slice / NS) & 1;
     mbar_wait(&ctl->a_ready[j], pp.a_use[j] & 1);       // A columns [64j, 64j+klen) written + fenced
     ++pp.a_use[j];
     if (tn) tl_mark(tl, 1, *tn, 100 + (int)j);
@@ -362,7 +364,7 @@ __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_b
       fence_acq_rel_cluster();
     }
     tc_fence_after();
-    const uint32_t b_base = ring_base + stage * STAGE_BYTES;
+    const uint32_t b_base = ring_base + stage * SB;
     for (uint32_t t = 0; t < klen / 16; ++t) {
       const uint64_t da = op_desc(a_base + (8u * j + 2u * t) * 128u, 128u, SBO_A);
       const uint64_t db = op_desc(b_base + (2u * t) * 128u, 128u, klen * 16u);
@@ -530,7 +532,7 @@ template <int CG>
 __device__ __forceinline__ SmemCtl* cta_setup(uint8_t* smem, int warp) {
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + SM_CTL);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) {
+    for (int i = 0; i < 2 * NSTAGE; ++i) {
       mbar_init(&ctl->full[i], 1);
       mbar_init(&ctl->empty[i], 1);
       mbar_init(&ctl->peer_ok[i], 1);
