@@ -359,10 +359,8 @@ __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_b
       ++pp.slice;
       continue;
     }
-    if (CG == 2) {
-      mbar_wait(&ctl->peer_ok[stage], phase);
-      fence_acq_rel_cluster();
-    }
+    if (CG == 2) mbar_wait_cluster(&ctl->peer_ok[stage], phase);
+    if (tn) tl_mark(tl, 1, *tn, 130 + (int)j);
     tc_fence_after();
     const uint32_t b_base = ring_base + stage * SB;
     for (uint32_t t = 0; t < klen / 16; ++t) {
