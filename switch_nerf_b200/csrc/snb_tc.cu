@@ -348,17 +348,21 @@ __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_b
     const uint32_t klen = min(64u, K16 - 64u * j);
     constexpr uint32_t NS = NSTAGE * CG, SB = STAGE_BYTES / CG;
     const uint32_t stage = pp.slice % NS, phase = (pp.slice / NS) & 1;
-    mbar_wait(&ctl->a_ready[j], pp.a_use[j] & 1);       // A columns [64j, 64j+klen) written + fenced
-    ++pp.a_use[j];
-    if (tn) tl_mark(tl, 1, *tn, 100 + (int)j);
-    mbar_wait(&ctl->full[stage], phase);                // weight slice (or this CTA's half of it) landed
-    if (tn) tl_mark(tl, 1, *tn, 110 + (int)j);
     if (CG == 2 && rank != 0) {
-      // peer: tell the leader; the slot is recycled through the multicast commit on empty[stage]
+      // peer: forward "my half of the weight slice landed" (normally far ahead of the MMAs); its A chunks are
+      // signalled by its epilogue warps directly on the leader's a_ready.  The slot is recycled through the
+      // multicast commit on empty[stage].
+      mbar_wait(&ctl->full[stage], phase);
       mbar_arrive_remote(mapa_shared(smem_u32(&ctl->peer_ok[stage]), 0));
       ++pp.slice;
       continue;
     }
+    if (CG == 2) mbar_wait_cluster(&ctl->a_ready[j], pp.a_use[j] & 1);   // 16 local + 16 remote warp arrivals
+    else mbar_wait(&ctl->a_ready[j], pp.a_use[j] & 1);  // A columns [64j, 64j+klen) written + fenced
+    ++pp.a_use[j];
+    if (tn) tl_mark(tl, 1, *tn, 100 + (int)j);
+    mbar_wait(&ctl->full[stage], phase);                // weight slice (or this CTA's half of it) landed
+    if (tn) tl_mark(tl, 1, *tn, 110 + (int)j);
     if (CG == 2) mbar_wait_cluster(&ctl->peer_ok[stage], phase);
     if (tn) tl_mark(tl, 1, *tn, 130 + (int)j);
     tc_fence_after();
@@ -386,6 +390,7 @@ struct EpiCtx {
   int lane, q, cs, row;     // TMEM lane quarter, column sub-slice (16 of every 64 columns), tile row
   int et;                   // 0..511
   uint32_t lane_base;       // (q*32) << 16
+  uint32_t remote_a_ready;  // CTA pairs, peer CTA only: cluster address of the LEADER's a_ready[0] (0 = arrive locally)
 };
 
 __device__ __forceinline__ void epi_wait_acc(SmemCtl* ctl, Pipe& pp, int buf) {
@@ -394,11 +399,16 @@ __device__ __forceinline__ void epi_wait_acc(SmemCtl* ctl, Pipe& pp, int buf) {
   tc_fence_after();
 }
 // every epilogue warp arrives once per chunk (a_ready count = 16): all lanes fence, lane 0 arrives
-__device__ __forceinline__ void epi_signal_chunk(SmemCtl* ctl, int c, int lane) {
+// CTA pairs: the MMAs are issued by the leader CTA only, so BOTH CTAs' epilogue warps arrive on the leader's
+// a_ready[c] (count 2 x 16): the leader's warps locally, the peer's through the cluster address.
+__device__ __forceinline__ void epi_signal_chunk(SmemCtl* ctl, int c, int lane, uint32_t remote_a_ready = 0) {
   fence_proxy_async_smem();    // my st.shared -> visible to the async proxy (tcgen05.mma operand reads)
   tc_fence_before();           // my tcgen05.ld of the old accumulator happen-before the MMA that overwrites it
   __syncwarp();
-  if (lane == 0) mbar_arrive(&ctl->a_ready[c]);
+  if (lane == 0) {
+    if (remote_a_ready) mbar_arrive_remote(remote_a_ready + (uint32_t)c * 8u);
+    else mbar_arrive(&ctl->a_ready[c]);
+  }
 }
 // stage the (bf16-rounded) bias of a layer into shared memory (double buffered by `slot`)
 __device__ __forceinline__ void epi_load_bias(const float* __restrict__ bias, int N, float* sbias, int slot, int et) {
@@ -467,7 +477,7 @@ __device__ __forceinline__ void epi_hidden(uint32_t tmem_acc, const float* sb, i
       st_shared_v4(a_chunk_addr(a_base, ec.row, col0 / 8), pk[0], pk[1], pk[2], pk[3]);
       st_shared_v4(a_chunk_addr(a_base, ec.row, col0 / 8 + 1), pk[4], pk[5], pk[6], pk[7]);
       if (tn) tl_mark(tl, 0, *tn, 60 + c2 + h);
-      epi_signal_chunk(ctl, c2 + h, ec.lane);
+      epi_signal_chunk(ctl, c2 + h, ec.lane, ec.remote_a_ready);
       if (tn) tl_mark(tl, 0, *tn, 80 + c2 + h);
     }
   }
@@ -537,7 +547,7 @@ __device__ __forceinline__ SmemCtl* cta_setup(uint8_t* smem, int warp) {
     }
     mbar_init(&ctl->acc_full[0], 1);
     mbar_init(&ctl->acc_full[1], 1);
-    for (int i = 0; i < NCHUNK; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS);
+    for (int i = 0; i < NCHUNK; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS * CG);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -564,8 +574,9 @@ __device__ __forceinline__ void cta_teardown(uint32_t tmem_base, int warp) {
     else tmem_dealloc<512>(tmem_base);
   }
 }
-__device__ __forceinline__ EpiCtx epi_ctx(int warp, int lane) {
+__device__ __forceinline__ EpiCtx epi_ctx(int warp, int lane, SmemCtl* ctl, int cg, uint32_t rank) {
   EpiCtx ec;
+  ec.remote_a_ready = (cg == 2 && rank != 0) ? mapa_shared(smem_u32(&ctl->a_ready[0]), 0) : 0u;
   ec.lane = lane;
   ec.q = warp & 3;                 // hardware rule: a warp reads the TMEM lanes 32*(warp_id % 4) ...
   ec.cs = (warp - 2) >> 2;         // ... so warps {2..5}, {6..9}, {10..13}, {14..17} cover all 4 quarters each
@@ -618,7 +629,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
       }
     }
   } else {
-    const EpiCtx ec = epi_ctx(warp, lane);
+    const EpiCtx ec = epi_ctx(warp, lane, ctl, CG, rank);
     const int row = ec.row;
     uint32_t li = 0;
     int tn = 0;
@@ -648,7 +659,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
         for (int i = NPE; i < NPAD; ++i) pe[i] = __float2bfloat16_rn(0.f);
         a_store_row(a_base, row, 0, pe, NPAD / 8);
       }
-      for (int c = 0; c < (NPAD + 63) / 64; ++c) epi_signal_chunk(ctl, c, lane);
+      for (int c = 0; c < (NPAD + 63) / 64; ++c) epi_signal_chunk(ctl, c, lane, ec.remote_a_ready);
       tl_mark(tl, 0, tn, 2);
       for (int l = 0; l < NL; ++l, ++li) {
         const int buf = (int)(li & 1);
@@ -690,7 +701,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
             }
             st_shared_v4(a_chunk_addr(a_base, row, col0 / 8), pk[0], pk[1], pk[2], pk[3]);
             st_shared_v4(a_chunk_addr(a_base, row, col0 / 8 + 1), pk[4], pk[5], pk[6], pk[7]);
-            epi_signal_chunk(ctl, c, lane);
+            epi_signal_chunk(ctl, c, lane, ec.remote_a_ready);
           }
           sred[(0 * 4 + ec.cs) * 128 + row] = sum;
           sred[(1 * 4 + ec.cs) * 128 + row] = sq;
@@ -851,7 +862,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
       }
     }
   } else {
-    const EpiCtx ec = epi_ctx(warp, lane);
+    const EpiCtx ec = epi_ctx(warp, lane, ctl, CG, rank);
     const int row = ec.row;
     const float b_sig = P.fblob[P.o_bsig];
     const float b_col0 = P.fblob[P.o_bcol], b_col1 = P.fblob[P.o_bcol + 1], b_col2 = P.fblob[P.o_bcol + 2];
@@ -922,7 +933,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           st_shared_v4(a_chunk_addr(a_base, ec.q * 32 + ec.cs * 8 + i, lane), hv[i].x, hv[i].y, hv[i].z, hv[i].w);
-        for (int c = 0; c < 4; ++c) epi_signal_chunk(ctl, c, lane);
+        for (int c = 0; c < 4; ++c) epi_signal_chunk(ctl, c, lane, ec.remote_a_ready);
       }
       nxt = fetch_row(t + t_stride);
       tl_mark(tl, 0, tn, 2);
@@ -959,7 +970,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
               }
               st_shared_v4(a_chunk_addr(a_base, row, col0 / 8), pk[0], pk[1], pk[2], pk[3]);
               st_shared_v4(a_chunk_addr(a_base, row, col0 / 8 + 1), pk[4], pk[5], pk[6], pk[7]);
-              epi_signal_chunk(ctl, c, lane);
+              epi_signal_chunk(ctl, c, lane, ec.remote_a_ready);
             }
           }
           tl_mark(tl, 0, tn, 30 + l);
@@ -973,7 +984,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
         epi_wait_acc(ctl, pp, buf);
         epi_hidden<false>(tmem_base + ec.lane_base + (uint32_t)buf * 256u, sbias + buf * 256, 4, a_base, ec, nullptr, ctl);
         const int nchunk2 = ((int)P.back[1].K16 + 63) / 64;
-        for (int c = 4; c < nchunk2; ++c) epi_signal_chunk(ctl, c, lane);
+        for (int c = 4; c < nchunk2; ++c) epi_signal_chunk(ctl, c, lane, ec.remote_a_ready);
         tl_mark(tl, 0, tn, 50);
         ++li;
       }
