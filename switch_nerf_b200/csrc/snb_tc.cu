@@ -357,13 +357,16 @@ __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_b
       ++pp.slice;
       continue;
     }
-    if (CG == 2) mbar_wait_cluster(&ctl->a_ready[j], pp.a_use[j] & 1);   // 16 local + 16 remote warp arrivals
-    else mbar_wait(&ctl->a_ready[j], pp.a_use[j] & 1);  // A columns [64j, 64j+klen) written + fenced
+    // CG == 2: 16 local + 16 remote (release.cluster) warp arrivals.  The waiting thread itself never reads the
+    // peer's data -- the MMA it issues reads each CTA's own shared memory through that CTA's async proxy, which the
+    // writers fenced (fence.proxy.async) before arriving -- so the plain (CTA-scope) wait is used: a cluster-scope
+    // acquire here costs an L1 invalidation per K-slice.
+    mbar_wait(&ctl->a_ready[j], pp.a_use[j] & 1);       // A columns [64j, 64j+klen) written + fenced
     ++pp.a_use[j];
     if (tn) tl_mark(tl, 1, *tn, 100 + (int)j);
     mbar_wait(&ctl->full[stage], phase);                // weight slice (or this CTA's half of it) landed
     if (tn) tl_mark(tl, 1, *tn, 110 + (int)j);
-    if (CG == 2) mbar_wait_cluster(&ctl->peer_ok[stage], phase);
+    if (CG == 2) mbar_wait(&ctl->peer_ok[stage], phase);
     if (tn) tl_mark(tl, 1, *tn, 130 + (int)j);
     tc_fence_after();
     const uint32_t b_base = ring_base + stage * SB;
