@@ -92,6 +92,8 @@ struct TcParams {
   uint32_t expert_b_stride; // floats between experts
   TcLayer back[2];          // layer "1", layer "2"
   uint32_t o_c0, o_c1, o_wsig, o_bsig, o_wcol, o_bcol;   // float offsets in fblob
+  uint32_t o_b3x;           // [E][256]: bias of the skip layer + bias of the xyz layer (h is re-accumulated by the MMA)
+  int recompute_h;          // 1: launch #2 recomputes h = xyz Linear(PE) per tile instead of gathering it from HBM
   int E, skip_layer, pos_xyz_freqs, pos_dir_freqs, appearance_dim, appearance_count, hidden2, x_cols;
   const float* emb_a;       // fp32 [count, A]
   unsigned long long* tl;   // debug timeline (nullable): [role][TL_N] (tag<<48 | clock) marks of CTA 0
@@ -145,6 +147,13 @@ __global__ void k_gate_consts(const float* __restrict__ ln_w, const float* __res
     a1 += __shfl_xor_sync(0xffffffffu, a1, o);
   }
   if (lane == 0) { c0[e] = (float)a0; c1[e] = (float)a1; }
+}
+
+// dst[e][n] = bf16(b_skip[e][n]) + bf16(b_xyz[n])
+__global__ void k_sum_bias(const float* __restrict__ b_skip, const float* __restrict__ b_xyz, int E, int N,
+                           float* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < E * N) dst[i] = bf16_round(b_skip[i]) + bf16_round(b_xyz[i % N]);
 }
 
 __global__ void k_round_copy(const float* __restrict__ src, int n, int round_bf16, float* __restrict__ dst) {
@@ -210,6 +219,8 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
     auto addf = [&](size_t n) { size_t o = nf; nf += align_up(n, 64); return (uint32_t)o; };
     p.o_c0 = addf(MAX_E); p.o_c1 = addf(MAX_E);
     p.o_wsig = addf(MW); p.o_bsig = addf(1); p.o_wcol = addf((size_t)3 * H2); p.o_bcol = addf(3);
+    p.o_b3x = addf((size_t)E * MW);
+    p.recompute_h = (getenv("SNB_GATHER_H") == nullptr && d.skip_layer >= 0) ? 1 : 0;
     p.E = E; p.skip_layer = d.skip_layer; p.pos_xyz_freqs = d.pos_xyz_freqs; p.pos_dir_freqs = d.pos_dir_freqs;
     p.appearance_dim = d.appearance_dim; p.appearance_count = d.appearance_count; p.hidden2 = H2; p.x_cols = m->x_cols;
     SNB_CHECK_CUDA(cudaMalloc((void**)&own->wblob, wbytes));
@@ -257,6 +268,10 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
   if ((rc = cpf(p.o_bsig, m->sigma_b, 1, 1))) return rc;
   if ((rc = cpf(p.o_wcol, m->color_w, 3 * d.hidden2, 1))) return rc;
   if ((rc = cpf(p.o_bcol, m->color_b, 3, 1))) return rc;
+  if (d.skip_layer >= 0) {
+    k_sum_bias<<<(unsigned)cdiv((int64_t)E * MW, 256), 256, 0, st>>>(m->exp_b[d.skip_layer], m->xyz_b, E, MW, own->h.fblob + p.o_b3x);
+    SNB_CHECK_LAUNCH("k_sum_bias");
+  }
   (void)w;
   return SNB_OK;
 }
@@ -337,10 +352,13 @@ __device__ __forceinline__ void produce_layer(const uint8_t* wsrc, uint32_t N, u
 // CG = 1: this CTA's 128 x N tile.  CG = 2: the leader CTA (rank 0) issues M = 256 instructions for the pair
 // (rows 0-127 = its own A tile / TMEM, rows 128-255 = the peer's); the peer CTA's warp 1 only forwards
 // "my A chunk and my weight half are in place" to the leader's peer_ok barrier of the ring slot.
+// `chunk0`: first 64-column chunk of the A tile this segment reads (its a_ready barriers are chunk0 + j);
+// `cont`: keep accumulating into the buffer (second segment of a layer); `commit`: this segment ends the layer.
 template <int CG>
 __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_base, uint32_t ring_base,
                                           uint32_t tmem_base, int buf, SmemCtl* ctl, Pipe& pp, uint32_t rank,
-                                          unsigned long long* tl = nullptr, int* tn = nullptr) {
+                                          unsigned long long* tl = nullptr, int* tn = nullptr, uint32_t chunk0 = 0,
+                                          bool cont = false, bool commit = true) {
   const uint32_t nsl = (K16 + 63) / 64;
   const uint32_t idesc = umma_idesc_bf16(TILE * CG, (int)N);
   const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
@@ -361,8 +379,8 @@ __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_b
     // peer's data -- the MMA it issues reads each CTA's own shared memory through that CTA's async proxy, which the
     // writers fenced (fence.proxy.async) before arriving -- so the plain (CTA-scope) wait is used: a cluster-scope
     // acquire here costs an L1 invalidation per K-slice.
-    mbar_wait(&ctl->a_ready[j], pp.a_use[j] & 1);       // A columns [64j, 64j+klen) written + fenced
-    ++pp.a_use[j];
+    mbar_wait(&ctl->a_ready[chunk0 + j], pp.a_use[chunk0 + j] & 1);   // A columns of this slice written + fenced
+    ++pp.a_use[chunk0 + j];
     if (tn) tl_mark(tl, 1, *tn, 100 + (int)j);
     mbar_wait(&ctl->full[stage], phase);                // weight slice (or this CTA's half of it) landed
     if (tn) tl_mark(tl, 1, *tn, 110 + (int)j);
@@ -371,19 +389,22 @@ __device__ __forceinline__ void mma_layer(uint32_t N, uint32_t K16, uint32_t a_b
     tc_fence_after();
     const uint32_t b_base = ring_base + stage * SB;
     for (uint32_t t = 0; t < klen / 16; ++t) {
-      const uint64_t da = op_desc(a_base + (8u * j + 2u * t) * 128u, 128u, SBO_A);
+      const uint64_t da = op_desc(a_base + (8u * (chunk0 + j) + 2u * t) * 128u, 128u, SBO_A);
       const uint64_t db = op_desc(b_base + (2u * t) * 128u, 128u, klen * 16u);
-      if (CG == 2) umma_bf16_pair(d_tmem, da, db, idesc, (j | t) ? 1u : 0u);
-      else umma_bf16(d_tmem, da, db, idesc, (j | t) ? 1u : 0u);
+      const uint32_t acc = (cont || (j | t)) ? 1u : 0u;
+      if (CG == 2) umma_bf16_pair(d_tmem, da, db, idesc, acc);
+      else umma_bf16(d_tmem, da, db, idesc, acc);
     }
     if (CG == 2) umma_commit_pair(&ctl->empty[stage], 3);   // frees the ring slot in BOTH CTAs
     else umma_commit(&ctl->empty[stage]);
     ++pp.slice;
   }
-  if (CG == 2) {
-    if (rank == 0) umma_commit_pair(&ctl->acc_full[buf], 3);  // accumulators complete -> both epilogues
-  } else {
-    umma_commit(&ctl->acc_full[buf]);
+  if (commit) {
+    if (CG == 2) {
+      if (rank == 0) umma_commit_pair(&ctl->acc_full[buf], 3);  // accumulators complete -> both epilogues
+    } else {
+      umma_commit(&ctl->acc_full[buf]);
+    }
   }
   if (tn) tl_mark(tl, 1, *tn, 120);
 }
@@ -667,7 +688,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
       for (int l = 0; l < NL; ++l, ++li) {
         const int buf = (int)(li & 1);
         epi_load_bias(P.fblob + P.front[l].b_off, MW, sbias, buf, ec.et);
-        if (l == 1) {
+        if (l == 1 && !P.recompute_h) {
           // h (written into the A tile by the L0 epilogue of ALL warps, complete after the barrier above) -> H:
           // coalesced 512-byte rows, overlapping the L1 MMAs; a second barrier fences the L1 epilogue's A writes
           const int64_t s0 = (int64_t)t * TILE;
@@ -844,9 +865,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
       for (int tb = t_first0; tb < n_tiles; tb += t_stride) {
       const int t = tb + (int)rank;
         const int e = tt.tile_expert[t];
-        if (e >= 0)
-          for (int l = 0; l < NE; ++l)
+        if (e >= 0) {
+          if (P.recompute_h) produce_layer<CG>(P.wblob + P.front[0].w_off, MW, P.front[0].K16, smem + SM_RING, ctl, pp, rank);
+          for (int l = 0; l < NE; ++l) {
             produce_layer<CG>(P.wblob + P.expert[l].w_off + (size_t)e * P.expert_w_stride, MW, MW, smem + SM_RING, ctl, pp, rank);
+            if (P.recompute_h && l == P.skip_layer)     // the skip term h is re-accumulated by the tensor core
+              produce_layer<CG>(P.wblob + P.front[0].w_off, MW, P.front[0].K16, smem + SM_RING, ctl, pp, rank);
+          }
+        }
         produce_layer<CG>(P.wblob + P.back[0].w_off, P.back[0].N, P.back[0].K16, smem + SM_RING, ctl, pp, rank);
         produce_layer<CG>(P.wblob + P.back[1].w_off, P.back[1].N, P.back[1].K16, smem + SM_RING, ctl, pp, rank);
       }
@@ -858,8 +884,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
       const int t = tb + (int)rank;
         const int e = tt.tile_expert[t];
         tl_mark(P.tl, 1, tn, 1);
-        if (e >= 0)
-          for (int l = 0; l < NE; ++l, ++li) mma_layer<CG>(MW, MW, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, rank, P.tl, &tn);
+        if (e >= 0) {
+          if (P.recompute_h) {      // h = xyz Linear(PE(xyz)); PE lives in A columns [256, 336) = chunks 4, 5
+            mma_layer<CG>(MW, P.front[0].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, rank, P.tl, &tn, 4);
+            ++li;
+          }
+          for (int l = 0; l < NE; ++l, ++li) {
+            if (P.recompute_h && l == P.skip_layer) {
+              mma_layer<CG>(MW, MW, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, rank, P.tl, &tn, 0, false, false);
+              mma_layer<CG>(MW, P.front[0].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, rank, P.tl, &tn, 4, true, true);
+            } else {
+              mma_layer<CG>(MW, MW, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, rank, P.tl, &tn);
+            }
+          }
+        }
         mma_layer<CG>(P.back[0].N, P.back[0].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, rank, P.tl, &tn); ++li;
         mma_layer<CG>(P.back[1].N, P.back[1].K16, a_base, ring_base, tmem_base, (int)(li & 1), ctl, pp, rank, P.tl, &tn); ++li;
       }
@@ -874,15 +912,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
     unsigned long long* tl = (warp == 2 && lane == 0) ? P.tl : nullptr;
     // per-row inputs of the tile are fetched one tile ahead (dependent-load chain row2sample -> x/gate is
     // hidden behind the previous tile); only the 512-byte h row is gathered at staging time
-    struct RowIn { int e, sidx; float g, d0, d1, d2; int ai; };
+    struct RowIn { int e, sidx; float g, d0, d1, d2, x0, x1, x2; int ai; };
     auto fetch_row = [&](int t) {
       RowIn r;
-      r.e = -1; r.sidx = -1; r.g = 0.f; r.d0 = r.d1 = r.d2 = 0.f; r.ai = 0;
+      r.e = -1; r.sidx = -1; r.g = 0.f; r.d0 = r.d1 = r.d2 = 0.f; r.x0 = r.x1 = r.x2 = 0.f; r.ai = 0;
       if (t < n_tiles) {
         r.e = tt.tile_expert[t];
         if (row < tt.tile_rows[t]) r.sidx = tt.row2sample[tt.tile_row0[t] + row];
         if (r.sidx >= 0) {
           if (r.e >= 0) r.g = gate[r.sidx];
+          if (ec.cs == 0 && P.recompute_h && r.e >= 0) {
+            const float* xr = x + (int64_t)r.sidx * P.x_cols;
+            r.x0 = xr[0]; r.x1 = xr[1]; r.x2 = xr[2];
+          }
           if (ec.cs == 1) {
             const float* xr = x + (int64_t)r.sidx * P.x_cols;
             r.d0 = xr[P.x_cols - 4]; r.d1 = xr[P.x_cols - 3]; r.d2 = xr[P.x_cols - 2];
@@ -902,17 +944,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
       const bool valid = sidx >= 0;
       const __nv_bfloat16* hrow = valid ? (H + (int64_t)sidx * MW) : nullptr;
       const float g = cur.g;
-      // ---- stage: expert input rows (or zeros for the dropped bucket); thread cs copies A chunk cs (128 B) ----
-      {
-        // warp (q, cs) gathers rows q*32 + cs*8 + i: one coalesced 512-byte row per instruction
-        uint4 hv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int sr = __shfl_sync(0xffffffffu, sidx, ec.cs * 8 + i);
-          hv[i] = make_uint4(0, 0, 0, 0);
-          if (sr >= 0 && e >= 0) hv[i] = *reinterpret_cast<const uint4*>(H + (int64_t)sr * MW + lane * 8);
-        }
-        // ---- [PE(dir) | appearance | 0-pad] -> A columns [256, K16 of layer "2")  (cs == 1 threads) ----
+      const bool rh = P.recompute_h && e >= 0;     // recompute h = xyz Linear(PE(xyz)) on the tensor core
+      // [PE(dir) | appearance | 0-pad] -> A columns [256, K16 of layer "2")  (cs == 1 threads)
+      auto write_cat = [&]() {
         if (ec.cs == 1) {
           constexpr int NDIR = 3 + 6 * FD;                   // 27
           constexpr int NCAT_MAX = KA_MAX - MW;              // 96
@@ -933,6 +967,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
           }
           a_store_row(a_base, row, MW / 8, cat, ((int)P.back[1].K16 - MW) / 8);
         }
+      };
+      if (rh) {
+        // ---- stage PE(xyz) into A columns [256, 336): operand of the xyz layer now and of the skip term later ----
+        if (ec.cs == 0) {
+          constexpr int NPE = 3 + 6 * 12, NPAD = (NPE + 15) / 16 * 16;
+          float pxyz[3] = {cur.x0, cur.x1, cur.x2};
+          __align__(16) __nv_bfloat16 pe[NPAD];
+          pe_to_bf16<12>(pxyz, pe);
+#pragma unroll
+          for (int i = NPE; i < NPAD; ++i) pe[i] = __float2bfloat16_rn(0.f);
+          a_store_row(a_base, row, MW / 8, pe, NPAD / 8);
+        }
+        epi_signal_chunk(ctl, 4, lane, ec.remote_a_ready);
+        epi_signal_chunk(ctl, 5, lane, ec.remote_a_ready);
+      } else {
+        // ---- stage: expert input rows gathered from H (or zeros for the dropped bucket) + the concat block ----
+        // warp (q, cs) gathers rows q*32 + cs*8 + i: one coalesced 512-byte row per instruction
+        uint4 hv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int sr = __shfl_sync(0xffffffffu, sidx, ec.cs * 8 + i);
+          hv[i] = make_uint4(0, 0, 0, 0);
+          if (sr >= 0 && e >= 0) hv[i] = *reinterpret_cast<const uint4*>(H + (int64_t)sr * MW + lane * 8);
+        }
+        write_cat();
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           st_shared_v4(a_chunk_addr(a_base, ec.q * 32 + ec.cs * 8 + i, lane), hv[i].x, hv[i].y, hv[i].z, hv[i].w);
@@ -942,16 +1001,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
       tl_mark(tl, 0, tn, 2);
       float sig_acc = 0.f;
       if (e >= 0) {
+        if (rh) {
+          // xyz layer (act none): h -> A[:, 0:256), the operand of expert layer 0
+          const int buf = (int)(li & 1);
+          epi_load_bias(P.fblob + P.front[0].b_off, MW, sbias, buf, ec.et);
+          epi_wait_acc(ctl, pp, buf);
+          epi_hidden<false>(tmem_base + ec.lane_base + (uint32_t)buf * 256u, sbias + buf * 256, 4, a_base, ec, nullptr, ctl);
+          if (P.skip_layer == 0) { epi_signal_chunk(ctl, 4, lane, ec.remote_a_ready); epi_signal_chunk(ctl, 5, lane, ec.remote_a_ready); }
+          ++li;
+        }
         for (int l = 0; l < NE; ++l, ++li) {
           const int buf = (int)(li & 1);
-          epi_load_bias(P.fblob + P.expert[l].b_off + (size_t)e * P.expert_b_stride, MW, sbias, buf, ec.et);
+          const bool skip_here = (l == P.skip_layer);
+          epi_load_bias((rh && skip_here) ? (P.fblob + P.o_b3x + (size_t)e * MW)
+                                          : (P.fblob + P.expert[l].b_off + (size_t)e * P.expert_b_stride), MW, sbias, buf, ec.et);
           tl_mark(tl, 0, tn, 10 + l);
           epi_wait_acc(ctl, pp, buf);
           tl_mark(tl, 0, tn, 20 + l);
+          if (rh && skip_here) write_cat();      // the skip layer's MMAs have retired: the PE(xyz) block is free
           const uint32_t tacc = tmem_base + ec.lane_base + (uint32_t)buf * 256u;
           const float* sb = sbias + buf * 256;
           if (l < NE - 1) {
-            epi_hidden<true>(tacc, sb, 4, a_base, ec, (l == P.skip_layer) ? hrow : nullptr, ctl);
+            epi_hidden<true>(tacc, sb, 4, a_base, ec, (skip_here && !rh) ? hrow : nullptr, ctl);
+            if (rh && l + 1 == P.skip_layer) {     // release the PE(xyz) chunks once more for the skip term
+              epi_signal_chunk(ctl, 4, lane, ec.remote_a_ready);
+              epi_signal_chunk(ctl, 5, lane, ec.remote_a_ready);
+            }
           } else {
             // last expert layer (no activation) -> combine: y = bf16(gate * bf16(out)) -> ReLU -> A;
             // sigma head accumulated on the fly (nerf_moe.py:384-400)
