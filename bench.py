@@ -109,7 +109,7 @@ def build_inputs(rank, device):
     from switch_nerf_b200 import synthetic as O
     from switch_nerf_b200.configs import make_hparams
     from switch_nerf_b200.nerf_moe import get_nerf_moe_inner
-    sd = O.synthetic_state_dict(num_experts=EXPERTS, appearance_count=2048, seed=0, gate_scale=4.0)
+    sd = O.benchmark_state_dict(num_experts=EXPERTS, appearance_count=2048, seed=0, n_rays=N_RAYS, coarse=COARSE)
     hp = make_hparams(num_experts=EXPERTS, capacity_factor=1.0, bpr=True, model_chunk_size=CHUNK,
                       coarse_samples=COARSE, fine_samples=FINE, amp_bf16=True, moe_return_gates=False)
     model = get_nerf_moe_inner(hp, 2048, 3)
@@ -145,7 +145,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import switch_nerf_oracle as O
-    sd = O.synthetic_state_dict(num_experts=EXPERTS, appearance_count=2048, seed=0, gate_scale=4.0)
+    from switch_nerf_b200.synthetic import benchmark_state_dict
+    sd = benchmark_state_dict(num_experts=EXPERTS, appearance_count=2048, seed=0, n_rays=N_RAYS, coarse=COARSE)
     cfg = O.default_cfg(sd, 1.0, True)
     n = 1024                                 # bounded sample of the workload: 1024 of the 8192 rays per step
     rays, idx = O.synthetic_rays(N_RAYS, 2048, seed=100)
@@ -180,7 +181,8 @@ def run_reference(args, rank, world):
 
 def cpu_baseline():
     from oracle import switch_nerf_oracle as O
-    sd = O.synthetic_state_dict(num_experts=EXPERTS, appearance_count=2048, seed=0, gate_scale=4.0)
+    from switch_nerf_b200.synthetic import benchmark_state_dict
+    sd = benchmark_state_dict(num_experts=EXPERTS, appearance_count=2048, seed=0, n_rays=N_RAYS, coarse=COARSE)
     cfg = O.default_cfg(sd, 1.0, True)
     n = 4096
     rays, idx = O.synthetic_rays(N_RAYS, 2048, seed=100)
@@ -282,6 +284,26 @@ def main():
     e2e_s = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
+    # routing statistics of this workload (one untimed pass): expert shares and the dropped fraction, per chunk
+    kept_frac, shares = 1.0, None
+    if rank == 0:
+        model.args.moe_return_gates = True
+        res = render_rays(model, None, rays_d, idx_d, hp, None, None, True, True, False)[0]
+        model.args.moe_return_gates = False
+        cap = int(1.0 * ((CHUNK + EXPERTS - 1) // EXPERTS))
+        dropped, total, hist = 0, 0, torch.zeros(EXPERTS, dtype=torch.float64)
+        for key in ("moe_gates_coarse", "moe_gates_fine"):
+            g = res[key].view(-1).cpu()
+            for i in range(0, g.numel(), CHUNK):
+                c = torch.bincount(g[i:i + CHUNK], minlength=EXPERTS)
+                capc = int(1.0 * ((min(CHUNK, g.numel() - i) + EXPERTS - 1) // EXPERTS))
+                dropped += int(torch.clamp(c - capc, min=0).sum())
+                total += int(c.sum())
+                hist += c.double()
+        kept_frac = 1.0 - dropped / max(total, 1)
+        shares = [round(float(v), 4) for v in (hist / hist.sum())]
+        del res
+
     if rank == 0:
         ms_per_step = ms_total / args.steps
         value = world * samples_per_step / (ms_per_step * 1e-3)
@@ -293,19 +315,22 @@ def main():
             # back-end figure (upper bound uses every sample as kept; dropped samples skip the expert stack).
             per_launch_samples = samples_per_step * args.steps / n_chunks
             avg_ms = back_ms / n_chunks
-            tf = per_launch_samples * FLOPS_BACK_KEPT / (avg_ms * 1e-3) / 1e12
+            flops_back = kept_frac * FLOPS_BACK_KEPT + (1.0 - kept_frac) * FLOPS_BACK_DROPPED   # per sample, this workload
+            tf = per_launch_samples * flops_back / (avg_ms * 1e-3) / 1e12
             roof = {"kernel": "k_back (gather+experts+combine+heads)", "bound": "tensor", "achieved": tf,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "peak_source": f"{which}, sustained bf16",
                     "avg_launch_ms": avg_ms, "traffic": ncu_traffic(), "traffic_unit": "bytes/launch (dram read+write, ncu)",
-                    "algorithmic_gflop_per_launch": per_launch_samples * FLOPS_BACK_KEPT / 1e9,
+                    "algorithmic_gflop_per_launch": per_launch_samples * flops_back / 1e9,
                     "phase_ms_per_step": {"front": front_ms / args.steps, "route": route_ms / args.steps,
                                           "back": back_ms / args.steps},
-                    "step_tflops": world * samples_per_step * FLOPS_PER_SAMPLE / (ms_per_step * 1e-3) / 1e12 / world}
+                    "step_tflops_per_gpu": samples_per_step * (FLOPS_PER_SAMPLE - (1.0 - kept_frac) * 917_504) / (ms_per_step * 1e-3) / 1e12}
         out = {
             "metric": "point-samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, min_warm), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "l2": "256 MiB buffer written between timed steps",
+                       "weights": "seeded random init, gate LayerNorm bias balanced on the ray batch (emulates the l_aux-trained gate)",
+                       "expert_shares": shares, "kept_fraction": round(kept_frac, 4),
                        "parallelism": f"dp{world} over rays, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": world * samples_per_step * args.steps / e2e_s, "unit": "samples/s",

@@ -16,8 +16,15 @@ N_RAYS, COARSE, FINE, CHUNK, E = 8192, 257, 257, 131072, 8
 rays, idx = O.synthetic_rays(N_RAYS, 2048, seed=100)
 rays, idx = rays.cuda(), idx.cuda()
 rows = []
-for gate_scale in (1.0, 4.0, 16.0):
-    sd = O.synthetic_state_dict(num_experts=E, appearance_count=2048, seed=0, gate_scale=gate_scale)
+base_sd = O.synthetic_state_dict(num_experts=E, appearance_count=2048, seed=0, gate_scale=4.0)
+r_cpu, _ = O.synthetic_rays(N_RAYS, 2048, seed=100)
+pick = torch.randperm(N_RAYS, generator=torch.Generator().manual_seed(7))[:512]
+tt = torch.linspace(0, 1, 64)
+zz = r_cpu[pick, 6:7] * (1 - tt) + r_cpu[pick, 7:8] * tt
+pts = (r_cpu[pick, None, 0:3] + r_cpu[pick, None, 3:6] * zz[..., None]).reshape(-1, 3)
+# gate skew: 0 = raw random init (3 experts take ~95 %), 3 / 8 = partially, 60 = fully balanced
+for gate_scale in (0, 3, 8, 60):
+    sd = O.balance_gate(base_sd, pts, iters=gate_scale) if gate_scale > 0 else base_sd
     for cf in (0.5, 1.0, 2.0):
         for bpr in (True, False):
             hp = make_hparams(num_experts=E, capacity_factor=cf, bpr=bpr, model_chunk_size=CHUNK, coarse_samples=COARSE,
@@ -38,14 +45,17 @@ for gate_scale in (1.0, 4.0, 16.0):
             gates = torch.cat([res["moe_gates_coarse"].view(-1), res["moe_gates_fine"].view(-1)])
             share = torch.bincount(gates, minlength=E).float() / gates.numel()
             # dropped fraction from one instrumented chunk
-            x = torch.cat([(torch.rand(CHUNK, 3, device="cuda") - 0.5) * 0.4, torch.nn.functional.normalize(torch.randn(CHUNK, 3, device="cuda"), dim=-1),
-                           torch.randint(0, 2048, (CHUNK, 1), device="cuda").float()], 1)
-            r = model(x, return_debug=True)
-            cap = int(cf * ((CHUNK + E - 1) // E))
-            dropped = float((r["extras"]["debug_loc"] >= cap).float().mean())
-            row = {"gate_scale": gate_scale, "capacity_factor": cf, "bpr": bpr, "ms_per_step": ms,
+            dropped_n, total_n = 0, 0
+            for key in ("moe_gates_coarse", "moe_gates_fine"):      # model chunks restart with every pass
+                gk = res[key].view(-1)
+                for i in range(0, gk.numel(), CHUNK):
+                    c = torch.bincount(gk[i:i + CHUNK], minlength=E)
+                    capc = int(cf * ((min(CHUNK, gk.numel() - i) + E - 1) // E))
+                    dropped_n += int(torch.clamp(c - capc, min=0).sum()); total_n += int(c.sum())
+            dropped = dropped_n / total_n
+            row = {"balance_iters": gate_scale, "capacity_factor": cf, "bpr": bpr, "ms_per_step": ms,
                    "msamples_per_s": N_RAYS * (COARSE + FINE) / ms / 1e3, "max_expert_share": float(share.max()),
-                   "dropped_frac_random_chunk": dropped}
+                   "dropped_fraction": dropped}
             rows.append(row)
             print(json.dumps(row), flush=True)
             model.release()

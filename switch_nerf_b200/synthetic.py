@@ -47,3 +47,46 @@ def synthetic_state_dict(num_experts=8, width=256, expert_layers=7, appearance_c
     sd["layers.gate_input_norm.bias"] = 0.1 * torch.randn(width, generator=g)
     sd["embedding_a.weight"] = torch.randn(appearance_count, appearance_dim, generator=g)
     return sd
+
+
+def _pe(x: Tensor, num_freqs: int) -> Tensor:
+    out = [x]
+    for k in range(num_freqs):
+        out += [torch.sin((2.0 ** k) * x), torch.cos((2.0 ** k) * x)]
+    return torch.cat(out, -1)
+
+
+def balance_gate(sd: Dict[str, Tensor], pts: Tensor, iters: int = 60) -> Dict[str, Tensor]:
+    """Emulate a load-balanced (trained with the l_aux balance loss) gate on random-init weights: the LayerNorm
+    bias of the gate input is shifted so that wg @ beta acts as a per-expert logit offset that equalises the
+    top-1 shares on `pts` [P,3].  Everything else stays the seeded random init.  Deterministic (CPU fp32)."""
+    with torch.no_grad():
+        E = sd["layers.0.gates.0.wg.weight"].shape[0]
+        h = F.linear(_pe(pts, 12), sd["layers.xyz.fcs.0.weight"], sd["layers.xyz.fcs.0.bias"])
+        g = F.linear(F.relu(F.linear(h, sd["layers.moe_external_gate.fcs.0.weight"], sd["layers.moe_external_gate.fcs.0.bias"])),
+                     sd["layers.moe_external_gate.fcs.1.weight"], sd["layers.moe_external_gate.fcs.1.bias"])
+        n = F.layer_norm(g, (g.shape[1],)) * sd["layers.gate_input_norm.weight"]
+        wg = sd["layers.0.gates.0.wg.weight"]
+        base = n @ wg.t()                                     # [P, E] logits without the LayerNorm bias
+        off = wg @ sd["layers.gate_input_norm.bias"]          # current per-expert offset
+        for _ in range(iters):
+            share = torch.bincount(torch.argmax(base + off, 1), minlength=E).float() / base.shape[0]
+            off = off - 0.5 * torch.log(share * E + 1e-2)
+        beta0 = sd["layers.gate_input_norm.bias"]
+        beta = beta0 + torch.linalg.pinv(wg) @ (off - wg @ beta0)
+        out = dict(sd)
+        out["layers.gate_input_norm.bias"] = beta.contiguous()
+        return out
+
+
+def benchmark_state_dict(num_experts=8, appearance_count=2048, seed=0, n_rays=8192, coarse=257, ray_seed=100):
+    """Weights of the bench / reference arms: seeded random init + a gate balanced on the coarse samples of the
+    benchmark's own ray batch (a trained Switch-NeRF gate is load-balanced by its auxiliary loss)."""
+    sd = synthetic_state_dict(num_experts=num_experts, appearance_count=appearance_count, seed=seed, gate_scale=4.0)
+    rays, _ = synthetic_rays(n_rays, appearance_count, seed=ray_seed)
+    g = torch.Generator().manual_seed(seed + 7)
+    pick = torch.randperm(n_rays, generator=g)[:512]
+    t = torch.linspace(0, 1, 64)
+    z = rays[pick, 6:7] * (1 - t) + rays[pick, 7:8] * t
+    pts = (rays[pick, None, 0:3] + rays[pick, None, 3:6] * z[..., None]).reshape(-1, 3)
+    return balance_gate(sd, pts)
