@@ -11,4 +11,3 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 500 -c 500 --kill 1
 ncu --set full --clock-control none --import-source on -k regex:k_back -s 40 -c 1 --kill 1 -o gpurun_out/prof_back_${TAG} python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_back.log 2>&1; tail -2 gpurun_out/ncu_back.log
 ncu --set full --clock-control none --import-source on -k regex:k_front -s 40 -c 1 --kill 1 -o gpurun_out/prof_front_${TAG} python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_front.log 2>&1; tail -2 gpurun_out/ncu_front.log
 ls -la gpurun_out | head -30
-python scripts/cf_sweep.py > gpurun_out/cf_sweep_${TAG}.log 2>&1; tail -20 gpurun_out/cf_sweep_${TAG}.log
