@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--parallelism", default="dp", choices=["dp", "ep"],
+                    help="dp: every expert on every GPU, rays sharded (the reference's shipped mode). "
+                         "ep: experts sharded E/N per GPU, P2P record exchange (BASELINE.json configs[2])")
     return ap.parse_args()
 
 
@@ -220,6 +223,11 @@ def main():
 
     model, hp, rays_h, idx_h, sd = build_inputs(rank, device)
     model.precision = args.precision
+    ep_group = None
+    if args.parallelism == "ep" and world > 1:
+        from switch_nerf_b200.expert_parallel import ExpertParallelGroup
+        ep_group = ExpertParallelGroup(EXPERTS, CHUNK, 1.0)
+        ep_group.attach(model)
     lib = L.lib()
     rays_pin, idx_pin = rays_h.pin_memory(), idx_h.to(torch.int32).pin_memory()
     rays_d, idx_d = rays_pin.to(device), idx_pin.to(device)
@@ -317,7 +325,7 @@ def main():
             avg_ms = back_ms / n_chunks
             flops_back = kept_frac * FLOPS_BACK_KEPT + (1.0 - kept_frac) * FLOPS_BACK_DROPPED   # per sample, this workload
             tf = per_launch_samples * flops_back / (avg_ms * 1e-3) / 1e12
-            roof = {"kernel": "k_back (gather+experts+combine+heads)", "bound": "tensor", "achieved": tf,
+            roof = {"kernel": "k_back (recompute h + expert stack + combine + sigma/colour heads)", "bound": "tensor", "achieved": tf,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "peak_source": f"{which}, sustained bf16",
                     "avg_launch_ms": avg_ms, "traffic": ncu_traffic(), "traffic_unit": "bytes/launch (dram read+write, ncu)",
                     "algorithmic_gflop_per_launch": per_launch_samples * flops_back / 1e9,
@@ -331,7 +339,9 @@ def main():
             "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "l2": "256 MiB buffer written between timed steps",
                        "weights": "seeded random init, gate LayerNorm bias balanced on the ray batch (emulates the l_aux-trained gate)",
                        "expert_shares": shares, "kept_fraction": round(kept_frac, 4),
-                       "parallelism": f"dp{world} over rays, no data-path collective"},
+                       "parallelism": (f"ep{world}: rays sharded, experts sharded {EXPERTS // world}/GPU, 48 B records out / "
+                                       "16 B rows back by P2P stores (no NCCL on the data path)") if ep_group is not None
+                       else f"dp{world} over rays, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": world * samples_per_step * args.steps / e2e_s, "unit": "samples/s",
                     "h2d_bytes_per_step": int(rays_pin.numel() * 4 + idx_pin.numel() * 4),
@@ -342,6 +352,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))
+    if ep_group is not None:
+        ep_group.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -117,6 +117,45 @@ void snb_model_destroy(snb_model_t* m);
  * `max_chunk_samples` rows and capacity factors up to `max_capacity_factor`. */
 size_t snb_workspace_bytes(const snb_model_t* m, int64_t max_chunk_samples, double max_capacity_factor);
 
+/* ---- (e) expert parallelism: experts sharded E/W per GPU, one process per GPU ------------------ */
+/* Replaces the two all_to_all_single calls around the experts (tutel_moe_layer_nobatch.py:164-218 via
+ * tutel_communicate_nobatch.py:15-54) and the `group`/`moe_local_expert_num` plumbing of
+ * moe_layer (tutel_moe_layer_nobatch.py:443-460, runner.py:100-101).  Each rank routes its own chunk
+ * (capacity from the local S and the global E, as the reference does); the exchange is done by the routing
+ * stage and by launch #2 themselves with st.global into peer memory + per-peer release/acquire flags --
+ * no NCCL call, no host synchronisation.  Because every non-expert weight is replicated, a sample travels
+ * as its 48-byte launch-#2 input record and comes back as its 16-byte {rgb, sigma} row (the reference ships
+ * two 512-byte activation rows).  Results are bit-identical to the single-GPU path.
+ *
+ *   snb_a2a_init        allocate this rank's symmetric region (device memory of the current device), sized
+ *                       for chunks of up to max_chunk_rows rows and capacity factors up to max_capacity_factor
+ *   snb_a2a_export      64-byte CUDA IPC handle of the region; exchange them with any host-side all-gather
+ *                       (torch.distributed.all_gather_object, MPI, files) ...
+ *   snb_a2a_connect     ... and map every peer (handles = world x 64 bytes, rank order).  A host barrier
+ *                       between snb_a2a_connect on all ranks and the first forward is the caller's job.
+ *   snb_a2a_connect_ptrs same-process peers / an external symmetric heap: base pointers, rank order
+ *                       (peer access must already be enabled)
+ *   snb_model_attach_a2a every following bf16 snb_moe_forward / snb_render_rays of the model runs
+ *                       expert-parallel: experts [rank*E/W, (rank+1)*E/W) are evaluated here for all ranks
+ *                       (NULL detaches).  All ranks must make the same sequence of model-chunk calls
+ *                       (the reference's all_to_all has the same requirement); a peer that never arrives
+ *                       traps the waiting kernel after 20 s.
+ *   snb_a2a_disconnect  unmap the peers (device-synchronising).  CUDA requires every importer to unmap a
+ *                       region before its owner frees it: disconnect on all ranks, host barrier, finalize.
+ *   snb_a2a_finalize    disconnect if still connected, free the region.                                     */
+typedef struct snb_a2a snb_a2a_t;
+int snb_a2a_init(int32_t rank, int32_t world, int32_t num_experts, int64_t max_chunk_rows,
+                 double max_capacity_factor, snb_a2a_t** out);
+int32_t snb_a2a_handle_bytes(void);
+int snb_a2a_export(snb_a2a_t* g, void* handle_out);
+int snb_a2a_connect(snb_a2a_t* g, const void* handles, size_t handles_bytes);
+int snb_a2a_connect_ptrs(snb_a2a_t* g, void* const* bases, int32_t n);
+void* snb_a2a_local_base(snb_a2a_t* g);
+size_t snb_a2a_region_bytes(const snb_a2a_t* g);
+int snb_model_attach_a2a(snb_model_t* m, snb_a2a_t* g);
+int snb_a2a_disconnect(snb_a2a_t* g);
+int snb_a2a_finalize(snb_a2a_t* g);
+
 /* ---- a9: routing ------------------------------------------------------------------------ */
 /* Replaces extract_critical (tutel_fast_dispatch.py:176-217, k=1) incl. one_hot (131-134),
  * compute_sorted_location (136-139), load_balance (141-150) and Tutel's fast_cumsum_sub_one:

@@ -67,6 +67,16 @@ _SIGNATURES = {
     "snb_model_update": (C.c_int, [C.c_void_p, C.POINTER(Weights), C.c_void_p]),
     "snb_model_destroy": (None, [C.c_void_p]),
     "snb_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_double]),
+    "snb_a2a_init": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_double, C.POINTER(C.c_void_p)]),
+    "snb_a2a_handle_bytes": (C.c_int32, []),
+    "snb_a2a_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "snb_a2a_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "snb_a2a_connect_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]),
+    "snb_a2a_local_base": (C.c_void_p, [C.c_void_p]),
+    "snb_a2a_region_bytes": (C.c_size_t, [C.c_void_p]),
+    "snb_model_attach_a2a": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "snb_a2a_disconnect": (C.c_int, [C.c_void_p]),
+    "snb_a2a_finalize": (C.c_int, [C.c_void_p]),
     "snb_route_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "snb_route_top1": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "snb_common.cuh"
+#include "snb_ep.cuh"
 
 namespace snb {
 
@@ -237,6 +238,40 @@ void snb_model_destroy(snb_model_t* mm) {
   delete m;
 }
 
+// ---- expert-parallel group (snb_ep.cu) ----
+int snb_a2a_init(int32_t rank, int32_t world, int32_t num_experts, int64_t max_chunk_rows, double max_cf,
+                 snb_a2a_t** out) {
+  return ep_create(rank, world, num_experts, max_chunk_rows, max_cf, (Ep**)out);
+}
+int32_t snb_a2a_handle_bytes(void) { return 64; }
+int snb_a2a_export(snb_a2a_t* g, void* handle_out) { return ep_export((Ep*)g, handle_out); }
+int snb_a2a_connect(snb_a2a_t* g, const void* handles, size_t handles_bytes) {
+  SNB_REQUIRE(g && handles_bytes >= (size_t)((Ep*)g)->world * 64, "snb_a2a_connect: need world x 64 handle bytes");
+  return ep_connect_ipc((Ep*)g, handles);
+}
+int snb_a2a_connect_ptrs(snb_a2a_t* g, void* const* bases, int32_t n) {
+  SNB_REQUIRE(g && n >= ((Ep*)g)->world, "snb_a2a_connect_ptrs: need one base per rank");
+  return ep_connect_ptrs((Ep*)g, bases);
+}
+void* snb_a2a_local_base(snb_a2a_t* g) { return g ? ((Ep*)g)->base : nullptr; }
+size_t snb_a2a_region_bytes(const snb_a2a_t* g) { return g ? ((const Ep*)g)->bytes : 0; }
+int snb_a2a_disconnect(snb_a2a_t* g) { return ep_disconnect((Ep*)g); }
+int snb_a2a_finalize(snb_a2a_t* g) { return ep_destroy((Ep*)g); }
+int snb_model_attach_a2a(snb_model_t* mm, snb_a2a_t* g) {
+  Model* m = (Model*)mm;
+  SNB_REQUIRE(m, "snb_model_attach_a2a: NULL model");
+  Ep* ep = (Ep*)g;
+  if (ep) {
+    SNB_REQUIRE(ep->E == m->d.num_experts, "snb_model_attach_a2a: group was built for %d experts, model has %d", ep->E,
+                m->d.num_experts);
+    SNB_REQUIRE(tc_supported(m) && m->x_cols == 7, "snb_model_attach_a2a: expert-parallel mode needs the tcgen05 path "
+                "(width 256, NeRFMoE rows)");
+    SNB_REQUIRE(ep->connected, "snb_model_attach_a2a: group is not connected");
+  }
+  m->ep = ep;
+  return SNB_OK;
+}
+
 size_t snb_workspace_bytes(const snb_model_t* mm, int64_t max_chunk_samples, double max_cf) {
   const Model* m = (const Model*)mm;
   if (!m) return 0;
@@ -281,6 +316,10 @@ int snb_moe_forward(snb_model_t* mm, const float* x, int64_t S, const float* sig
   if (S == 0) {
     if (l_aux) SNB_CHECK_CUDA(cudaMemsetAsync(l_aux, 0, sizeof(float), st));
     return SNB_OK;
+  }
+  if (m->ep && precision != SNB_PREC_BF16) {
+    set_error("expert-parallel mode runs on the bf16 tcgen05 path only (precision=%d)", precision);
+    return SNB_EUNSUPPORTED;
   }
   if (precision == SNB_PREC_FP32)
     return fp32_forward(m, x, S, sigma_noise, opts, out, moe_idx, l_aux, dbg_gates, dbg_loc, ws, st);

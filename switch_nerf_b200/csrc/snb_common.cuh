@@ -66,6 +66,8 @@ struct Arena {
 // Activation codes for the fp32 linear kernel epilogue.
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_SOFTPLUS_SHIFT = 3 };
 
+struct Ep;   // expert-parallel group (snb_ep.cuh)
+
 // Device-side model storage (library-owned copies, see snb_model_create).
 struct Model {
   snb_model_desc d;
@@ -87,6 +89,8 @@ struct Model {
   // software pipelining of render_rays: routing kernels run on this stream
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_front[4] = {nullptr, nullptr, nullptr, nullptr}, ev_route[4] = {nullptr, nullptr, nullptr, nullptr};
+  // expert-parallel group attached by snb_model_attach_a2a (not owned); nullptr = every expert is local
+  Ep* ep = nullptr;
 };
 
 // ---- entry points implemented in the individual .cu files ----

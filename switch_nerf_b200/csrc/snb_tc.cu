@@ -40,6 +40,7 @@
 #include <stdlib.h>
 
 #include "snb_umma.cuh"
+#include "snb_ep.cuh"
 
 namespace snb {
 using namespace ptx;
@@ -779,15 +780,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_front(TcParams P, const float* _
 // ------------------------------------------------------------------------------------------
 // tile table for launch #2
 // ------------------------------------------------------------------------------------------
-struct TileTable {
-  int* n_tiles;       // [1]
-  int* tile_expert;   // [max_tiles]  (-1 = dropped bucket)
-  int* tile_row0;     // [max_tiles]
-  int* tile_rows;     // [max_tiles]  valid rows in the tile
-  int* seg_start;     // [E+1] first row of each expert segment (+ dropped segment)
-  int* drop_counter;  // [1]
-  int* row2sample;    // [max_rows]
-};
+static_assert(TILE == EP_TILE, "tile height shared with the expert-parallel plan");
 
 __global__ void __launch_bounds__(256) k_tile_plan(const int* __restrict__ counts, const int* __restrict__ cap_dev, int E,
                                                    int no_batch, int64_t S, int pair, TileTable tt) {
@@ -836,10 +829,11 @@ __global__ void k_scatter_rows(const int* __restrict__ idx, const int* __restric
 // launch #2: gather -> experts -> combine -> heads
 // ------------------------------------------------------------------------------------------
 template <int FD, int CG>
-__global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, const float* __restrict__ x,
-                                                     const __nv_bfloat16* __restrict__ H,
-                                                     const float* __restrict__ gate, const float* __restrict__ noise,
-                                                     float* __restrict__ out) {
+__global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, RowIO io,
+                                                     const __nv_bfloat16* __restrict__ H) {
+  const float* __restrict__ x = io.x;
+  const float* __restrict__ gate = io.gate;
+  const float* __restrict__ noise = io.noise;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -920,13 +914,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
         r.e = tt.tile_expert[t];
         if (row < tt.tile_rows[t]) r.sidx = tt.row2sample[tt.tile_row0[t] + row];
         if (r.sidx >= 0) {
-          if (r.e >= 0) r.g = gate[r.sidx];
+          if (r.e >= 0) r.g = gate[(int64_t)r.sidx * io.g_stride];
           if (ec.cs == 0 && P.recompute_h && r.e >= 0) {
-            const float* xr = x + (int64_t)r.sidx * P.x_cols;
+            const float* xr = x + (int64_t)r.sidx * io.x_stride;
             r.x0 = xr[0]; r.x1 = xr[1]; r.x2 = xr[2];
           }
           if (ec.cs == 1) {
-            const float* xr = x + (int64_t)r.sidx * P.x_cols;
+            const float* xr = x + (int64_t)r.sidx * io.x_stride;
             r.d0 = xr[P.x_cols - 4]; r.d1 = xr[P.x_cols - 3]; r.d2 = xr[P.x_cols - 2];
             r.ai = min(max((int)xr[P.x_cols - 1], 0), P.appearance_count - 1);
           }
@@ -1098,20 +1092,34 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, c
                                           sred[(v * 4 + 2) * 128 + row] + sred[(v * 4 + 3) * 128 + row]; };
           // sigma = softplus(bf16(W_sigma h + b) + noise - 1)
           float sr = bf16_round(rsum(0) + b_sig);
-          if (noise) sr += noise[sidx];
+          if (noise) sr += noise[(int64_t)sidx * io.n_stride];
           const float tt_ = sr - 1.f;
           const float sigma = (tt_ > 20.f) ? tt_ : log1pf(expf(tt_));
           auto sg = [](float v) { return bf16_round(1.f / (1.f + expf(-bf16_round(v)))); };
           float4 o = make_float4(sg(rsum(1) + b_col0), sg(rsum(2) + b_col1), sg(rsum(3) + b_col2), sigma);
-          reinterpret_cast<float4*>(out)[sidx] = o;
+          if (io.ep) {      // expert-parallel: the row goes back to the rank that owns the sample (P2P store)
+            const float* rec = x + (int64_t)sidx * io.x_stride;
+            reinterpret_cast<float4*>(io.ret[__float_as_int(rec[10])])[__float_as_int(rec[9])] = o;
+          } else {
+            reinterpret_cast<float4*>(io.out)[sidx] = o;
+          }
         }
         epi_bar_sync();                       // sred is reused by the next tile
         tl_mark(tl, 0, tn, 51);
         ++li;
       }
     }
+    if (io.ep) __threadfence_system();      // this thread's P2P result stores are ordered before the CTA's count below
   }
   cta_teardown<CG>(tmem_base, warp);
+  if (io.ep && threadIdx.x == 0) {          // last CTA to finish: raise flag B on every peer
+    if (atomicAdd(io.done, 1) == (int)gridDim.x - 1) {
+      *io.done = 0;
+      __threadfence_system();
+      for (int w = 0; w < io.world; ++w)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(io.flag_b[w]), "r"(io.epoch) : "memory");
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1130,8 +1138,12 @@ size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf) {
   (void)max_cf;
   const int E = m->d.num_experts;
   if (S < 1) S = 1;
-  const int64_t max_rows = S + (int64_t)TILE * (E + 2);
-  const int64_t max_tiles = cdiv(S, TILE) + 2 * (E + 2);
+  int64_t max_rows = S + (int64_t)TILE * (E + 2);
+  int64_t max_tiles = cdiv(S, TILE) + 2 * (E + 2);
+  if (m->ep) {
+    if (ep_max_rows(m->ep, S) > max_rows) max_rows = ep_max_rows(m->ep, S);
+    if (ep_max_tiles(m->ep, S) > max_tiles) max_tiles = ep_max_tiles(m->ep, S);
+  }
   size_t b = 0;
   b += align_up((size_t)S * MW * 2, 256);            // H
   b += align_up((size_t)S * E * 4, 256);             // gates
@@ -1166,6 +1178,7 @@ struct TcChunk {
   size_t rbytes;
   int64_t max_rows, max_tiles;
   PhaseEvents* pe;
+  int set;                  // expert-parallel buffer set of this chunk
   int grid_cap;             // CTAs of the persistent kernels (<= SM count)
   int cg;                   // 1 = independent CTAs, 2 = CTA pairs (tcgen05 cta_group::2)
 };
@@ -1195,6 +1208,14 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
   c.dbg_gates = dbg_gates; c.dbg_loc = dbg_loc;
   c.max_rows = S + (int64_t)TILE * (E + 2);
   c.max_tiles = cdiv(S, TILE) + 2 * (E + 2);
+  c.set = 0;
+  if (m->ep) {
+    SNB_REQUIRE(c.Pf.recompute_h, "expert-parallel launch #2 recomputes h (SNB_GATHER_H is a single-GPU debug switch)");
+    SNB_REQUIRE(!o->no_batch, "expert-parallel mode implements the capacity (batched) dispatch only");
+    SNB_REQUIRE(!dbg_gates && !dbg_loc, "expert-parallel mode has no debug taps");
+    if (ep_max_rows(m->ep, S) > c.max_rows) c.max_rows = ep_max_rows(m->ep, S);
+    if (ep_max_tiles(m->ep, S) > c.max_tiles) c.max_tiles = ep_max_tiles(m->ep, S);
+  }
   c.H = ws.take<__nv_bfloat16>((size_t)S * MW);
   c.gates = ws.take<float>((size_t)S * E);
   c.idx = ws.take<int>(S);
@@ -1212,7 +1233,10 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
   c.tt.seg_start = small + E + 1;
   c.tt.n_tiles = small + 2 * E + 4;
   c.tt.drop_counter = small + 2 * E + 5;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};     // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& attr_done = attr_done_dev[dev & 63];
   if (!attr_done) {
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
@@ -1256,10 +1280,18 @@ static int tc_route(Model* m, TcChunk& c, cudaStream_t st) {
                       c.cap_dev, c.l_aux, c.rws, c.rbytes, st);
   if (rc) return rc;
   SNB_CHECK_CUDA(cudaMemsetAsync(c.tt.row2sample, 0xFF, (size_t)c.max_rows * sizeof(int), st));
-  k_tile_plan<<<1, 256, 0, st>>>(c.counts, c.cap_dev, E, c.o.no_batch, c.S, c.cg == 2, c.tt);
-  SNB_CHECK_LAUNCH("k_tile_plan");
-  k_scatter_rows<<<(unsigned)cdiv(c.S, 256), 256, 0, st>>>(c.idx, c.loc, c.cap_dev, E, c.o.no_batch, c.S, c.tt);
-  SNB_CHECK_LAUNCH("k_scatter_rows");
+  if (m->ep) {
+    // experts live on other ranks: one kernel scatters this rank's records into the owners' memory (P2P stores +
+    // per-peer flags), one plans the tiles over what the peers sent here
+    rc = ep_dispatch_plan(m->ep, c.set, c.x, m->x_cols, c.gate, c.noise, c.idx, c.loc, c.counts, c.cap_dev, c.S,
+                          capacity_of(c.S, E, c.o.capacity_factor), c.cg == 2, c.tt, st);
+    if (rc) return rc;
+  } else {
+    k_tile_plan<<<1, 256, 0, st>>>(c.counts, c.cap_dev, E, c.o.no_batch, c.S, c.cg == 2, c.tt);
+    SNB_CHECK_LAUNCH("k_tile_plan");
+    k_scatter_rows<<<(unsigned)cdiv(c.S, 256), 256, 0, st>>>(c.idx, c.loc, c.cap_dev, E, c.o.no_batch, c.S, c.tt);
+    SNB_CHECK_LAUNCH("k_scatter_rows");
+  }
   if (c.moe_idx) SNB_CHECK_CUDA(cudaMemcpyAsync(c.moe_idx, c.idx, sizeof(int) * c.S, cudaMemcpyDeviceToDevice, st));
   if (c.dbg_gates) SNB_CHECK_CUDA(cudaMemcpyAsync(c.dbg_gates, c.gates, sizeof(float) * c.S * E, cudaMemcpyDeviceToDevice, st));
   if (c.dbg_loc) SNB_CHECK_CUDA(cudaMemcpyAsync(c.dbg_loc, c.loc, sizeof(int) * c.S, cudaMemcpyDeviceToDevice, st));
@@ -1269,6 +1301,15 @@ static int tc_route(Model* m, TcChunk& c, cudaStream_t st) {
 
 static int tc_back(Model* m, TcChunk& c, cudaStream_t st) {
   int grid2 = (int)(c.max_tiles < c.grid_cap ? c.max_tiles : c.grid_cap);
+  RowIO io = {};
+  if (m->ep) {
+    ep_row_io(m->ep, c.set, &io);
+  } else {
+    io.x = c.x; io.x_stride = m->x_cols;
+    io.gate = c.gate; io.g_stride = 1;
+    io.noise = c.noise; io.n_stride = 1;
+    io.out = c.out;
+  }
   if (c.pe) cudaEventRecord(c.pe->e[4], st);
   if (c.cg == 2) {
     grid2 &= ~1;
@@ -1278,11 +1319,15 @@ static int tc_back(Model* m, TcChunk& c, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    SNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_back<4, 2>, c.Pb, c.tt, c.x, (const __nv_bfloat16*)c.H, (const float*)c.gate, c.noise, c.out));
+    SNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_back<4, 2>, c.Pb, c.tt, io, (const __nv_bfloat16*)c.H));
   } else {
-    k_back<4, 1><<<grid2, THREADS, SM_TOTAL, st>>>(c.Pb, c.tt, c.x, c.H, c.gate, c.noise, c.out);
+    k_back<4, 1><<<grid2, THREADS, SM_TOTAL, st>>>(c.Pb, c.tt, io, c.H);
   }
   SNB_CHECK_LAUNCH("k_back");
+  if (m->ep) {
+    int rc = ep_finish(m->ep, c.set, c.out, c.S, st);
+    if (rc) return rc;
+  }
   if (c.pe) cudaEventRecord(c.pe->e[5], st);
   return SNB_OK;
 }
@@ -1304,6 +1349,7 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
                       int32_t* moe_idx, float* l_aux, void* ws_base, size_t ws_stride, int nsets, cudaStream_t st) {
   if (B <= 0) return SNB_OK;
   constexpr int MAXSETS = 4;
+  static_assert(MAXSETS <= EP_SETS, "one expert-parallel buffer set per workspace set");
   if (!m->side_stream) {
     int prio_lo = 0, prio_hi = 0;
     SNB_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -1335,6 +1381,7 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
     if ((rc = tc_chunk_init(m, cc[k], x + i * m->x_cols, rows, nullptr, o, out + i * 4, moe_idx ? moe_idx + i : nullptr,
                             l_aux ? l_aux + ci : nullptr, nullptr, nullptr, a, st)))
       return rc;
+    cc[k].set = k;
     cc[k].grid_cap = grid_cap;
     if ((rc = tc_front(m, cc[k], st))) return rc;
     if (back_full) cc[k].grid_cap = m->sm_count;

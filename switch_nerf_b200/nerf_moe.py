@@ -73,11 +73,14 @@ class MOELayer(nn.Module):
     `experts.0.{weights,bias}.{j}`, `gates.0.wg.weight`; `moe_no_batch` toggled by
     Runner.set_no_batch (runner.py:947-956)."""
 
-    def __init__(self, gate_type, model_dim, experts, seeds=None, moe_no_batch=False, return_gates=False, **_):
+    def __init__(self, gate_type, model_dim, experts, seeds=None, moe_no_batch=False, return_gates=False,
+                 ep_world=1, **_):
         super().__init__()
         assert gate_type["type"] == "top" and gate_type["k"] == 1, "hot path = top-1 switch routing"
         assert experts["type"] == "expertmlp", "expert type of the training configs (README.md:70)"
-        self.num_local_experts = self.num_global_experts = experts["count_per_node"]
+        # MOELayer.global_expert_count (tutel_moe_layer_nobatch.py:480): local experts x ranks of the MoE group
+        self.num_local_experts = experts["count_per_node"]
+        self.num_global_experts = self.num_local_experts * int(ep_world)
         self.model_dim, self.moe_no_batch, self.return_gates = model_dim, moe_no_batch, return_gates
         if seeds is not None and seeds[1] is not None:
             torch.manual_seed(seeds[1])
@@ -92,6 +95,26 @@ class MOELayer(nn.Module):
 
 
 moe_layer = MOELayer
+
+
+def expert_parallel_env(args):
+    """(rank, world) of the MoE process group.  The reference passes `group=args.single_data_group`
+    (nerf_moe.py:289): a 1-rank group when `no_expert_parallel` (always true upstream, opts.py:125), else WORLD."""
+    if getattr(args, "no_expert_parallel", True):
+        return 0, 1
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(), dist.get_world_size()
+
+
+def gather_expert_shards(t: torch.Tensor, group=None) -> torch.Tensor:
+    """[E_local, ...] on every rank -> [E, ...] in rank order (expert e lives on rank e // E_local)."""
+    import torch.distributed as dist
+    t = t.contiguous()
+    parts = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(parts, t, group=group)
+    return torch.cat(parts, 0)
 
 
 class NeRFMoE(nn.Module):
@@ -109,6 +132,7 @@ class NeRFMoE(nn.Module):
         self.xyz_dim, self.pos_xyz_dim, self.pos_dir_dim = xyz_dim, pos_xyz_dim, pos_dir_dim
         self.appearance_dim, self.appearance_count = appearance_dim, appearance_count
         self._ddp_params_and_buffers_to_ignore = []
+        self._ep_rank, self._ep_world = 0, 1
         self.precision = "bf16" if getattr(args, "amp_use_bfloat16", False) else "fp32"
         self.embedding_a = nn.Embedding(appearance_count, appearance_dim)
         self.layers = nn.ModuleDict()
@@ -126,14 +150,17 @@ class NeRFMoE(nn.Module):
                            "count_per_node": c.get("local_expert_num") or args.moe_local_expert_num,
                            "layer_num": c["num"], "skips": c["skips"], "init_factor": c["init_factor"]}
                 rank = getattr(getattr(args, "parallel_env", None), "global_rank", 0)
+                self._ep_rank, self._ep_world = expert_parallel_env(args)
                 self.layers[tag] = moe_layer(gate_type=gate_type, model_dim=c["in_ch"], experts=experts,
                                              seeds=(1, rank + 1, 1), moe_no_batch=False,
-                                             return_gates=getattr(args, "moe_return_gates", False))
+                                             return_gates=getattr(args, "moe_return_gates", False),
+                                             ep_world=self._ep_world)
             elif c["type"] == "layernorm":
                 self.layers[tag] = nn.LayerNorm(c["in_ch"])
         self._handle = None
         self._packed_versions = None
         self._packed_device = None
+        self._ep_group = None      # ExpertParallelGroup once attached (expert_parallel.py)
 
     # -- reference API -----------------------------------------------------------------
     @staticmethod
@@ -179,7 +206,10 @@ class NeRFMoE(nn.Module):
         moe = lay["0"]
         w.wg = p(moe.gates[0].wg.weight)
         for j in range(moe.experts[0].layer_num):
-            w.expert_w[j], w.expert_b[j] = p(moe.experts[0].weights[j]), p(moe.experts[0].bias[j])
+            ew, eb = moe.experts[0].weights[j], moe.experts[0].bias[j]
+            if self._ep_world > 1:      # parameters are sharded E/W per rank: launch #2 packs the full set
+                ew, eb = gather_expert_shards(ew.detach()), gather_expert_shards(eb.detach())
+            w.expert_w[j], w.expert_b[j] = p(ew), p(eb)
         w.l1_w, w.l1_b = p(lay["1"].fcs[0].weight), p(lay["1"].fcs[0].bias)
         w.l2_w, w.l2_b = p(lay["2"].fcs[0].weight), p(lay["2"].fcs[0].bias)
         w.sigma_w, w.sigma_b = p(lay["sigma"].fcs[0].weight), p(lay["sigma"].fcs[0].bias)
@@ -215,6 +245,15 @@ class NeRFMoE(nn.Module):
                 h = C.c_void_p()
                 L.check(lib.snb_model_create(C.byref(self._desc()), C.byref(w), L.stream_handle(), C.byref(h)))
                 self._handle, self._packed_versions, self._packed_device = h, versions, dev
+                if self._ep_group is None and self._ep_world > 1:
+                    from .expert_parallel import ExpertParallelGroup
+                    self._ep_group = ExpertParallelGroup(
+                        self.layers["0"].num_global_experts, int(getattr(self.args, "model_chunk_size", 131072)),
+                        float(self.layers["0"].gates[0].capacity_factor), rank=self._ep_rank, world=self._ep_world,
+                        device=dev)
+                    self._ep_group._models.append(self)
+                if self._ep_group is not None:
+                    L.check(lib.snb_model_attach_a2a(h, self._ep_group._h))
             elif versions != self._packed_versions:
                 w, keep = self._weights_struct()
                 L.check(lib.snb_model_update(self._handle, C.byref(w), L.stream_handle()))

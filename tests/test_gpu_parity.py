@@ -3,6 +3,7 @@ golden fixtures (written by the unmodified reference).  Integer outputs bit-exac
 within 1e-3 abs (BASELINE.json north_star), fp32 path in practice ~1e-6."""
 import ctypes as C
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -391,3 +392,19 @@ def test_model_bf16_cta_pair_and_gather_variants(built_lib, tmp_path):
         assert same.mean() > 0.995
         d = np.abs(o - base)[same]
         assert np.isfinite(o).all() and d.mean() < 3e-4 and np.quantile(d, 0.999) < 2e-2, (name, float(d.mean()), float(d.max()))
+
+
+@pytest.mark.gpu
+def test_expert_parallel_matches_local(built_lib):
+    """configs[2] / SURVEY 8e: experts sharded over 2 GPUs with the P2P record exchange == all experts local,
+    bit for bit, on every rank's own ray shard (tests/ep_worker.py under torchrun)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("expert-parallel parity needs 2 GPUs (gpurun --gpus 2)")
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ep_worker.py")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29741", worker]
+    r = subprocess.run(cmd, timeout=900, capture_output=True, text=True)
+    tail = r.stdout[-6000:] + "\n" + r.stderr[-3000:]
+    assert r.returncode == 0 and "EP_PARITY_OK" in r.stdout, tail

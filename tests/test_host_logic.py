@@ -1,6 +1,7 @@
 """CPU: host-side mirror of the reference interface (state_dict layout, init parity, error behaviour)."""
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -59,3 +60,52 @@ def test_set_no_batch_toggles_moe_layers():
     assert m.layers["0"].moe_no_batch is False
     m.set_no_batch(True)
     assert m.layers["0"].moe_no_batch is True and m.route_opts().no_batch == 1
+
+
+# ---- expert-parallel exchange (csrc/snb_ep.cu): protocol algebra on the CPU ---------------------------------
+@pytest.mark.parametrize("world,E,cf,bpr", [(2, 8, 1.0, True), (2, 4, 0.5, True), (4, 8, 2.0, False), (8, 8, 1.0, True)])
+def test_expert_parallel_protocol_equals_local(world, E, cf, bpr):
+    """routing decided per source rank + row-wise experts => the exchanged result equals the
+    all-local one on every rank, every sample is evaluated exactly once by the owner of its expert, dropped
+    samples never leave their rank."""
+    from oracle import ep_protocol as P
+    from oracle import switch_nerf_oracle as O
+    g = torch.Generator().manual_seed(world * 100 + E)
+    routing, S_max = [], 0
+    for r in range(world):
+        S = 700 + 37 * r
+        gates = torch.softmax(torch.randn(S, E, generator=g) * 2.0, 1)
+        idx, loc, gate_val, cap, _ = O.route_top1(gates, cf, bpr)
+        payload = torch.randn(S, 3, generator=g).numpy()
+        routing.append((idx.numpy().astype(np.int64), loc.numpy().astype(np.int64), cap, payload))
+        S_max = max(S_max, S)
+    capmax = O.capacity_of(S_max, E, cf)
+    row_fn = lambda e, row: (e + 1) * row.sum()
+    drop_fn = lambda row: -1.0
+    ret = P.exchange(world, E, capmax, routing, row_fn, drop_fn)
+    for r, (idx, loc, cap, payload) in enumerate(routing):
+        assert sorted(ret[r]) == list(range(len(idx)))
+        for s in range(len(idx)):
+            want = row_fn(int(idx[s]), payload[s]) if loc[s] < cap else drop_fn(payload[s])
+            assert ret[r][s] == want
+
+
+def test_expert_parallel_owner_map():
+    from switch_nerf_b200.expert_parallel import local_experts, owner_of_expert
+    assert [owner_of_expert(e, 8, 2) for e in range(8)] == [0, 0, 0, 0, 1, 1, 1, 1]
+    assert list(local_experts(3, 8, 8)) == [3] and list(local_experts(1, 8, 2)) == [4, 5, 6, 7]
+    with pytest.raises(ValueError):
+        owner_of_expert(0, 8, 3)
+
+
+def test_a2a_init_fails_loudly_without_cuda(built_lib):
+    """No CPU fallback for the exchange either: without a CUDA device the group cannot be created."""
+    import ctypes as C
+    from switch_nerf_b200 import _lib as L
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    h = C.c_void_p()
+    rc = L.lib().snb_a2a_init(0, 2, 8, 4096, 1.0, C.byref(h))
+    assert rc != 0 and not h.value
+    assert L.lib().snb_a2a_init(0, 3, 8, 4096, 1.0, C.byref(h)) != 0      # 8 experts over 3 ranks
+    assert b"shard" in L.lib().snb_last_error()
