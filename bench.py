@@ -293,6 +293,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # routing statistics of this workload (one untimed pass): expert shares and the dropped fraction, per chunk
+    if ep_group is not None:
+        barrier()
+        ep_group.detach(model)      # rank 0 alone renders below: routing is per source rank, identical either way
     kept_frac, shares = 1.0, None
     if rank == 0:
         model.args.moe_return_gates = True
