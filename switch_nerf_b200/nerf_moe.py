@@ -161,6 +161,18 @@ class NeRFMoE(nn.Module):
         self._packed_versions = None
         self._packed_device = None
         self._ep_group = None      # ExpertParallelGroup once attached (expert_parallel.py)
+        # checkpoints in the seqexperts layout / with DDP's `module.` prefix load as they are (checkpoint.py)
+        self._register_load_state_dict_pre_hook(self._normalise_state_dict)
+
+    @staticmethod
+    def _normalise_state_dict(state_dict, prefix, *_):
+        if prefix:
+            return
+        from .checkpoint import to_expertmlp
+        if any(k.startswith("module.") or ".experts.0.experts." in k for k in state_dict):
+            fixed = to_expertmlp(state_dict)
+            state_dict.clear()
+            state_dict.update(fixed)
 
     # -- reference API -----------------------------------------------------------------
     @staticmethod

@@ -109,3 +109,36 @@ def test_a2a_init_fails_loudly_without_cuda(built_lib):
     assert rc != 0 and not h.value
     assert L.lib().snb_a2a_init(0, 3, 8, 4096, 1.0, C.byref(h)) != 0      # 8 experts over 3 ranks
     assert b"shard" in L.lib().snb_last_error()
+
+
+# ---- checkpoint interop (reference models/model_utils.py:12-28, 136-151) -------------------------------------
+def test_checkpoint_layouts_roundtrip_and_load():
+    from switch_nerf_b200.checkpoint import load_checkpoint, to_expertmlp, to_seqexperts
+    sd = S.synthetic_state_dict(num_experts=4, appearance_count=8, seed=2)
+    seq = to_seqexperts(sd)
+    assert "layers.0.experts.0.experts.3.layers.6.weight" in seq and not any(".weights." in k for k in seq)
+    assert seq["layers.0.experts.0.experts.1.layers.2.weight"].shape == (256, 256)
+    assert seq["layers.0.experts.0.experts.1.layers.2.bias"].shape == (256,)
+    back = to_expertmlp({"module." + k: v for k, v in seq.items()})      # DDP prefix + seqexperts layout
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    hp = make_hparams(num_experts=4)
+    a, b, c = (get_nerf_moe_inner(hp, 8, 3) for _ in range(3))
+    a.load_state_dict(sd)
+    b.load_state_dict({"module." + k: v for k, v in seq.items()})         # pre-hook normalises
+    load_checkpoint(c, {"model_state_dict": seq})
+    for k, v in a.state_dict().items():
+        assert torch.equal(v, b.state_dict()[k]) and torch.equal(v, c.state_dict()[k]), k
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not mounted")
+def test_seqexperts_layout_matches_reference_converter():
+    from oracle import ref_shims  # noqa: F401  (installs the tutel/timm import shims)
+    from switch_nerf.models.model_utils import convert_to_seqexperts
+    from switch_nerf_b200.checkpoint import to_seqexperts
+    sd = S.synthetic_state_dict(num_experts=4, appearance_count=8, seed=4)
+    ref = convert_to_seqexperts({k: v.clone() for k, v in sd.items()})
+    ours = to_seqexperts(sd)
+    ref = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in ref.items()}
+    assert set(ref) == set(ours)
+    for k in ref:
+        assert torch.equal(ref[k], ours[k]), k
