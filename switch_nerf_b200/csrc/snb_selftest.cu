@@ -2,7 +2,8 @@
 // kernels rely on -- canonical no-swizzle K-major core-matrix operands in shared memory, UMMA
 // shared-memory + instruction descriptors, single-thread tcgen05.mma issue, tcgen05.commit ->
 // mbarrier, TMEM allocation and tcgen05.ld epilogue, and (variant bit 1) a 1-D bulk async copy
-// of a pre-packed B image.  tests/test_umma_selftest.py checks it against a float reference,
+// of a pre-packed B image, and (variant bit 2) the A operand taken from tensor memory (tcgen05.st by the
+// row-owning threads, TS-form tcgen05.mma).  tests/test_gpu_parity.py checks it against a float reference,
 // which pins the descriptor encodings on real hardware before the large kernels depend on them.
 #include "snb_common.cuh"
 #include "snb_umma.cuh"
@@ -41,7 +42,11 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const __nv_bfloat16* __re
     mbar_init(&bar_copy, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+  const bool a_tmem = (variant & 4) != 0;      // TS form: accumulator columns [0,256), A columns [256, 256+K/2)
+  if (warp == 0) {
+    if (a_tmem) tmem_alloc<512>(&tmem_base_s);
+    else tmem_alloc<256>(&tmem_base_s);
+  }
   // A: generic-proxy stores into the canonical layout (what the epilogue warps do in the fused kernels)
   for (int i = threadIdx.x; i < 128 * (K / 8); i += blockDim.x) {
     int r = i / (K / 8), kc = i % (K / 8);
@@ -61,6 +66,20 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const __nv_bfloat16* __re
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (a_tmem) {
+    // thread (warp, lane) owns row 32*warp + lane = TMEM lane; two bf16 per 32-bit column, K ascending
+    const int r = warp * 32 + lane;
+    for (int k = 0; k < K / 16; ++k) {
+      const uint4 lo = *reinterpret_cast<const uint4*>(A + (size_t)r * K + k * 16);
+      const uint4 hi = *reinterpret_cast<const uint4*>(A + (size_t)r * K + k * 16 + 8);
+      uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      tmem_st8(tmem_base + ((uint32_t)(warp * 32) << 16) + 256u + (uint32_t)k * 8u, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
 
   if (warp == 1 && lane == 0) {
     if (use_bulk) {
@@ -77,7 +96,8 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const __nv_bfloat16* __re
       uint32_t b_addr = smem_u32(sB) + (uint32_t)k * 2 * lbo;
       uint64_t da = swap ? umma_smem_desc(a_addr, sboA, lbo) : umma_smem_desc(a_addr, lbo, sboA);
       uint64_t db = swap ? umma_smem_desc(b_addr, sboB, lbo) : umma_smem_desc(b_addr, lbo, sboB);
-      umma_bf16(tmem_base, da, db, idesc, k > 0 ? 1u : 0u);
+      if (a_tmem) umma_bf16_ts(tmem_base, tmem_base + 256u + (uint32_t)k * 8u, db, idesc, k > 0 ? 1u : 0u);
+      else umma_bf16(tmem_base, da, db, idesc, k > 0 ? 1u : 0u);
     }
     umma_commit(&bar_mma);
   }
@@ -95,7 +115,10 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const __nv_bfloat16* __re
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem_base);
+  if (warp == 0) {
+    if (a_tmem) tmem_dealloc<512>(tmem_base);
+    else tmem_dealloc<256>(tmem_base);
+  }
 }
 
 int umma_selftest(const void* a, const void* b, int N, int K, float* d, int variant, cudaStream_t st) {

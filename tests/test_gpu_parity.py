@@ -42,9 +42,10 @@ def _route(gates, cf, bpr):
 
 # ----------------------------------------------------------------------------- tcgen05 building block
 @pytest.mark.parametrize("N,K", [(256, 256), (128, 336), (256, 80), (64, 64), (16, 16)])
-@pytest.mark.parametrize("variant", [0, 2])
+@pytest.mark.parametrize("variant", [0, 2, 4, 6])
 def test_umma_selftest(built_lib, N, K, variant):
-    """128xNxK bf16 tile through UMMA descriptors + TMEM (+ bulk copy when variant&2)."""
+    """128xNxK bf16 tile through UMMA descriptors + TMEM (+ bulk copy when variant&2; A operand staged in tensor
+    memory by tcgen05.st and consumed by the TS-form MMA when variant&4)."""
     from switch_nerf_b200 import _lib as L
     g = torch.Generator().manual_seed(N * 1000 + K)
     a = torch.randn(128, K, generator=g).bfloat16().cuda()
