@@ -14,10 +14,11 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
+# every rank must make the same number of model-chunk calls (rays x samples / chunk, rounded up, per pass)
 CASES = [
     # name, rays on rank r, coarse, fine, chunk, experts, capacity factor, bpr, balanced gate
     dict(name="small_e4", rays=lambda r: 300 - 10 * r, coarse=32, fine=32, chunk=4096, E=4, cf=1.0, bpr=True, balance=True),
-    dict(name="drops_e8_cf05", rays=lambda r: 256 + 3 * r, coarse=64, fine=0, chunk=4096, E=8, cf=0.5, bpr=True, balance=False),
+    dict(name="drops_e8_cf05", rays=lambda r: 256 - 3 * r, coarse=64, fine=0, chunk=4096, E=8, cf=0.5, bpr=True, balance=False),
     dict(name="nobpr_e2", rays=lambda r: 200, coarse=48, fine=16, chunk=2048, E=2, cf=2.0, bpr=False, balance=True),
     dict(name="full_chunk_e8", rays=lambda r: 1024, coarse=257, fine=257, chunk=131072, E=8, cf=1.0, bpr=True, balance=True),
 ]
