@@ -164,12 +164,17 @@ __device__ __forceinline__ void ts_mma_layer(const TsShape s, uint32_t acat_base
     const bool last = ss ? (s.nts == 0 && k == s.nss - 1) : (k == s.nts - 1);
     if (last) umma_commit(&ctl->acc_full[q]);
   };
-  const int n = s.nq > s.nts ? s.nq : s.nts;
-  for (int c = 0; c < n; ++c) {
+  const int n = s.nq > s.nts ? s.nq : s.nts;      // <= 4
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c >= n) break;
     if (c < s.nts) { mbar_wait(&ctl->a_ready[c], pp.a_use[c] & 1); ++pp.a_use[c]; }
     if (c < s.nq) { mbar_wait(&ctl->acc_free[c], (pp.accw[c] & 1) ^ 1); ++pp.accw[c]; }
-    if (c == 0)
-      for (int i = 0; i < s.nss; ++i) { mbar_wait(&ctl->s_ready[i], pp.s_use[i] & 1); ++pp.s_use[i]; }
+    if (c == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (i < s.nss) { mbar_wait(&ctl->s_ready[i], pp.s_use[i] & 1); ++pp.s_use[i]; }
+    }
     tc_fence_after();
     if (c < s.nts) for (int q = 0; q < ts_imin(c, s.nq); ++q) block(q, 0, c);
     if (c < s.nq) {
@@ -204,6 +209,7 @@ __device__ __forceinline__ void ts_signal_smem(TsCtl* ctl, int i, int lane) {
 template <bool RELU>
 __device__ __forceinline__ void ts_epi_hidden(uint32_t tmem_base, const float* sb, const EpiCtx& ec, TsCtl* ctl, TsPipe& pp) {
   const uint32_t a_w = tmem_base + ec.lane_base + TS_ACOL + (pp.abuf & 1u) * 128u;
+#pragma unroll
   for (int c = 0; c < 4; ++c) {
     ts_wait_acc(ctl, pp, c);
     const int col0 = c * 64 + ec.cs * 16;
@@ -383,6 +389,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           } else {
             // last expert layer (no activation) -> combine: y = bf16(gate * bf16(out)) -> ReLU -> A; sigma head on the fly
             const uint32_t a_w = tmem_base + ec.lane_base + TS_ACOL + (pp.abuf & 1u) * 128u;
+#pragma unroll
             for (int c = 0; c < 4; ++c) {
               ts_wait_acc(ctl, pp, c);
               const int col0 = c * 64 + ec.cs * 16;
@@ -434,7 +441,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         epi_load_bias(P.fblob + P.back[1].b_off, H2, sbias, buf, ec.et);
         const float* sb = sbias + buf * 256;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-        for (int c = 0; c < H2 / 64; ++c) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c >= H2 / 64) break;
           ts_wait_acc(ctl, pp, c);
           const int col0 = c * 64 + ec.cs * 16;
           uint32_t v[16];

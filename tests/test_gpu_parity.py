@@ -365,12 +365,8 @@ def test_model_bf16_no_batch_mode(built_lib):
     assert d.mean() < 2e-3 and np.isfinite(d).all()
 
 
-def test_model_bf16_cta_pair_and_gather_variants(built_lib, tmp_path):
-    """The fused kernels have two build-time variants selected by environment switches read once per process:
-    SNB_CG=2 (tcgen05 cta_group::2 CTA pairs, M=256 MMAs issued by the leader CTA of a 2-CTA cluster) and
-    SNB_GATHER_H=1 (launch #2 gathers h from HBM instead of recomputing it).  Each must agree with the default
-    variant on the same inputs (same rounding points; the h-recompute variant sums the skip term in fp32)."""
-    import subprocess, sys, os
+def _check_bf16_variants(tmp_path, variants):
+    import subprocess, sys
     g = load_golden("model_e8_cf1_bpr_bf16cpu.npz")
     sd = golden_sd(g)
     model, _ = make_model(sd, 1.0, True, False, "bf16")
@@ -384,15 +380,31 @@ def test_model_bf16_cta_pair_and_gather_variants(built_lib, tmp_path):
         "np.save(sys.argv[1], r['outputs'].cpu().numpy()); np.save(sys.argv[1] + '.idx.npy', r['extras']['moe_gates'][0].cpu().numpy())"
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     idx0 = model(x)["extras"]["moe_gates"][0].cpu().numpy()
-    for name, env in (("pair", {"SNB_CG": "2"}), ("gather", {"SNB_GATHER_H": "1"}), ("pair_gather", {"SNB_CG": "2", "SNB_GATHER_H": "1"})):
+    for name, env in variants:
         out_path = str(tmp_path / f"{name}.npy")
         r = subprocess.run([sys.executable, "-c", script, out_path], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
-        assert r.returncode == 0, r.stderr[-2000:]
+        assert r.returncode == 0, (name, r.stdout[-1500:], r.stderr[-2000:])
         o = np.load(out_path)
         same = (np.load(out_path + ".idx.npy") == idx0).reshape(-1)
         assert same.mean() > 0.995
         d = np.abs(o - base)[same]
         assert np.isfinite(o).all() and d.mean() < 3e-4 and np.quantile(d, 0.999) < 2e-2, (name, float(d.mean()), float(d.max()))
+
+
+def test_model_bf16_cta_pair_and_gather_variants(built_lib, tmp_path):
+    """The fused kernels have variants selected by environment switches read once per process:
+    SNB_CG=2 (tcgen05 cta_group::2 CTA pairs, M=256 MMAs issued by the leader CTA of a 2-CTA cluster) and
+    SNB_GATHER_H=1 (launch #2 gathers h from HBM instead of recomputing it).  Each must agree with the default
+    variant on the same inputs (same rounding points; the h-recompute variant sums the skip term in fp32)."""
+    _check_bf16_variants(tmp_path, (("pair", {"SNB_CG": "2"}), ("gather", {"SNB_GATHER_H": "1"}),
+                                    ("pair_gather", {"SNB_CG": "2", "SNB_GATHER_H": "1"})))
+
+
+def test_model_bf16_tmem_operand_variant(built_lib, tmp_path):
+    """SNB_TS=1: launch #2 keeps the hidden activations in tensor memory (tcgen05.st by the epilogue, A operand of
+    tcgen05.mma taken from TMEM, 64x64 block schedule -- csrc/snb_tc_ts.cuh).  Same rounding points as the default
+    kernel; only the fp32 accumulation order inside a layer differs."""
+    _check_bf16_variants(tmp_path, (("ts", {"SNB_TS": "1"}),))
 
 
 @pytest.mark.gpu
