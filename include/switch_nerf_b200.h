@@ -269,6 +269,12 @@ int snb_sample_pdf(const float* bins, const float* weights, const float* u, int6
 int snb_umma_selftest(const void* a_bf16, const void* b_bf16, int32_t N, int32_t K, float* d,
                       int32_t variant, void* stream);
 
+/* Measurement aid: clocks for `reps` back-to-back tcgen05.mma (M=128, K=16, bf16, given N) with the A operand in
+ * shared memory (a_in_tmem=0) or tensor memory (1); flags&1 adds a stream of 8 KB bulk copies landing in shared
+ * memory, flags&2 adds four warps of tcgen05.ld readers.  out6 = {clocks, copies, ld iterations x4}.  Synchronises
+ * the stream. */
+int snb_umma_microbench(int32_t N, int32_t a_in_tmem, int32_t flags, int32_t reps, uint64_t* out6, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,7 @@ int merge_composite_launch(const float* zf, const float* zc, const float* raw_f,
                            const float* last_delta, int64_t N, int Sf, int Sc, int presorted, int white_bkgd,
                            float* rgb, float* depth, float* var, float* lam, cudaStream_t st);
 int umma_selftest(const void* a, const void* b, int N, int K, float* d, int variant, cudaStream_t st);
+int umma_microbench(int N, int ts, int flags, int reps, unsigned long long* host_out6, cudaStream_t st);
 int mip_fill_x_launch(const float* rays, const float* radii, const int* image_indices, const float* ze, int64_t N,
                       int Se, float* x, cudaStream_t st);
 int mip_composite_launch(const float* ze, const float* raw, const float* last_delta, int64_t N, int Se,
@@ -531,6 +532,11 @@ int snb_umma_selftest(const void* a_bf16, const void* b_bf16, int32_t N, int32_t
                       void* stream) {
   SNB_REQUIRE(a_bf16 && b_bf16 && d, "snb_umma_selftest: NULL pointer");
   return umma_selftest(a_bf16, b_bf16, N, K, d, variant, (cudaStream_t)stream);
+}
+
+int snb_umma_microbench(int32_t N, int32_t a_in_tmem, int32_t flags, int32_t reps, uint64_t* out6, void* stream) {
+  SNB_REQUIRE(out6, "snb_umma_microbench: NULL out");
+  return umma_microbench(N, a_in_tmem, flags, reps, (unsigned long long*)out6, (cudaStream_t)stream);
 }
 
 }  // extern "C"

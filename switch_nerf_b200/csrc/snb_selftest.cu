@@ -140,3 +140,100 @@ int umma_selftest(const void* a, const void* b, int N, int K, float* d, int vari
 }
 
 }  // namespace snb
+
+// ------------------------------------------------------------------------------------------------------------
+// snb_umma_microbench: issue rate of tcgen05.mma (M = 128, K = 16, bf16) for a given N with the A operand in
+// shared memory (SS) or tensor memory (TS), optionally under the two kinds of traffic the fused kernels add:
+// a stream of 8 KB bulk copies landing in shared memory (flags & 1) and epilogue-style tcgen05.ld readers
+// (flags & 2).  Operand contents are irrelevant (uninitialised shared memory); only clocks are reported.
+// ------------------------------------------------------------------------------------------------------------
+namespace snb {
+using namespace ptx;
+
+__global__ void __launch_bounds__(192) k_umma_bench(int N, int ts, int flags, int reps, const uint8_t* __restrict__ src,
+                                                    unsigned long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_mma, bar_full[4];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int done;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sA = smem;                       // 128 x 64 bf16 canonical (16 KB)
+  uint8_t* sB = smem + 16384;               // 256 x 64 bf16 canonical (32 KB)
+  uint8_t* sL = smem + 49152;               // landing zone 4 x 8 KB
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_mma, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_full[i], 1);
+    fence_mbar_init();
+    done = 0;
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, N);
+      const unsigned long long t0 = clock64();
+      for (int i = 0; i < reps; ++i) {
+        const uint32_t t = (uint32_t)(i & 3);
+        const uint64_t db = umma_smem_desc(smem_u32(sB) + 2u * t * 128u, 128u, 64u * 16u);
+        const uint32_t d = tmem_base + (uint32_t)((i >> 2) % (256 / N)) * (uint32_t)N;
+        if (ts) umma_bf16_ts(d, tmem_base + 256u + t * 8u, db, idesc, 1u);
+        else umma_bf16(d, umma_smem_desc(smem_u32(sA) + 2u * t * 128u, 128u, 64u * 16u), db, idesc, 1u);
+      }
+      umma_commit(&bar_mma);
+      mbar_wait(&bar_mma, 0);
+      const unsigned long long t1 = clock64();
+      out[0] = t1 - t0;
+      done = 1;
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && (flags & 1)) {
+      uint32_t n = 0;
+      while (!done) {
+        const uint32_t s = n & 3, ph = (n >> 2) & 1;
+        mbar_arrive_expect_tx(&bar_full[s], 8192);
+        bulk_g2s(sL + s * 8192, src + (size_t)(n & 1023) * 8192, 8192, &bar_full[s]);
+        mbar_wait(&bar_full[s], ph);
+        ++n;
+      }
+      out[1] = n;
+    }
+  } else if (flags & 2) {
+    unsigned long long n = 0;
+    uint32_t acc = 0;
+    while (!done) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)((warp - 2) * 32) << 16) + (uint32_t)((n & 7) * 32), v);
+      tmem_ld_wait();
+      acc ^= v[0];
+      ++n;
+    }
+    if (lane == 0) out[2 + (warp - 2)] = n + (acc == 0x12345u);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+int umma_microbench(int N, int ts, int flags, int reps, unsigned long long* host_out6, cudaStream_t st) {
+  SNB_REQUIRE(N == 64 || N == 128 || N == 256, "microbench: N must be 64, 128 or 256");
+  SNB_REQUIRE(reps > 0 && reps <= (1 << 20), "microbench: bad reps");
+  const size_t smem = 49152 + 4 * 8192 + 1024;
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(k_umma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  uint8_t* src = nullptr;
+  unsigned long long* out = nullptr;
+  SNB_CHECK_CUDA(cudaMalloc((void**)&src, (size_t)1024 * 8192));
+  SNB_CHECK_CUDA(cudaMalloc((void**)&out, 6 * sizeof(unsigned long long)));
+  SNB_CHECK_CUDA(cudaMemsetAsync(out, 0, 6 * sizeof(unsigned long long), st));
+  k_umma_bench<<<1, 192, smem, st>>>(N, ts, flags, reps, src, out);
+  SNB_CHECK_LAUNCH("k_umma_bench");
+  SNB_CHECK_CUDA(cudaMemcpyAsync(host_out6, out, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  SNB_CHECK_CUDA(cudaStreamSynchronize(st));
+  cudaFree(src);
+  cudaFree(out);
+  return SNB_OK;
+}
+
+}  // namespace snb
