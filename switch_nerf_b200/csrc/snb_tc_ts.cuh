@@ -143,7 +143,8 @@ __device__ __forceinline__ void ts_produce(const uint8_t* src, const TsShape s, 
 
 // ---- MMA issuer: one layer ----
 __device__ __forceinline__ void ts_mma_layer(const TsShape s, uint32_t acat_base, uint32_t ring_base, uint32_t tmem_base,
-                                             TsCtl* ctl, TsPipe& pp) {
+                                             TsCtl* ctl, TsPipe& pp, unsigned long long* tl = nullptr, int* tn = nullptr,
+                                             int lid = 0) {
   const uint32_t idesc = umma_idesc_bf16(TILE, 64);
   const uint32_t a_tmem = tmem_base + TS_ACOL + (pp.abuf & 1u) * 128u;
   auto block = [&](int q, int ss, int k) {
@@ -176,6 +177,7 @@ __device__ __forceinline__ void ts_mma_layer(const TsShape s, uint32_t acat_base
         if (i < s.nss) { mbar_wait(&ctl->s_ready[i], pp.s_use[i] & 1); ++pp.s_use[i]; }
     }
     tc_fence_after();
+    if (tn) tl_mark(tl, 1, *tn, 100 * lid + 10 + c);
     if (c < s.nts) for (int q = 0; q < ts_imin(c, s.nq); ++q) block(q, 0, c);
     if (c < s.nq) {
       for (int i = 0; i < s.nss; ++i) block(c, 1, i);
@@ -183,6 +185,7 @@ __device__ __forceinline__ void ts_mma_layer(const TsShape s, uint32_t acat_base
     }
   }
   if (s.nts) ++pp.abuf;
+  if (tn) tl_mark(tl, 1, *tn, 100 * lid + 20);
 }
 
 // ---- epilogue helpers ----
@@ -207,11 +210,13 @@ __device__ __forceinline__ void ts_signal_smem(TsCtl* ctl, int i, int lane) {
 }
 // hidden layer: y = act(acc + bias) -> bf16 -> TMEM A buffer (pp.abuf & 1); thread owns columns [64c + 16cs, +16)
 template <bool RELU>
-__device__ __forceinline__ void ts_epi_hidden(uint32_t tmem_base, const float* sb, const EpiCtx& ec, TsCtl* ctl, TsPipe& pp) {
+__device__ __forceinline__ void ts_epi_hidden(uint32_t tmem_base, const float* sb, const EpiCtx& ec, TsCtl* ctl, TsPipe& pp,
+                                              unsigned long long* tl = nullptr, int* tn = nullptr, int lid = 0) {
   const uint32_t a_w = tmem_base + ec.lane_base + TS_ACOL + (pp.abuf & 1u) * 128u;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     ts_wait_acc(ctl, pp, c);
+    if (tn) tl_mark(tl, 0, *tn, 100 * lid + 1 + c);
     const int col0 = c * 64 + ec.cs * 16;
     uint32_t v[16];
     tmem_ld16(tmem_base + ec.lane_base + (uint32_t)col0, v);
@@ -227,6 +232,7 @@ __device__ __forceinline__ void ts_epi_hidden(uint32_t tmem_base, const float* s
     tmem_st8(a_w + (uint32_t)(c * 32 + ec.cs * 8), pk);
     tmem_st_wait();
     ts_signal(ctl, c, ec.lane, true, true);
+    if (tn) tl_mark(tl, 0, *tn, 100 * lid + 5 + c);
   }
   ++pp.abuf;
 }
@@ -288,17 +294,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         ts_produce(P.tsblob + P.ts_back_off[1], SH_L2, smem + TSM_RING, ctl, pp);
       }
   } else if (warp == 1) {
-    if (lane == 0)
+    if (lane == 0) {
+      int tn = 0;
       for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
         const int e = tt.tile_expert[t];
+        tl_mark(P.tl, 1, tn, 1);
         if (e >= 0) {
-          ts_mma_layer(SH_XYZ, acat_base, ring_base, tmem_base, ctl, pp);
+          ts_mma_layer(SH_XYZ, acat_base, ring_base, tmem_base, ctl, pp, P.tl, &tn, 1);
           for (int l = 0; l < NE; ++l)
-            ts_mma_layer(l == P.skip_layer ? SH_SKIP : SH_EXP, acat_base, ring_base, tmem_base, ctl, pp);
+            ts_mma_layer(l == P.skip_layer ? SH_SKIP : SH_EXP, acat_base, ring_base, tmem_base, ctl, pp, P.tl, &tn, 2 + l);
         }
-        ts_mma_layer(SH_L1, acat_base, ring_base, tmem_base, ctl, pp);
-        ts_mma_layer(SH_L2, acat_base, ring_base, tmem_base, ctl, pp);
+        ts_mma_layer(SH_L1, acat_base, ring_base, tmem_base, ctl, pp, P.tl, &tn, 20);
+        ts_mma_layer(SH_L2, acat_base, ring_base, tmem_base, ctl, pp, P.tl, &tn, 21);
       }
+    }
   } else {
     EpiCtx ec;
     ec.remote_a_ready = 0; ec.lane = lane; ec.q = warp & 3; ec.cs = (warp - 2) >> 2; ec.row = ec.q * 32 + lane;
@@ -327,9 +336,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       return r;
     };
     RowIn nxt = fetch_row((int)blockIdx.x);
+    int tn = 0;
+    unsigned long long* tl = (warp == 2 && lane == 0) ? P.tl : nullptr;
     for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
       const RowIn cur = nxt;
       const int e = cur.e, sidx = cur.sidx;
+      tl_mark(tl, 0, tn, 1);
       const bool valid = sidx >= 0;
       const float g = cur.g;
       // [PE(dir) | appearance | 0-pad] -> cat block (cs == 1 threads)
@@ -372,7 +384,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         {
           const int buf = (int)(li & 1);
           epi_load_bias(P.fblob + P.front[0].b_off, MW, sbias, buf, ec.et);
-          ts_epi_hidden<false>(tmem_base, sbias + buf * 256, ec, ctl, pp);
+          tl_mark(tl, 0, tn, 2);
+          ts_epi_hidden<false>(tmem_base, sbias + buf * 256, ec, ctl, pp, tl, &tn, 1);
           if (P.skip_layer == 0) for (int i = 0; i < SH_XYZ.nss; ++i) ts_signal_smem(ctl, i, lane);
           ++li;
         }
@@ -383,7 +396,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
                                   : (P.fblob + P.expert[l].b_off + (size_t)e * P.expert_b_stride), MW, sbias, buf, ec.et);
           const float* sb = sbias + buf * 256;
           if (l < NE - 1) {
-            ts_epi_hidden<true>(tmem_base, sb, ec, ctl, pp);
+            ts_epi_hidden<true>(tmem_base, sb, ec, ctl, pp, tl, &tn, 2 + l);
             if (skip_here) write_cat();          // every MMA of the skip layer has retired: the PE(xyz) block is free
             if (l + 1 == P.skip_layer) for (int i = 0; i < SH_XYZ.nss; ++i) ts_signal_smem(ctl, i, lane);
           } else {
@@ -431,7 +444,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       {
         const int buf = (int)(li & 1);
         epi_load_bias(P.fblob + P.back[0].b_off, MW, sbias, buf, ec.et);
-        ts_epi_hidden<false>(tmem_base, sbias + buf * 256, ec, ctl, pp);
+        ts_epi_hidden<false>(tmem_base, sbias + buf * 256, ec, ctl, pp, tl, &tn, 20);
         for (int i = 0; i < SH_L2.nss; ++i) ts_signal_smem(ctl, i, lane);
         ++li;
       }
@@ -480,6 +493,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           }
         }
         epi_bar_sync();
+        tl_mark(tl, 0, tn, 2200);
         ++li;
       }
     }
