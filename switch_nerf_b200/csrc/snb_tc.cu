@@ -98,9 +98,6 @@ struct TcParams {
   int E, skip_layer, pos_xyz_freqs, pos_dir_freqs, appearance_dim, appearance_count, hidden2, x_cols;
   const float* emb_a;       // fp32 [count, A]
   unsigned long long* tl;   // debug timeline (nullable): [role][TL_N] (tag<<48 | clock) marks of CTA 0
-  // TS variant of launch #2 (snb_tc_ts.cuh): weights as (quarter, K-chunk) block streams
-  const uint8_t* tsblob;
-  uint32_t ts_xyz_off, ts_expert_off[16], ts_expert_stride, ts_back_off[2];
 };
 
 // canonical image: slices of 64 k; inside a slice (n/8)*(klen*16) + (kk/8)*128 + (n%8)*16 + (kk%8)*2 bytes
@@ -178,19 +175,16 @@ bool tc_supported(const Model* m) {
          d.appearance_dim % 4 == 0 && d.pos_xyz_freqs == 12 && d.pos_dir_freqs == 4;
 }
 
-struct TcOwner { TcHost h; uint8_t* wblob; uint8_t* tsblob; };
+struct TcOwner { TcHost h; uint8_t* wblob; };
 
 void tc_release(Model* m) {
   TcOwner* own = (TcOwner*)m->tc_blob;
   if (!own) return;
   if (own->wblob) cudaFree(own->wblob);
-  if (own->tsblob) cudaFree(own->tsblob);
   if (own->h.fblob) cudaFree(own->h.fblob);
   delete own;
   m->tc_blob = nullptr;
 }
-
-static int ts_pack_all(Model* m, TcOwner* own, cudaStream_t st);   // block streams of the TS kernel (defined below)
 
 int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
   const snb_model_desc& d = m->d;
@@ -280,7 +274,7 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
     SNB_CHECK_LAUNCH("k_sum_bias");
   }
   (void)w;
-  return ts_pack_all(m, own, st);
+  return SNB_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1130,46 +1124,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, R
 
 #include "snb_tc_ts.cuh"
 
-static int ts_pack_all(Model* m, TcOwner* own, cudaStream_t st) {
-  const snb_model_desc& d = m->d;
-  TcParams& p = own->h.p;
-  if (d.skip_layer < 0) { p.tsblob = nullptr; return SNB_OK; }      // the TS kernel is the recompute-h flow
-  const int E = d.num_experts, L = d.expert_layers, H2 = d.hidden2;
-  const int kss_xyz = (int)p.front[0].K16, kss_cat = (int)p.back[1].K16 - MW;
-  if (kss_xyz > (int)TS_CAT_COLS || kss_cat > (int)TS_CAT_COLS || kss_cat <= 0) { p.tsblob = nullptr; return SNB_OK; }
-  const TsShape SH_XYZ = {4, 0, (kss_xyz + 63) / 64, kss_xyz}, SH_EXP = {4, 4, 0, 0},
-                SH_SKIP = {4, 4, (kss_xyz + 63) / 64, kss_xyz}, SH_L1 = {4, 4, 0, 0},
-                SH_L2 = {H2 / 64, 4, (kss_cat + 63) / 64, kss_cat};
-  if (!own->tsblob) {
-    size_t off = 0;
-    auto add = [&](size_t n) { size_t o = off; off += align_up(n, 128); return (uint32_t)o; };
-    p.ts_xyz_off = add(ts_stream_bytes(SH_XYZ));
-    p.ts_back_off[0] = add(ts_stream_bytes(SH_L1));
-    p.ts_back_off[1] = add(ts_stream_bytes(SH_L2));
-    const size_t e0 = off;
-    for (int l = 0; l < L; ++l) p.ts_expert_off[l] = add(ts_stream_bytes(l == d.skip_layer ? SH_SKIP : SH_EXP));
-    p.ts_expert_stride = (uint32_t)(off - e0);
-    off = e0 + (size_t)p.ts_expert_stride * E;
-    SNB_CHECK_CUDA(cudaMalloc((void**)&own->tsblob, off));
-    p.tsblob = own->tsblob;
-  }
-  int rc;
-  if ((rc = ts_pack_stream(SH_XYZ, nullptr, 0, m->xyz_w, m->xyz_in, m->xyz_in, own->tsblob + p.ts_xyz_off, st))) return rc;
-  if ((rc = ts_pack_stream(SH_L1, m->l1_w, MW, nullptr, 0, 0, own->tsblob + p.ts_back_off[0], st))) return rc;
-  if ((rc = ts_pack_stream(SH_L2, m->l2_w, m->cat_in, m->l2_w + MW, m->cat_in, m->cat_in - MW,
-                           own->tsblob + p.ts_back_off[1], st)))
-    return rc;
-  for (int e = 0; e < E; ++e)
-    for (int l = 0; l < L; ++l) {
-      const bool sk = (l == d.skip_layer);
-      if ((rc = ts_pack_stream(sk ? SH_SKIP : SH_EXP, m->exp_w[l] + (size_t)e * MW * MW, MW, sk ? m->xyz_w : nullptr,
-                               sk ? m->xyz_in : 0, sk ? m->xyz_in : 0,
-                               own->tsblob + p.ts_expert_off[l] + (size_t)e * p.ts_expert_stride, st)))
-        return rc;
-    }
-  return SNB_OK;
-}
-
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -1362,7 +1316,8 @@ static int tc_back(Model* m, TcChunk& c, cudaStream_t st) {
   if (c.pe) cudaEventRecord(c.pe->e[4], st);
   // SNB_TS=1: hidden activations in tensor memory (snb_tc_ts.cuh) -- A/B switch while the variant is being tuned
   static const bool use_ts = getenv("SNB_TS") != nullptr && atoi(getenv("SNB_TS")) != 0;
-  if (use_ts && c.cg == 1 && c.Pb.recompute_h && c.Pb.tsblob) {
+  if (use_ts && c.cg == 1 && c.Pb.recompute_h && c.Pb.back[1].K16 > MW && c.Pb.back[1].K16 - MW <= TS_CAT_COLS &&
+      c.Pb.front[0].K16 <= TS_CAT_COLS) {
     k_back_ts<4><<<grid2, THREADS, TSM_TOTAL, st>>>(c.Pb, c.tt, io);
   } else if (c.cg == 2) {
     grid2 &= ~1;

@@ -1,108 +1,40 @@
 // Launch #2, "TS" variant: hidden activations live in TENSOR MEMORY instead of shared memory.
-// (included by snb_tc.cu after k_back; shares its constants, TcParams and epilogue helpers)
+// (included by snb_tc.cu after k_back; shares its constants, TcParams, packed weight images and epilogue helpers)
 //
-// Why.  k_back is shared-memory-bandwidth bound: per 128x256x16 MMA (128 clk at the tensor-pipe floor) the SM
-// moves A 4 KB + B 8 KB operand reads, 8 KB of weight landing and 4 KB of epilogue stores = 192 B/clk against
-// 128 B/clk of shared-memory bandwidth, so the MMAs run at ~250 clk.  Here the epilogue writes the next layer's
-// A operand with tcgen05.st into TMEM and the MMA takes it from there (tcgen05.mma with the A operand in tensor
-// memory): shared memory only carries the weights (and the 80 PE / [dir|appearance] columns).
+// Why (profiles/r1i_*): in k_back a layer costs ~5.7K clk against 2K clk of MMA work, and the time goes to the
+// epilogue, not the tensor pipe: writing the next A operand to shared memory (st.shared + fence.proxy.async per
+// 64-column chunk) paces the chunks at ~950 clk each, and the MMAs read that A back from shared memory at 171 clk
+// per 128x256x16 instruction (floor 128).  Here the epilogue packs its bf16 result with tcgen05.st straight into
+// tensor memory (~340 clk per chunk, no proxy fence) and the MMA takes the A operand from there (138 clk).
 //
-// TMEM map (512 columns): accumulator [0,256) as four 64-column quarters, A ping [256,384), A pong [384,512)
-// (128 columns = 256 bf16 of K, two per 32-bit column).  There is no second accumulator buffer to hide the
-// epilogue behind, so a layer is scheduled in 64x64 blocks instead: the epilogue of layer l drains quarter c
-// and writes K-chunk c of the next A; the moment that lands, layer l+1 may issue every block that needs only
-// quarters <= c and chunks <= c.  The weights are packed as a stream of (quarter, K-chunk) blocks in exactly
-// that order, one 8 KB ring slot per block, consumed once, in order:
-//     for c = 0 .. max(nq, nts)-1:
-//         if c < nts: for q < min(c, nq):  (q, TMEM chunk c)          -- old quarters take the new chunk
-//         if c < nq:  for s < nss:         (c, smem chunk s)           -- the new quarter: PE / cat chunks ...
-//                     for k <= min(c, nts-1): (c, TMEM chunk k)        -- ... and every TMEM chunk so far
-// nq = N/64 quarters, nts = K-chunks taken from TMEM (0 or 4), nss = K-chunks taken from shared memory.
+// TMEM map: two 256-column buffers B0 / B1 as in k_back; layer li accumulates into B[li & 1].  Its epilogue drains
+// the fp32 accumulator chunk by chunk and writes the packed bf16 result IN PLACE into columns [0,128) of the same
+// buffer (chunk c: fp32 columns [64c, 64c+64) -> bf16 pairs in columns [32c, 32c+32)); layer li+1 reads that as
+// its A operand while accumulating into the other buffer.  The packed chunk c only ever overwrites fp32 columns of
+// chunks 0/1, so one 128-thread barrier per layer (after the four warps of a lane quarter have loaded chunks 0 and
+// 1) makes the in-place update safe.  A 64x64-block schedule with N=64 instructions was tried first and is 1.7x
+// slower: a tcgen05.mma costs ~123 clk for any N <= 128 (profiles/r1i_umma_microbench.json).
+//
+// The PE(xyz) / [PE(dir) | appearance] columns stay in shared memory (24 KB); the weight ring has 5 x 32 KB stages.
 #pragma once
 
 static constexpr uint32_t TS_CAT_COLS = 96;                       // PE(xyz) / [PE(dir) | appearance] block
 static constexpr uint32_t TS_SBO = TS_CAT_COLS / 8 * 128;         // 1536 B between 8-row groups
 static constexpr uint32_t TS_ACAT_BYTES = TILE / 8 * TS_SBO;      // 24576
-static constexpr int TS_NSLOT = 20;
-static constexpr uint32_t TS_SLOT = 64 * 64 * 2;                  // one (quarter, 64-wide K chunk) weight block
-static constexpr uint32_t TS_ACOL = 256;                          // first TMEM column of the A ping buffer
+static constexpr int TS_NST = 5;
 
-struct TsShape { int nq, nts, nss, kss; };     // kss = shared-memory K columns (multiple of 16)
-__host__ __device__ inline int ts_ss_klen(const TsShape& s, int i) { const int r = s.kss - 64 * i; return r < 64 ? r : 64; }
-__host__ __device__ inline int ts_imin(int a, int b) { return a < b ? a : b; }
-// f(q, is_smem_chunk, k)
-template <typename F>
-__host__ __device__ inline void ts_for_each_block(const TsShape& s, F&& f) {
-  const int n = s.nq > s.nts ? s.nq : s.nts;
-  for (int c = 0; c < n; ++c) {
-    if (c < s.nts) for (int q = 0; q < ts_imin(c, s.nq); ++q) f(q, 0, c);
-    if (c < s.nq) {
-      for (int i = 0; i < s.nss; ++i) f(c, 1, i);
-      for (int k = 0; k <= ts_imin(c, s.nts - 1); ++k) f(c, 0, k);
-    }
-  }
-}
-inline size_t ts_stream_bytes(const TsShape& s) {
-  size_t b = 0;
-  ts_for_each_block(s, [&](int, int ss, int k) { b += (size_t)64 * (ss ? ts_ss_klen(s, k) : 64) * 2; });
-  return b;
-}
-
-// ---- packing: fp32 [N][K] row-major sources -> bf16 block stream --------------------------------------------
-struct TsPackTab {
-  int n;
-  struct { short q, ss, k, klen; int dst; } b[32];
-};
-// main: TMEM-chunk columns (k*64 ..), aux: shared-memory-chunk columns (k*64 .. of the aux matrix, zero padded)
-__global__ void k_pack_ts(TsPackTab tab, const float* __restrict__ main_w, int main_ld, const float* __restrict__ aux_w,
-                          int aux_ld, int aux_k, uint8_t* __restrict__ dst) {
-  const int bi = blockIdx.x;
-  const int q = tab.b[bi].q, ss = tab.b[bi].ss, k = tab.b[bi].k, klen = tab.b[bi].klen;
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst + tab.b[bi].dst);
-  for (int i = threadIdx.x; i < 64 * klen; i += blockDim.x) {
-    const int n = i / klen, kk = i % klen;
-    float v;
-    if (ss) {
-      const int col = k * 64 + kk;
-      v = (col < aux_k) ? aux_w[(size_t)(q * 64 + n) * aux_ld + col] : 0.f;
-    } else {
-      v = main_w[(size_t)(q * 64 + n) * main_ld + k * 64 + kk];
-    }
-    // canonical K-major core-matrix image of a 64 x klen block
-    out[((size_t)(n / 8) * (klen * 16) + (size_t)(kk / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2) / 2] = __float2bfloat16_rn(v);
-  }
-}
-static int ts_pack_stream(const TsShape& s, const float* main_w, int main_ld, const float* aux_w, int aux_ld, int aux_k,
-                          uint8_t* dst, cudaStream_t st) {
-  TsPackTab tab;
-  tab.n = 0;
-  int off = 0;
-  ts_for_each_block(s, [&](int q, int ss, int k) {
-    const int klen = ss ? ts_ss_klen(s, k) : 64;
-    tab.b[tab.n].q = (short)q; tab.b[tab.n].ss = (short)ss; tab.b[tab.n].k = (short)k; tab.b[tab.n].klen = (short)klen;
-    tab.b[tab.n].dst = off;
-    off += 64 * klen * 2;
-    ++tab.n;
-  });
-  k_pack_ts<<<tab.n, 256, 0, st>>>(tab, main_w, main_ld, aux_w, aux_ld, aux_k, dst);
-  SNB_CHECK_LAUNCH("k_pack_ts");
-  return SNB_OK;
-}
-
-// ---- shared-memory carve-up ------------------------------------------------------------------------------------
 struct __align__(16) TsCtl {
-  uint64_t full[TS_NSLOT];
-  uint64_t empty[TS_NSLOT];
-  uint64_t acc_full[4];     // MMA -> epilogue: accumulator quarter complete
-  uint64_t acc_free[4];     // epilogue -> MMA: accumulator quarter drained
-  uint64_t a_ready[4];      // epilogue -> MMA: K-chunk of the next A operand written to TMEM
+  uint64_t full[TS_NST];
+  uint64_t empty[TS_NST];
+  uint64_t acc_full[2];
+  uint64_t a_ready[4];      // epilogue -> MMA: K-chunk of the next A operand packed into TMEM
   uint64_t s_ready[2];      // epilogue -> MMA: shared-memory K-chunk (PE / cat block) written
   uint32_t tmem_base;
   uint32_t pad;
 };
 static constexpr size_t TSM_ACAT = 0;
 static constexpr size_t TSM_RING = TS_ACAT_BYTES;
-static constexpr size_t TSM_BIAS = TSM_RING + (size_t)TS_NSLOT * TS_SLOT;
+static constexpr size_t TSM_BIAS = TSM_RING + (size_t)TS_NST * STAGE_BYTES;
 static constexpr size_t TSM_VEC = TSM_BIAS + 2 * 256 * 4;
 static constexpr size_t TSM_RED = TSM_VEC + SM_VEC_FLOATS * 4;
 static constexpr size_t TSM_CTL = TSM_RED + SM_RED_FLOATS * 4;
@@ -110,11 +42,10 @@ static constexpr size_t TSM_TOTAL = TSM_CTL + sizeof(TsCtl) + 1024;
 static_assert(TSM_TOTAL <= 227 * 1024, "shared memory budget (TS kernel)");
 
 struct TsPipe {
-  uint32_t blk = 0;                    // weight blocks produced / consumed
-  uint32_t a_use[4] = {0, 0, 0, 0};    // a_ready waits (MMA) / -
+  uint32_t slice = 0;                  // weight slices produced / consumed
+  uint32_t a_use[4] = {0, 0, 0, 0};
   uint32_t s_use[2] = {0, 0};
-  uint32_t accw[4] = {0, 0, 0, 0};     // MMA: writes started into quarter q; epilogue: acc_full waits of quarter q
-  uint32_t abuf = 0;                   // A tiles produced (epilogue) / consumed (MMA): buffer = abuf & 1
+  uint32_t acc_use[2] = {0, 0};
 };
 
 __device__ __forceinline__ uint32_t ts_cat_addr(uint32_t base, int row, int col8) {
@@ -127,114 +58,99 @@ __device__ __forceinline__ void ts_cat_store_row(uint32_t base, int row, const _
     st_shared_v4(ts_cat_addr(base, row, g), t.x, t.y, t.z, t.w);
   }
 }
+// the four warps (cs = 0..3) that share TMEM lane quarter q
+__device__ __forceinline__ void ts_quarter_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory"); }
 
-// ---- producer: one layer's block stream through the ring ----
-__device__ __forceinline__ void ts_produce(const uint8_t* src, const TsShape s, uint8_t* ring, TsCtl* ctl, TsPipe& pp) {
-  ts_for_each_block(s, [&](int, int ss, int k) {
-    const uint32_t bytes = 64u * (uint32_t)(ss ? ts_ss_klen(s, k) : 64) * 2u;
-    const uint32_t slot = pp.blk % TS_NSLOT, phase = (pp.blk / TS_NSLOT) & 1;
-    mbar_wait(&ctl->empty[slot], phase ^ 1);
-    mbar_arrive_expect_tx(&ctl->full[slot], bytes);
-    bulk_g2s(ring + (size_t)slot * TS_SLOT, src, bytes, &ctl->full[slot]);
-    src += bytes;
-    ++pp.blk;
-  });
+// ---- producer: the K-slices of one packed layer image (same images as k_back) ----
+__device__ __forceinline__ void ts_produce(const uint8_t* wsrc, uint32_t N, uint32_t K16, uint8_t* ring, TsCtl* ctl, TsPipe& pp) {
+  const uint32_t nsl = (K16 + 63) / 64;
+  for (uint32_t j = 0; j < nsl; ++j) {
+    const uint32_t klen = min(64u, K16 - 64u * j);
+    const uint32_t bytes = N * klen * 2;
+    const uint32_t stage = pp.slice % TS_NST, phase = (pp.slice / TS_NST) & 1;
+    mbar_wait(&ctl->empty[stage], phase ^ 1);
+    mbar_arrive_expect_tx(&ctl->full[stage], bytes);
+    bulk_g2s(ring + (size_t)stage * STAGE_BYTES, wsrc + (size_t)N * 64 * 2 * j, bytes, &ctl->full[stage]);
+    ++pp.slice;
+  }
 }
 
-// ---- MMA issuer: one layer ----
-__device__ __forceinline__ void ts_mma_layer(const TsShape s, uint32_t acat_base, uint32_t ring_base, uint32_t tmem_base,
-                                             TsCtl* ctl, TsPipe& pp, unsigned long long* tl = nullptr, int* tn = nullptr,
-                                             int lid = 0) {
-  const uint32_t idesc = umma_idesc_bf16(TILE, 64);
-  const uint32_t a_tmem = tmem_base + TS_ACOL + (pp.abuf & 1u) * 128u;
-  auto block = [&](int q, int ss, int k) {
-    const uint32_t klen = (uint32_t)(ss ? ts_ss_klen(s, k) : 64);
-    const uint32_t slot = pp.blk % TS_NSLOT, phase = (pp.blk / TS_NSLOT) & 1;
-    mbar_wait(&ctl->full[slot], phase);
+// ---- MMA issuer: one segment of a layer = consecutive K-slices whose A operand is all in TMEM (ts) or all in the
+// shared-memory cat block.  `a_tmem`: first column of the packed A operand; `cont`: accumulate onto an earlier segment.
+__device__ __forceinline__ void ts_mma_seg(uint32_t N, uint32_t K, bool ts, uint32_t a_tmem, uint32_t acat_base,
+                                           uint32_t ring_base, uint32_t d_tmem, TsCtl* ctl, TsPipe& pp, bool cont,
+                                           unsigned long long* tl, int* tn) {
+  const uint32_t nsl = (K + 63) / 64;
+  const uint32_t idesc = umma_idesc_bf16(TILE, (int)N);
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j) {
+    if (j >= nsl) break;
+    const uint32_t klen = min(64u, K - 64u * j);
+    const uint32_t stage = pp.slice % TS_NST, phase = (pp.slice / TS_NST) & 1;
+    if (ts) { mbar_wait(&ctl->a_ready[j], pp.a_use[j] & 1); ++pp.a_use[j]; }
+    else if (j < 2) { mbar_wait(&ctl->s_ready[j], pp.s_use[j] & 1); ++pp.s_use[j]; }
+    if (tn) tl_mark(tl, 1, *tn, 100 + (int)j);
+    mbar_wait(&ctl->full[stage], phase);
+    if (tn) tl_mark(tl, 1, *tn, 110 + (int)j);
     tc_fence_after();
-    const uint32_t b_base = ring_base + slot * TS_SLOT;
-    const bool first = ss ? (k == 0) : (s.nss == 0 && k == 0);    // first block of this quarter in this layer
+    const uint32_t b_base = ring_base + stage * STAGE_BYTES;
     for (uint32_t t = 0; t < klen / 16; ++t) {
       const uint64_t db = op_desc(b_base + (2u * t) * 128u, 128u, klen * 16u);
-      const uint32_t acc = (first && t == 0) ? 0u : 1u;
-      if (ss) umma_bf16(tmem_base + (uint32_t)q * 64u, op_desc(acat_base + (8u * (uint32_t)k + 2u * t) * 128u, 128u, TS_SBO), db, idesc, acc);
-      else umma_bf16_ts(tmem_base + (uint32_t)q * 64u, a_tmem + (uint32_t)k * 32u + t * 8u, db, idesc, acc);
+      const uint32_t acc = (cont || (j | t)) ? 1u : 0u;
+      if (ts) umma_bf16_ts(d_tmem, a_tmem + j * 32u + t * 8u, db, idesc, acc);
+      else umma_bf16(d_tmem, op_desc(acat_base + (8u * j + 2u * t) * 128u, 128u, TS_SBO), db, idesc, acc);
     }
-    umma_commit(&ctl->empty[slot]);
-    ++pp.blk;
-    const bool last = ss ? (s.nts == 0 && k == s.nss - 1) : (k == s.nts - 1);
-    if (last) umma_commit(&ctl->acc_full[q]);
-  };
-  const int n = s.nq > s.nts ? s.nq : s.nts;      // <= 4
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c >= n) break;
-    if (c < s.nts) { mbar_wait(&ctl->a_ready[c], pp.a_use[c] & 1); ++pp.a_use[c]; }
-    if (c < s.nq) { mbar_wait(&ctl->acc_free[c], (pp.accw[c] & 1) ^ 1); ++pp.accw[c]; }
-    if (c == 0) {
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-        if (i < s.nss) { mbar_wait(&ctl->s_ready[i], pp.s_use[i] & 1); ++pp.s_use[i]; }
-    }
-    tc_fence_after();
-    if (tn) tl_mark(tl, 1, *tn, 100 * lid + 10 + c);
-    if (c < s.nts) for (int q = 0; q < ts_imin(c, s.nq); ++q) block(q, 0, c);
-    if (c < s.nq) {
-      for (int i = 0; i < s.nss; ++i) block(c, 1, i);
-      for (int k = 0; k <= ts_imin(c, s.nts - 1); ++k) block(c, 0, k);
-    }
+    umma_commit(&ctl->empty[stage]);
+    ++pp.slice;
   }
-  if (s.nts) ++pp.abuf;
-  if (tn) tl_mark(tl, 1, *tn, 100 * lid + 20);
 }
 
 // ---- epilogue helpers ----
-__device__ __forceinline__ void ts_wait_acc(TsCtl* ctl, TsPipe& pp, int q) {
-  mbar_wait_backoff(&ctl->acc_full[q], pp.accw[q] & 1);
-  ++pp.accw[q];
+__device__ __forceinline__ void ts_wait_acc(TsCtl* ctl, TsPipe& pp, int buf) {
+  mbar_wait_backoff(&ctl->acc_full[buf], pp.acc_use[buf] & 1);
+  ++pp.acc_use[buf];
   tc_fence_after();
 }
-// all lanes have finished their tcgen05.ld of quarter c (and tcgen05.st of A chunk c when `wrote_a`)
-__device__ __forceinline__ void ts_signal(TsCtl* ctl, int c, int lane, bool wrote_a, bool drained) {
+// my tcgen05.ld of the accumulator chunk and tcgen05.st of A chunk c have completed (wait::ld / wait::st done)
+__device__ __forceinline__ void ts_signal(TsCtl* ctl, int c, int lane) {
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) {
-    if (wrote_a) mbar_arrive(&ctl->a_ready[c]);
-    if (drained) mbar_arrive(&ctl->acc_free[c]);
-  }
+  if (lane == 0) mbar_arrive(&ctl->a_ready[c]);
 }
 __device__ __forceinline__ void ts_signal_smem(TsCtl* ctl, int i, int lane) {
   fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) mbar_arrive(&ctl->s_ready[i]);
 }
-// hidden layer: y = act(acc + bias) -> bf16 -> TMEM A buffer (pp.abuf & 1); thread owns columns [64c + 16cs, +16)
+// hidden layer: y = act(acc + bias) -> bf16, packed in place into columns [0,128) of the drained buffer.
+// Thread owns fp32 columns [64c + 16cs, +16) of every chunk c and writes packed columns [32c + 8cs, +8).
 template <bool RELU>
-__device__ __forceinline__ void ts_epi_hidden(uint32_t tmem_base, const float* sb, const EpiCtx& ec, TsCtl* ctl, TsPipe& pp,
-                                              unsigned long long* tl = nullptr, int* tn = nullptr, int lid = 0) {
-  const uint32_t a_w = tmem_base + ec.lane_base + TS_ACOL + (pp.abuf & 1u) * 128u;
+__device__ __forceinline__ void ts_epi_hidden(uint32_t tbuf /* tmem_base + lane_base + buf*256 */, const float* sb,
+                                              const EpiCtx& ec, TsCtl* ctl, unsigned long long* tl, int* tn) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    ts_wait_acc(ctl, pp, c);
-    if (tn) tl_mark(tl, 0, *tn, 100 * lid + 1 + c);
-    const int col0 = c * 64 + ec.cs * 16;
-    uint32_t v[16];
-    tmem_ld16(tmem_base + ec.lane_base + (uint32_t)col0, v);
+  for (int c2 = 0; c2 < 4; c2 += 2) {
+    uint32_t v[2][16];
+    tmem_ld16(tbuf + (uint32_t)(c2 * 64 + ec.cs * 16), v[0]);
+    tmem_ld16(tbuf + (uint32_t)(c2 * 64 + 64 + ec.cs * 16), v[1]);
     tmem_ld_wait();
-    const float4* b4 = reinterpret_cast<const float4*>(sb + col0);
-    uint32_t pk[8];
+    if (c2 == 0) ts_quarter_sync(ec.q);      // chunks 0/1 of this lane quarter are in registers everywhere
 #pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-      const float4 b = b4[j4];
-      pk[2 * j4] = pack2<RELU>(__uint_as_float(v[4 * j4 + 0]) + b.x, __uint_as_float(v[4 * j4 + 1]) + b.y);
-      pk[2 * j4 + 1] = pack2<RELU>(__uint_as_float(v[4 * j4 + 2]) + b.z, __uint_as_float(v[4 * j4 + 3]) + b.w);
+    for (int h = 0; h < 2; ++h) {
+      const int c = c2 + h, col0 = c * 64 + ec.cs * 16;
+      const float4* b4 = reinterpret_cast<const float4*>(sb + col0);
+      uint32_t pk[8];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b = b4[j4];
+        pk[2 * j4] = pack2<RELU>(__uint_as_float(v[h][4 * j4 + 0]) + b.x, __uint_as_float(v[h][4 * j4 + 1]) + b.y);
+        pk[2 * j4 + 1] = pack2<RELU>(__uint_as_float(v[h][4 * j4 + 2]) + b.z, __uint_as_float(v[h][4 * j4 + 3]) + b.w);
+      }
+      tmem_st8(tbuf + (uint32_t)(c * 32 + ec.cs * 8), pk);
+      tmem_st_wait();
+      ts_signal(ctl, c, ec.lane);
+      if (tn) tl_mark(tl, 0, *tn, 60 + c);
     }
-    tmem_st8(a_w + (uint32_t)(c * 32 + ec.cs * 8), pk);
-    tmem_st_wait();
-    ts_signal(ctl, c, ec.lane, true, true);
-    if (tn) tl_mark(tl, 0, *tn, 100 * lid + 5 + c);
   }
-  ++pp.abuf;
 }
 
 template <int FD>
@@ -247,12 +163,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TsCtl* ctl = reinterpret_cast<TsCtl*>(smem + TSM_CTL);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TS_NSLOT; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&ctl->acc_full[i], 1);
-      mbar_init(&ctl->acc_free[i], EPI_WARPS);
-      mbar_init(&ctl->a_ready[i], EPI_WARPS);
-    }
+    for (int i = 0; i < TS_NST; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+    mbar_init(&ctl->acc_full[0], 1);
+    mbar_init(&ctl->acc_full[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS);
     mbar_init(&ctl->s_ready[0], EPI_WARPS);
     mbar_init(&ctl->s_ready[1], EPI_WARPS);
     fence_mbar_init();
@@ -272,12 +186,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
   const uint32_t acat_base = smem_u32(smem + TSM_ACAT), ring_base = smem_u32(smem + TSM_RING);
   const int n_tiles = *tt.n_tiles;
   const int NE = P.n_expert;
-  const int kss_xyz = (int)P.front[0].K16, kss_cat = (int)P.back[1].K16 - MW;
-  const TsShape SH_XYZ = {4, 0, (kss_xyz + 63) / 64, kss_xyz};
-  const TsShape SH_EXP = {4, 4, 0, 0};
-  const TsShape SH_SKIP = {4, 4, (kss_xyz + 63) / 64, kss_xyz};
-  const TsShape SH_L1 = {4, 4, 0, 0};
-  const TsShape SH_L2 = {H2 / 64, 4, (kss_cat + 63) / 64, kss_cat};
+  const uint32_t K_xyz = P.front[0].K16, K_cat = P.back[1].K16 - MW;     // shared-memory operand widths (80, 80)
   TsPipe pp;
 
   if (warp == 0) {
@@ -285,27 +194,47 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
         const int e = tt.tile_expert[t];
         if (e >= 0) {
-          ts_produce(P.tsblob + P.ts_xyz_off, SH_XYZ, smem + TSM_RING, ctl, pp);
-          for (int l = 0; l < NE; ++l)
-            ts_produce(P.tsblob + P.ts_expert_off[l] + (size_t)e * P.ts_expert_stride, l == P.skip_layer ? SH_SKIP : SH_EXP,
-                       smem + TSM_RING, ctl, pp);
+          ts_produce(P.wblob + P.front[0].w_off, MW, K_xyz, smem + TSM_RING, ctl, pp);
+          for (int l = 0; l < NE; ++l) {
+            ts_produce(P.wblob + P.expert[l].w_off + (size_t)e * P.expert_w_stride, MW, MW, smem + TSM_RING, ctl, pp);
+            if (l == P.skip_layer) ts_produce(P.wblob + P.front[0].w_off, MW, K_xyz, smem + TSM_RING, ctl, pp);
+          }
         }
-        ts_produce(P.tsblob + P.ts_back_off[0], SH_L1, smem + TSM_RING, ctl, pp);
-        ts_produce(P.tsblob + P.ts_back_off[1], SH_L2, smem + TSM_RING, ctl, pp);
+        ts_produce(P.wblob + P.back[0].w_off, P.back[0].N, P.back[0].K16, smem + TSM_RING, ctl, pp);
+        ts_produce(P.wblob + P.back[1].w_off, P.back[1].N, P.back[1].K16, smem + TSM_RING, ctl, pp);
       }
   } else if (warp == 1) {
     if (lane == 0) {
+      uint32_t li = 0;
       int tn = 0;
+      // layer li accumulates into buffer li & 1; a TMEM A operand sits in columns [0,128) of the other buffer
+      auto acc_of = [&](uint32_t l) { return tmem_base + (l & 1u) * 256u; };
+      auto a_of = [&](uint32_t l) { return tmem_base + ((l & 1u) ^ 1u) * 256u; };
       for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
         const int e = tt.tile_expert[t];
         tl_mark(P.tl, 1, tn, 1);
         if (e >= 0) {
-          ts_mma_layer(SH_XYZ, acat_base, ring_base, tmem_base, ctl, pp, P.tl, &tn, 1);
-          for (int l = 0; l < NE; ++l)
-            ts_mma_layer(l == P.skip_layer ? SH_SKIP : SH_EXP, acat_base, ring_base, tmem_base, ctl, pp, P.tl, &tn, 2 + l);
+          ts_mma_seg(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, false, P.tl, &tn);
+          umma_commit(&ctl->acc_full[li & 1]);
+          tl_mark(P.tl, 1, tn, 120);
+          ++li;
+          for (int l = 0; l < NE; ++l, ++li) {
+            ts_mma_seg(MW, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, P.tl, &tn);
+            if (l == P.skip_layer)
+              ts_mma_seg(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, P.tl, &tn);
+            umma_commit(&ctl->acc_full[li & 1]);
+            tl_mark(P.tl, 1, tn, 120);
+          }
         }
-        ts_mma_layer(SH_L1, acat_base, ring_base, tmem_base, ctl, pp, P.tl, &tn, 20);
-        ts_mma_layer(SH_L2, acat_base, ring_base, tmem_base, ctl, pp, P.tl, &tn, 21);
+        ts_mma_seg(P.back[0].N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, P.tl, &tn);
+        umma_commit(&ctl->acc_full[li & 1]);
+        tl_mark(P.tl, 1, tn, 120);
+        ++li;
+        ts_mma_seg(P.back[1].N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, P.tl, &tn);
+        ts_mma_seg(P.back[1].N, K_cat, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, P.tl, &tn);
+        umma_commit(&ctl->acc_full[li & 1]);
+        tl_mark(P.tl, 1, tn, 120);
+        ++li;
       }
     }
   } else {
@@ -315,7 +244,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
     const int row = ec.row;
     const float b_sig = P.fblob[P.o_bsig];
     const float b_col0 = P.fblob[P.o_bcol], b_col1 = P.fblob[P.o_bcol + 1], b_col2 = P.fblob[P.o_bcol + 2];
-    uint32_t li = 0;      // bias double buffer
+    uint32_t li = 0;
+    int tn = 0;
+    unsigned long long* tl = (warp == 2 && lane == 0) ? P.tl : nullptr;
+    auto tbuf_of = [&](uint32_t l) { return tmem_base + ec.lane_base + (l & 1u) * 256u; };
     struct RowIn { int e, sidx; float g, d0, d1, d2, x0, x1, x2; int ai; };
     auto fetch_row = [&](int t) {
       RowIn r;
@@ -336,14 +268,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       return r;
     };
     RowIn nxt = fetch_row((int)blockIdx.x);
-    int tn = 0;
-    unsigned long long* tl = (warp == 2 && lane == 0) ? P.tl : nullptr;
     for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
       const RowIn cur = nxt;
       const int e = cur.e, sidx = cur.sidx;
-      tl_mark(tl, 0, tn, 1);
       const bool valid = sidx >= 0;
       const float g = cur.g;
+      tl_mark(tl, 0, tn, 1);
       // [PE(dir) | appearance | 0-pad] -> cat block (cs == 1 threads)
       auto write_cat = [&]() {
         if (ec.cs == 1) {
@@ -363,9 +293,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
               cat[NDIR + 4 * i + 3] = __float2bfloat16_rn(f.w);
             }
           }
-          ts_cat_store_row(acat_base, row, cat, kss_cat / 8);
+          ts_cat_store_row(acat_base, row, cat, (int)K_cat / 8);
         }
       };
+      const int n_sxyz = ((int)K_xyz + 63) / 64, n_scat = ((int)K_cat + 63) / 64;
       float sig_acc = 0.f;
       if (e >= 0) {
         // ---- PE(xyz) -> cat block: operand of the xyz layer now and of the skip term later ----
@@ -378,15 +309,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           for (int i = NPE; i < NPAD; ++i) pe[i] = __float2bfloat16_rn(0.f);
           ts_cat_store_row(acat_base, row, pe, NPAD / 8);
         }
-        for (int i = 0; i < SH_XYZ.nss; ++i) ts_signal_smem(ctl, i, lane);
+        for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane);
         nxt = fetch_row(t + (int)gridDim.x);
-        // ---- xyz layer (act none): h -> A ----
+        tl_mark(tl, 0, tn, 2);
+        // ---- xyz layer (act none): h -> packed A ----
         {
           const int buf = (int)(li & 1);
           epi_load_bias(P.fblob + P.front[0].b_off, MW, sbias, buf, ec.et);
-          tl_mark(tl, 0, tn, 2);
-          ts_epi_hidden<false>(tmem_base, sbias + buf * 256, ec, ctl, pp, tl, &tn, 1);
-          if (P.skip_layer == 0) for (int i = 0; i < SH_XYZ.nss; ++i) ts_signal_smem(ctl, i, lane);
+          ts_wait_acc(ctl, pp, buf);
+          ts_epi_hidden<false>(tbuf_of(li), sbias + buf * 256, ec, ctl, tl, &tn);
+          if (P.skip_layer == 0) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane);
           ++li;
         }
         for (int l = 0; l < NE; ++l, ++li) {
@@ -395,57 +327,64 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           epi_load_bias(skip_here ? (P.fblob + P.o_b3x + (size_t)e * MW)
                                   : (P.fblob + P.expert[l].b_off + (size_t)e * P.expert_b_stride), MW, sbias, buf, ec.et);
           const float* sb = sbias + buf * 256;
+          tl_mark(tl, 0, tn, 10 + l);
+          ts_wait_acc(ctl, pp, buf);
+          tl_mark(tl, 0, tn, 20 + l);
+          if (skip_here) write_cat();          // every MMA of the skip layer has retired: the PE(xyz) block is free
+          const uint32_t tb = tbuf_of(li);
           if (l < NE - 1) {
-            ts_epi_hidden<true>(tmem_base, sb, ec, ctl, pp, tl, &tn, 2 + l);
-            if (skip_here) write_cat();          // every MMA of the skip layer has retired: the PE(xyz) block is free
-            if (l + 1 == P.skip_layer) for (int i = 0; i < SH_XYZ.nss; ++i) ts_signal_smem(ctl, i, lane);
+            ts_epi_hidden<true>(tb, sb, ec, ctl, tl, &tn);
+            if (l + 1 == P.skip_layer) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane);
           } else {
-            // last expert layer (no activation) -> combine: y = bf16(gate * bf16(out)) -> ReLU -> A; sigma head on the fly
-            const uint32_t a_w = tmem_base + ec.lane_base + TS_ACOL + (pp.abuf & 1u) * 128u;
+            // last expert layer (no activation) -> combine: y = bf16(gate * bf16(out)) -> ReLU -> packed A; sigma head
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              ts_wait_acc(ctl, pp, c);
-              const int col0 = c * 64 + ec.cs * 16;
-              uint32_t v[16];
-              tmem_ld16(tmem_base + ec.lane_base + (uint32_t)col0, v);
+            for (int c2 = 0; c2 < 4; c2 += 2) {
+              uint32_t v[2][16];
+              tmem_ld16(tb + (uint32_t)(c2 * 64 + ec.cs * 16), v[0]);
+              tmem_ld16(tb + (uint32_t)(c2 * 64 + 64 + ec.cs * 16), v[1]);
               tmem_ld_wait();
-              uint32_t pk[8];
+              if (c2 == 0) ts_quarter_sync(ec.q);
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                float f0 = bf16_round(__uint_as_float(v[j]) + sb[col0 + j]);
-                float f1 = bf16_round(__uint_as_float(v[j + 1]) + sb[col0 + j + 1]);
-                f0 = fmaxf(bf16_round(f0 * g), 0.f);
-                f1 = fmaxf(bf16_round(f1 * g), 0.f);
-                sig_acc = fmaf(f0, s_wsig[col0 + j], sig_acc);
-                sig_acc = fmaf(f1, s_wsig[col0 + j + 1], sig_acc);
-                pk[j / 2] = pack_bf16x2(f0, f1);
+              for (int h = 0; h < 2; ++h) {
+                const int c = c2 + h, col0 = c * 64 + ec.cs * 16;
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  float f0 = bf16_round(__uint_as_float(v[h][j]) + sb[col0 + j]);
+                  float f1 = bf16_round(__uint_as_float(v[h][j + 1]) + sb[col0 + j + 1]);
+                  f0 = fmaxf(bf16_round(f0 * g), 0.f);
+                  f1 = fmaxf(bf16_round(f1 * g), 0.f);
+                  sig_acc = fmaf(f0, s_wsig[col0 + j], sig_acc);
+                  sig_acc = fmaf(f1, s_wsig[col0 + j + 1], sig_acc);
+                  pk[j / 2] = pack_bf16x2(f0, f1);
+                }
+                tmem_st8(tb + (uint32_t)(c * 32 + ec.cs * 8), pk);
+                tmem_st_wait();
+                ts_signal(ctl, c, lane);
               }
-              tmem_st8(a_w + (uint32_t)(c * 32 + ec.cs * 8), pk);
-              tmem_st_wait();
-              ts_signal(ctl, c, lane, true, true);
             }
-            ++pp.abuf;
-            if (skip_here) write_cat();
           }
+          tl_mark(tl, 0, tn, 30 + l);
         }
       } else {
-        // dropped bucket: h = relu(0) = 0 -> zero A operand for layer "1"; the cat block is still needed
+        // dropped bucket: h = relu(0) = 0 -> zero A operand for layer "1" (it accumulates into B[li&1], reads B[~li&1])
         nxt = fetch_row(t + (int)gridDim.x);
-        const uint32_t a_w = tmem_base + ec.lane_base + TS_ACOL + (pp.abuf & 1u) * 128u;
+        const uint32_t ta = tbuf_of(li + 1);
         const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int c = 0; c < 4; ++c) tmem_st8(a_w + (uint32_t)(c * 32 + ec.cs * 8), z);
+        for (int c = 0; c < 4; ++c) tmem_st8(ta + (uint32_t)(c * 32 + ec.cs * 8), z);
         tmem_st_wait();
-        for (int c = 0; c < 4; ++c) ts_signal(ctl, c, lane, true, false);
-        ++pp.abuf;
+        for (int c = 0; c < 4; ++c) ts_signal(ctl, c, lane);
         write_cat();
       }
       sred[(0 * 4 + ec.cs) * 128 + row] = sig_acc;
-      // ---- layer "1" (act none) -> A; then release the cat chunks ----
+      // ---- layer "1" (act none) -> packed A; then release the cat chunks ----
       {
         const int buf = (int)(li & 1);
         epi_load_bias(P.fblob + P.back[0].b_off, MW, sbias, buf, ec.et);
-        ts_epi_hidden<false>(tmem_base, sbias + buf * 256, ec, ctl, pp, tl, &tn, 20);
-        for (int i = 0; i < SH_L2.nss; ++i) ts_signal_smem(ctl, i, lane);
+        ts_wait_acc(ctl, pp, buf);
+        ts_epi_hidden<false>(tbuf_of(li), sbias + buf * 256, ec, ctl, tl, &tn);
+        for (int i = 0; i < n_scat; ++i) ts_signal_smem(ctl, i, lane);
+        tl_mark(tl, 0, tn, 50);
         ++li;
       }
       // ---- layer "2" (ReLU) + colour head ----
@@ -453,16 +392,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         const int buf = (int)(li & 1);
         epi_load_bias(P.fblob + P.back[1].b_off, H2, sbias, buf, ec.et);
         const float* sb = sbias + buf * 256;
+        ts_wait_acc(ctl, pp, buf);
+        const uint32_t tb = tbuf_of(li);
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c >= H2 / 64) break;
-          ts_wait_acc(ctl, pp, c);
+        for (int c = 0; c < H2 / 64; ++c) {
           const int col0 = c * 64 + ec.cs * 16;
           uint32_t v[16];
-          tmem_ld16(tmem_base + ec.lane_base + (uint32_t)col0, v);
+          tmem_ld16(tb + (uint32_t)col0, v);
           tmem_ld_wait();
-          ts_signal(ctl, c, lane, false, true);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int k = col0 + j;
@@ -472,6 +409,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
             c2 = fmaf(h2, s_wcol[2 * H2 + k], c2);
           }
         }
+        tc_fence_before();
         sred[(1 * 4 + ec.cs) * 128 + row] = c0;
         sred[(2 * 4 + ec.cs) * 128 + row] = c1;
         sred[(3 * 4 + ec.cs) * 128 + row] = c2;
@@ -493,7 +431,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           }
         }
         epi_bar_sync();
-        tl_mark(tl, 0, tn, 2200);
+        tl_mark(tl, 0, tn, 51);
         ++li;
       }
     }
