@@ -1244,7 +1244,8 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
-    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_ts<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSM_TOTAL));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_ts<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSM_TOTAL));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_ts<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSM_TOTAL));
     attr_done = true;
   }
   static const int cg_env = getenv("SNB_CG") ? atoi(getenv("SNB_CG")) : 1;
@@ -1314,20 +1315,22 @@ static int tc_back(Model* m, TcChunk& c, cudaStream_t st) {
     io.out = c.out;
   }
   if (c.pe) cudaEventRecord(c.pe->e[4], st);
-  // SNB_TS=1: hidden activations in tensor memory (snb_tc_ts.cuh) -- A/B switch while the variant is being tuned
-  static const bool use_ts = getenv("SNB_TS") != nullptr && atoi(getenv("SNB_TS")) != 0;
-  if (use_ts && c.cg == 1 && c.Pb.recompute_h && c.Pb.back[1].K16 > MW && c.Pb.back[1].K16 - MW <= TS_CAT_COLS &&
-      c.Pb.front[0].K16 <= TS_CAT_COLS) {
-    k_back_ts<4><<<grid2, THREADS, TSM_TOTAL, st>>>(c.Pb, c.tt, io);
-  } else if (c.cg == 2) {
+  // launch #2 variants: SNB_TS=0 falls back to the shared-memory A operand (k_back); SNB_CG=2 runs CTA pairs
+  static const bool use_ts = !(getenv("SNB_TS") && atoi(getenv("SNB_TS")) == 0);
+  const bool ts_ok = use_ts && c.Pb.recompute_h && c.Pb.back[1].K16 > MW && c.Pb.back[1].K16 - MW <= TS_CAT_COLS &&
+                     c.Pb.front[0].K16 <= TS_CAT_COLS;
+  if (c.cg == 2) {
     grid2 &= ~1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid2); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SM_TOTAL; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)grid2); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = ts_ok ? TSM_TOTAL : SM_TOTAL; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    SNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_back<4, 2>, c.Pb, c.tt, io, (const __nv_bfloat16*)c.H));
+    if (ts_ok) SNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_back_ts<4, 2>, c.Pb, c.tt, io));
+    else SNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_back<4, 2>, c.Pb, c.tt, io, (const __nv_bfloat16*)c.H));
+  } else if (ts_ok) {
+    k_back_ts<4, 1><<<grid2, THREADS, TSM_TOTAL, st>>>(c.Pb, c.tt, io);
   } else {
     k_back<4, 1><<<grid2, THREADS, SM_TOTAL, st>>>(c.Pb, c.tt, io, c.H);
   }

@@ -26,6 +26,7 @@ static constexpr int TS_NST = 5;
 struct __align__(16) TsCtl {
   uint64_t full[TS_NST];
   uint64_t empty[TS_NST];
+  uint64_t peer_ok[TS_NST]; // CTA pairs, leader only: the peer's half of the weight slice landed
   uint64_t acc_full[2];
   uint64_t a_ready[4];      // epilogue -> MMA: K-chunk of the next A operand packed into TMEM
   uint64_t s_ready[2];      // epilogue -> MMA: shared-memory K-chunk (PE / cat block) written
@@ -62,46 +63,74 @@ __device__ __forceinline__ void ts_cat_store_row(uint32_t base, int row, const _
 __device__ __forceinline__ void ts_quarter_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory"); }
 
 // ---- producer: the K-slices of one packed layer image (same images as k_back) ----
-__device__ __forceinline__ void ts_produce(const uint8_t* wsrc, uint32_t N, uint32_t K16, uint8_t* ring, TsCtl* ctl, TsPipe& pp) {
+// CG = 2 (CTA pair): each CTA streams its own half of the slice (output rows [rank*N/2, +N/2) are the contiguous half)
+template <int CG>
+__device__ __forceinline__ void ts_produce(const uint8_t* wsrc, uint32_t N, uint32_t K16, uint8_t* ring, TsCtl* ctl, TsPipe& pp,
+                                           uint32_t rank) {
   const uint32_t nsl = (K16 + 63) / 64;
   for (uint32_t j = 0; j < nsl; ++j) {
     const uint32_t klen = min(64u, K16 - 64u * j);
-    const uint32_t bytes = N * klen * 2;
+    const uint32_t bytes = N * klen * 2 / CG;
     const uint32_t stage = pp.slice % TS_NST, phase = (pp.slice / TS_NST) & 1;
     mbar_wait(&ctl->empty[stage], phase ^ 1);
     mbar_arrive_expect_tx(&ctl->full[stage], bytes);
-    bulk_g2s(ring + (size_t)stage * STAGE_BYTES, wsrc + (size_t)N * 64 * 2 * j, bytes, &ctl->full[stage]);
+    bulk_g2s(ring + (size_t)stage * STAGE_BYTES, wsrc + (size_t)N * 64 * 2 * j + (size_t)rank * bytes, bytes, &ctl->full[stage]);
     ++pp.slice;
   }
 }
 
 // ---- MMA issuer: one segment of a layer = consecutive K-slices whose A operand is all in TMEM (ts) or all in the
 // shared-memory cat block.  `a_tmem`: first column of the packed A operand; `cont`: accumulate onto an earlier segment.
+// CG = 2: the leader CTA (rank 0) issues M = 256 instructions for the pair (each CTA's own TMEM / cat block supplies
+// its 128 rows of A, each CTA's ring slot half of B); the peer's warp 1 only forwards "my weight half landed".
+template <int CG>
 __device__ __forceinline__ void ts_mma_seg(uint32_t N, uint32_t K, bool ts, uint32_t a_tmem, uint32_t acat_base,
                                            uint32_t ring_base, uint32_t d_tmem, TsCtl* ctl, TsPipe& pp, bool cont,
-                                           unsigned long long* tl, int* tn) {
+                                           uint32_t rank, unsigned long long* tl, int* tn) {
   const uint32_t nsl = (K + 63) / 64;
-  const uint32_t idesc = umma_idesc_bf16(TILE, (int)N);
+  const uint32_t idesc = umma_idesc_bf16(TILE * CG, (int)N);
 #pragma unroll
   for (uint32_t j = 0; j < 4; ++j) {
     if (j >= nsl) break;
     const uint32_t klen = min(64u, K - 64u * j);
     const uint32_t stage = pp.slice % TS_NST, phase = (pp.slice / TS_NST) & 1;
+    if (CG == 2 && rank != 0) {
+      mbar_wait(&ctl->full[stage], phase);
+      mbar_arrive_remote(mapa_shared(smem_u32(&ctl->peer_ok[stage]), 0));
+      ++pp.slice;
+      continue;
+    }
     if (ts) { mbar_wait(&ctl->a_ready[j], pp.a_use[j] & 1); ++pp.a_use[j]; }
     else if (j < 2) { mbar_wait(&ctl->s_ready[j], pp.s_use[j] & 1); ++pp.s_use[j]; }
     if (tn) tl_mark(tl, 1, *tn, 100 + (int)j);
     mbar_wait(&ctl->full[stage], phase);
+    if (CG == 2) mbar_wait(&ctl->peer_ok[stage], phase);
     if (tn) tl_mark(tl, 1, *tn, 110 + (int)j);
     tc_fence_after();
     const uint32_t b_base = ring_base + stage * STAGE_BYTES;
     for (uint32_t t = 0; t < klen / 16; ++t) {
       const uint64_t db = op_desc(b_base + (2u * t) * 128u, 128u, klen * 16u);
       const uint32_t acc = (cont || (j | t)) ? 1u : 0u;
-      if (ts) umma_bf16_ts(d_tmem, a_tmem + j * 32u + t * 8u, db, idesc, acc);
-      else umma_bf16(d_tmem, op_desc(acat_base + (8u * j + 2u * t) * 128u, 128u, TS_SBO), db, idesc, acc);
+      if (ts) {
+        if (CG == 2) umma_bf16_ts_pair(d_tmem, a_tmem + j * 32u + t * 8u, db, idesc, acc);
+        else umma_bf16_ts(d_tmem, a_tmem + j * 32u + t * 8u, db, idesc, acc);
+      } else {
+        const uint64_t da = op_desc(acat_base + (8u * j + 2u * t) * 128u, 128u, TS_SBO);
+        if (CG == 2) umma_bf16_pair(d_tmem, da, db, idesc, acc);
+        else umma_bf16(d_tmem, da, db, idesc, acc);
+      }
     }
-    umma_commit(&ctl->empty[stage]);
+    if (CG == 2) umma_commit_pair(&ctl->empty[stage], 3);    // frees the ring slot in BOTH CTAs
+    else umma_commit(&ctl->empty[stage]);
     ++pp.slice;
+  }
+}
+template <int CG>
+__device__ __forceinline__ void ts_commit_acc(TsCtl* ctl, uint32_t buf, uint32_t rank) {
+  if (CG == 2) {
+    if (rank == 0) umma_commit_pair(&ctl->acc_full[buf], 3);
+  } else {
+    umma_commit(&ctl->acc_full[buf]);
   }
 }
 
@@ -112,15 +141,23 @@ __device__ __forceinline__ void ts_wait_acc(TsCtl* ctl, TsPipe& pp, int buf) {
   tc_fence_after();
 }
 // my tcgen05.ld of the accumulator chunk and tcgen05.st of A chunk c have completed (wait::ld / wait::st done)
-__device__ __forceinline__ void ts_signal(TsCtl* ctl, int c, int lane) {
+// CTA pairs: the peer CTA's warps arrive on the LEADER's barriers (`remote` = cluster address of the leader's
+// a_ready[0] / s_ready[0]; 0 = arrive locally)
+__device__ __forceinline__ void ts_signal(TsCtl* ctl, int c, int lane, uint32_t remote) {
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(&ctl->a_ready[c]);
+  if (lane == 0) {
+    if (remote) mbar_arrive_remote(remote + (uint32_t)c * 8u);
+    else mbar_arrive(&ctl->a_ready[c]);
+  }
 }
-__device__ __forceinline__ void ts_signal_smem(TsCtl* ctl, int i, int lane) {
+__device__ __forceinline__ void ts_signal_smem(TsCtl* ctl, int i, int lane, uint32_t remote) {
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) mbar_arrive(&ctl->s_ready[i]);
+  if (lane == 0) {
+    if (remote) mbar_arrive_remote(remote + (uint32_t)i * 8u);
+    else mbar_arrive(&ctl->s_ready[i]);
+  }
 }
 // hidden layer: y = act(acc + bias) -> bf16, packed in place into columns [0,128) of the drained buffer.
 // Thread owns fp32 columns [64c + 16cs, +16) of every chunk c and writes packed columns [32c + 8cs, +8).
@@ -147,13 +184,13 @@ __device__ __forceinline__ void ts_epi_hidden(uint32_t tbuf /* tmem_base + lane_
       }
       tmem_st8(tbuf + (uint32_t)(c * 32 + ec.cs * 8), pk);
       tmem_st_wait();
-      ts_signal(ctl, c, ec.lane);
+      ts_signal(ctl, c, ec.lane, ec.remote_a_ready);
       if (tn) tl_mark(tl, 0, *tn, 60 + c);
     }
   }
 }
 
-template <int FD>
+template <int FD, int CG>
 __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt, RowIO io) {
   const float* __restrict__ x = io.x;
   const float* __restrict__ gate = io.gate;
@@ -161,17 +198,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int t_first0 = CG * ((int)blockIdx.x / CG), t_stride = (int)gridDim.x;   // pairs of tiles share the expert
   TsCtl* ctl = reinterpret_cast<TsCtl*>(smem + TSM_CTL);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TS_NST; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+    for (int i = 0; i < TS_NST; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); mbar_init(&ctl->peer_ok[i], 1); }
     mbar_init(&ctl->acc_full[0], 1);
     mbar_init(&ctl->acc_full[1], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS);
-    mbar_init(&ctl->s_ready[0], EPI_WARPS);
-    mbar_init(&ctl->s_ready[1], EPI_WARPS);
+    for (int i = 0; i < 4; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS * CG);
+    mbar_init(&ctl->s_ready[0], EPI_WARPS * CG);
+    mbar_init(&ctl->s_ready[1], EPI_WARPS * CG);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(&ctl->tmem_base);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_pair<512>(&ctl->tmem_base);
+    else tmem_alloc<512>(&ctl->tmem_base);
+  }
   float* sbias = reinterpret_cast<float*>(smem + TSM_BIAS);
   float* svec = reinterpret_cast<float*>(smem + TSM_VEC);
   float* sred = reinterpret_cast<float*>(smem + TSM_RED);
@@ -180,7 +222,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
   for (int i = threadIdx.x; i < MW; i += THREADS) s_wsig[i] = P.fblob[P.o_wsig + i];
   for (int i = threadIdx.x; i < 3 * H2; i += THREADS) s_wcol[i] = P.fblob[P.o_wcol + i];
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
   const uint32_t acat_base = smem_u32(smem + TSM_ACAT), ring_base = smem_u32(smem + TSM_RING);
@@ -191,17 +234,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
 
   if (warp == 0) {
     if (lane == 0)
-      for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
-        const int e = tt.tile_expert[t];
+      for (int tb = t_first0; tb < n_tiles; tb += t_stride) {
+        const int e = tt.tile_expert[tb + (int)rank];
         if (e >= 0) {
-          ts_produce(P.wblob + P.front[0].w_off, MW, K_xyz, smem + TSM_RING, ctl, pp);
+          ts_produce<CG>(P.wblob + P.front[0].w_off, MW, K_xyz, smem + TSM_RING, ctl, pp, rank);
           for (int l = 0; l < NE; ++l) {
-            ts_produce(P.wblob + P.expert[l].w_off + (size_t)e * P.expert_w_stride, MW, MW, smem + TSM_RING, ctl, pp);
-            if (l == P.skip_layer) ts_produce(P.wblob + P.front[0].w_off, MW, K_xyz, smem + TSM_RING, ctl, pp);
+            ts_produce<CG>(P.wblob + P.expert[l].w_off + (size_t)e * P.expert_w_stride, MW, MW, smem + TSM_RING, ctl, pp, rank);
+            if (l == P.skip_layer) ts_produce<CG>(P.wblob + P.front[0].w_off, MW, K_xyz, smem + TSM_RING, ctl, pp, rank);
           }
         }
-        ts_produce(P.wblob + P.back[0].w_off, P.back[0].N, P.back[0].K16, smem + TSM_RING, ctl, pp);
-        ts_produce(P.wblob + P.back[1].w_off, P.back[1].N, P.back[1].K16, smem + TSM_RING, ctl, pp);
+        ts_produce<CG>(P.wblob + P.back[0].w_off, P.back[0].N, P.back[0].K16, smem + TSM_RING, ctl, pp, rank);
+        ts_produce<CG>(P.wblob + P.back[1].w_off, P.back[1].N, P.back[1].K16, smem + TSM_RING, ctl, pp, rank);
       }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -210,36 +253,38 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       // layer li accumulates into buffer li & 1; a TMEM A operand sits in columns [0,128) of the other buffer
       auto acc_of = [&](uint32_t l) { return tmem_base + (l & 1u) * 256u; };
       auto a_of = [&](uint32_t l) { return tmem_base + ((l & 1u) ^ 1u) * 256u; };
-      for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
-        const int e = tt.tile_expert[t];
+      for (int tb = t_first0; tb < n_tiles; tb += t_stride) {
+        const int e = tt.tile_expert[tb + (int)rank];
         tl_mark(P.tl, 1, tn, 1);
         if (e >= 0) {
-          ts_mma_seg(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, false, P.tl, &tn);
-          umma_commit(&ctl->acc_full[li & 1]);
+          ts_mma_seg<CG>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, false, rank, P.tl, &tn);
+          ts_commit_acc<CG>(ctl, li & 1, rank);
           tl_mark(P.tl, 1, tn, 120);
           ++li;
           for (int l = 0; l < NE; ++l, ++li) {
-            ts_mma_seg(MW, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, P.tl, &tn);
+            ts_mma_seg<CG>(MW, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, rank, P.tl, &tn);
             if (l == P.skip_layer)
-              ts_mma_seg(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, P.tl, &tn);
-            umma_commit(&ctl->acc_full[li & 1]);
+              ts_mma_seg<CG>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, rank, P.tl, &tn);
+            ts_commit_acc<CG>(ctl, li & 1, rank);
             tl_mark(P.tl, 1, tn, 120);
           }
         }
-        ts_mma_seg(P.back[0].N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, P.tl, &tn);
-        umma_commit(&ctl->acc_full[li & 1]);
+        ts_mma_seg<CG>(P.back[0].N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, rank, P.tl, &tn);
+        ts_commit_acc<CG>(ctl, li & 1, rank);
         tl_mark(P.tl, 1, tn, 120);
         ++li;
-        ts_mma_seg(P.back[1].N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, P.tl, &tn);
-        ts_mma_seg(P.back[1].N, K_cat, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, P.tl, &tn);
-        umma_commit(&ctl->acc_full[li & 1]);
+        ts_mma_seg<CG>(P.back[1].N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, rank, P.tl, &tn);
+        ts_mma_seg<CG>(P.back[1].N, K_cat, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, rank, P.tl, &tn);
+        ts_commit_acc<CG>(ctl, li & 1, rank);
         tl_mark(P.tl, 1, tn, 120);
         ++li;
       }
     }
   } else {
     EpiCtx ec;
-    ec.remote_a_ready = 0; ec.lane = lane; ec.q = warp & 3; ec.cs = (warp - 2) >> 2; ec.row = ec.q * 32 + lane;
+    ec.remote_a_ready = (CG == 2 && rank != 0) ? mapa_shared(smem_u32(&ctl->a_ready[0]), 0) : 0u;
+    const uint32_t remote_s = (CG == 2 && rank != 0) ? mapa_shared(smem_u32(&ctl->s_ready[0]), 0) : 0u;
+    ec.lane = lane; ec.q = warp & 3; ec.cs = (warp - 2) >> 2; ec.row = ec.q * 32 + lane;
     ec.et = (int)threadIdx.x - 64; ec.lane_base = (uint32_t)(ec.q * 32) << 16;
     const int row = ec.row;
     const float b_sig = P.fblob[P.o_bsig];
@@ -267,8 +312,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       }
       return r;
     };
-    RowIn nxt = fetch_row((int)blockIdx.x);
-    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
+    RowIn nxt = fetch_row(t_first0 + (int)rank);
+    for (int tb = t_first0; tb < n_tiles; tb += t_stride) {
+      const int t = tb + (int)rank;
       const RowIn cur = nxt;
       const int e = cur.e, sidx = cur.sidx;
       const bool valid = sidx >= 0;
@@ -309,8 +355,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           for (int i = NPE; i < NPAD; ++i) pe[i] = __float2bfloat16_rn(0.f);
           ts_cat_store_row(acat_base, row, pe, NPAD / 8);
         }
-        for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane);
-        nxt = fetch_row(t + (int)gridDim.x);
+        for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane, remote_s);
+        nxt = fetch_row(t + t_stride);
         tl_mark(tl, 0, tn, 2);
         // ---- xyz layer (act none): h -> packed A ----
         {
@@ -318,7 +364,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           epi_load_bias(P.fblob + P.front[0].b_off, MW, sbias, buf, ec.et);
           ts_wait_acc(ctl, pp, buf);
           ts_epi_hidden<false>(tbuf_of(li), sbias + buf * 256, ec, ctl, tl, &tn);
-          if (P.skip_layer == 0) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane);
+          if (P.skip_layer == 0) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane, remote_s);
           ++li;
         }
         for (int l = 0; l < NE; ++l, ++li) {
@@ -334,7 +380,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           const uint32_t tb = tbuf_of(li);
           if (l < NE - 1) {
             ts_epi_hidden<true>(tb, sb, ec, ctl, tl, &tn);
-            if (l + 1 == P.skip_layer) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane);
+            if (l + 1 == P.skip_layer) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane, remote_s);
           } else {
             // last expert layer (no activation) -> combine: y = bf16(gate * bf16(out)) -> ReLU -> packed A; sigma head
 #pragma unroll
@@ -360,7 +406,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
                 }
                 tmem_st8(tb + (uint32_t)(c * 32 + ec.cs * 8), pk);
                 tmem_st_wait();
-                ts_signal(ctl, c, lane);
+                ts_signal(ctl, c, lane, ec.remote_a_ready);
               }
             }
           }
@@ -368,12 +414,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         }
       } else {
         // dropped bucket: h = relu(0) = 0 -> zero A operand for layer "1" (it accumulates into B[li&1], reads B[~li&1])
-        nxt = fetch_row(t + (int)gridDim.x);
+        nxt = fetch_row(t + t_stride);
         const uint32_t ta = tbuf_of(li + 1);
         const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int c = 0; c < 4; ++c) tmem_st8(ta + (uint32_t)(c * 32 + ec.cs * 8), z);
         tmem_st_wait();
-        for (int c = 0; c < 4; ++c) ts_signal(ctl, c, lane);
+        for (int c = 0; c < 4; ++c) ts_signal(ctl, c, lane, ec.remote_a_ready);
         write_cat();
       }
       sred[(0 * 4 + ec.cs) * 128 + row] = sig_acc;
@@ -383,7 +429,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         epi_load_bias(P.fblob + P.back[0].b_off, MW, sbias, buf, ec.et);
         ts_wait_acc(ctl, pp, buf);
         ts_epi_hidden<false>(tbuf_of(li), sbias + buf * 256, ec, ctl, tl, &tn);
-        for (int i = 0; i < n_scat; ++i) ts_signal_smem(ctl, i, lane);
+        for (int i = 0; i < n_scat; ++i) ts_signal_smem(ctl, i, lane, remote_s);
         tl_mark(tl, 0, tn, 50);
         ++li;
       }
@@ -438,8 +484,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
     if (io.ep) __threadfence_system();
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (CG == 2) cluster_sync_all();     // the peer may still arrive on this CTA's barriers
+  else __syncthreads();
+  if (warp == 1) {
+    if (CG == 2) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
   if (io.ep && threadIdx.x == 0) {
     if (atomicAdd(io.done, 1) == (int)gridDim.x - 1) {
       *io.done = 0;

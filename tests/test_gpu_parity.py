@@ -392,19 +392,15 @@ def _check_bf16_variants(tmp_path, variants):
 
 
 def test_model_bf16_cta_pair_and_gather_variants(built_lib, tmp_path):
-    """The fused kernels have variants selected by environment switches read once per process:
-    SNB_CG=2 (tcgen05 cta_group::2 CTA pairs, M=256 MMAs issued by the leader CTA of a 2-CTA cluster) and
-    SNB_GATHER_H=1 (launch #2 gathers h from HBM instead of recomputing it).  Each must agree with the default
-    variant on the same inputs (same rounding points; the h-recompute variant sums the skip term in fp32)."""
-    _check_bf16_variants(tmp_path, (("pair", {"SNB_CG": "2"}), ("gather", {"SNB_GATHER_H": "1"}),
+    """Launch #2 has variants selected by environment switches read once per process.  Default: hidden activations in
+    tensor memory (tcgen05.st by the epilogue, A operand of tcgen05.mma taken from TMEM, csrc/snb_tc_ts.cuh).
+    SNB_CG=2: tcgen05 cta_group::2 CTA pairs (M=256 MMAs issued by the leader CTA of a 2-CTA cluster).
+    SNB_TS=0: A operand staged in shared memory (k_back).  SNB_GATHER_H=1: launch #2 gathers h from HBM instead of
+    recomputing it (shared-memory kernel only).  Each must agree with the default on the same inputs (same rounding
+    points; only the fp32 accumulation order inside a layer differs)."""
+    _check_bf16_variants(tmp_path, (("ts_pair", {"SNB_CG": "2"}), ("smem", {"SNB_TS": "0"}),
+                                    ("smem_pair", {"SNB_TS": "0", "SNB_CG": "2"}), ("gather", {"SNB_GATHER_H": "1"}),
                                     ("pair_gather", {"SNB_CG": "2", "SNB_GATHER_H": "1"})))
-
-
-def test_model_bf16_tmem_operand_variant(built_lib, tmp_path):
-    """SNB_TS=1: launch #2 keeps the hidden activations in tensor memory (tcgen05.st by the epilogue, A operand of
-    tcgen05.mma taken from TMEM, 64x64 block schedule -- csrc/snb_tc_ts.cuh).  Same rounding points as the default
-    kernel; only the fp32 accumulation order inside a layer differs."""
-    _check_bf16_variants(tmp_path, (("ts", {"SNB_TS": "1"}),))
 
 
 @pytest.mark.gpu
