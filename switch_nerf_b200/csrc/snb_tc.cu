@@ -1182,7 +1182,8 @@ struct TcChunk {
   PhaseEvents* pe;
   int set;                  // expert-parallel buffer set of this chunk
   int grid_cap;             // CTAs of the persistent kernels (<= SM count)
-  int cg;                   // 1 = independent CTAs, 2 = CTA pairs (tcgen05 cta_group::2)
+  int cg;                   // launch #1: 1 = independent CTAs, 2 = CTA pairs (tcgen05 cta_group::2)
+  int cg_back;              // launch #2 (SNB_CG sets both, SNB_CG_FRONT / SNB_CG_BACK one of them)
 };
 
 static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const float* sigma_noise,
@@ -1249,7 +1250,10 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
     attr_done = true;
   }
   static const int cg_env = getenv("SNB_CG") ? atoi(getenv("SNB_CG")) : 1;
-  c.cg = (cg_env == 2) ? 2 : 1;
+  static const int cg_front_env = getenv("SNB_CG_FRONT") ? atoi(getenv("SNB_CG_FRONT")) : cg_env;
+  static const int cg_back_env = getenv("SNB_CG_BACK") ? atoi(getenv("SNB_CG_BACK")) : cg_env;
+  c.cg = (cg_front_env == 2) ? 2 : 1;
+  c.cg_back = (cg_back_env == 2) ? 2 : 1;
   c.pe = profile_next();
   c.grid_cap = m->sm_count;
   return SNB_OK;
@@ -1288,10 +1292,10 @@ static int tc_route(Model* m, TcChunk& c, cudaStream_t st) {
     // experts live on other ranks: one kernel scatters this rank's records into the owners' memory (P2P stores +
     // per-peer flags), one plans the tiles over what the peers sent here
     rc = ep_dispatch_plan(m->ep, c.set, c.x, m->x_cols, c.gate, c.noise, c.idx, c.loc, c.counts, c.cap_dev, c.S,
-                          capacity_of(c.S, E, c.o.capacity_factor), c.cg == 2, c.tt, st);
+                          capacity_of(c.S, E, c.o.capacity_factor), c.cg_back == 2, c.tt, st);
     if (rc) return rc;
   } else {
-    k_tile_plan<<<1, 256, 0, st>>>(c.counts, c.cap_dev, E, c.o.no_batch, c.S, c.cg == 2, c.tt);
+    k_tile_plan<<<1, 256, 0, st>>>(c.counts, c.cap_dev, E, c.o.no_batch, c.S, c.cg_back == 2, c.tt);
     SNB_CHECK_LAUNCH("k_tile_plan");
     k_scatter_rows<<<(unsigned)cdiv(c.S, 256), 256, 0, st>>>(c.idx, c.loc, c.cap_dev, E, c.o.no_batch, c.S, c.tt);
     SNB_CHECK_LAUNCH("k_scatter_rows");
@@ -1319,7 +1323,7 @@ static int tc_back(Model* m, TcChunk& c, cudaStream_t st) {
   static const bool use_ts = !(getenv("SNB_TS") && atoi(getenv("SNB_TS")) == 0);
   const bool ts_ok = use_ts && c.Pb.recompute_h && c.Pb.back[1].K16 > MW && c.Pb.back[1].K16 - MW <= TS_CAT_COLS &&
                      c.Pb.front[0].K16 <= TS_CAT_COLS;
-  if (c.cg == 2) {
+  if (c.cg_back == 2) {
     grid2 &= ~1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid2); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = ts_ok ? TSM_TOTAL : SM_TOTAL; cfg.stream = st;
