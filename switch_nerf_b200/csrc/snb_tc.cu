@@ -1245,6 +1245,7 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front_ts<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_ts<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_ts<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSM_TOTAL));
     attr_done = true;
@@ -1274,7 +1275,13 @@ static int tc_front(Model* m, TcChunk& c, cudaStream_t st) {
     cfg.attrs = at; cfg.numAttrs = 1;
     SNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_front<12, 2>, c.Pf, c.x, c.S, c.H, c.gates));
   } else {
-    k_front<12, 1><<<grid1, THREADS, SM_TOTAL, st>>>(c.Pf, c.x, c.S, c.H, c.gates);
+    // SNB_TS_FRONT=0 / SNB_TS=0: shared-memory A operand (k_front)
+    static const bool ts_front = !(getenv("SNB_TS") && atoi(getenv("SNB_TS")) == 0) &&
+                                 !(getenv("SNB_TS_FRONT") && atoi(getenv("SNB_TS_FRONT")) == 0);
+    if (ts_front && c.Pf.recompute_h && c.Pf.front[0].K16 <= TS_CAT_COLS)
+      k_front_ts<12><<<grid1, THREADS, TSM_TOTAL, st>>>(c.Pf, c.x, c.S, c.gates);
+    else
+      k_front<12, 1><<<grid1, THREADS, SM_TOTAL, st>>>(c.Pf, c.x, c.S, c.H, c.gates);
   }
   SNB_CHECK_LAUNCH("k_front");
   if (c.pe) cudaEventRecord(c.pe->e[1], st);

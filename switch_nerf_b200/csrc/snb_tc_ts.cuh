@@ -8,12 +8,13 @@
 // tensor memory (~340 clk per chunk, no proxy fence) and the MMA takes the A operand from there (138 clk).
 //
 // TMEM map: two 256-column buffers B0 / B1 as in k_back; layer li accumulates into B[li & 1].  Its epilogue drains
-// the fp32 accumulator chunk by chunk and writes the packed bf16 result IN PLACE into columns [0,128) of the same
-// buffer (chunk c: fp32 columns [64c, 64c+64) -> bf16 pairs in columns [32c, 32c+32)); layer li+1 reads that as
-// its A operand while accumulating into the other buffer.  The packed chunk c only ever overwrites fp32 columns of
-// chunks 0/1, so one 128-thread barrier per layer (after the four warps of a lane quarter have loaded chunks 0 and
-// 1) makes the in-place update safe.  A 64x64-block schedule with N=64 instructions was tried first and is 1.7x
-// slower: a tcgen05.mma costs ~123 clk for any N <= 128 (profiles/r1i_umma_microbench.json).
+// the fp32 accumulator and writes the packed bf16 result IN PLACE: the thread that read fp32 columns
+// [64c + 16t, +16) of its row writes the 16 bf16 values as 8 packed columns [64c + 16t, +8) -- exactly the 8
+// columns one K=16 tcgen05.mma reads as its A operand, so the operand of instruction (chunk c, step t) of layer
+// li+1 sits at column 64c + 16t of B[li & 1] while that layer accumulates into the other buffer.  A thread only
+// ever overwrites columns it has itself already loaded: no cross-warp hazard, no barrier.
+// Tried and rejected (profiles/): a 64x64-block schedule with N=64 instructions (a tcgen05.mma costs ~123 clk for
+// any N <= 128, r1i_umma_microbench.json) and cta_group::2 pairs of this kernel (pair MMAs ran at ~380 clk, r1k).
 //
 // The PE(xyz) / [PE(dir) | appearance] columns stay in shared memory (24 KB); the weight ring has 5 x 32 KB stages.
 #pragma once
@@ -59,8 +60,14 @@ __device__ __forceinline__ void ts_cat_store_row(uint32_t base, int row, const _
     st_shared_v4(ts_cat_addr(base, row, g), t.x, t.y, t.z, t.w);
   }
 }
-// the four warps (cs = 0..3) that share TMEM lane quarter q
-__device__ __forceinline__ void ts_quarter_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory"); }
+// tcgen05.wait::ld that also "produces" the loaded registers, so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
 
 // ---- producer: the K-slices of one packed layer image (same images as k_back) ----
 // CG = 2 (CTA pair): each CTA streams its own half of the slice (output rows [rank*N/2, +N/2) are the contiguous half)
@@ -112,8 +119,8 @@ __device__ __forceinline__ void ts_mma_seg(uint32_t N, uint32_t K, bool ts, uint
       const uint64_t db = op_desc(b_base + (2u * t) * 128u, 128u, klen * 16u);
       const uint32_t acc = (cont || (j | t)) ? 1u : 0u;
       if (ts) {
-        if (CG == 2) umma_bf16_ts_pair(d_tmem, a_tmem + j * 32u + t * 8u, db, idesc, acc);
-        else umma_bf16_ts(d_tmem, a_tmem + j * 32u + t * 8u, db, idesc, acc);
+        if (CG == 2) umma_bf16_ts_pair(d_tmem, a_tmem + j * 64u + t * 16u, db, idesc, acc);
+        else umma_bf16_ts(d_tmem, a_tmem + j * 64u + t * 16u, db, idesc, acc);
       } else {
         const uint64_t da = op_desc(acat_base + (8u * j + 2u * t) * 128u, 128u, TS_SBO);
         if (CG == 2) umma_bf16_pair(d_tmem, da, db, idesc, acc);
@@ -159,34 +166,31 @@ __device__ __forceinline__ void ts_signal_smem(TsCtl* ctl, int i, int lane, uint
     else mbar_arrive(&ctl->s_ready[i]);
   }
 }
-// hidden layer: y = act(acc + bias) -> bf16, packed in place into columns [0,128) of the drained buffer.
-// Thread owns fp32 columns [64c + 16cs, +16) of every chunk c and writes packed columns [32c + 8cs, +8).
+// hidden layer: y = act(acc + bias) -> bf16, packed in place.  Thread owns fp32 columns [64c + 16cs, +16) of every
+// chunk c and writes the packed values to columns [64c + 16cs, +8).  The load of chunk c+1 is in flight while chunk c
+// is converted and stored.
 template <bool RELU>
 __device__ __forceinline__ void ts_epi_hidden(uint32_t tbuf /* tmem_base + lane_base + buf*256 */, const float* sb,
                                               const EpiCtx& ec, TsCtl* ctl, unsigned long long* tl, int* tn) {
+  uint32_t v[2][16];
+  tmem_ld16(tbuf + (uint32_t)(ec.cs * 16), v[0]);
 #pragma unroll
-  for (int c2 = 0; c2 < 4; c2 += 2) {
-    uint32_t v[2][16];
-    tmem_ld16(tbuf + (uint32_t)(c2 * 64 + ec.cs * 16), v[0]);
-    tmem_ld16(tbuf + (uint32_t)(c2 * 64 + 64 + ec.cs * 16), v[1]);
-    tmem_ld_wait();
-    if (c2 == 0) ts_quarter_sync(ec.q);      // chunks 0/1 of this lane quarter are in registers everywhere
+  for (int c = 0; c < 4; ++c) {
+    tmem_ld_wait16(v[c & 1]);
+    if (c < 3) tmem_ld16(tbuf + (uint32_t)((c + 1) * 64 + ec.cs * 16), v[(c + 1) & 1]);
+    const int col0 = c * 64 + ec.cs * 16;
+    const float4* b4 = reinterpret_cast<const float4*>(sb + col0);
+    uint32_t pk[8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int c = c2 + h, col0 = c * 64 + ec.cs * 16;
-      const float4* b4 = reinterpret_cast<const float4*>(sb + col0);
-      uint32_t pk[8];
-#pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        const float4 b = b4[j4];
-        pk[2 * j4] = pack2<RELU>(__uint_as_float(v[h][4 * j4 + 0]) + b.x, __uint_as_float(v[h][4 * j4 + 1]) + b.y);
-        pk[2 * j4 + 1] = pack2<RELU>(__uint_as_float(v[h][4 * j4 + 2]) + b.z, __uint_as_float(v[h][4 * j4 + 3]) + b.w);
-      }
-      tmem_st8(tbuf + (uint32_t)(c * 32 + ec.cs * 8), pk);
-      tmem_st_wait();
-      ts_signal(ctl, c, ec.lane, ec.remote_a_ready);
-      if (tn) tl_mark(tl, 0, *tn, 60 + c);
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 b = b4[j4];
+      pk[2 * j4] = pack2<RELU>(__uint_as_float(v[c & 1][4 * j4 + 0]) + b.x, __uint_as_float(v[c & 1][4 * j4 + 1]) + b.y);
+      pk[2 * j4 + 1] = pack2<RELU>(__uint_as_float(v[c & 1][4 * j4 + 2]) + b.z, __uint_as_float(v[c & 1][4 * j4 + 3]) + b.w);
     }
+    tmem_st8(tbuf + (uint32_t)col0, pk);
+    tmem_st_wait();
+    ts_signal(ctl, c, ec.lane, ec.remote_a_ready);
+    if (tn) tl_mark(tl, 0, *tn, 60 + c);
   }
 }
 
@@ -383,31 +387,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
             if (l + 1 == P.skip_layer) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane, remote_s);
           } else {
             // last expert layer (no activation) -> combine: y = bf16(gate * bf16(out)) -> ReLU -> packed A; sigma head
+            uint32_t v[2][16];
+            tmem_ld16(tb + (uint32_t)(ec.cs * 16), v[0]);
 #pragma unroll
-            for (int c2 = 0; c2 < 4; c2 += 2) {
-              uint32_t v[2][16];
-              tmem_ld16(tb + (uint32_t)(c2 * 64 + ec.cs * 16), v[0]);
-              tmem_ld16(tb + (uint32_t)(c2 * 64 + 64 + ec.cs * 16), v[1]);
-              tmem_ld_wait();
-              if (c2 == 0) ts_quarter_sync(ec.q);
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld_wait16(v[c & 1]);
+              if (c < 3) tmem_ld16(tb + (uint32_t)((c + 1) * 64 + ec.cs * 16), v[(c + 1) & 1]);
+              const int col0 = c * 64 + ec.cs * 16;
+              uint32_t pk[8];
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int c = c2 + h, col0 = c * 64 + ec.cs * 16;
-                uint32_t pk[8];
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                  float f0 = bf16_round(__uint_as_float(v[h][j]) + sb[col0 + j]);
-                  float f1 = bf16_round(__uint_as_float(v[h][j + 1]) + sb[col0 + j + 1]);
-                  f0 = fmaxf(bf16_round(f0 * g), 0.f);
-                  f1 = fmaxf(bf16_round(f1 * g), 0.f);
-                  sig_acc = fmaf(f0, s_wsig[col0 + j], sig_acc);
-                  sig_acc = fmaf(f1, s_wsig[col0 + j + 1], sig_acc);
-                  pk[j / 2] = pack_bf16x2(f0, f1);
-                }
-                tmem_st8(tb + (uint32_t)(c * 32 + ec.cs * 8), pk);
-                tmem_st_wait();
-                ts_signal(ctl, c, lane, ec.remote_a_ready);
+              for (int j = 0; j < 16; j += 2) {
+                float f0 = bf16_round(__uint_as_float(v[c & 1][j]) + sb[col0 + j]);
+                float f1 = bf16_round(__uint_as_float(v[c & 1][j + 1]) + sb[col0 + j + 1]);
+                f0 = fmaxf(bf16_round(f0 * g), 0.f);
+                f1 = fmaxf(bf16_round(f1 * g), 0.f);
+                sig_acc = fmaf(f0, s_wsig[col0 + j], sig_acc);
+                sig_acc = fmaf(f1, s_wsig[col0 + j + 1], sig_acc);
+                pk[j / 2] = pack_bf16x2(f0, f1);
               }
+              tmem_st8(tb + (uint32_t)col0, pk);
+              tmem_st_wait();
+              ts_signal(ctl, c, lane, ec.remote_a_ready);
             }
           }
           tl_mark(tl, 0, tn, 30 + l);
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         nxt = fetch_row(t + t_stride);
         const uint32_t ta = tbuf_of(li + 1);
         const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int c = 0; c < 4; ++c) tmem_st8(ta + (uint32_t)(c * 32 + ec.cs * 8), z);
+        for (int c = 0; c < 4; ++c) tmem_st8(ta + (uint32_t)(c * 64 + ec.cs * 16), z);
         tmem_st_wait();
         for (int c = 0; c < 4; ++c) ts_signal(ctl, c, lane, ec.remote_a_ready);
         write_cat();
@@ -498,4 +498,187 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(io.flag_b[w]), "r"(io.epoch) : "memory");
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Launch #1, TS variant: PE -> xyz layer -> external gate MLP -> folded LayerNorm + gate GEMM -> softmax, with the
+// hidden activations packed in tensor memory exactly as in k_back_ts (h is not written: launch #2 recomputes it).
+// ------------------------------------------------------------------------------------------------------------
+template <int FX>
+__global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float* __restrict__ x, int64_t S,
+                                                         float* __restrict__ gates) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TsCtl* ctl = reinterpret_cast<TsCtl*>(smem + TSM_CTL);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TS_NST; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); mbar_init(&ctl->peer_ok[i], 1); }
+    mbar_init(&ctl->acc_full[0], 1);
+    mbar_init(&ctl->acc_full[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS);
+    mbar_init(&ctl->s_ready[0], EPI_WARPS);
+    mbar_init(&ctl->s_ready[1], EPI_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&ctl->tmem_base);
+  float* sbias = reinterpret_cast<float*>(smem + TSM_BIAS);
+  float* sred = reinterpret_cast<float*>(smem + TSM_RED);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  const uint32_t acat_base = smem_u32(smem + TSM_ACAT), ring_base = smem_u32(smem + TSM_RING);
+  const int n_tiles = (int)((S + TILE - 1) / TILE);
+  const int NL = P.n_front;                       // xyz layer + gate MLP layers
+  const uint32_t K_xyz = P.front[0].K16;
+  const int n_sxyz = ((int)K_xyz + 63) / 64;
+  TsPipe pp;
+
+  if (warp == 0) {
+    if (lane == 0)
+      for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
+        for (int l = 0; l < NL; ++l)
+          ts_produce<1>(P.wblob + P.front[l].w_off, P.front[l].N, P.front[l].K16, smem + TSM_RING, ctl, pp, 0);
+        ts_produce<1>(P.wblob + P.gate.w_off, GATE_N, MW, smem + TSM_RING, ctl, pp, 0);
+      }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t li = 0;
+      int tn = 0;
+      auto acc_of = [&](uint32_t l) { return tmem_base + (l & 1u) * 256u; };
+      auto a_of = [&](uint32_t l) { return tmem_base + ((l & 1u) ^ 1u) * 256u; };
+      for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
+        tl_mark(P.tl, 1, tn, 1);
+        ts_mma_seg<1>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, false, 0, P.tl, &tn);
+        ts_commit_acc<1>(ctl, li & 1, 0);
+        ++li;
+        for (int l = 1; l < NL; ++l, ++li) {
+          ts_mma_seg<1>(MW, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, 0, P.tl, &tn);
+          ts_commit_acc<1>(ctl, li & 1, 0);
+          tl_mark(P.tl, 1, tn, 120);
+        }
+        ts_mma_seg<1>(GATE_N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, 0, P.tl, &tn);
+        ts_commit_acc<1>(ctl, li & 1, 0);
+        tl_mark(P.tl, 1, tn, 120);
+        ++li;
+      }
+    }
+  } else {
+    EpiCtx ec;
+    ec.remote_a_ready = 0; ec.lane = lane; ec.q = warp & 3; ec.cs = (warp - 2) >> 2; ec.row = ec.q * 32 + lane;
+    ec.et = (int)threadIdx.x - 64; ec.lane_base = (uint32_t)(ec.q * 32) << 16;
+    const int row = ec.row;
+    uint32_t li = 0;
+    int tn = 0;
+    unsigned long long* tl = (warp == 2 && lane == 0) ? P.tl : nullptr;
+    auto tbuf_of = [&](uint32_t l) { return tmem_base + ec.lane_base + (l & 1u) * 256u; };
+    float pn[3] = {0.f, 0.f, 0.f};          // xyz of this thread's row in the NEXT tile
+    if (ec.cs == 0) {
+      const int64_t s0 = (int64_t)blockIdx.x * TILE + row;
+      if ((int)blockIdx.x < n_tiles && s0 < S) { pn[0] = x[s0 * P.x_cols]; pn[1] = x[s0 * P.x_cols + 1]; pn[2] = x[s0 * P.x_cols + 2]; }
+    }
+    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
+      const int64_t s = (int64_t)t * TILE + row;
+      const bool valid = s < S;
+      tl_mark(tl, 0, tn, 1);
+      constexpr int NPE = 3 + 6 * FX, NPAD = (NPE + 15) / 16 * 16;
+      if (ec.cs == 0) {
+        float p[3] = {pn[0], pn[1], pn[2]};
+        {
+          const int64_t sn = s + (int64_t)gridDim.x * TILE;
+          pn[0] = pn[1] = pn[2] = 0.f;
+          if (t + (int)gridDim.x < n_tiles && sn < S) { pn[0] = x[sn * P.x_cols]; pn[1] = x[sn * P.x_cols + 1]; pn[2] = x[sn * P.x_cols + 2]; }
+        }
+        __align__(16) __nv_bfloat16 pe[NPAD];
+        pe_to_bf16<FX>(p, pe);
+#pragma unroll
+        for (int i = NPE; i < NPAD; ++i) pe[i] = __float2bfloat16_rn(0.f);
+        ts_cat_store_row(acat_base, row, pe, NPAD / 8);
+      }
+      for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane, 0);
+      tl_mark(tl, 0, tn, 2);
+      float sum = 0.f, sq = 0.f;
+      for (int l = 0; l < NL; ++l, ++li) {
+        const int buf = (int)(li & 1);
+        epi_load_bias(P.fblob + P.front[l].b_off, MW, sbias, buf, ec.et);
+        const float* sb = sbias + buf * 256;
+        tl_mark(tl, 0, tn, 10 + l);
+        ts_wait_acc(ctl, pp, buf);
+        tl_mark(tl, 0, tn, 20 + l);
+        const uint32_t tb = tbuf_of(li);
+        if (l == 0) {
+          ts_epi_hidden<false>(tb, sb, ec, ctl, tl, &tn);       // h = xyz Linear (act none)
+        } else if (l < NL - 1) {
+          ts_epi_hidden<true>(tb, sb, ec, ctl, tl, &tn);
+        } else {
+          // last gate-MLP layer: g = bf16(Linear) -> packed A of the folded gate GEMM + LayerNorm statistics
+          uint32_t v[2][16];
+          tmem_ld16(tb + (uint32_t)(ec.cs * 16), v[0]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            tmem_ld_wait16(v[c & 1]);
+            if (c < 3) tmem_ld16(tb + (uint32_t)((c + 1) * 64 + ec.cs * 16), v[(c + 1) & 1]);
+            const int col0 = c * 64 + ec.cs * 16;
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float g0 = bf16_round(__uint_as_float(v[c & 1][j]) + sb[col0 + j]);
+              const float g1 = bf16_round(__uint_as_float(v[c & 1][j + 1]) + sb[col0 + j + 1]);
+              sum += g0 + g1;
+              sq = fmaf(g0, g0, fmaf(g1, g1, sq));
+              pk[j / 2] = pack_bf16x2(g0, g1);
+            }
+            tmem_st8(tb + (uint32_t)col0, pk);
+            tmem_st_wait();
+            ts_signal(ctl, c, lane, 0);
+          }
+          sred[(0 * 4 + ec.cs) * 128 + row] = sum;
+          sred[(1 * 4 + ec.cs) * 128 + row] = sq;
+        }
+        tl_mark(tl, 0, tn, 30 + l);
+      }
+      // ---- folded LayerNorm + gate GEMM epilogue: logits = rstd*(G_hi + G_lo - mean*c1) + c0 ; softmax ----
+      {
+        const int buf = (int)(li & 1);
+        epi_bar_sync();                       // LayerNorm partial sums of all 4 column sub-slices are in sred
+        ts_wait_acc(ctl, pp, buf);
+        tl_mark(tl, 0, tn, 40);
+        if (ec.cs == 0) {
+          const float tsum = sred[0 * 128 + row] + sred[1 * 128 + row] + sred[2 * 128 + row] + sred[3 * 128 + row];
+          const float tsq = sred[4 * 128 + row] + sred[5 * 128 + row] + sred[6 * 128 + row] + sred[7 * 128 + row];
+          const float mean = tsum * (1.f / MW);
+          const float var = fmaxf(tsq * (1.f / MW) - mean * mean, 0.f);
+          const float rstd = rsqrtf(var + 1e-5f);
+          const uint32_t tacc = tbuf_of(li);
+          uint32_t hi[16], lo[16];
+          tmem_ld16(tacc, hi);
+          tmem_ld16(tacc + 16u, lo);
+          tmem_ld_wait();
+          float lg[MAX_E];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < MAX_E; ++e) {
+            lg[e] = rstd * (__uint_as_float(hi[e]) + __uint_as_float(lo[e]) - mean * P.fblob[P.o_c1 + e]) + P.fblob[P.o_c0 + e];
+            if (e < P.E) mx = fmaxf(mx, lg[e]);
+          }
+          float den = 0.f;
+#pragma unroll
+          for (int e = 0; e < MAX_E; ++e)
+            if (e < P.E) { lg[e] = expf(lg[e] - mx); den += lg[e]; }
+          if (valid) {
+#pragma unroll
+            for (int e = 0; e < MAX_E; ++e)
+              if (e < P.E) gates[s * P.E + e] = lg[e] / den;
+          }
+        }
+        tc_fence_before();
+        epi_bar_sync();                       // sred is reused by the next tile
+        tl_mark(tl, 0, tn, 41);
+        ++li;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
 }

@@ -398,7 +398,7 @@ def test_model_bf16_cta_pair_and_gather_variants(built_lib, tmp_path):
     SNB_TS=0: A operand staged in shared memory (k_back).  SNB_GATHER_H=1: launch #2 gathers h from HBM instead of
     recomputing it (shared-memory kernel only).  Each must agree with the default on the same inputs (same rounding
     points; only the fp32 accumulation order inside a layer differs)."""
-    _check_bf16_variants(tmp_path, (("ts_pair", {"SNB_CG": "2"}), ("smem", {"SNB_TS": "0"}),
+    _check_bf16_variants(tmp_path, (("ts_pair", {"SNB_CG": "2"}), ("smem", {"SNB_TS": "0"}), ("smem_front", {"SNB_TS_FRONT": "0"}),
                                     ("smem_pair", {"SNB_TS": "0", "SNB_CG": "2"}), ("gather", {"SNB_GATHER_H": "1"}),
                                     ("pair_gather", {"SNB_CG": "2", "SNB_GATHER_H": "1"})))
 
