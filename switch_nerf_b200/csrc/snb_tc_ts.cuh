@@ -16,7 +16,8 @@
 // Tried and rejected (profiles/): a 64x64-block schedule with N=64 instructions (a tcgen05.mma costs ~123 clk for
 // any N <= 128, r1i_umma_microbench.json) and cta_group::2 pairs of this kernel (pair MMAs ran at ~380 clk, r1k).
 //
-// The PE(xyz) / [PE(dir) | appearance] columns stay in shared memory (24 KB); the weight ring has 5 x 32 KB stages.
+// The PE(xyz) / [PE(dir) | appearance] columns stay in shared memory (2 x 24 KB, alternating per tile so the next
+// tile's PE(xyz) is staged while this tile waits for the tensor pipe); the weight ring has 5 x 32 KB stages.
 #pragma once
 
 static constexpr uint32_t TS_CAT_COLS = 96;                       // PE(xyz) / [PE(dir) | appearance] block
@@ -30,12 +31,12 @@ struct __align__(16) TsCtl {
   uint64_t peer_ok[TS_NST]; // CTA pairs, leader only: the peer's half of the weight slice landed
   uint64_t acc_full[2];
   uint64_t a_ready[4];      // epilogue -> MMA: K-chunk of the next A operand packed into TMEM
-  uint64_t s_ready[2];      // epilogue -> MMA: shared-memory K-chunk (PE / cat block) written
+  uint64_t s_ready[2][2];   // epilogue -> MMA: shared-memory K-chunk written, [cat block][chunk]
   uint32_t tmem_base;
   uint32_t pad;
 };
 static constexpr size_t TSM_ACAT = 0;
-static constexpr size_t TSM_RING = TS_ACAT_BYTES;
+static constexpr size_t TSM_RING = 2 * TS_ACAT_BYTES;      // two cat blocks: tile t+1's PE(xyz) is staged during tile t
 static constexpr size_t TSM_BIAS = TSM_RING + (size_t)TS_NST * STAGE_BYTES;
 static constexpr size_t TSM_VEC = TSM_BIAS + 2 * 256 * 4;
 static constexpr size_t TSM_RED = TSM_VEC + SM_VEC_FLOATS * 4;
@@ -46,7 +47,7 @@ static_assert(TSM_TOTAL <= 227 * 1024, "shared memory budget (TS kernel)");
 struct TsPipe {
   uint32_t slice = 0;                  // weight slices produced / consumed
   uint32_t a_use[4] = {0, 0, 0, 0};
-  uint32_t s_use[2] = {0, 0};
+  uint32_t s_use[2][2] = {{0, 0}, {0, 0}};
   uint32_t acc_use[2] = {0, 0};
 };
 
@@ -93,7 +94,7 @@ __device__ __forceinline__ void ts_produce(const uint8_t* wsrc, uint32_t N, uint
 template <int CG>
 __device__ __forceinline__ void ts_mma_seg(uint32_t N, uint32_t K, bool ts, uint32_t a_tmem, uint32_t acat_base,
                                            uint32_t ring_base, uint32_t d_tmem, TsCtl* ctl, TsPipe& pp, bool cont,
-                                           uint32_t rank, unsigned long long* tl, int* tn) {
+                                           uint32_t rank, unsigned long long* tl, int* tn, uint32_t cb = 0) {
   const uint32_t nsl = (K + 63) / 64;
   const uint32_t idesc = umma_idesc_bf16(TILE * CG, (int)N);
 #pragma unroll
@@ -108,7 +109,7 @@ __device__ __forceinline__ void ts_mma_seg(uint32_t N, uint32_t K, bool ts, uint
       continue;
     }
     if (ts) { mbar_wait(&ctl->a_ready[j], pp.a_use[j] & 1); ++pp.a_use[j]; }
-    else if (j < 2) { mbar_wait(&ctl->s_ready[j], pp.s_use[j] & 1); ++pp.s_use[j]; }
+    else if (j < 2) { mbar_wait(&ctl->s_ready[cb][j], pp.s_use[cb][j] & 1); ++pp.s_use[cb][j]; }
     if (tn) tl_mark(tl, 1, *tn, 100 + (int)j);
     mbar_wait(&ctl->full[stage], phase);
     if (CG == 2) mbar_wait(&ctl->peer_ok[stage], phase);
@@ -122,7 +123,7 @@ __device__ __forceinline__ void ts_mma_seg(uint32_t N, uint32_t K, bool ts, uint
         if (CG == 2) umma_bf16_ts_pair(d_tmem, a_tmem + j * 64u + t * 16u, db, idesc, acc);
         else umma_bf16_ts(d_tmem, a_tmem + j * 64u + t * 16u, db, idesc, acc);
       } else {
-        const uint64_t da = op_desc(acat_base + (8u * j + 2u * t) * 128u, 128u, TS_SBO);
+        const uint64_t da = op_desc(acat_base + cb * TS_ACAT_BYTES + (8u * j + 2u * t) * 128u, 128u, TS_SBO);
         if (CG == 2) umma_bf16_pair(d_tmem, da, db, idesc, acc);
         else umma_bf16(d_tmem, da, db, idesc, acc);
       }
@@ -158,12 +159,12 @@ __device__ __forceinline__ void ts_signal(TsCtl* ctl, int c, int lane, uint32_t 
     else mbar_arrive(&ctl->a_ready[c]);
   }
 }
-__device__ __forceinline__ void ts_signal_smem(TsCtl* ctl, int i, int lane, uint32_t remote) {
+__device__ __forceinline__ void ts_signal_smem(TsCtl* ctl, int cb, int i, int lane, uint32_t remote) {
   fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) {
-    if (remote) mbar_arrive_remote(remote + (uint32_t)i * 8u);
-    else mbar_arrive(&ctl->s_ready[i]);
+    if (remote) mbar_arrive_remote(remote + (uint32_t)(cb * 2 + i) * 8u);
+    else mbar_arrive(&ctl->s_ready[cb][i]);
   }
 }
 // hidden layer: y = act(acc + bias) -> bf16, packed in place.  Thread owns fp32 columns [64c + 16cs, +16) of every
@@ -210,8 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
     mbar_init(&ctl->acc_full[0], 1);
     mbar_init(&ctl->acc_full[1], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS * CG);
-    mbar_init(&ctl->s_ready[0], EPI_WARPS * CG);
-    mbar_init(&ctl->s_ready[1], EPI_WARPS * CG);
+    for (int i = 0; i < 4; ++i) mbar_init(&ctl->s_ready[i >> 1][i & 1], EPI_WARPS * CG);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -257,18 +257,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       // layer li accumulates into buffer li & 1; a TMEM A operand sits in columns [0,128) of the other buffer
       auto acc_of = [&](uint32_t l) { return tmem_base + (l & 1u) * 256u; };
       auto a_of = [&](uint32_t l) { return tmem_base + ((l & 1u) ^ 1u) * 256u; };
-      for (int tb = t_first0; tb < n_tiles; tb += t_stride) {
+      uint32_t cb = 0;                 // cat block of this tile (alternates)
+      for (int tb = t_first0; tb < n_tiles; tb += t_stride, cb ^= 1u) {
         const int e = tt.tile_expert[tb + (int)rank];
         tl_mark(P.tl, 1, tn, 1);
         if (e >= 0) {
-          ts_mma_seg<CG>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, false, rank, P.tl, &tn);
+          ts_mma_seg<CG>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, false, rank, P.tl, &tn, cb);
           ts_commit_acc<CG>(ctl, li & 1, rank);
           tl_mark(P.tl, 1, tn, 120);
           ++li;
           for (int l = 0; l < NE; ++l, ++li) {
             ts_mma_seg<CG>(MW, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, rank, P.tl, &tn);
             if (l == P.skip_layer)
-              ts_mma_seg<CG>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, rank, P.tl, &tn);
+              ts_mma_seg<CG>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, rank, P.tl, &tn, cb);
             ts_commit_acc<CG>(ctl, li & 1, rank);
             tl_mark(P.tl, 1, tn, 120);
           }
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         tl_mark(P.tl, 1, tn, 120);
         ++li;
         ts_mma_seg<CG>(P.back[1].N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, rank, P.tl, &tn);
-        ts_mma_seg<CG>(P.back[1].N, K_cat, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, rank, P.tl, &tn);
+        ts_mma_seg<CG>(P.back[1].N, K_cat, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, rank, P.tl, &tn, cb);
         ts_commit_acc<CG>(ctl, li & 1, rank);
         tl_mark(P.tl, 1, tn, 120);
         ++li;
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
   } else {
     EpiCtx ec;
     ec.remote_a_ready = (CG == 2 && rank != 0) ? mapa_shared(smem_u32(&ctl->a_ready[0]), 0) : 0u;
-    const uint32_t remote_s = (CG == 2 && rank != 0) ? mapa_shared(smem_u32(&ctl->s_ready[0]), 0) : 0u;
+    const uint32_t remote_s = (CG == 2 && rank != 0) ? mapa_shared(smem_u32(&ctl->s_ready[0][0]), 0) : 0u;
     ec.lane = lane; ec.q = warp & 3; ec.cs = (warp - 2) >> 2; ec.row = ec.q * 32 + lane;
     ec.et = (int)threadIdx.x - 64; ec.lane_base = (uint32_t)(ec.q * 32) << 16;
     const int row = ec.row;
@@ -316,13 +317,30 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       }
       return r;
     };
+    const int n_sxyz = ((int)K_xyz + 63) / 64, n_scat = ((int)K_cat + 63) / 64;
+    // PE(xyz) of a tile -> cat block `blk` (cs == 0 threads) + release of its chunks to the MMA issuer
+    auto stage_pe = [&](const RowIn& r, int blk) {
+      if (ec.cs == 0) {
+        constexpr int NPE = 3 + 6 * 12, NPAD = (NPE + 15) / 16 * 16;
+        float pxyz[3] = {r.x0, r.x1, r.x2};
+        __align__(16) __nv_bfloat16 pe[NPAD];
+        pe_to_bf16<12>(pxyz, pe);
+#pragma unroll
+        for (int i = NPE; i < NPAD; ++i) pe[i] = __float2bfloat16_rn(0.f);
+        ts_cat_store_row(acat_base + (uint32_t)blk * TS_ACAT_BYTES, row, pe, NPAD / 8);
+      }
+      for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, blk, i, lane, remote_s);
+    };
     RowIn nxt = fetch_row(t_first0 + (int)rank);
-    for (int tb = t_first0; tb < n_tiles; tb += t_stride) {
+    if (nxt.e >= 0) stage_pe(nxt, 0);          // first tile of this CTA; later tiles are staged one tile ahead
+    int cb = 0;
+    for (int tb = t_first0; tb < n_tiles; tb += t_stride, cb ^= 1) {
       const int t = tb + (int)rank;
       const RowIn cur = nxt;
       const int e = cur.e, sidx = cur.sidx;
       const bool valid = sidx >= 0;
       const float g = cur.g;
+      const uint32_t acat_cur = acat_base + (uint32_t)cb * TS_ACAT_BYTES;
       tl_mark(tl, 0, tn, 1);
       // [PE(dir) | appearance | 0-pad] -> cat block (cs == 1 threads)
       auto write_cat = [&]() {
@@ -343,24 +361,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
               cat[NDIR + 4 * i + 3] = __float2bfloat16_rn(f.w);
             }
           }
-          ts_cat_store_row(acat_base, row, cat, (int)K_cat / 8);
+          ts_cat_store_row(acat_cur, row, cat, (int)K_cat / 8);
         }
       };
-      const int n_sxyz = ((int)K_xyz + 63) / 64, n_scat = ((int)K_cat + 63) / 64;
       float sig_acc = 0.f;
+      nxt = fetch_row(t + t_stride);
       if (e >= 0) {
-        // ---- PE(xyz) -> cat block: operand of the xyz layer now and of the skip term later ----
-        if (ec.cs == 0) {
-          constexpr int NPE = 3 + 6 * 12, NPAD = (NPE + 15) / 16 * 16;
-          float pxyz[3] = {cur.x0, cur.x1, cur.x2};
-          __align__(16) __nv_bfloat16 pe[NPAD];
-          pe_to_bf16<12>(pxyz, pe);
-#pragma unroll
-          for (int i = NPE; i < NPAD; ++i) pe[i] = __float2bfloat16_rn(0.f);
-          ts_cat_store_row(acat_base, row, pe, NPAD / 8);
-        }
-        for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane, remote_s);
-        nxt = fetch_row(t + t_stride);
+        // PE(xyz) of this tile was staged into block cb one tile ago (operand of the xyz layer and of the skip term)
         tl_mark(tl, 0, tn, 2);
         // ---- xyz layer (act none): h -> packed A ----
         {
@@ -368,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           epi_load_bias(P.fblob + P.front[0].b_off, MW, sbias, buf, ec.et);
           ts_wait_acc(ctl, pp, buf);
           ts_epi_hidden<false>(tbuf_of(li), sbias + buf * 256, ec, ctl, tl, &tn);
-          if (P.skip_layer == 0) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane, remote_s);
+          if (P.skip_layer == 0) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, cb, i, lane, remote_s);
           ++li;
         }
         for (int l = 0; l < NE; ++l, ++li) {
@@ -384,7 +391,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           const uint32_t tb = tbuf_of(li);
           if (l < NE - 1) {
             ts_epi_hidden<true>(tb, sb, ec, ctl, tl, &tn);
-            if (l + 1 == P.skip_layer) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane, remote_s);
+            if (l + 1 == P.skip_layer) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, cb, i, lane, remote_s);
           } else {
             // last expert layer (no activation) -> combine: y = bf16(gate * bf16(out)) -> ReLU -> packed A; sigma head
             uint32_t v[2][16];
@@ -414,7 +421,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         }
       } else {
         // dropped bucket: h = relu(0) = 0 -> zero A operand for layer "1" (it accumulates into B[li&1], reads B[~li&1])
-        nxt = fetch_row(t + t_stride);
         const uint32_t ta = tbuf_of(li + 1);
         const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int c = 0; c < 4; ++c) tmem_st8(ta + (uint32_t)(c * 64 + ec.cs * 16), z);
@@ -427,9 +433,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       {
         const int buf = (int)(li & 1);
         epi_load_bias(P.fblob + P.back[0].b_off, MW, sbias, buf, ec.et);
+        // the tensor pipe is busy with layer "1": stage the next tile's PE(xyz) into the other cat block now
+        // (its last reader, layer "2" of the previous tile, retired before this tile started)
+        if (nxt.e >= 0) stage_pe(nxt, cb ^ 1);
         ts_wait_acc(ctl, pp, buf);
         ts_epi_hidden<false>(tbuf_of(li), sbias + buf * 256, ec, ctl, tl, &tn);
-        for (int i = 0; i < n_scat; ++i) ts_signal_smem(ctl, i, lane, remote_s);
+        for (int i = 0; i < n_scat; ++i) ts_signal_smem(ctl, cb, i, lane, remote_s);
         tl_mark(tl, 0, tn, 50);
         ++li;
       }
@@ -516,8 +525,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
     mbar_init(&ctl->acc_full[0], 1);
     mbar_init(&ctl->acc_full[1], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS);
-    mbar_init(&ctl->s_ready[0], EPI_WARPS);
-    mbar_init(&ctl->s_ready[1], EPI_WARPS);
+    for (int i = 0; i < 4; ++i) mbar_init(&ctl->s_ready[i >> 1][i & 1], EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&ctl->tmem_base);
@@ -547,9 +555,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
       int tn = 0;
       auto acc_of = [&](uint32_t l) { return tmem_base + (l & 1u) * 256u; };
       auto a_of = [&](uint32_t l) { return tmem_base + ((l & 1u) ^ 1u) * 256u; };
-      for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
+      uint32_t cb = 0;
+      for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x, cb ^= 1u) {
         tl_mark(P.tl, 1, tn, 1);
-        ts_mma_seg<1>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, false, 0, P.tl, &tn);
+        ts_mma_seg<1>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, false, 0, P.tl, &tn, cb);
         ts_commit_acc<1>(ctl, li & 1, 0);
         ++li;
         for (int l = 1; l < NL; ++l, ++li) {
@@ -572,36 +581,44 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
     int tn = 0;
     unsigned long long* tl = (warp == 2 && lane == 0) ? P.tl : nullptr;
     auto tbuf_of = [&](uint32_t l) { return tmem_base + ec.lane_base + (l & 1u) * 256u; };
-    float pn[3] = {0.f, 0.f, 0.f};          // xyz of this thread's row in the NEXT tile
-    if (ec.cs == 0) {
-      const int64_t s0 = (int64_t)blockIdx.x * TILE + row;
-      if ((int)blockIdx.x < n_tiles && s0 < S) { pn[0] = x[s0 * P.x_cols]; pn[1] = x[s0 * P.x_cols + 1]; pn[2] = x[s0 * P.x_cols + 2]; }
-    }
-    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
-      const int64_t s = (int64_t)t * TILE + row;
-      const bool valid = s < S;
-      tl_mark(tl, 0, tn, 1);
-      constexpr int NPE = 3 + 6 * FX, NPAD = (NPE + 15) / 16 * 16;
+    constexpr int NPE = 3 + 6 * FX, NPAD = (NPE + 15) / 16 * 16;
+    auto load_xyz = [&](int tile, float (&p)[3]) {
+      p[0] = p[1] = p[2] = 0.f;
+      const int64_t sr = (int64_t)tile * TILE + row;
+      if (ec.cs == 0 && tile < n_tiles && sr < S) { p[0] = x[sr * P.x_cols]; p[1] = x[sr * P.x_cols + 1]; p[2] = x[sr * P.x_cols + 2]; }
+    };
+    // PE(xyz) of a tile -> cat block `blk` (cs == 0 threads) + release of its chunks to the MMA issuer
+    auto stage_pe = [&](const float (&p)[3], int blk) {
       if (ec.cs == 0) {
-        float p[3] = {pn[0], pn[1], pn[2]};
-        {
-          const int64_t sn = s + (int64_t)gridDim.x * TILE;
-          pn[0] = pn[1] = pn[2] = 0.f;
-          if (t + (int)gridDim.x < n_tiles && sn < S) { pn[0] = x[sn * P.x_cols]; pn[1] = x[sn * P.x_cols + 1]; pn[2] = x[sn * P.x_cols + 2]; }
-        }
         __align__(16) __nv_bfloat16 pe[NPAD];
         pe_to_bf16<FX>(p, pe);
 #pragma unroll
         for (int i = NPE; i < NPAD; ++i) pe[i] = __float2bfloat16_rn(0.f);
-        ts_cat_store_row(acat_base, row, pe, NPAD / 8);
+        ts_cat_store_row(acat_base + (uint32_t)blk * TS_ACAT_BYTES, row, pe, NPAD / 8);
       }
-      for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, i, lane, 0);
+      for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, blk, i, lane, 0);
+    };
+    float pn[3];                             // xyz of this thread's row in the NEXT tile (staged one tile ahead)
+    load_xyz((int)blockIdx.x, pn);
+    if ((int)blockIdx.x < n_tiles) stage_pe(pn, 0);
+    load_xyz((int)blockIdx.x + (int)gridDim.x, pn);
+    int cb = 0;
+    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x, cb ^= 1) {
+      const int64_t s = (int64_t)t * TILE + row;
+      const bool valid = s < S;
+      tl_mark(tl, 0, tn, 1);
       tl_mark(tl, 0, tn, 2);
       float sum = 0.f, sq = 0.f;
       for (int l = 0; l < NL; ++l, ++li) {
         const int buf = (int)(li & 1);
         epi_load_bias(P.fblob + P.front[l].b_off, MW, sbias, buf, ec.et);
         const float* sb = sbias + buf * 256;
+        if (l == 1 && t + (int)gridDim.x < n_tiles) {
+          // the tensor pipe is busy with the first gate-MLP layer: stage the next tile's PE(xyz) into the other cat
+          // block (its reader, the xyz layer of the previous tile, retired long ago) and prefetch the one after
+          stage_pe(pn, cb ^ 1);
+          load_xyz(t + 2 * (int)gridDim.x, pn);
+        }
         tl_mark(tl, 0, tn, 10 + l);
         ts_wait_acc(ctl, pp, buf);
         tl_mark(tl, 0, tn, 20 + l);
