@@ -1385,7 +1385,7 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
   // launch #1 run ahead of launch #2 (1..3); SNB_ROUTE_SMS = SMs left free for the routing kernels
   static const bool no_overlap = getenv("SNB_NO_OVERLAP") != nullptr;
   static const int depth_env = getenv("SNB_PIPE_DEPTH") ? atoi(getenv("SNB_PIPE_DEPTH")) : 2;
-  static const int route_sms = getenv("SNB_ROUTE_SMS") ? atoi(getenv("SNB_ROUTE_SMS")) : 20;
+  static const int route_sms = getenv("SNB_ROUTE_SMS") ? atoi(getenv("SNB_ROUTE_SMS")) : 28;   // r1n sweep: 12/20/28/36
   static const bool back_full = getenv("SNB_BACK_PART") == nullptr;   // launch #2 keeps every SM (tile rounds!)
   int D = depth_env < 1 ? 1 : depth_env;
   if (D > nsets - 1) D = nsets - 1;
