@@ -70,6 +70,16 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
                : "memory");
 }
 
+// round two fp32 values to bf16 (RN, optional ReLU after rounding): returns the packed pair (lo = a) and the rounded
+// values as fp32 -- one cvt instead of two round trips
+template <bool RELU>
+__device__ __forceinline__ uint32_t ts_round2(float a, float b, float& ra, float& rb) {
+  const uint32_t p = pack2<RELU>(a, b);
+  ra = __uint_as_float(p << 16);
+  rb = __uint_as_float(p & 0xffff0000u);
+  return p;
+}
+
 // ---- producer: the K-slices of one packed layer image (same images as k_back) ----
 // CG = 2 (CTA pair): each CTA streams its own half of the slice (output rows [rank*N/2, +N/2) are the contiguous half)
 template <int CG>
@@ -404,13 +414,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
               uint32_t pk[8];
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                float f0 = bf16_round(__uint_as_float(v[c & 1][j]) + sb[col0 + j]);
-                float f1 = bf16_round(__uint_as_float(v[c & 1][j + 1]) + sb[col0 + j + 1]);
-                f0 = fmaxf(bf16_round(f0 * g), 0.f);
-                f1 = fmaxf(bf16_round(f1 * g), 0.f);
+                float f0, f1;
+                ts_round2<false>(__uint_as_float(v[c & 1][j]) + sb[col0 + j], __uint_as_float(v[c & 1][j + 1]) + sb[col0 + j + 1], f0, f1);
+                pk[j / 2] = ts_round2<true>(f0 * g, f1 * g, f0, f1);      // relu(bf16(gate * bf16(out)))
                 sig_acc = fmaf(f0, s_wsig[col0 + j], sig_acc);
                 sig_acc = fmaf(f1, s_wsig[col0 + j + 1], sig_acc);
-                pk[j / 2] = pack_bf16x2(f0, f1);
               }
               tmem_st8(tb + (uint32_t)col0, pk);
               tmem_st_wait();
@@ -456,12 +464,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           tmem_ld16(tb + (uint32_t)col0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 16; j += 2) {
             const int k = col0 + j;
-            const float h2 = bf16_round(fmaxf(__uint_as_float(v[j]) + sb[k], 0.f));
-            c0 = fmaf(h2, s_wcol[k], c0);
-            c1 = fmaf(h2, s_wcol[H2 + k], c1);
-            c2 = fmaf(h2, s_wcol[2 * H2 + k], c2);
+            float ha, hb;                               // bf16(relu(x)) == relu(bf16(x))
+            ts_round2<true>(__uint_as_float(v[j]) + sb[k], __uint_as_float(v[j + 1]) + sb[k + 1], ha, hb);
+            c0 = fmaf(ha, s_wcol[k], c0);
+            c1 = fmaf(ha, s_wcol[H2 + k], c1);
+            c2 = fmaf(ha, s_wcol[2 * H2 + k], c2);
+            c0 = fmaf(hb, s_wcol[k + 1], c0);
+            c1 = fmaf(hb, s_wcol[H2 + k + 1], c1);
+            c2 = fmaf(hb, s_wcol[2 * H2 + k + 1], c2);
           }
         }
         tc_fence_before();
@@ -639,11 +651,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
             uint32_t pk[8];
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-              const float g0 = bf16_round(__uint_as_float(v[c & 1][j]) + sb[col0 + j]);
-              const float g1 = bf16_round(__uint_as_float(v[c & 1][j + 1]) + sb[col0 + j + 1]);
+              float g0, g1;
+              pk[j / 2] = ts_round2<false>(__uint_as_float(v[c & 1][j]) + sb[col0 + j],
+                                           __uint_as_float(v[c & 1][j + 1]) + sb[col0 + j + 1], g0, g1);
               sum += g0 + g1;
               sq = fmaf(g0, g0, fmaf(g1, g1, sq));
-              pk[j / 2] = pack_bf16x2(g0, g1);
             }
             tmem_st8(tb + (uint32_t)col0, pk);
             tmem_st_wait();
@@ -660,7 +672,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
         epi_bar_sync();                       // LayerNorm partial sums of all 4 column sub-slices are in sred
         ts_wait_acc(ctl, pp, buf);
         tl_mark(tl, 0, tn, 40);
-        if (ec.cs == 0) {
+        {
+          // the four threads of a row (cs = 0..3, different warps) take experts [4cs, 4cs+4): partial max and partial
+          // denominator are exchanged through sred values 2 and 3
           const float tsum = sred[0 * 128 + row] + sred[1 * 128 + row] + sred[2 * 128 + row] + sred[3 * 128 + row];
           const float tsq = sred[4 * 128 + row] + sred[5 * 128 + row] + sred[6 * 128 + row] + sred[7 * 128 + row];
           const float mean = tsum * (1.f / MW);
@@ -671,21 +685,38 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
           tmem_ld16(tacc, hi);
           tmem_ld16(tacc + 16u, lo);
           tmem_ld_wait();
-          float lg[MAX_E];
+          const int e0 = 4 * ec.cs;
+          float lg[4];
           float mx = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < MAX_E; ++e) {
-            lg[e] = rstd * (__uint_as_float(hi[e]) + __uint_as_float(lo[e]) - mean * P.fblob[P.o_c1 + e]) + P.fblob[P.o_c0 + e];
-            if (e < P.E) mx = fmaxf(mx, lg[e]);
+          for (int q4 = 0; q4 < 4; ++q4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (ec.cs == q4) {          // static register indices
+                const int e = 4 * q4 + j;
+                lg[j] = rstd * (__uint_as_float(hi[e]) + __uint_as_float(lo[e]) - mean * P.fblob[P.o_c1 + e]) + P.fblob[P.o_c0 + e];
+                if (e < P.E) mx = fmaxf(mx, lg[j]);
+              }
           }
+          sred[(2 * 4 + ec.cs) * 128 + row] = mx;
+          epi_bar_sync();
+          mx = fmaxf(fmaxf(sred[8 * 128 + row], sred[9 * 128 + row]), fmaxf(sred[10 * 128 + row], sred[11 * 128 + row]));
           float den = 0.f;
 #pragma unroll
-          for (int e = 0; e < MAX_E; ++e)
-            if (e < P.E) { lg[e] = expf(lg[e] - mx); den += lg[e]; }
+          for (int j = 0; j < 4; ++j)
+            if (e0 + j < P.E) { lg[j] = expf(lg[j] - mx); den += lg[j]; }
+          sred[(3 * 4 + ec.cs) * 128 + row] = den;
+          epi_bar_sync();
+          den = (sred[12 * 128 + row] + sred[13 * 128 + row]) + (sred[14 * 128 + row] + sred[15 * 128 + row]);
           if (valid) {
+            const float inv = 1.f / den;
+            if ((P.E & 3) == 0 && e0 < P.E) {
+              *reinterpret_cast<float4*>(gates + s * P.E + e0) = make_float4(lg[0] * inv, lg[1] * inv, lg[2] * inv, lg[3] * inv);
+            } else {
 #pragma unroll
-            for (int e = 0; e < MAX_E; ++e)
-              if (e < P.E) gates[s * P.E + e] = lg[e] / den;
+              for (int j = 0; j < 4; ++j)
+                if (e0 + j < P.E) gates[s * P.E + e0 + j] = lg[j] * inv;
+            }
           }
         }
         tc_fence_before();
