@@ -1384,10 +1384,13 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
   // tuning / A-B switches (read once): SNB_NO_OVERLAP routes on the caller's stream; SNB_PIPE_DEPTH = how many
   // launch #1 run ahead of launch #2 (1..3); SNB_ROUTE_SMS = SMs left free for the routing kernels
   static const bool no_overlap = getenv("SNB_NO_OVERLAP") != nullptr;
-  static const int depth_env = getenv("SNB_PIPE_DEPTH") ? atoi(getenv("SNB_PIPE_DEPTH")) : 2;
-  static const int route_sms = getenv("SNB_ROUTE_SMS") ? atoi(getenv("SNB_ROUTE_SMS")) : 28;   // r1n sweep: 12/20/28/36
+  // defaults from the sweeps in profiles/: local experts depth 2 / 28 SMs (r1n: 12/20/28/36 SMs); expert-parallel
+  // depth 3 / 36 SMs (r1q/r1r: the routing stage also scatters records to the peers and waits for theirs)
+  static const int depth_env = getenv("SNB_PIPE_DEPTH") ? atoi(getenv("SNB_PIPE_DEPTH")) : 0;
+  static const int route_env = getenv("SNB_ROUTE_SMS") ? atoi(getenv("SNB_ROUTE_SMS")) : -1;
   static const bool back_full = getenv("SNB_BACK_PART") == nullptr;   // launch #2 keeps every SM (tile rounds!)
-  int D = depth_env < 1 ? 1 : depth_env;
+  const int route_sms = route_env >= 0 ? route_env : (m->ep ? 36 : 28);
+  int D = depth_env >= 1 ? depth_env : (m->ep ? 3 : 2);
   if (D > nsets - 1) D = nsets - 1;
   if (D > MAXSETS - 1) D = MAXSETS - 1;
   const int NS = D + 1;
