@@ -271,7 +271,8 @@ int snb_umma_selftest(const void* a_bf16, const void* b_bf16, int32_t N, int32_t
 
 /* Measurement aid: clocks for `reps` back-to-back tcgen05.mma (M=128, K=16, bf16, given N) with the A operand in
  * shared memory (a_in_tmem=0) or tensor memory (1); flags&1 adds a stream of 8 KB bulk copies landing in shared
- * memory, flags&2 adds four warps of tcgen05.ld readers.  out6 = {clocks, copies, ld iterations x4}.  Synchronises
+ * memory, flags&2 adds four warps of tcgen05.ld readers, flags&4 runs a 2-CTA cluster issuing cta_group::2 (M=256)
+ * instructions instead.  out6 = {clocks, copies, ld iterations x4}.  Synchronises
  * the stream. */
 int snb_umma_microbench(int32_t N, int32_t a_in_tmem, int32_t flags, int32_t reps, uint64_t* out6, void* stream);
 

@@ -217,6 +217,46 @@ __global__ void __launch_bounds__(192) k_umma_bench(int N, int ts, int flags, in
   if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
+// CTA-pair variant (flags & 4): a 2-CTA cluster, the leader issues M = 256 cta_group::2 instructions (each CTA supplies
+// its 128 rows of A and half of B), multicast commit.  out[0] = clocks on the leader.
+__global__ void __launch_bounds__(192) k_umma_bench_pair(int N, int ts, int reps, unsigned long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  uint8_t* sA = smem;                       // 128 x 64 bf16 canonical (16 KB)
+  uint8_t* sB = smem + 16384;               // this CTA's N/2 x 64 half of B (<= 16 KB)
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc_pair<512>(&tmem_base_s);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (warp == 0 && lane == 0) {
+    unsigned long long t0 = 0;
+    if (rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, N);
+      t0 = clock64();
+      for (int i = 0; i < reps; ++i) {
+        const uint32_t t = (uint32_t)(i & 3);
+        const uint64_t db = umma_smem_desc(smem_u32(sB) + 2u * t * 128u, 128u, 64u * 16u);
+        if (ts) umma_bf16_ts_pair(tmem_base, tmem_base + 256u + t * 16u, db, idesc, 1u);
+        else umma_bf16_pair(tmem_base, umma_smem_desc(smem_u32(sA) + 2u * t * 128u, 128u, 64u * 16u), db, idesc, 1u);
+      }
+      umma_commit_pair(&bar_mma, 3);
+    }
+    mbar_wait(&bar_mma, 0);
+    if (rank == 0) out[0] = clock64() - t0;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair<512>(tmem_base);
+}
+
 int umma_microbench(int N, int ts, int flags, int reps, unsigned long long* host_out6, cudaStream_t st) {
   SNB_REQUIRE(N == 64 || N == 128 || N == 256, "microbench: N must be 64, 128 or 256");
   SNB_REQUIRE(reps > 0 && reps <= (1 << 20), "microbench: bad reps");
@@ -227,7 +267,18 @@ int umma_microbench(int N, int ts, int flags, int reps, unsigned long long* host
   SNB_CHECK_CUDA(cudaMalloc((void**)&src, (size_t)1024 * 8192));
   SNB_CHECK_CUDA(cudaMalloc((void**)&out, 6 * sizeof(unsigned long long)));
   SNB_CHECK_CUDA(cudaMemsetAsync(out, 0, 6 * sizeof(unsigned long long), st));
-  k_umma_bench<<<1, 192, smem, st>>>(N, ts, flags, reps, src, out);
+  if (flags & 4) {
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_umma_bench_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_umma_bench_pair, N, ts, reps, out));
+  } else {
+    k_umma_bench<<<1, 192, smem, st>>>(N, ts, flags, reps, src, out);
+  }
   SNB_CHECK_LAUNCH("k_umma_bench");
   SNB_CHECK_CUDA(cudaMemcpyAsync(host_out6, out, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   SNB_CHECK_CUDA(cudaStreamSynchronize(st));
