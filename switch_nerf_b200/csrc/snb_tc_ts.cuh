@@ -26,9 +26,9 @@ static constexpr uint32_t TS_ACAT_BYTES = TILE / 8 * TS_SBO;      // 24576
 static constexpr int TS_NST = 5;
 
 struct __align__(16) TsCtl {
-  uint64_t full[TS_NST];
-  uint64_t empty[TS_NST];
-  uint64_t peer_ok[TS_NST]; // CTA pairs, leader only: the peer's half of the weight slice landed
+  uint64_t full[2 * TS_NST];      // CTA pairs use 2*TS_NST half-size ring slots (each CTA streams half of a slice)
+  uint64_t empty[2 * TS_NST];
+  uint64_t peer_ok[2 * TS_NST];   // CTA pairs, leader only: the peer's half of the weight slice landed
   uint64_t acc_full[2];
   uint64_t a_ready[4];      // epilogue -> MMA: K-chunk of the next A operand packed into TMEM
   uint64_t s_ready[2][2];   // epilogue -> MMA: shared-memory K-chunk written, [cat block][chunk]
@@ -89,10 +89,11 @@ __device__ __forceinline__ void ts_produce(const uint8_t* wsrc, uint32_t N, uint
   for (uint32_t j = 0; j < nsl; ++j) {
     const uint32_t klen = min(64u, K16 - 64u * j);
     const uint32_t bytes = N * klen * 2 / CG;
-    const uint32_t stage = pp.slice % TS_NST, phase = (pp.slice / TS_NST) & 1;
+    constexpr uint32_t NS = TS_NST * CG, SB = STAGE_BYTES / CG;
+    const uint32_t stage = pp.slice % NS, phase = (pp.slice / NS) & 1;
     mbar_wait(&ctl->empty[stage], phase ^ 1);
     mbar_arrive_expect_tx(&ctl->full[stage], bytes);
-    bulk_g2s(ring + (size_t)stage * STAGE_BYTES, wsrc + (size_t)N * 64 * 2 * j + (size_t)rank * bytes, bytes, &ctl->full[stage]);
+    bulk_g2s(ring + (size_t)stage * SB, wsrc + (size_t)N * 64 * 2 * j + (size_t)rank * bytes, bytes, &ctl->full[stage]);
     ++pp.slice;
   }
 }
@@ -111,7 +112,8 @@ __device__ __forceinline__ void ts_mma_seg(uint32_t N, uint32_t K, bool ts, uint
   for (uint32_t j = 0; j < 4; ++j) {
     if (j >= nsl) break;
     const uint32_t klen = min(64u, K - 64u * j);
-    const uint32_t stage = pp.slice % TS_NST, phase = (pp.slice / TS_NST) & 1;
+    constexpr uint32_t NS = TS_NST * CG, SB = STAGE_BYTES / CG;
+    const uint32_t stage = pp.slice % NS, phase = (pp.slice / NS) & 1;
     if (CG == 2 && rank != 0) {
       mbar_wait(&ctl->full[stage], phase);
       mbar_arrive_remote(mapa_shared(smem_u32(&ctl->peer_ok[stage]), 0));
@@ -125,7 +127,7 @@ __device__ __forceinline__ void ts_mma_seg(uint32_t N, uint32_t K, bool ts, uint
     if (CG == 2) mbar_wait(&ctl->peer_ok[stage], phase);
     if (tn) tl_mark(tl, 1, *tn, 110 + (int)j);
     tc_fence_after();
-    const uint32_t b_base = ring_base + stage * STAGE_BYTES;
+    const uint32_t b_base = ring_base + stage * SB;
     for (uint32_t t = 0; t < klen / 16; ++t) {
       const uint64_t db = op_desc(b_base + (2u * t) * 128u, 128u, klen * 16u);
       const uint32_t acc = (cont || (j | t)) ? 1u : 0u;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
   const int t_first0 = CG * ((int)blockIdx.x / CG), t_stride = (int)gridDim.x;   // pairs of tiles share the expert
   TsCtl* ctl = reinterpret_cast<TsCtl*>(smem + TSM_CTL);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TS_NST; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); mbar_init(&ctl->peer_ok[i], 1); }
+    for (int i = 0; i < 2 * TS_NST; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); mbar_init(&ctl->peer_ok[i], 1); }
     mbar_init(&ctl->acc_full[0], 1);
     mbar_init(&ctl->acc_full[1], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS * CG);
@@ -533,7 +535,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TsCtl* ctl = reinterpret_cast<TsCtl*>(smem + TSM_CTL);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TS_NST; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); mbar_init(&ctl->peer_ok[i], 1); }
+    for (int i = 0; i < 2 * TS_NST; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); mbar_init(&ctl->peer_ok[i], 1); }
     mbar_init(&ctl->acc_full[0], 1);
     mbar_init(&ctl->acc_full[1], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS);
