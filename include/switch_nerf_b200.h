@@ -253,6 +253,18 @@ int snb_render_rays_mip(snb_model_t* m, const float* rays, const float* radii, c
                         float weights_resample_padding, float rgb_padding, const snb_render_out* out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- a7/a8: the MoE layer as an operator ------------------------------------------------- */
+/* Replaces MOELayer.forward (tutel_moe_layer_nobatch.py:733-797) -> TopKGate.apply_on_expert_fn /
+ * apply_on_expert_fn_nobatch (98-352) for one layer with an external gate input: gates =
+ * softmax(gate_input @ wg^T) in fp32 (105-126), routing (snb_route_top1 semantics), dispatch, the expert stack,
+ * combine with the gate value (dropped rows = 0).  input / gate_input / y: fp32 [S, width]; gate_input == NULL uses
+ * `input` (the reference's default).  No activation is applied to y (NeRFMoE applies its ReLU afterwards,
+ * nerf_moe.py:384).  fp32 CUDA path; workspace: snb_workspace_bytes(m, S, capacity_factor).  moe_idx int32[S]
+ * (nullable) = topk indices of every sample; l_aux fp32[1]. */
+int snb_moe_layer_forward(snb_model_t* m, const float* input, const float* gate_input, int64_t S,
+                          const snb_route_opts* opts, float* y, int32_t* moe_idx, float* l_aux, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* Stand-alone composite (rendering.py:436-494, flip=False): z [N,S] ascending, raw [N,S,4]. */
 int snb_composite(const float* z, const float* raw, const float* last_delta, int64_t n_rays,
                   int32_t n_samples, int32_t white_bkgd, float* rgb, float* depth,

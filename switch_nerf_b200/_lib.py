@@ -87,6 +87,8 @@ _SIGNATURES = {
     "snb_moe_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(RouteOpts), C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_size_t, C.c_void_p]),
+    "snb_moe_layer_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(RouteOpts), C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "snb_render_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.POINTER(RenderOpts)]),
     "snb_render_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(RenderOpts),
                                   C.POINTER(RenderOut), C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -276,7 +276,7 @@ int snb_model_attach_a2a(snb_model_t* mm, snb_a2a_t* g) {
 size_t snb_workspace_bytes(const snb_model_t* mm, int64_t max_chunk_samples, double max_cf) {
   const Model* m = (const Model*)mm;
   if (!m) return 0;
-  size_t a = fp32_workspace_bytes(m, max_chunk_samples, max_cf);
+  size_t a = fp32_workspace_bytes(m, max_chunk_samples, max_cf);      // >= fp32_moe_layer_workspace_bytes
   size_t b = tc_supported(m) ? tc_workspace_bytes(m, max_chunk_samples, max_cf) : 0;
   return (a > b ? a : b) + 4096;
 }
@@ -334,6 +334,23 @@ int snb_moe_forward(snb_model_t* mm, const float* x, int64_t S, const float* sig
   }
   set_error("unknown precision %d", precision);
   return SNB_EINVAL;
+}
+
+int snb_moe_layer_forward(snb_model_t* mm, const float* input, const float* gate_input, int64_t S,
+                          const snb_route_opts* opts, float* y, int32_t* moe_idx, float* l_aux, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  Model* m = (Model*)mm;
+  SNB_REQUIRE(m && opts, "snb_moe_layer_forward: NULL model/opts");
+  SNB_REQUIRE(S >= 0 && S < (1ll << 31) / 16, "snb_moe_layer_forward: bad S");
+  SNB_REQUIRE(S == 0 || (input && y), "snb_moe_layer_forward: NULL input/output");
+  SNB_REQUIRE(opts->capacity_factor > 0, "capacity_factor must be > 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S == 0) {
+    if (l_aux) SNB_CHECK_CUDA(cudaMemsetAsync(l_aux, 0, sizeof(float), st));
+    return SNB_OK;
+  }
+  Arena ws(workspace, workspace_bytes);
+  return fp32_moe_layer(m, input, gate_input ? gate_input : input, S, opts, y, moe_idx, l_aux, ws, st);
 }
 
 int snb_composite(const float* z, const float* raw, const float* last_delta, int64_t n_rays, int32_t n_samples,

@@ -98,6 +98,9 @@ int fp32_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, 
                  float* out, int32_t* moe_idx, float* l_aux, float* dbg_gates, int32_t* dbg_loc,
                  Arena& ws, cudaStream_t st);
 size_t fp32_workspace_bytes(const Model* m, int64_t S, double max_cf);
+int fp32_moe_layer(Model* m, const float* input, const float* gate_input, int64_t S, const snb_route_opts* o, float* y,
+                   int32_t* moe_idx, float* l_aux, Arena& ws, cudaStream_t st);
+size_t fp32_moe_layer_workspace_bytes(const Model* m, int64_t S, double max_cf);
 
 int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st);
 int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* o,

@@ -153,6 +153,7 @@ static int launch_linear(int act, const float* A, int lda, const float* W, const
 // ------------------------------------------------------------------------------------------
 // k_ln_gate: gate_input = LayerNorm(g) (eps 1e-5, biased var); logits = wg @ gate_input;
 // gates = softmax(logits).  One warp per row.  (nerf_moe.py:372; tutel_moe_layer_nobatch.py:105-126)
+// ln_w == nullptr: g already is the gate input (the standalone MoE-layer operator, snb_moe_layer_forward).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ln_gate(const float* __restrict__ g, int64_t S, int M, int E,
                                                  const float* __restrict__ ln_w, const float* __restrict__ ln_b,
@@ -164,23 +165,27 @@ __global__ void __launch_bounds__(256) k_ln_gate(const float* __restrict__ g, in
   const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
   if (s >= S) return;
   const float* row = g + s * M;
-  float sum = 0.f;
-  for (int k = lane; k < M; k += 32) sum += row[k];
+  const bool ln = (ln_w != nullptr);
+  float mean = 0.f, rstd = 1.f;
+  if (ln) {
+    float sum = 0.f;
+    for (int k = lane; k < M; k += 32) sum += row[k];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / (float)M;
-  float var = 0.f;
-  for (int k = lane; k < M; k += 32) { float d = row[k] - mean; var += d * d; }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mean = sum / (float)M;
+    float var = 0.f;
+    for (int k = lane; k < M; k += 32) { float d = row[k] - mean; var += d * d; }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-  const float rstd = rsqrtf(var / (float)M + 1e-5f);
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    rstd = rsqrtf(var / (float)M + 1e-5f);
+  }
   float mx = -INFINITY;
   for (int e0 = 0; e0 < E; e0 += 32) {
     float keep = -INFINITY;
     for (int e = e0; e < min(E, e0 + 32); ++e) {
       float acc = 0.f;
       for (int k = lane; k < M; k += 32) {
-        float v = (row[k] - mean) * rstd * ln_w[k] + ln_b[k];
+        const float v = ln ? (row[k] - mean) * rstd * ln_w[k] + ln_b[k] : row[k];
         acc = fmaf(v, s_wg[e * M + k], acc);
       }
 #pragma unroll
@@ -298,6 +303,79 @@ size_t fp32_workspace_bytes(const Model* m, int64_t S, double max_cf) {
   add((size_t)S * 3);               // rgb
   b += 4096;
   return b + route_workspace_bytes(S, E);
+}
+
+// ------------------------------------------------------------------------------------------
+// Standalone MoE-layer operator (fp32): MOELayer.forward -> TopKGate.apply_on_expert_fn[_nobatch] with an external
+// gate input (tutel_moe_layer_nobatch.py:733-797, 98-352): gates = softmax(gate_input @ wg^T) -> routing ->
+// dispatch -> expert stack -> combine (no activation: the ReLU of nerf_moe.py:384 belongs to the caller).
+// ------------------------------------------------------------------------------------------
+size_t fp32_moe_layer_workspace_bytes(const Model* m, int64_t S, double max_cf) {
+  const int M = m->d.width, E = m->d.num_experts;
+  if (S < 1) S = 1;
+  int64_t cap = capacity_of(S, E, max_cf > 1.0 ? max_cf : 1.0);
+  int64_t rows = (int64_t)E * cap;
+  if (rows < S) rows = S;
+  size_t b = 0;
+  auto add = [&](size_t n) { b += align_up(n * sizeof(float), 256); };
+  add((size_t)S * E);               // gates
+  add((size_t)S); add((size_t)S); add((size_t)S);   // idx, loc, gate
+  add((size_t)rows * M); add((size_t)rows * M); add((size_t)rows * M);   // buf0, buf1, bufx
+  b += 4096 + 4096;
+  return b + route_workspace_bytes(S, E);
+}
+
+int fp32_moe_layer(Model* m, const float* input, const float* gate_input, int64_t S, const snb_route_opts* o, float* y,
+                   int32_t* moe_idx, float* l_aux, Arena& ws, cudaStream_t st) {
+  const int M = m->d.width, E = m->d.num_experts, L = m->d.expert_layers;
+  if (S == 0) return SNB_OK;
+  const double cf = o->capacity_factor;
+  const int64_t cap_host = capacity_of(S, E, cf);
+  int64_t rows = o->no_batch ? S : (int64_t)E * cap_host;
+  if (rows < 1) rows = 1;
+  float* gates = ws.take<float>((size_t)S * E);
+  int* idx = ws.take<int>(S);
+  int* loc = ws.take<int>(S);
+  float* gate = ws.take<float>(S);
+  float* buf0 = ws.take<float>((size_t)rows * M);
+  float* buf1 = ws.take<float>((size_t)rows * M);
+  float* bufx = ws.take<float>((size_t)rows * M);
+  int* small = ws.take<int>(1024);
+  const size_t rbytes = route_workspace_bytes(S, E);
+  char* rws = ws.take<char>(rbytes);
+  if (!ws.ok) { set_error("snb_moe_layer_forward: workspace too small"); return SNB_EWORKSPACE; }
+  SNB_REQUIRE(4 * E + 8 <= 1024, "too many experts");
+  int *counts = small, *cap_dev = small + E, *ebase = small + E + 1, *erows = ebase + E, *begin = erows + E;
+  {
+    const size_t smem = (size_t)E * M * sizeof(float);
+    SNB_REQUIRE(smem <= 200 * 1024, "wg too large for shared memory");
+    if (smem > 48 * 1024) SNB_CHECK_CUDA(cudaFuncSetAttribute(k_ln_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ln_gate<<<(unsigned)cdiv(S, 8), 256, smem, st>>>(gate_input, S, M, E, nullptr, nullptr, m->wg, gates);
+    SNB_CHECK_LAUNCH("k_ln_gate");
+  }
+  int rc;
+  if ((rc = route_top1(gates, S, E, cf, o->no_batch ? 0 : o->bpr, idx, loc, gate, counts, cap_dev, l_aux, rws, rbytes, st))) return rc;
+  k_expert_ranges<<<1, 32, 0, st>>>(counts, cap_dev, E, o->no_batch, ebase, erows, begin);
+  SNB_CHECK_LAUNCH("k_expert_ranges");
+  if (moe_idx) SNB_CHECK_CUDA(cudaMemcpyAsync(moe_idx, idx, sizeof(int) * S, cudaMemcpyDeviceToDevice, st));
+  if ((rc = snb_dispatch_impl(input, idx, loc, o->no_batch ? begin : nullptr, cap_dev, 0, S, M, rows, bufx, false, st))) return rc;
+  const float* in = bufx;
+  float* outb = buf0;
+  const int64_t max_rows = o->no_batch ? S : cap_host;
+  for (int j = 0; j < L; ++j) {
+    const bool skip = (j == m->d.skip_layer);
+    if (max_rows > 0) {
+      dim3 grid((unsigned)cdiv(max_rows, 64), (unsigned)cdiv(M, 64), (unsigned)E);
+      if (j < L - 1)
+        k_linear<ACT_RELU><<<grid, 256, 0, st>>>(in, M, m->exp_w[j], m->exp_b[j], skip ? bufx : nullptr, M, outb, M, 0, M, M, ebase, erows, nullptr);
+      else
+        k_linear<ACT_NONE><<<grid, 256, 0, st>>>(in, M, m->exp_w[j], m->exp_b[j], skip ? bufx : nullptr, M, outb, M, 0, M, M, ebase, erows, nullptr);
+      SNB_CHECK_LAUNCH("k_linear(expert)");
+    }
+    in = outb;
+    outb = (outb == buf0) ? buf1 : buf0;
+  }
+  return snb_combine_impl(in, idx, loc, o->no_batch ? begin : nullptr, gate, cap_dev, 0, S, M, rows, y, false, st);
 }
 
 __global__ void k_pack_out(const float* __restrict__ rgb, const float* __restrict__ sigma, int64_t S,

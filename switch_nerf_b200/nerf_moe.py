@@ -16,6 +16,7 @@ Scope: forward only (inference / evaluation and the forward half of a training s
 backward of the fused path is SURVEY.md 8f rank 1 ("next").
 """
 import ctypes as C
+import weakref
 from typing import Optional
 
 import torch
@@ -68,6 +69,10 @@ class TopKGate(nn.Module):
         self.top_k = 1
 
 
+# NeRFMoE instances by id (weak): lets MOELayer.forward find the model handle without a reference cycle in the module tree
+_OWNERS = weakref.WeakValueDictionary()
+
+
 class MOELayer(nn.Module):
     """Parameter layout of reference MOELayer (tutel_moe_layer_nobatch.py:428-731):
     `experts.0.{weights,bias}.{j}`, `gates.0.wg.weight`; `moe_no_batch` toggled by
@@ -92,6 +97,54 @@ class MOELayer(nn.Module):
                                              gate_type["capacity_factor"], gate_type["batch_prioritized_routing"])])
         if seeds is not None and len(seeds) > 2 and seeds[2] is not None:
             torch.manual_seed(seeds[2])
+        self.l_aux = None
+        self.gate_extras = None
+        self._owner_key = None      # key of the NeRFMoE that owns the packed weights in _OWNERS (set by NeRFMoE.__init__)
+
+    def _find_owner(self):
+        o = _OWNERS.get(self._owner_key) if self._owner_key is not None else None
+        if o is not None and any(l is self for l in o.layers.values()):
+            return o
+        for o in list(_OWNERS.values()):           # e.g. after copy.deepcopy of the model
+            if any(l is self for l in o.layers.values()):
+                self._owner_key = id(o)
+                return o
+        return None
+
+    def forward(self, input: torch.Tensor, gate_index=0, **kwargs):
+        """reference MOELayer.forward (tutel_moe_layer_nobatch.py:733-797): top-1 capacity routing on
+        softmax(gate_input @ wg^T), expert stack, combine.  Returns the result reshaped like `input`, carrying
+        `.l_aux` and (if return_gates) `.gate_extras` as attributes, exactly like the reference.  Runs the fp32 CUDA
+        path through snb_moe_layer_forward; NeRFMoE.forward itself uses the fused kernels and never calls this."""
+        owner = self._find_owner()
+        if owner is None:
+            raise L.SnbError("MOELayer.forward needs the owning NeRFMoE (packed weights live in its model handle)")
+        if gate_index != 0:
+            raise NotImplementedError("the hot path has one gate per MoE layer")
+        gate_input = kwargs.get("gate_input")
+        original_shape, original_dtype = input.shape, input.dtype
+        assert len(input.shape) >= 2, "Input data must be at least 2D tensor: (s)amples, .., (m)odel_dim"
+        x = L.require_cuda_f32(input.reshape(-1, input.shape[-1]), "input", self.model_dim)
+        g = None if gate_input is None else L.require_cuda_f32(gate_input.reshape(-1, gate_input.shape[-1]), "gate_input",
+                                                               self.model_dim)
+        S = x.shape[0]
+        h = owner.handle()
+        lib = L.lib()
+        gate = self.gates[0]
+        opts = L.RouteOpts(gate.capacity_factor, int(gate.batch_prioritized_routing), int(self.moe_no_batch))
+        y = torch.empty(S, self.model_dim, dtype=torch.float32, device=x.device)
+        idx = torch.empty(S, dtype=torch.int32, device=x.device)
+        l_aux = torch.zeros(1, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            nbytes = lib.snb_workspace_bytes(h, S, opts.capacity_factor)
+            ws = L.Workspace.get(nbytes, x.device)
+            L.check(lib.snb_moe_layer_forward(h, L.ptr(x), L.ptr(g), S, C.byref(opts), L.ptr(y), L.ptr(idx), L.ptr(l_aux),
+                                              L.ptr(ws), ws.numel(), L.stream_handle()))
+        out = y.view(original_shape).to(original_dtype)
+        self.l_aux = out.l_aux = l_aux[0]
+        if self.return_gates:
+            self.gate_extras = out.gate_extras = {"gates": idx.long().view(-1, 1)}     # topk(gates, 1).indices (:227-229)
+        return out
 
 
 moe_layer = MOELayer
@@ -155,6 +208,8 @@ class NeRFMoE(nn.Module):
                                              seeds=(1, rank + 1, 1), moe_no_batch=False,
                                              return_gates=getattr(args, "moe_return_gates", False),
                                              ep_world=self._ep_world)
+                self.layers[tag]._owner_key = id(self)
+                _OWNERS[id(self)] = self
             elif c["type"] == "layernorm":
                 self.layers[tag] = nn.LayerNorm(c["in_ch"])
         self._handle = None
@@ -173,6 +228,16 @@ class NeRFMoE(nn.Module):
             fixed = to_expertmlp(state_dict)
             state_dict.clear()
             state_dict.update(fixed)
+
+    # copies / pickles never share the C handle (it is re-created on first use of the copy)
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_handle"], st["_packed_versions"], st["_packed_device"], st["_ep_group"] = None, None, None, None
+        return st
+
+    def __setstate__(self, st):
+        super().__setstate__(st)
+        _OWNERS[id(self)] = self
 
     # -- reference API -----------------------------------------------------------------
     @staticmethod

@@ -417,3 +417,35 @@ def test_expert_parallel_matches_local(built_lib):
     r = subprocess.run(cmd, timeout=900, capture_output=True, text=True)
     tail = r.stdout[-6000:] + "\n" + r.stderr[-3000:]
     assert r.returncode == 0 and "EP_PARITY_OK" in r.stdout, tail
+
+
+@pytest.mark.parametrize("cf,bpr,nobatch", [(1.0, True, False), (0.5, False, False), (2.0, True, False), (1.0, False, True)])
+def test_moe_layer_operator_vs_oracle(built_lib, cf, bpr, nobatch):
+    """SURVEY 8b "MoE operator": `moe_layer(...).forward(input, gate_input=...)` (tutel_moe_layer_nobatch.py:733-797)
+    through snb_moe_layer_forward == the oracle's MOELayer restatement: routing indices exact, outputs to fp32
+    round-off, `.l_aux` / `.gate_extras` carried as tensor attributes."""
+    from switch_nerf_b200 import synthetic as SY
+    sd = SY.synthetic_state_dict(num_experts=4, appearance_count=8, seed=11, gate_scale=3.0)
+    model, _ = make_model(sd, cf, bpr, nobatch, "fp32")
+    g = torch.Generator().manual_seed(5)
+    S = 3001
+    h = torch.randn(S, 256, generator=g) * 0.5
+    gi = torch.randn(S, 256, generator=g)
+    cfg = O.default_cfg(sd, cf, bpr, nobatch)
+    y_ref, ex = O.moe_layer(h, gi, sd, "0", cfg, "fp32")
+    moe = model.layers["0"]
+    y = moe(h.view(S, 1, 256).cuda(), gate_input=gi.view(S, 1, 256).cuda())
+    torch.cuda.synchronize()
+    assert y.shape == (S, 1, 256) and hasattr(y, "l_aux") and hasattr(y, "gate_extras")
+    idx = y.gate_extras["gates"].view(-1).cpu()
+    same = idx == ex["idx"].long()
+    assert same.float().mean() > 0.999, "top-1 expert differs from the oracle beyond fp32 near-ties"
+    d = (y.view(S, 256).cpu() - y_ref).abs().amax(1)
+    bad = (d > 5e-5) & same
+    assert bad.float().mean() < 2e-3, (float(d[same].max()), int(bad.sum()))      # capacity-boundary near-ties only
+    assert abs(float(y.l_aux) - float(ex["l_aux"])) < 1e-5 * max(1.0, abs(float(ex["l_aux"])))
+    # default gate input = the layer input itself (reference: gate_input=None)
+    y2 = moe(h.cuda())
+    y2_ref, _ = O.moe_layer(h, h, sd, "0", cfg, "fp32")
+    d2 = (y2.cpu() - y2_ref).abs().amax(1)
+    assert (d2 > 5e-5).float().mean() < 5e-3

@@ -142,3 +142,22 @@ def test_seqexperts_layout_matches_reference_converter():
     assert set(ref) == set(ours)
     for k in ref:
         assert torch.equal(ref[k], ours[k]), k
+
+
+def test_model_copies_do_not_share_the_c_handle_and_moe_layer_finds_its_owner():
+    import copy
+    import ctypes as C
+    from switch_nerf_b200.nerf_moe import _OWNERS
+    hp = make_hparams(num_experts=4)
+    m = get_nerf_moe_inner(hp, 8, 3)
+    m._handle = C.c_void_p(1234)                       # pretend a packed model exists
+    try:
+        m2 = copy.deepcopy(m)
+    finally:
+        m._handle = None
+    assert m2._handle is None and m2 is not m
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    assert m.layers["0"]._find_owner() is m and m2.layers["0"]._find_owner() is m2
+    assert id(m2) in _OWNERS
+    with pytest.raises(Exception):                     # no CPU path for the operator either
+        m.layers["0"](torch.zeros(4, 256))
