@@ -190,13 +190,22 @@ __global__ void __launch_bounds__(192) k_umma_bench(int N, int ts, int flags, in
     }
   } else if (warp == 1) {
     if (lane == 0 && (flags & 1)) {
+      // keep four 8 KB copies in flight (one per landing slot), like the weight ring of the fused kernels
       uint32_t n = 0;
+      for (uint32_t s2 = 0; s2 < 4; ++s2) {
+        mbar_arrive_expect_tx(&bar_full[s2], 8192);
+        bulk_g2s(sL + s2 * 8192, src + (size_t)s2 * 8192, 8192, &bar_full[s2]);
+      }
       while (!done) {
-        const uint32_t s = n & 3, ph = (n >> 2) & 1;
-        mbar_arrive_expect_tx(&bar_full[s], 8192);
-        bulk_g2s(sL + s * 8192, src + (size_t)(n & 1023) * 8192, 8192, &bar_full[s]);
-        mbar_wait(&bar_full[s], ph);
+        const uint32_t s2 = n & 3, ph = (n >> 2) & 1;
+        mbar_wait(&bar_full[s2], ph);
         ++n;
+        mbar_arrive_expect_tx(&bar_full[s2], 8192);
+        bulk_g2s(sL + s2 * 8192, src + (size_t)((n + 3) & 1023) * 8192, 8192, &bar_full[s2]);
+      }
+      for (uint32_t k = 0; k < 4; ++k) {            // drain what is still in flight before the CTA exits
+        const uint32_t s2 = (n + k) & 3, ph = ((n + k) >> 2) & 1;
+        mbar_wait(&bar_full[s2], ph);
       }
       out[1] = n;
     }
