@@ -52,3 +52,27 @@ def test_sass_has_blackwell_instructions(built_lib):
     sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
     for mnem in ("UTCHMMA", "LDTM", "UBLKCP"):
         assert mnem in sass, f"{mnem} missing from SASS"
+    # hidden activations in tensor memory: tcgen05.st -> STTM, and the MMA form that takes its A operand from TMEM
+    assert "STTM" in sass, "tcgen05.st (STTM) missing from SASS"
+    assert re.search(r"UTCHMMA(\.2CTA)? tmem\[", sass), "no tcgen05.mma with the A operand in tensor memory"
+    # the default kernels of the fused path
+    for k in ("k_front_ts", "k_back_ts", "k_ep_dispatch", "k_ep_plan"):
+        assert k in sass, f"kernel {k} missing"
+
+
+def test_argument_errors_are_reported_not_crashed(built_lib):
+    """Entry points validate their arguments before touching the device: non-zero status + snb_last_error()."""
+    from switch_nerf_b200 import _lib as L
+    lib = L.lib()
+    opts = L.RouteOpts(1.0, 1, 0)
+    assert lib.snb_moe_layer_forward(None, None, None, 16, C.byref(opts), None, None, None, None, 0, None) != 0
+    assert b"NULL" in lib.snb_last_error()
+    assert lib.snb_moe_forward(None, None, 16, None, C.byref(opts), 1, None, None, None, None, None, None, 0, None) != 0
+    assert lib.snb_model_attach_a2a(None, None) != 0
+    h = C.c_void_p()
+    assert lib.snb_a2a_init(5, 4, 8, 1024, 1.0, C.byref(h)) != 0 and b"rank" in lib.snb_last_error()
+    assert lib.snb_a2a_init(0, 9, 9, 1024, 1.0, C.byref(h)) != 0
+    assert lib.snb_a2a_connect(None, None, 0) != 0
+    out = (C.c_uint64 * 6)()
+    assert lib.snb_umma_microbench(96, 0, 0, 16, out, None) != 0 and b"N must be" in lib.snb_last_error()
+    assert lib.snb_a2a_handle_bytes() == 64
