@@ -355,7 +355,8 @@ def render_rays(sd: Dict[str, Tensor], cfg: dict, rays: Tensor, image_indices: T
             res[f"{k}_coarse"] = comp_c[k]
         return res
     z_mid = 0.5 * (z_vals[:, :-1] + z_vals[:, 1:])                                        # :238
-    z_fine = sample_pdf(z_mid, comp_c["weights"][:, 1:-1], fine_samples, det=(perturb == 0), u=u_fine)
+    # rendering.py:240 samples from the DETACHED coarse weights: no gradient flows through the sample positions
+    z_fine = sample_pdf(z_mid, comp_c["weights"][:, 1:-1].detach(), fine_samples, det=(perturb == 0), u=u_fine)
     xyz_f = rays_o.unsqueeze(1) + rays_d.unsqueeze(1) * z_fine.unsqueeze(-1)
     out_f, l_aux_f, gates_f = _run_model_chunks(xyz_f, rays_d, image_indices, sd, cfg, mode, model_chunk_size, flavor)
     res["gate_loss_fine"], res["moe_gates_fine"] = l_aux_f, gates_f
@@ -437,7 +438,7 @@ def _run_mip_chunks(mean, cov, rays_d, image_indices, sd, cfg, mode, chunk, flav
 def render_rays_mip(sd: Dict[str, Tensor], cfg: dict, rays: Tensor, radii: Tensor, image_indices: Tensor, *,
                     coarse_samples: int, fine_samples: int, model_chunk_size: int, mode: str = "fp32",
                     weights_resample_padding: float = 0.01, rgb_padding: Optional[float] = 0.001,
-                    flavor: str = "cuda") -> Dict[str, Tensor]:
+                    flavor: str = "cuda", stop_level_grad: bool = True) -> Dict[str, Tensor]:
     """rendering_mip.render_rays (133-174) + _get_results (177-261) + _inference (264-425), eval mode
     (perturb = 0, deterministic resampling)."""
     n_rays = rays.shape[0]
@@ -461,6 +462,8 @@ def render_rays_mip(sd: Dict[str, Tensor], cfg: dict, rays: Tensor, radii: Tenso
     w_max = torch.maximum(w_pad[..., :-1], w_pad[..., 1:])
     w_blur = 0.5 * (w_max[..., :-1] + w_max[..., 1:])
     z_samples = sorted_piecewise_constant_pdf(z_vals, w_blur + weights_resample_padding, fine_samples)
+    if stop_level_grad:                                                        # :227-228 (opts.py:245: always true)
+        z_samples = z_samples.detach()
     z_fine, _ = torch.sort(z_samples, -1)
     mean, cov = mip_cast_rays(rays_o, rays_d, radii, z_fine)
     out_f, l_f, g_f = _run_mip_chunks(mean, cov, rays_d, image_indices, sd, cfg, mode, model_chunk_size, flavor)

@@ -95,3 +95,23 @@ def test_render_mip_golden(tag):
                             torch.from_numpy(g["image_indices"]), coarse_samples=int(cs), fine_samples=int(fs), model_chunk_size=int(chunk))
     for k in ("rgb_coarse", "rgb_fine", "depth_fine", "depth_variance_fine", "gate_loss_coarse", "gate_loss_fine"):
         assert np.array_equal(res[k].numpy(), g[k]), k
+
+
+def test_oracle_gradients_vs_reference_golden():
+    """Next scope row (backward): the oracle's autograd through the restated path reproduces the parameter
+    gradients the UNMODIFIED reference produced for one training-style step (oracle/make_golden_grad.py): identical
+    loss and bit-identical gradients (fp32, CPU).  This also pins which paths are cut: the fine samples come from DETACHED coarse weights
+    (rendering.py:240)."""
+    from oracle import make_golden_grad as G
+    g = load_golden("grad_config1.npz")
+    loss, grads = G.oracle_grads()
+    assert loss == float(g["loss"][0])
+    scale = float(g["scale"][0])
+    names = [k[len("sample/"):] for k in g if k.startswith("sample/")]
+    assert len(names) == 32 and set(names) == set(grads)
+    for k in names:
+        mine = G.sample_of(grads[k])
+        ref = torch.from_numpy(g["sample/" + k])
+        assert torch.equal(mine, ref), k              # same torch ops in the same order -> bit-identical on CPU
+        st = g["stats/" + k]
+        assert float(grads[k].double().abs().sum()) == st[1] and float(grads[k].abs().max()) == st[2], k
