@@ -115,3 +115,60 @@ def test_oracle_gradients_vs_reference_golden():
         assert torch.equal(mine, ref), k              # same torch ops in the same order -> bit-identical on CPU
         st = g["stats/" + k]
         assert float(grads[k].double().abs().sum()) == st[1] and float(grads[k].abs().max()) == st[2], k
+
+
+def test_backward_plan_model_chunk_equals_autograd():
+    """oracle/backward_plan.py (the stage-by-stage backward the CUDA kernels will implement) == autograd of the pinned
+    forward restatement, for one model chunk with drops (cf 0.5) and BPR: every parameter gradient."""
+    from oracle import backward_plan as B
+    from switch_nerf_b200 import synthetic as SY
+    torch.manual_seed(0)
+    sd = SY.synthetic_state_dict(num_experts=4, appearance_count=8, seed=21, gate_scale=3.0)
+    S = 700
+    x = torch.cat([torch.rand(S, 3) - 0.5, torch.nn.functional.normalize(torch.randn(S, 3), dim=1),
+                   torch.randint(0, 8, (S, 1)).float()], 1)
+    for cf, bpr in ((0.5, True), (1.0, False), (2.0, True)):
+        cfg = O.default_cfg(sd, cf, bpr)
+        sdg = {k: v.clone().double().requires_grad_(True) for k, v in sd.items()}
+        R = torch.randn(S, 4).double()
+        c_aux = 0.37
+        orig_float = torch.Tensor.float
+        torch.Tensor.float = lambda self, *a, **k: self.double()      # run the restatement in fp64 (tight comparison)
+        try:
+            out, ex = O.nerf_moe_forward(x.double(), sdg, cfg, "fp32")
+            ((out * R).sum() + c_aux * ex["l_aux"]).backward()
+            sd64 = {k: v.double() for k, v in sd.items()}
+            torch.set_default_dtype(torch.float64)
+            try:
+                grads = B.model_chunk_backward(x.double(), sd64, cfg, R, c_aux)
+            finally:
+                torch.set_default_dtype(torch.float32)
+        finally:
+            torch.Tensor.float = orig_float
+        assert (ex["loc"] >= ex["capacity"]).any() or cf >= 2.0          # the cf 0.5 / 1.0 cases really drop samples
+        assert set(grads) == {k for k, v in sdg.items() if v.grad is not None}
+        for k, g in grads.items():
+            ref = sdg[k].grad
+            err = float((g - ref).abs().max())
+            assert err <= 1e-9 * max(1.0, float(ref.abs().max())), (cf, bpr, k, err)
+
+
+def test_backward_plan_composite_and_merge_equal_autograd():
+    from oracle import backward_plan as B
+    g = torch.Generator().manual_seed(3)
+    N, Sf, Sc = 37, 9, 13
+    zf = torch.sort(torch.rand(N, Sf, generator=g, dtype=torch.float64) * 0.9 + 0.05, -1)[0]
+    zc = torch.sort(torch.rand(N, Sc, generator=g, dtype=torch.float64) * 0.9 + 0.05, -1)[0]
+    raw_f = torch.rand(N, Sf, 4, generator=g, dtype=torch.float64).requires_grad_(True)
+    raw_c = torch.rand(N, Sc, 4, generator=g, dtype=torch.float64).requires_grad_(True)
+    last = 1e10 * torch.ones(N, 1, dtype=torch.float64)
+    z_all, order = torch.sort(torch.cat([zf, zc], -1), -1)
+    rgbs = torch.gather(torch.cat([raw_f[..., :3], raw_c[..., :3]], 1), 1, order.unsqueeze(-1).expand(-1, -1, 3))
+    sig = torch.gather(torch.cat([raw_f[..., 3] * 30, raw_c[..., 3] * 30], 1), 1, order)
+    comp = O.composite(z_all, rgbs, sig, last)
+    d_rgb = torch.randn(N, 3, generator=g, dtype=torch.float64)
+    (comp["rgb"] * d_rgb).sum().backward()
+    d_rgbs, d_sig = B.composite_backward(z_all, rgbs.detach(), sig.detach(), last, d_rgb)
+    (drf, dsf), (drc, dsc) = B.merge_backward(order, Sf, d_rgbs, d_sig)
+    for mine, ref in ((drf, raw_f.grad[..., :3]), (dsf * 30, raw_f.grad[..., 3]), (drc, raw_c.grad[..., :3]), (dsc * 30, raw_c.grad[..., 3])):
+        assert float((mine - ref).abs().max()) <= 1e-10 * max(1.0, float(ref.abs().max()))
