@@ -20,6 +20,20 @@ from . import _lib as L
 from .nerf_moe import NeRFMoE
 
 
+_WARNED = False
+
+
+def _warn_forward_only(model):
+    """The fused path has no backward yet: say so once instead of letting loss.backward() fail later
+    with an unrelated-looking autograd error."""
+    global _WARNED
+    if not _WARNED and model.training and torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
+        import warnings
+        warnings.warn("switch_nerf_b200.render_rays is forward-only: the results carry no autograd graph "
+                      "(backward of the fused path is the next scope row)", RuntimeWarning, stacklevel=3)
+        _WARNED = True
+
+
 def _unwrap(nerf):
     return nerf.module if hasattr(nerf, "module") and isinstance(nerf.module, NeRFMoE) else nerf
 
@@ -44,6 +58,7 @@ def render_rays(nerf, bg_nerf, rays: torch.Tensor, image_indices: Optional[torch
     if image_indices is not None:
         idx32 = image_indices.to(device=dev, dtype=torch.int32).contiguous()
     perturb = float(hparams.perturb) if model.training else 0.0          # rendering.py:32
+    _warn_forward_only(model)
     typ = "fine" if Sf > 0 else "coarse"
 
     opts = L.RenderOpts()
