@@ -37,7 +37,10 @@ from argparse import Namespace
 
 import torch
 
-REFERENCE_ROOT = "/root/reference"
+from oracle.install_ref import reference_root
+
+# /root/reference in the build container, the verbatim copy under baseline/_ref on the GPU box (oracle/install_ref.py)
+REFERENCE_ROOT = reference_root() or "/root/reference"
 
 
 def _sparse_module():

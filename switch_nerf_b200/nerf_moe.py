@@ -58,6 +58,55 @@ class ExpertMLP(nn.Module):
             self.bias.append(b)
 
 
+class SingleExpert(nn.Module):
+    """Parameter layout of reference SingleExpert (tutel_moe_layer_nobatch.py:927-985), the per-expert module of the
+    `seqexperts` checkpoint layout: `layers.{j}.weight [out, in]`, `layers.{j}.bias [out]`.  A container only: the fused
+    path packs the stacked `expertmlp` layout (checkpoint.to_expertmlp converts)."""
+
+    def __init__(self, model_dim, layer_num, skips=None, init_factor=1.0, **_):
+        super().__init__()
+        self.model_dim, self.layer_num, self.skips = model_dim, layer_num, skips
+        self.layers = nn.ModuleList()
+        for _i in range(layer_num):
+            fc = nn.Linear(model_dim, model_dim)
+            if init_factor != 1.0:
+                with torch.no_grad():
+                    fc.weight.multiply_(init_factor)
+                    fc.bias.multiply_(init_factor)
+            self.layers.append(fc)
+
+
+def fast_cumsum_sub_one(mask: torch.Tensor, dim: int = 0) -> torch.Tensor:
+    """Tutel `jit_kernels.gating.fast_cumsum_sub_one` (re-exported by tutel_moe_nobatch.py:6; call sites
+    tutel_fast_dispatch.py:138, 190): inclusive cumsum over samples minus one, for a one-hot [S, E] CUDA mask.
+    Computed by the routing kernel: for a one-hot row the only entry callers read is locations[s, idx[s]]
+    (tutel_fast_dispatch.py:192-194), which is `loc[s]` of snb_route_top1 in sample order; the other entries are the
+    running counts of the other experts, rebuilt here from the same per-expert locations."""
+    if dim != 0 or mask.dim() != 2 or not mask.is_cuda:
+        raise L.SnbError("fast_cumsum_sub_one: expects a CUDA [S, E] mask and dim=0 (no CPU path)")
+    S, E = mask.shape
+    gates = mask.to(torch.float32).contiguous()            # one-hot rows: argmax == the hot expert
+    dev = mask.device
+    idx = torch.empty(S, dtype=torch.int32, device=dev)
+    loc = torch.empty(S, dtype=torch.int32, device=dev)
+    gv = torch.empty(S, dtype=torch.float32, device=dev)
+    counts = torch.empty(E, dtype=torch.int32, device=dev)
+    cap = torch.empty(1, dtype=torch.int32, device=dev)
+    l_aux = torch.empty(1, dtype=torch.float32, device=dev)
+    lib = L.lib()
+    with torch.cuda.device(dev):
+        nb = lib.snb_route_workspace_bytes(S, E)
+        ws = L.Workspace.get(nb, dev)
+        L.check(lib.snb_route_top1(L.ptr(gates), S, E, 1.0, 0, L.ptr(idx), L.ptr(loc), L.ptr(gv), L.ptr(counts), L.ptr(cap),
+                                   L.ptr(l_aux), L.ptr(ws), nb, L.stream_handle()))
+    # running count of every expert at every sample: scatter the hot entries, then carry them forward
+    out = torch.full((S, E), -1, dtype=mask.dtype, device=dev)
+    hot = mask.sum(1) > 0                                   # all-zero rows route nowhere
+    rows = torch.nonzero(hot).view(-1)
+    out[rows, idx.long()[rows]] = loc.to(mask.dtype)[rows]
+    return torch.cummax(out, 0).values
+
+
 class TopKGate(nn.Module):
     """Parameter layout of reference TopKGate (tutel_moe_layer_nobatch.py:29-96): `wg.weight` [E, gate_dim]."""
 
@@ -97,6 +146,11 @@ class MOELayer(nn.Module):
                                              gate_type["capacity_factor"], gate_type["batch_prioritized_routing"])])
         if seeds is not None and len(seeds) > 2 and seeds[2] is not None:
             torch.manual_seed(seeds[2])
+        if int(ep_world) > 1:
+            # scan_expert_func of the reference (nerf_moe.py:139, 284; tutel_moe_layer_nobatch.py:675-678): sharded
+            # expert parameters differ per rank, DDP must neither broadcast nor all-reduce them
+            for p in self.experts.parameters():
+                setattr(p, "skip_allreduce", True)
         self.l_aux = None
         self.gate_extras = None
         self._owner_key = None      # key of the NeRFMoE that owns the packed weights in _OWNERS (set by NeRFMoE.__init__)

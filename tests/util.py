@@ -46,3 +46,29 @@ def make_model(sd, capacity_factor=1.0, bpr=True, no_batch=False, precision="fp3
     model = model.to(device).eval()
     model.set_no_batch(no_batch)
     return model, hp
+
+
+def bf16_ulp(x):
+    """Spacing of bf16 numbers at |x| (8 significant bits)."""
+    e = torch.floor(torch.log2(x.abs().clamp_min(2.0 ** -126)))
+    return torch.pow(2.0, e - 7)
+
+
+def bf16_contract_stats(out, ref_out, idx, ref_idx, kept=None, ref_kept=None):
+    """Per-sample [rgb, sigma] of a bf16 path vs the UNMODIFIED reference's CUDA-autocast output (tests/golden/*bf16cuda*):
+    routing agreement, and on the samples both sides routed identically the distribution of |d rgb| in bf16 output ulps
+    (sigmoid(rgb) is a bf16 value on both sides) and the sigma error (fp32 softplus of a bf16 pre-activation)."""
+    same = idx.view(-1).long() == ref_idx.view(-1).long()
+    if kept is not None and ref_kept is not None:
+        same &= kept.view(-1) == ref_kept.view(-1)
+    d_rgb = (out[same, :3] - ref_out[same, :3]).abs()
+    ulps = (d_rgb / bf16_ulp(ref_out[same, :3])).round()
+    d_sig = (out[same, 3] - ref_out[same, 3]).abs()
+    n = max(int(ulps.numel()), 1)
+    return {"route_agree": float(same.float().mean()),
+            "rgb_ulp0": float((ulps == 0).sum()) / n, "rgb_ulp_le1": float((ulps <= 1).sum()) / n,
+            "rgb_ulp_le2": float((ulps <= 2).sum()) / n, "rgb_max_abs": float(d_rgb.max()) if n else 0.0,
+            "rgb_frac_le_1e-3": float((d_rgb <= 1e-3).float().mean()),
+            "sigma_max_abs": float(d_sig.max()), "sigma_frac_le_1e-3": float((d_sig <= 1e-3).float().mean()),
+            "sigma_max_rel": float((d_sig / ref_out[same, 3].abs().clamp_min(1e-2)).max()),
+            "mean_abs_all": float((out - ref_out).abs().mean())}
