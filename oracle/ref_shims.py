@@ -108,8 +108,15 @@ def install_shims():
 
     class _JitCompiler:
         @staticmethod
-        def generate_kernel(*a, **k):
-            raise RuntimeError("tutel JitCompiler is not available in the oracle shim")
+        def generate_kernel(keyword_dict, template):
+            """CUDA tensors: the real Tutel compiles the reference's kernel strings (tutel_sparse_nobatch.py:21-35,
+            42-64, 71-134) with NVRTC; the shim recognises which of the three it was handed and returns the same
+            torch restatement `generate_cpu_kernel` gives (the ops run on whatever device the tensors live on)."""
+            if "atomicAdd" in template:
+                return _JitCompiler.generate_cpu_kernel(0)
+            if "grad_gates1_s" in template:
+                return _JitCompiler.generate_cpu_kernel(2)
+            return _JitCompiler.generate_cpu_kernel(1)
 
         @staticmethod
         def generate_cpu_kernel(kernel_type):

@@ -242,11 +242,18 @@ def nerf_moe_forward(x: Tensor, sd: Dict[str, Tensor], cfg: dict, mode: str = "f
     h = F.relu(h)                                                         # :384-386
     sigma = linear(h, sd["layers.sigma.fcs.0.weight"], sd["layers.sigma.fcs.0.bias"], mode)  # :396-397
     if sigma_noise is not None:
-        sigma = sigma + sigma_noise
+        sigma = sigma + sigma_noise                                       # in-place on the (bf16) Linear output, :407-408
+        if mode == "bf16":
+            sigma = _r(sigma)
     if mode == "bf16" and flavor == "cpu":
         sigma = _r(shifted_softplus(_r(sigma)))
+    elif mode == "bf16":
+        # cuda autocast: `sigma += noise` and `x - 1` (nerf.py:68) are plain bf16 tensor ops -- each rounds to bf16 --
+        # and only F.softplus itself is promoted to fp32.  Pinned by tests/golden/model_*_bf16cuda.npz (the unmodified
+        # reference on a B200): without the rounding of x - 1, 97 % of the sigmas are off by up to 1e-3.
+        sigma = F.softplus(_r(_r(sigma) - 1.0).float())
     else:
-        sigma = shifted_softplus(sigma.float())                           # :416 (softplus is fp32 under autocast)
+        sigma = shifted_softplus(sigma.float())                           # :416
     h = mlp(h, sd, "layers.1", 1, mode)                                   # layer "1", act none
     d_pe = embedding(x[:, xd:xd + 3], cfg["pos_dir_dim"])                 # :424
     emb = sd["embedding_a.weight"][x[:, -1].long()]                       # :427

@@ -10,6 +10,8 @@
 //   k_loc         warp-ballot (match_any) rank inside a 256-sample block + scanned block offsets
 // No host round trip: capacity / counts / l_aux stay in device memory.
 #include "snb_common.cuh"
+#include "snb_ep.cuh"
+#include "snb_select.cuh"
 
 namespace snb {
 
@@ -363,6 +365,317 @@ int route_top1_generic(const float* gates, int64_t S, int32_t E, double cf, int3
                        int32_t* loc, float* gate, int32_t* counts, int32_t* capacity, float* l_aux, void* ws,
                        size_t ws_bytes, cudaStream_t st) {
   return route_impl(gates, S, E, cf, bpr, 0, idx, loc, gate, counts, capacity, l_aux, ws, ws_bytes, st);
+}
+
+// =========================================================================================
+// Routing as a per-expert radix SELECT (fused bf16 path): launch #2 only needs, per expert, the SET of samples
+// whose batch-prioritised rank is below the capacity -- not their order.  Input: one packed word per sample
+// (expert id << 26 | key, key = bits(1.0f) - bits(max gate): ascending key == descending gate), written either by
+// launch #1 itself (k_front_ts) or by k_pack_top1 below, plus the histogram of the top 9 key bits per expert.
+// One CTA per expert: radix descent to the composite threshold T over the unique 58-bit value (key << 32 | sample)
+// -- ties between equal gates resolve to the lower sample index exactly as the stable sort of the full path does --
+// then ONE ordered pass that hands every kept sample its row (index order) and every dropped sample a row of the
+// dropped bucket.  No atomics on the output, no memset, deterministic row order.
+// reference: tutel_fast_dispatch.py:136-139, 176-217 (the kept set == {s : locations_s < capacity}).
+// =========================================================================================
+static constexpr int SEL_THREADS = 1024;
+static constexpr int SEL_LIST = 4096;       // candidates of the threshold digit bucket resolved in shared memory
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// gates [S,E] -> packed words, level-1 histogram, partial column sums (the part of launch #1's softmax epilogue that
+// k_front_ts does itself); one block per 2048 samples.  pm: [gridDim.x][SEL_PM_STRIDE]
+__global__ void __launch_bounds__(256) k_pack_top1(const float* __restrict__ gates, int64_t S, int E,
+                                                   uint32_t* __restrict__ w, int* __restrict__ hist1,
+                                                   float* __restrict__ pm) {
+  __shared__ float s_me[8][SEL_MAX_E];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int e = lane; e < SEL_MAX_E; e += 32) s_me[wid][e] = 0.f;
+  __syncwarp();
+  for (int j = 0; j < 8; ++j) {
+    const int64_t s = (int64_t)blockIdx.x * 2048 + j * 256 + threadIdx.x;
+    const bool valid = s < S;
+    int best = 0;
+    float bv = 0.f;
+    for (int e = 0; e < E; ++e) {
+      const float g = valid ? gates[s * E + e] : 0.f;
+      if (valid && (e == 0 || g > bv)) { best = e; bv = g; }
+      float v = g;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_me[wid][e] += v;
+    }
+    if (valid) {
+      const uint32_t key = sel_key(bv);
+      w[s] = sel_pack(best, key);
+      atomicAdd(&hist1[best * SEL_HBINS + (int)(key >> SEL_L1_SHIFT)], 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < SEL_PM_STRIDE) {
+    float a = 0.f;
+    if ((int)threadIdx.x < E)
+      for (int ww = 0; ww < 8; ++ww) a += s_me[ww][threadIdx.x];
+    pm[(int64_t)blockIdx.x * SEL_PM_STRIDE + threadIdx.x] = a;
+  }
+}
+
+struct SelShared {
+  int cnt[SEL_MAX_E + 1];
+  int hist[SEL_HBINS];
+  int wsum[2][32];
+  int wtot[32];
+  unsigned long long list[SEL_LIST];
+  int n_list;
+  int last;
+  int ch_d, ch_need, ch_hc;       // digit chosen by the current level
+};
+
+// smallest digit d with (inclusive prefix count up to d) >= need; returns through shared memory (all threads sync)
+__device__ __forceinline__ void sel_choose(SelShared& sh, int nbins, int need, int tid, int lane, int wid) {
+  const int v = (tid < nbins) ? sh.hist[tid] : 0;
+  int inc = warp_incl_scan(v, lane);
+  if (lane == 31) sh.wtot[wid] = inc;
+  __syncthreads();
+  int base = 0;
+  for (int ww = 0; ww < wid; ++ww) base += sh.wtot[ww];
+  inc += base;
+  if (tid < nbins && inc >= need && inc - v < need) { sh.ch_d = tid; sh.ch_need = need - (inc - v); sh.ch_hc = v; }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
+  __shared__ SelShared sh;
+  const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int E = a.E;
+  const int64_t S = a.S;
+  if (tid <= SEL_MAX_E) sh.cnt[tid] = 0;
+  if (tid == 0) sh.n_list = 0;
+  __syncthreads();
+  // ---- per-expert totals (all experts: segment starts) + this expert's level-1 histogram ----
+  for (int ee = 0; ee < E; ++ee) {
+    int v = (tid < SEL_HBINS) ? a.hist1[ee * SEL_HBINS + tid] : 0;
+    if (ee == e && tid < SEL_HBINS) sh.hist[tid] = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && v) atomicAdd(&sh.cnt[ee], v);
+  }
+  __syncthreads();
+  // the histogram is zeroed again (for the next chunk that uses this workspace set) by the last CTA that has read it
+  if (tid == 0) {
+    __threadfence();
+    sh.last = (atomicAdd(a.ticket, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (sh.last) {
+    for (int i = tid; i < SEL_MAX_E * SEL_HBINS; i += SEL_THREADS) a.hist1[i] = 0;
+    if (tid == 0) *a.ticket = 0;
+  }
+  const int cap = capacity_of(S, E, a.cf);
+  const int keep_cap = a.no_batch ? 0x7fffffff : cap;
+  const int cnt = sh.cnt[e];
+  int seg0 = 0, drop0 = 0, drop_before = 0;        // first row of my segment / of the dropped segment; dropped rows of experts < e
+  {
+    int row = 0;
+    for (int ee = 0; ee < E; ++ee) {
+      const int kc = min(sh.cnt[ee], keep_cap);
+      if (ee == e) seg0 = row;
+      if (ee < e) drop_before += sh.cnt[ee] - kc;
+      row += (kc + EP_TILE - 1) / EP_TILE * EP_TILE;
+    }
+    drop0 = row;
+  }
+  // ---- threshold: T = composite value (key << 32 | sample) of the keep_cap-th element in batch-prioritised order ----
+  unsigned long long T = ~0ull;
+  if (a.bpr && !a.no_batch && cnt > cap) {
+    int sbits = 1;
+    while (sbits < 32 && (1ll << sbits) < S) ++sbits;
+    unsigned long long pmask = 0, pval = 0;
+    int need = cap, level = 0;
+    bool from_list = false, have_hist = true;
+    while (true) {
+      int dshift, dbits;
+      if (level == 0) { dshift = 32 + SEL_L1_SHIFT; dbits = SEL_KEY_BITS - SEL_L1_SHIFT; }
+      else if (level == 1) { dshift = 32 + 8; dbits = SEL_L1_SHIFT - 8; }
+      else if (level == 2) { dshift = 32; dbits = 8; }
+      else { const int hi = sbits - 9 * (level - 3); dshift = hi > 9 ? hi - 9 : 0; dbits = hi - dshift; }
+      const unsigned long long dmask = (1ull << dbits) - 1;
+      if (!have_hist) {
+        for (int i = tid; i < SEL_HBINS; i += SEL_THREADS) sh.hist[i] = 0;
+        __syncthreads();
+        if (from_list) {
+          for (int i = tid; i < sh.n_list; i += SEL_THREADS) {
+            const unsigned long long c = sh.list[i];
+            if ((c & pmask) == pval) atomicAdd(&sh.hist[(int)((c >> dshift) & dmask)], 1);
+          }
+        } else {
+          for (int64_t s = tid; s < S; s += SEL_THREADS) {
+            const uint32_t wv = a.w[s];
+            if ((int)(wv >> SEL_KEY_BITS) != e) continue;
+            const unsigned long long c = ((unsigned long long)(wv & SEL_KEY_MASK) << 32) | (unsigned long long)s;
+            if ((c & pmask) == pval) atomicAdd(&sh.hist[(int)((c >> dshift) & dmask)], 1);
+          }
+        }
+        __syncthreads();
+      }
+      sel_choose(sh, 1 << dbits, need, tid, lane, wid);
+      const int d = sh.ch_d, hc = sh.ch_hc;
+      need = sh.ch_need;
+      pval |= (unsigned long long)d << dshift;
+      pmask |= dmask << dshift;
+      if (need == hc || dshift == 0) { T = pval | ((1ull << dshift) - 1); break; }   // the whole digit bucket is kept
+      if (!from_list && hc <= SEL_LIST) {
+        // the undecided bucket fits in shared memory: gather it once, finish the descent there
+        for (int64_t s = tid; s < S; s += SEL_THREADS) {
+          const uint32_t wv = a.w[s];
+          if ((int)(wv >> SEL_KEY_BITS) != e) continue;
+          const unsigned long long c = ((unsigned long long)(wv & SEL_KEY_MASK) << 32) | (unsigned long long)s;
+          if ((c & pmask) == pval) sh.list[atomicAdd(&sh.n_list, 1)] = c;
+        }
+        __syncthreads();
+        from_list = true;
+      }
+      have_hist = false;
+      ++level;
+      __syncthreads();
+    }
+  }
+  // ---- ordered pass: rows for the kept samples (index order) and for the dropped ones ----
+  {
+    int run_keep = 0, run_drop = 0;          // block-uniform running totals
+    const bool by_rank = !(a.bpr && !a.no_batch);     // plain order: kept iff the index-order rank is below the capacity
+    int parity = 0;
+    for (int64_t base = 0; base < S; base += 4 * SEL_THREADS, parity ^= 1) {
+      const int64_t s0 = base + 4 * (int64_t)tid;
+      uint32_t wv[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      if (s0 + 3 < S) {
+        const uint4 q = *reinterpret_cast<const uint4*>(a.w + s0);
+        wv[0] = q.x; wv[1] = q.y; wv[2] = q.z; wv[3] = q.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (s0 + j < S) wv[j] = a.w[s0 + j];
+      }
+      int mine[4], kp[4];
+      int packed = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mine[j] = (s0 + j < S) && ((int)(wv[j] >> SEL_KEY_BITS) == e);
+        const unsigned long long c = ((unsigned long long)(wv[j] & SEL_KEY_MASK) << 32) | (unsigned long long)(s0 + j);
+        kp[j] = mine[j] && (by_rank || c <= T);
+        packed += by_rank ? mine[j] : (kp[j] + ((mine[j] && !kp[j]) << 16));
+      }
+      int inc = warp_incl_scan(packed, lane);
+      if (lane == 31) sh.wsum[parity][wid] = inc;
+      __syncthreads();
+      int wt = warp_incl_scan(sh.wsum[parity][lane], lane);
+      const int total = __shfl_sync(0xffffffffu, wt, 31);
+      const int wbase = __shfl_sync(0xffffffffu, wt, wid > 0 ? wid - 1 : 0);
+      int pre = inc - packed + (wid > 0 ? wbase : 0);          // exclusive prefix of this thread inside the round
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (mine[j]) {
+          const int64_t s = s0 + j;
+          int slot, kept;
+          if (by_rank) {
+            const int r = run_keep + pre;
+            kept = r < keep_cap;
+            slot = kept ? r : r - keep_cap;
+            pre += 1;
+          } else {
+            kept = kp[j];
+            slot = kept ? run_keep + (pre & 0xffff) : run_drop + (pre >> 16);
+            pre += kept ? 1 : (1 << 16);
+          }
+          if (a.tt.row2sample) a.tt.row2sample[kept ? seg0 + slot : drop0 + drop_before + slot] = (int)s;
+          if (a.loc) a.loc[s] = kept ? slot : cap + slot;
+          if (a.idx) a.idx[s] = e;
+          if (a.moe_idx) a.moe_idx[s] = e;
+          if (a.gate) a.gate[s] = sel_gate(wv[j]);
+        }
+      }
+      if (by_rank) run_keep += total;
+      else { run_keep += total & 0xffff; run_drop += total >> 16; }
+    }
+  }
+  // ---- CTA 0: counts, capacity, l_aux and the tile table of launch #2 ----
+  if (e == 0) {
+    if (tid < E && a.counts) a.counts[tid] = sh.cnt[tid];
+    if (tid == 0) {
+      if (a.cap_dev) *a.cap_dev = cap;
+      if (a.l_aux) {
+        float acc = 0.f;
+        for (int ee = 0; ee < E; ++ee) {
+          double me = 0.0;
+          for (int i = 0; i < a.npm; ++i) me += (double)a.pm[(int64_t)i * SEL_PM_STRIDE + ee];
+          acc += (float)me * (float)sh.cnt[ee];           // me * ce in fp32 (tutel_fast_dispatch.py:143-145)
+        }
+        *a.l_aux = (float)((double)acc * ((double)E / ((double)S * (double)S)));
+      }
+    }
+    if (a.tt.n_tiles) {
+      int row = 0, nt = 0, kept_total = 0;
+      for (int ee = 0; ee <= E; ++ee) {
+        int kc;
+        if (ee < E) { kc = min(sh.cnt[ee], keep_cap); kept_total += kc; }
+        else kc = (int)S - kept_total;
+        int n = (kc + EP_TILE - 1) / EP_TILE;
+        if (a.pair) n = (n + 1) & ~1;
+        for (int i = tid; i < n; i += SEL_THREADS) {
+          a.tt.tile_expert[nt + i] = (ee < E) ? ee : -1;
+          a.tt.tile_row0[nt + i] = row + i * EP_TILE;
+          a.tt.tile_rows[nt + i] = max(0, min(EP_TILE, kc - i * EP_TILE));
+        }
+        if (tid == 0) a.tt.seg_start[ee] = row;
+        row += (kc + EP_TILE - 1) / EP_TILE * EP_TILE;
+        nt += n;
+      }
+      if (tid == 0) { *a.tt.n_tiles = nt; *a.tt.drop_counter = 0; }
+    }
+  }
+}
+
+int route_select_launch(const SelectArgs& a, cudaStream_t st) {
+  SNB_REQUIRE(a.E >= 1 && a.E <= SEL_MAX_E, "route_select: E=%d out of range [1,%d]", a.E, SEL_MAX_E);
+  SNB_REQUIRE(a.S >= 1 && a.S < (1ll << 31), "route_select: S=%lld out of range", (long long)a.S);
+  k_select<<<a.E, SEL_THREADS, 0, st>>>(a);
+  SNB_CHECK_LAUNCH("k_select");
+  return SNB_OK;
+}
+
+size_t route_select_workspace_bytes(int64_t S) {
+  const int64_t Sx = S > 0 ? S : 1;
+  return align_up((size_t)Sx * 4, 256) + align_up((size_t)(SEL_MAX_E * SEL_HBINS + 64) * 4, 256) +
+         align_up((size_t)cdiv(Sx, 2048) * SEL_PM_STRIDE * 4, 256) + 1024;
+}
+
+// stand-alone form (gates in global memory): pack + select.  Used by the fp32 path's callers of the select
+// semantics and by the parity tests that compare the kept set with the full-order routing.
+int route_select_from_gates(const float* gates, int64_t S, int32_t E, double cf, int32_t bpr, int32_t no_batch,
+                            int32_t* idx, int32_t* loc, float* gate, int32_t* counts, int32_t* capacity, float* l_aux,
+                            void* ws, size_t ws_bytes, cudaStream_t st) {
+  SNB_REQUIRE(E >= 1 && E <= SEL_MAX_E, "route_select: E=%d out of range [1,%d]", E, SEL_MAX_E);
+  SNB_REQUIRE(S >= 1 && S < (1ll << 31), "route_select: S=%lld out of range", (long long)S);
+  Arena ar(ws, ws_bytes);
+  uint32_t* w = ar.take<uint32_t>(S);
+  int* hist = ar.take<int>(SEL_MAX_E * SEL_HBINS + 64);
+  const int nblk = (int)cdiv(S, 2048);
+  float* pm = ar.take<float>((size_t)nblk * SEL_PM_STRIDE);
+  if (!ar.ok) { set_error("route_select: workspace too small (%zu bytes given)", ws_bytes); return SNB_EWORKSPACE; }
+  SNB_CHECK_CUDA(cudaMemsetAsync(hist, 0, (SEL_MAX_E * SEL_HBINS + 64) * sizeof(int), st));
+  k_pack_top1<<<nblk, 256, 0, st>>>(gates, S, E, w, hist, pm);
+  SNB_CHECK_LAUNCH("k_pack_top1");
+  SelectArgs a = {};
+  a.w = w; a.hist1 = hist; a.ticket = hist + SEL_MAX_E * SEL_HBINS; a.pm = pm; a.npm = nblk;
+  a.S = S; a.E = E; a.cf = cf; a.bpr = bpr; a.no_batch = no_batch;
+  a.idx = idx; a.loc = loc; a.gate = gate; a.counts = counts; a.cap_dev = capacity; a.l_aux = l_aux;
+  return route_select_launch(a, st);
 }
 
 }  // namespace snb

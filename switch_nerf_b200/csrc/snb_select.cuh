@@ -1,0 +1,53 @@
+// Packed routing word shared by launch #1 (k_front_ts writes it), k_select and launch #2 (reads the gate value back):
+//   w = (expert id << 26) | key,   key = bits(1.0f) - bits(max gate)  (26 bits for E <= 16: max gate >= ~1/E)
+// Ascending key == descending gate, so the batch-prioritised order (tutel_fast_dispatch.py:136-139, 186-188) is the
+// ascending order of (key, sample index).
+#pragma once
+#include "snb_common.cuh"
+#include "snb_ep.cuh"
+
+namespace snb {
+
+constexpr int SEL_MAX_E = 16;
+constexpr int SEL_KEY_BITS = 26;
+constexpr uint32_t SEL_KEY_MASK = (1u << SEL_KEY_BITS) - 1u;
+constexpr int SEL_L1_SHIFT = 17;                 // level-1 digit = key bits [17, 26): 512 bins per expert
+constexpr int SEL_HBINS = 1 << (SEL_KEY_BITS - SEL_L1_SHIFT);
+constexpr int SEL_PM_STRIDE = 16;                // floats per partial-column-sum record
+
+__host__ __device__ __forceinline__ uint32_t sel_key_bits(uint32_t gate_bits) {
+  const uint32_t k = (gate_bits <= 0x3F800000u) ? (0x3F800000u - gate_bits) : 0u;
+  return k > SEL_KEY_MASK ? SEL_KEY_MASK : k;
+}
+__device__ __forceinline__ uint32_t sel_key(float g) { return sel_key_bits(__float_as_uint(g)); }
+__device__ __forceinline__ uint32_t sel_pack(int e, uint32_t key) { return ((uint32_t)e << SEL_KEY_BITS) | key; }
+__device__ __forceinline__ float sel_gate(uint32_t w) { return __uint_as_float(0x3F800000u - (w & SEL_KEY_MASK)); }
+
+struct SelectArgs {
+  const uint32_t* w;        // [S] packed words
+  int* hist1;               // [SEL_MAX_E][SEL_HBINS] level-1 histogram; zeroed again by the last CTA that read it
+  int* ticket;              // [1] readers-done counter (self-resetting)
+  const float* pm;          // [npm][SEL_PM_STRIDE] partial column sums of the gates (load-balance loss)
+  int npm;
+  int64_t S;
+  int E;
+  double cf;
+  int bpr, no_batch;
+  TileTable tt;             // local mode: row2sample + tile table of launch #2 (all pointers nullable together)
+  int pair;
+  int* idx;                 // per-sample taps (expert-parallel dispatch, debug): nullable
+  int* loc;                 //   kept: row inside the expert bucket (index order); dropped: capacity + drop slot
+  float* gate;
+  int* counts;              // [E]
+  int* cap_dev;             // [1]
+  float* l_aux;             // [1]
+  int* moe_idx;             // [S] nullable
+};
+
+int route_select_launch(const SelectArgs& a, cudaStream_t st);
+size_t route_select_workspace_bytes(int64_t S);
+int route_select_from_gates(const float* gates, int64_t S, int32_t E, double cf, int32_t bpr, int32_t no_batch,
+                            int32_t* idx, int32_t* loc, float* gate, int32_t* counts, int32_t* capacity, float* l_aux,
+                            void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace snb

@@ -486,9 +486,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         if (ec.cs == 0 && valid) {
           auto rsum = [&](int v) { return sred[(v * 4 + 0) * 128 + row] + sred[(v * 4 + 1) * 128 + row] +
                                           sred[(v * 4 + 2) * 128 + row] + sred[(v * 4 + 3) * 128 + row]; };
+          // reference under cuda autocast: the Linear output, `sigma += noise` and `x - 1` (nerf.py:68) are bf16 tensor
+          // ops (each rounds to bf16); only F.softplus runs in fp32 -- pinned by tests/golden/model_*_bf16cuda.npz
           float sr = bf16_round(rsum(0) + b_sig);
-          if (noise) sr += noise[(int64_t)sidx * io.n_stride];
-          const float tt_ = sr - 1.f;
+          if (noise) sr = bf16_round(sr + noise[(int64_t)sidx * io.n_stride]);
+          const float tt_ = bf16_round(sr - 1.f);
           const float sigma = (tt_ > 20.f) ? tt_ : log1pf(expf(tt_));
           auto sg = [](float v) { return bf16_round(1.f / (1.f + expf(-bf16_round(v)))); };
           float4 o = make_float4(sg(rsum(1) + b_col0), sg(rsum(2) + b_col1), sg(rsum(3) + b_col2), sigma);

@@ -45,11 +45,16 @@ def test_reference_render_rays_drives_plugin_model(built_lib, precision):
     torch.cuda.synchronize()
     # same model chunks, same per-sample outputs; only the ray-side torch ops (linspace, cumprod, searchsorted) differ
     # from the fused ray kernels by fp32 rounding
+    # bf16: xyz = o + d*z differs in the last fp32 bit between torch and the fused point generation, which flips a bf16
+    # rounding of PE(xyz) on a few samples (one output ulp, 2^-9) -- the per-ray composite moves by < 2e-3
+    tol = 2e-4 if precision == "fp32" else 2e-3
     for k in ("rgb_fine", "depth_fine", "depth_variance_fine"):
-        assert float((ref[k] - mine[k]).abs().max()) < 2e-4, k
+        err = float((ref[k] - mine[k]).abs().max())
+        assert err < tol, (k, err)
     for k in ("gate_loss_coarse", "gate_loss_fine"):
-        assert torch.allclose(ref[k], mine[k], rtol=1e-5, atol=1e-7), k
-    assert torch.equal(ref["moe_gates_coarse"], mine["moe_gates_coarse"])
+        assert torch.allclose(ref[k], mine[k], rtol=1e-5 if precision == "fp32" else 5e-3, atol=1e-7), k   # bf16: a few routes flip
+    agree = float((ref["moe_gates_coarse"] == mine["moe_gates_coarse"]).float().mean())
+    assert agree == 1.0 if precision == "fp32" else agree > 0.99, agree
 
 
 def test_integration_snippets_inside_reference_moe_layer(built_lib):
