@@ -11,10 +11,13 @@ import torch
 
 from oracle import switch_nerf_oracle as O
 from oracle.make_golden import ROUTE_CASES, make_gates
-from tests.util import golden_sd, load_golden, make_model
+from tests.util import (CUDA_MODEL_GOLDENS, bf16_contract_check, cuda_golden_case, golden_sd, load_golden,
+                        make_model)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3  # BASELINE.json north_star: "within 1e-3 abs on RGB/sigma"
+RENDER_BF16_RGB_MAX = 2e-3     # per-ray composite, bf16 path vs the reference's CUDA-autocast render (measured: see profiles/r2c_*)
+RENDER_BF16_DEPTH_REL = 5e-3
 
 
 def _sha(t):
@@ -235,55 +238,60 @@ def test_render_perturb_is_stratified(built_lib):
 
 
 # ----------------------------------------------------------------------------- bf16 tcgen05 path
-def _bf16_stats(out, ref, ok):
-    d = np.abs(out - ref)[ok]
-    return float(d.max()), float(d.mean()), float((d > TOL).mean())
+def _run_bf16(c, chunked=False):
+    model, _ = make_model(c["sd"], c["cf"], c["bpr"], c["no_batch"], "bf16")
+    with torch.no_grad():
+        r = model(c["x"].cuda(), return_debug=True)
+    torch.cuda.synchronize()
+    out = r["outputs"].cpu()
+    idx = r["extras"]["moe_gates"][0].view(-1).cpu()
+    kept = None if c["no_batch"] else r["extras"]["debug_loc"].cpu() < c["cap"]
+    return out, idx, kept, r
 
 
-@pytest.mark.parametrize("tag,cf,bpr", [("e8_cf1_bpr_bf16cpu", 1.0, True), ("e8_cf05_nobpr_fp32", 0.5, False),
-                                        ("e4_cf1_bpr_fp32", 1.0, True), ("e8_cf1_bpr_fp32_s777", 1.0, True)])
-def test_model_bf16_tcgen05(built_lib, tag, cf, bpr):
-    """Fused tcgen05 path (SNB_PREC_BF16) on the golden inputs.
+@pytest.mark.parametrize("tag", CUDA_MODEL_GOLDENS)
+def test_model_bf16_tcgen05_vs_reference_cuda_golden(built_lib, tag):
+    """Fused tcgen05 path (SNB_PREC_BF16) vs the UNMODIFIED reference run on a B200 under torch.autocast("cuda", bf16)
+    (tests/golden/model_*_bf16cuda.npz): cf 0.5/1/2, BPR on/off, E 4/8, no-batch mode, and one full Building chunk
+    (S = 131072, E = 8, the weights and rays bench.py times).  Contract C1-C3 of tests/util.py: routing >= 99.8 %
+    identical; on identically routed samples every rgb within one bf16 output ulp and >= 98 % bit-identical; sigma within
+    1e-3 + 2^-7 sigma everywhere and within 1e-3 on >= 95 %."""
+    c = cuda_golden_case(tag)
+    out, idx, kept, r = _run_bf16(c)
+    st = bf16_contract_check(out, idx, kept, c)
+    assert abs(float(r["extras"]["moe_loss"][0]) - float(c["g"]["l_aux"][0])) < 2e-3 * abs(float(c["g"]["l_aux"][0])), st
+    # the samples the fused path routes differently are near-ties of the reference's own gate: the reference's top-2
+    # margin on them is tiny
+    flip = idx != c["ref_idx"]
+    if flip.any():
+        assert float(torch.from_numpy(c["g"]["gate_margin"].astype(np.float32))[flip].max()) < 2e-2
 
-    bf16 operands cannot reproduce an fp32 result to 1e-3 per sample (the reference's own autocast
-    path differs from its fp32 path by ~3e-3 max / 8e-4 mean on these inputs, and its rgb output is
-    itself quantised to bf16, ulp 2^-8).  The gates therefore are:
-      (1) vs the oracle's bf16 rounding map (pinned against the reference under autocast): same-route
-          samples agree to <= 2 output ulps (2^-7) max, <= 1e-3 for >= 97%, mean <= 2e-4;
-      (2) vs the fp32 reference golden: error no larger than 1.25x the reference-autocast map's own
-          error (mean) -- i.e. the fused path is as accurate as what it replaces;
-      (3) routing: expert ids agree with the fp32 reference for >= 97% of samples (near-tie flips).
-    """
-    g = load_golden(f"model_{tag}.npz")
-    sd = golden_sd(g)
-    x = torch.from_numpy(g["x"])
-    cfg = O.default_cfg(sd, cf, bpr)
-    o_bf, ex_bf = O.nerf_moe_forward(x, sd, cfg, mode="bf16", flavor="cuda")
-    o_32, ex_32 = O.nerf_moe_forward(x, sd, cfg, mode="fp32")
-    model, _ = make_model(sd, cf, bpr, False, "bf16")
+
+def test_model_bf16_vs_fp32_reference_golden(built_lib):
+    """bf16 path vs the reference's FP32 output: no worse than the reference's own autocast run is (mean error ratio
+    <= 1.25), routing >= 97 % identical to the fp32 routing."""
+    g32 = load_golden("model_e8_cf1_bpr_fp32_s777.npz")
+    sd = golden_sd(g32)
+    x = torch.from_numpy(g32["x"])
+    model, _ = make_model(sd, 1.0, True, False, "bf16")
     r = model(x.cuda(), return_debug=True)
     torch.cuda.synchronize()
     out = r["outputs"].cpu().numpy()
     idx = r["extras"]["moe_gates"][0].view(-1).cpu().numpy()
-    loc = r["extras"]["debug_loc"].cpu().numpy()
-    cap = ex_bf["capacity"]
-    assert np.isfinite(out).all()
-    assert (idx == ex_32["idx"].numpy()).mean() >= 0.97
-    ok = (idx == ex_bf["idx"].numpy()) & ((loc < cap) == (ex_bf["loc"].numpy() < cap))
-    assert ok.mean() >= 0.98
-    mx, mean, frac = _bf16_stats(out, o_bf.numpy(), ok)
-    assert mx <= 2 ** -7 * max(1.0, float(o_bf.abs().max())) + 1e-6, f"max abs err vs bf16 map {mx}"
-    assert frac <= 0.03 and mean <= 2e-4, (mx, mean, frac)
-    ok32 = (idx == ex_32["idx"].numpy()) & ((loc < cap) == (ex_32["loc"].numpy() < cap))
-    _, mean32, _ = _bf16_stats(out, o_32.numpy(), ok32)
-    ok_ref = (ex_bf["idx"] == ex_32["idx"]).numpy() & ((ex_bf["loc"] < cap) == (ex_32["loc"] < cap)).numpy()
-    _, mean_ref, _ = _bf16_stats(o_bf.numpy(), o_32.numpy(), ok_ref)
-    assert mean32 <= 1.25 * mean_ref + 1e-5, (mean32, mean_ref)
-    assert abs(float(r["extras"]["moe_loss"][0]) - float(ex_32["l_aux"])) < 5e-3
+    o_bf, ex_bf = O.nerf_moe_forward(x, sd, O.default_cfg(sd, 1.0, True), mode="bf16", flavor="cuda")
+    same = idx == g32["idx"]
+    assert same.mean() >= 0.97
+    same_ref = ex_bf["idx"].numpy() == g32["idx"]
+    mean_mine = np.abs(out - g32["outputs"])[same].mean()
+    mean_ref = np.abs(o_bf.numpy() - g32["outputs"])[same_ref].mean()
+    assert mean_mine <= 1.25 * mean_ref + 1e-5, (mean_mine, mean_ref)
 
 
 def test_model_bf16_vs_fp32_path_full_chunk(built_lib):
-    """Building chunk size (S=131072, E=8, cf=1, BPR): fused tcgen05 path vs the fp32 CUDA path on device."""
+    """Building chunk size (S=131072, E=8, cf=1, BPR): fused tcgen05 path vs the fp32 CUDA path on device: routing
+    >= 97 % identical, on identically routed samples rgb within 3 bf16 output ulps (the fp32 path is not bf16-quantised),
+    sigma within 1e-3 + 2^-6 sigma, PSNR of per-sample rgb > 45 dB.  (The contract test against the reference's own CUDA
+    run at this size is test_model_bf16_tcgen05_vs_reference_cuda_golden[bench_chunk].)"""
     sd = O.synthetic_state_dict(num_experts=8, appearance_count=64, seed=11, gate_scale=4.0)
     S = 131072
     g = torch.Generator().manual_seed(5)
@@ -300,27 +308,54 @@ def test_model_bf16_vs_fp32_path_full_chunk(built_lib):
     k32, k16 = r32["extras"]["debug_loc"] < cap, r16["extras"]["debug_loc"] < cap
     ok = (i32 == i16) & (k32 == k16)
     assert ok.float().mean().item() >= 0.97
-    d = (r32["outputs"] - r16["outputs"]).abs()[ok]
     assert torch.isfinite(r16["outputs"]).all()
-    assert d.mean().item() < 2e-3 and d.max().item() < 0.25
+    d = (r32["outputs"] - r16["outputs"]).abs()[ok]
+    assert d[:, :3].max().item() <= 3 * 2.0 ** -8, d[:, :3].max().item()
+    sig = r32["outputs"][ok][:, 3]
+    assert (d[:, 3] <= 1e-3 + 2.0 ** -6 * sig.abs()).all(), float((d[:, 3] / (1e-3 + 2.0 ** -6 * sig.abs())).max())
+    assert d.mean().item() < 1e-3
     mse = ((r32["outputs"][ok][:, :3] - r16["outputs"][ok][:, :3]) ** 2).mean().item()
     assert -10 * np.log10(mse) > 45.0          # PSNR of per-sample rgb, bf16 path vs fp32 path
 
 
-def test_render_bf16_config1(built_lib):
+@pytest.mark.parametrize("tag,n,chunk", [("config1", 256, 4096), ("bench_building", 8192, 131072)])
+def test_render_bf16_vs_reference_cuda_golden(built_lib, tag, n, chunk):
+    """Per-ray outputs of snb_render_rays (bf16) vs the UNMODIFIED reference's rendering.render_rays on a B200 under cuda
+    autocast: BASELINE.json configs[0] and the benchmark configuration itself (8192 rays x (257+257), E = 8, bench
+    weights).  A ray averages ~514 per-sample values that each sit within one bf16 ulp of the reference's (contract
+    C2/C3), so the composite agrees far better than a single sample: rgb max <= 2e-3, mean <= 1e-4, PSNR >= 60 dB."""
+    from oracle.make_golden_cuda import bench_inputs
+    from oracle import ref_shims as R
+    from switch_nerf_b200 import synthetic as SY
     from switch_nerf_b200.rendering import render_rays
-    g = load_golden("render_config1.npz")
-    sd = golden_sd(g)
-    model, hp = make_model(sd, 1.0, True, False, "bf16")
-    hp.coarse_samples, hp.fine_samples, hp.model_chunk_size = 32, 32, 4096
-    res, _ = render_rays(model, None, torch.from_numpy(g["rays"]).cuda(), torch.from_numpy(g["image_indices"]).cuda(),
-                         hp, None, None, True, True, False)
+    g = load_golden(f"render_{tag}_bf16cuda.npz")
+    if tag == "config1":
+        sd = SY.synthetic_state_dict(num_experts=4, appearance_count=16, seed=5, gate_scale=4.0)
+        rays, idx = SY.synthetic_rays(256, 16, seed=6)
+        E, cs, fs = 4, 32, 32
+    else:
+        sd, rays, idx = bench_inputs()
+        E, cs, fs = 8, 257, 257
+    from tests.util import sd_checksum
+    assert abs(sd_checksum(sd) - float(g["sd_checksum"][0])) < 1e-6 * float(g["sd_checksum"][0])
+    model, _ = make_model(sd, 1.0, True, False, "bf16", moe_return_gates=(tag == "config1"))
+    hp = R.make_hparams(num_experts=E, capacity_factor=1.0, bpr=True, model_chunk_size=chunk, coarse_samples=cs,
+                        fine_samples=fs, amp_bf16=True, moe_return_gates=(tag == "config1"))
+    with torch.no_grad():
+        res, _ = render_rays(model, None, rays[:n].cuda(), idx[:n].cuda(), hp, None, None, True, True, False)
     torch.cuda.synchronize()
-    rgb = res["rgb_fine"].cpu().numpy()
-    err = np.abs(rgb - g["rgb_fine"])
-    # per-ray composite averages the per-sample bf16 error; routing flips near capacity move single samples
-    assert np.median(err) < 2e-3 and err.mean() < 4e-3
-    assert O.psnr(torch.from_numpy(rgb), torch.from_numpy(g["rgb_fine"])) > 40.0
+    rgb, ref = res["rgb_fine"].cpu(), torch.from_numpy(g["rgb_fine"])
+    err = (rgb - ref).abs()
+    stats = {"rgb_max": float(err.max()), "rgb_mean": float(err.mean()), "psnr": O.psnr(rgb, ref),
+             "depth_max_rel": float(((res["depth_fine"].cpu() - torch.from_numpy(g["depth_fine"])).abs()
+                                     / torch.from_numpy(g["depth_fine"]).abs().clamp_min(1e-3)).max())}
+    print(tag, stats)
+    assert stats["rgb_max"] <= RENDER_BF16_RGB_MAX and stats["rgb_mean"] <= 1e-4 and stats["psnr"] >= 60.0, stats
+    assert stats["depth_max_rel"] <= RENDER_BF16_DEPTH_REL, stats
+    for k in ("gate_loss_coarse", "gate_loss_fine"):
+        assert np.allclose(res[k].cpu().numpy(), g[k], rtol=2e-3), k
+    if tag == "config1":
+        assert (res["moe_gates_coarse"].cpu().numpy().reshape(-1) == g["moe_gates_coarse"].reshape(-1)).mean() >= 0.998
 
 
 # ----------------------------------------------------------------------------- a15 mip renderer (Mission Bay)
@@ -351,7 +386,10 @@ def test_render_mip_fp32_vs_reference_golden(built_lib, tag):
 
 
 def test_model_bf16_no_batch_mode(built_lib):
-    """moe_no_batch (capacity-free eval routing, tutel_moe_layer_nobatch.py:237-352) through the fused path."""
+    """moe_no_batch (capacity-free eval routing, tutel_moe_layer_nobatch.py:237-352) through the fused path vs the
+    reference's FP32 output (the contract test against its CUDA-autocast output is
+    test_model_bf16_tcgen05_vs_reference_cuda_golden[e4_nobatch]): same routing on >= 97 %, every identically routed
+    rgb within 3 bf16 output ulps, mean error <= 1e-3."""
     g = load_golden("model_e4_nobatch_fp32.npz")
     sd = golden_sd(g)
     x = torch.from_numpy(g["x"])
@@ -362,7 +400,7 @@ def test_model_bf16_no_batch_mode(built_lib):
     ok = idx == g["idx"]
     assert ok.mean() >= 0.97
     d = np.abs(r["outputs"].cpu().numpy() - g["outputs"])[ok]
-    assert d.mean() < 2e-3 and np.isfinite(d).all()
+    assert np.isfinite(d).all() and d[:, :3].max() <= 3 * 2.0 ** -8 and d.mean() < 1e-3, (d[:, :3].max(), d.mean())
 
 
 def _check_bf16_variants(tmp_path, variants):
@@ -374,7 +412,8 @@ def _check_bf16_variants(tmp_path, variants):
     base = model(x)["outputs"].cpu().numpy()
     script = (
         "import sys, numpy as np, torch; sys.path.insert(0, %r);"
-        "from tests.util import golden_sd, load_golden, make_model;"
+        "from tests.util import (CUDA_MODEL_GOLDENS, bf16_contract_check, cuda_golden_case, golden_sd, load_golden,
+                        make_model);"
         "g = load_golden('model_e8_cf1_bpr_bf16cpu.npz'); m, _ = make_model(golden_sd(g), 1.0, True, False, 'bf16');"
         "r = m(torch.from_numpy(g['x']).cuda()); torch.cuda.synchronize();"
         "np.save(sys.argv[1], r['outputs'].cpu().numpy()); np.save(sys.argv[1] + '.idx.npy', r['extras']['moe_gates'][0].cpu().numpy())"

@@ -8,7 +8,8 @@ import torch
 
 from oracle import switch_nerf_oracle as O
 from oracle.make_golden import ROUTE_CASES, make_gates, model_inputs
-from tests.util import golden_sd, load_golden
+from tests.util import (CUDA_MIP_GOLDENS, CUDA_MODEL_GOLDENS, bf16_contract_check, cuda_golden_case, golden_sd,
+                        load_golden)
 
 
 def _sha(t):
@@ -69,6 +70,21 @@ def test_model_golden_bf16():
     assert d[same_route].max() <= 2 ** -7 + 1e-6      # <= 2 bf16 ulps of a value in [0.5, 1)
     assert (d > 1e-3).mean() < 0.03
     assert d.mean() < 1e-4
+
+
+@pytest.mark.parametrize("tag", CUDA_MODEL_GOLDENS + CUDA_MIP_GOLDENS)
+def test_oracle_cuda_flavor_pinned_to_reference_on_b200(tag):
+    """The rounding map the tcgen05 path is held to (mode="bf16", flavor="cuda") vs the UNMODIFIED reference run on a
+    B200 under torch.autocast("cuda", bfloat16) (oracle/make_golden_cuda.py; incl. one full 131072-row Building chunk
+    with the benchmark's weights): the bf16 contract of tests/util.py with >= 99.9 % identical routing (the host CPU's GEMM accumulation order moves a few near-ties)."""
+    c = cuda_golden_case(tag)
+    cfg = O.default_cfg(c["sd"], c["cf"], c["bpr"], moe_no_batch=c["no_batch"], mip=c["mip"])
+    out, ex = O.nerf_moe_forward(c["x"], c["sd"], cfg, mode="bf16", flavor="cuda")
+    kept = None if c["no_batch"] else ex["loc"] < c["cap"]
+    if not c["no_batch"]:
+        assert ex["capacity"] == c["cap"]
+    bf16_contract_check(out, ex["idx"], kept, c, route_min=0.999)
+    assert abs(float(ex["l_aux"]) - float(c["g"]["l_aux"][0])) < 2e-3 * abs(float(c["g"]["l_aux"][0]))
 
 
 @pytest.mark.parametrize("tag", ["config1", "config1_coarse_only", "ragged_chunks"])

@@ -72,3 +72,58 @@ def bf16_contract_stats(out, ref_out, idx, ref_idx, kept=None, ref_kept=None):
             "sigma_max_abs": float(d_sig.max()), "sigma_frac_le_1e-3": float((d_sig <= 1e-3).float().mean()),
             "sigma_max_rel": float((d_sig / ref_out[same, 3].abs().clamp_min(1e-2)).max()),
             "mean_abs_all": float((out - ref_out).abs().mean())}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# bf16 contract of the tcgen05 path, stated against the UNMODIFIED reference run on a B200 under
+# torch.autocast("cuda", bfloat16) (tests/golden/model_*_bf16cuda.npz, written by oracle/make_golden_cuda.py):
+#   C1  routing: expert id and kept/dropped status equal the reference's on >= 99.8 % of the samples (the fp32 gate sees
+#       bf16 GEMM outputs whose fp32 accumulation order differs; only near-ties can flip);
+#   C2  rgb, on samples routed identically: EVERY value within one bf16 output ulp of the reference (sigmoid output is a
+#       bf16 number on both sides; one ulp <= 2^-8), >= 98 % bit-identical -- i.e. <= 1e-3 abs wherever the
+#       reference's own rounding did not flip;
+#   C3  sigma, same samples: |d sigma| <= 1e-3 + 2^-7 * sigma_ref for every sample (two bf16 ulps of the pre-activation
+#       through the fp32 softplus), <= 1e-3 abs on >= 95 %.
+# The oracle's flavor="cuda" rounding map is pinned to the same files with the same bounds and >= 99.9 % routing.
+# ----------------------------------------------------------------------------------------------------------------
+CUDA_MODEL_GOLDENS = ("e8_cf1_bpr", "e8_cf05_nobpr", "e8_cf2_bpr", "e4_cf1_bpr", "e4_nobatch", "bench_chunk")
+CUDA_MIP_GOLDENS = ("mip_e4_w256", "mip_e8_w512")
+
+
+def cuda_golden_case(tag):
+    """Inputs of a model_<tag>_bf16cuda.npz fixture, regenerated from its seeds and checked against its checksum."""
+    from oracle.make_golden_cuda import bench_chunk_x, bench_inputs
+    from switch_nerf_b200 import synthetic as SY
+    g = load_golden(f"model_{tag}_bf16cuda.npz")
+    p = g["params"]
+    c = dict(E=int(p[0]), cf=float(p[1]), bpr=bool(p[2]), S=int(p[3]), seed=int(p[4]), gate_scale=float(p[5]),
+             count=int(p[6]), no_batch=bool(p[7]), width=int(p[9]), mip=bool(p[10]), g=g)
+    if tag == "bench_chunk":
+        sd, rays, idx = bench_inputs()
+        x = bench_chunk_x(rays, idx, 257, c["S"])
+    else:
+        sd = SY.synthetic_state_dict(num_experts=c["E"], appearance_count=c["count"], seed=c["seed"],
+                                     gate_scale=c["gate_scale"], width=c["width"])
+        x = torch.from_numpy(g["x"])
+    assert abs(sd_checksum(sd) - float(g["sd_checksum"][0])) < 1e-6 * float(g["sd_checksum"][0]), \
+        "weight generator drifted from the one the golden fixture was made with"
+    c.update(sd=sd, x=x, cap=int(g["capacity"][0]), ref_out=torch.from_numpy(g["outputs"]),
+             ref_idx=torch.from_numpy(g["idx"]).long(), ref_kept=torch.from_numpy(g["loc"]) < int(g["capacity"][0]))
+    return c
+
+
+def bf16_contract_check(out, idx, kept, case, route_min=0.998):
+    """Assert C1-C3 for per-sample outputs [S,4] / expert ids / kept mask against a cuda_golden_case(); returns the stats."""
+    ref_out, ref_idx, ref_kept = case["ref_out"], case["ref_idx"], case["ref_kept"]
+    st = bf16_contract_stats(out, ref_out, idx, ref_idx, kept, ref_kept)
+    same = idx.view(-1).long() == ref_idx.view(-1)
+    if kept is not None:
+        same &= kept.view(-1) == ref_kept.view(-1)
+    d_sig = (out[same, 3] - ref_out[same, 3]).abs()
+    st["sigma_worst_over_bound"] = float((d_sig / (1e-3 + 2.0 ** -7 * ref_out[same, 3].abs())).max())
+    assert torch.isfinite(out).all()
+    assert st["route_agree"] >= route_min, st                                        # C1
+    assert st["rgb_ulp_le1"] == 1.0 and st["rgb_ulp0"] >= 0.98, st                  # C2
+    assert st["rgb_max_abs"] <= 2.0 ** -8 + 1e-9, st
+    assert st["sigma_worst_over_bound"] <= 1.0 and st["sigma_frac_le_1e-3"] >= 0.95, st   # C3
+    return st
