@@ -172,6 +172,20 @@ int snb_route_top1(const float* gates, int64_t S, int32_t E, double capacity_fac
                    int32_t* idx, int32_t* loc, float* gate, int32_t* counts, int32_t* capacity,
                    float* l_aux, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Routing as the fused path runs it (one launch, E CTAs): the same top-1 decision as snb_route_top1, but only the
+ * kept SET per expert is computed -- {s : locations_s < capacity} of tutel_fast_dispatch.py:136-139, 176-217 -- not
+ * the batch-prioritised order inside it.  idx, gate, counts, capacity, l_aux as snb_route_top1;
+ *   loc[s] <  capacity : kept; the sample's rank among the kept samples of its expert in SAMPLE-INDEX order
+ *   loc[s] >= capacity : dropped (capacity + a running number)
+ * so (loc < capacity) equals the reference's kept mask bit for bit (ties between equal gates go to the lower sample
+ * index, as with a stable argsort), while the value of a kept loc is a different -- equally valid -- slot numbering.
+ * no_batch = 1: nothing is dropped (extract_critical_nobatch, tutel_fast_dispatch_nobatch.py).  E <= 16.
+ * workspace: snb_route_select_workspace_bytes(S). */
+size_t snb_route_select_workspace_bytes(int64_t S);
+int snb_route_select(const float* gates, int64_t S, int32_t E, double capacity_factor, int32_t bpr,
+                     int32_t no_batch, int32_t* idx, int32_t* loc, float* gate, int32_t* counts,
+                     int32_t* capacity, float* l_aux, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a10/a12/a13: dispatch + combine (Tutel K4/K5, in-tree K1/K2) ----------------------- */
 /* Replaces GatingEncoder.forward (tutel_fast_dispatch.py:15-28; _nobatch.py:16-37):
  *   out = zeros[rows_out, H];  out[row(s)] = x[s]  for kept samples

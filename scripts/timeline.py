@@ -23,8 +23,8 @@ for _ in range(3):
     model(x)
 torch.cuda.synchronize()
 TL_N = 2048
-buf = (C.c_uint64 * (4 * TL_N))()
-n = L.lib().snb_debug_timeline(buf, 4 * TL_N)
+buf = (C.c_uint64 * (5 * TL_N))()
+n = L.lib().snb_debug_timeline(buf, 5 * TL_N)
 names = ["front/epi", "front/mma", "back/epi", "back/mma"]
 for r in range(4):
     marks = [(buf[r * TL_N + i] >> 48, buf[r * TL_N + i] & 0xFFFFFFFFFFFF) for i in range(TL_N) if buf[r * TL_N + i]]
@@ -40,3 +40,8 @@ for r in range(4):
         t0 = seg[0][1]
         print("  tile", ti, "total cycles", seg[-1][1] - t0)
         print("   ", " ".join(f"{t}:{c - t0}" for t, c in seg))
+
+sel = [(buf[4 * TL_N + i] >> 48, buf[4 * TL_N + i] & 0xFFFFFFFFFFFF) for i in range(64) if buf[4 * TL_N + i]]
+if sel:
+    print("== k_select CTA 0 (1 start, 2 counted, 10+l level chosen, 3 threshold, 4 ordered pass done, 5 end):",
+          " ".join(f"{t}:{c - sel[0][1]}" for t, c in sel))

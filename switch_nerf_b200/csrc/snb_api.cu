@@ -7,6 +7,7 @@
 
 #include "snb_common.cuh"
 #include "snb_ep.cuh"
+#include "snb_select.cuh"
 
 namespace snb {
 
@@ -289,6 +290,17 @@ int snb_route_top1(const float* gates, int64_t S, int32_t E, double capacity_fac
   SNB_REQUIRE(capacity_factor > 0, "capacity_factor must be > 0 (dynamic capacity is not part of the hot path)");
   return route_top1_generic(gates, S, E, capacity_factor, bpr, idx, loc, gate, counts, capacity, l_aux, workspace,
                             workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t snb_route_select_workspace_bytes(int64_t S) { return route_select_workspace_bytes(S); }
+
+int snb_route_select(const float* gates, int64_t S, int32_t E, double capacity_factor, int32_t bpr, int32_t no_batch,
+                     int32_t* idx, int32_t* loc, float* gate, int32_t* counts, int32_t* capacity, float* l_aux,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  SNB_REQUIRE(capacity_factor > 0, "capacity_factor must be > 0 (dynamic capacity is not part of the hot path)");
+  SNB_REQUIRE(gates && workspace, "snb_route_select: NULL pointer");
+  return route_select_from_gates(gates, S, E, capacity_factor, bpr, no_batch, idx, loc, gate, counts, capacity, l_aux,
+                                 workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int snb_dispatch_fwd(const float* x, const int32_t* idx, const int32_t* loc, const int32_t* begin, int64_t S,

@@ -39,6 +39,7 @@ struct RowIO {
   int x_stride;
   const float* gate;
   int g_stride;
+  const uint32_t* wsel;                // local mode with select routing: gate value decoded from the packed routing word (gate unused)
   const float* noise;
   int n_stride;
   float* out;

@@ -371,15 +371,18 @@ int route_top1_generic(const float* gates, int64_t S, int32_t E, double cf, int3
 // Routing as a per-expert radix SELECT (fused bf16 path): launch #2 only needs, per expert, the SET of samples
 // whose batch-prioritised rank is below the capacity -- not their order.  Input: one packed word per sample
 // (expert id << 26 | key, key = bits(1.0f) - bits(max gate): ascending key == descending gate), written either by
-// launch #1 itself (k_front_ts) or by k_pack_top1 below, plus the histogram of the top 9 key bits per expert.
-// One CTA per expert: radix descent to the composite threshold T over the unique 58-bit value (key << 32 | sample)
-// -- ties between equal gates resolve to the lower sample index exactly as the stable sort of the full path does --
-// then ONE ordered pass that hands every kept sample its row (index order) and every dropped sample a row of the
-// dropped bucket.  No atomics on the output, no memset, deterministic row order.
+// launch #1 itself (k_front_ts) or by k_pack_top1 below.
+// One CTA per expert, ONE launch: a counting pass (all experts' totals + this expert's histogram of the top 9 key
+// bits), radix descent to the composite threshold T over the unique 58-bit value (key << 32 | sample) -- ties
+// between equal gates resolve to the lower sample index exactly as the stable sort of the full path does -- then ONE
+// ordered pass that hands every kept sample its row (index order) and every dropped sample a row of the dropped
+// bucket.  No atomics on the output, no memset, deterministic row order; CTA 0 also writes counts, capacity, l_aux
+// and the tile table of launch #2.
 // reference: tutel_fast_dispatch.py:136-139, 176-217 (the kept set == {s : locations_s < capacity}).
 // =========================================================================================
 static constexpr int SEL_THREADS = 1024;
-static constexpr int SEL_LIST = 4096;       // candidates of the threshold digit bucket resolved in shared memory
+static constexpr int SEL_LIST = 3072;       // candidates of the threshold digit bucket resolved in shared memory
+static_assert(SEL_MAX_E <= 32, "one lane per expert in the count reduction");
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
@@ -390,10 +393,10 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   return v;
 }
 
-// gates [S,E] -> packed words, level-1 histogram, partial column sums (the part of launch #1's softmax epilogue that
-// k_front_ts does itself); one block per 2048 samples.  pm: [gridDim.x][SEL_PM_STRIDE]
+// gates [S,E] -> packed words, level-0 histogram, partial column sums (what k_front_ts does in its softmax epilogue);
+// one block per 2048 samples.  pm: [gridDim.x][SEL_PM_STRIDE]
 __global__ void __launch_bounds__(256) k_pack_top1(const float* __restrict__ gates, int64_t S, int E,
-                                                   uint32_t* __restrict__ w, int* __restrict__ hist1,
+                                                   uint32_t* __restrict__ w, int* __restrict__ hist0,
                                                    float* __restrict__ pm) {
   __shared__ float s_me[8][SEL_MAX_E];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__(256) k_pack_top1(const float* __restrict__ gat
     if (valid) {
       const uint32_t key = sel_key(bv);
       w[s] = sel_pack(best, key);
-      atomicAdd(&hist1[best * SEL_HBINS + (int)(key >> SEL_L1_SHIFT)], 1);
+      atomicAdd(&hist0[best * SEL_HBINS + (int)(key >> SEL_L1_SHIFT)], 1);
     }
   }
   __syncthreads();
@@ -427,16 +430,44 @@ __global__ void __launch_bounds__(256) k_pack_top1(const float* __restrict__ gat
   }
 }
 
+static constexpr int SEL_SEG = 128;          // samples per warp-visit of the ordered passes (4 per lane)
+static constexpr int SEL_SEG_SMEM = 2048;    // segments whose (kept, dropped) counts are scanned in shared memory
+static_assert((SEL_SEG_SMEM + 32 * SEL_SEG) * 4 <= SEL_LIST * 8, "ordered-pass scratch aliases the candidate list");
+
 struct SelShared {
-  int cnt[SEL_MAX_E + 1];
-  int hist[SEL_HBINS];
-  int wsum[2][32];
+  int cnt[SEL_MAX_E];
+  int hist[1024];                 // digit histogram of the current level (<= 10 bits)
   int wtot[32];
+  double red[32][SEL_MAX_E];
   unsigned long long list[SEL_LIST];
+  uint32_t seg[SEL_SEG_SMEM];       // per 128-sample segment: kept count | dropped count << 16, then exclusive prefixes
   int n_list;
-  int last;
   int ch_d, ch_need, ch_hc;       // digit chosen by the current level
 };
+
+// visit the words of this chunk, 4 per 16-byte load, 4 independent loads in flight per thread.  f(word, sample, valid)
+// is called the same number of times by every lane of a warp (warp-collective code is allowed inside f).
+template <typename F>
+__device__ __forceinline__ void sel_for_each(const uint32_t* __restrict__ w, int64_t S, int tid, F&& f) {
+  const int64_t nq = S >> 2;
+  const uint4* w4 = reinterpret_cast<const uint4*>(w);
+  for (int64_t q0 = 0; q0 < nq; q0 += 4 * SEL_THREADS) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t q = q0 + u * SEL_THREADS + tid;
+      v[u] = (q < nq) ? w4[q] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t q = q0 + u * SEL_THREADS + tid;
+      const bool ok = q < nq;
+      f(v[u].x, 4 * q, ok); f(v[u].y, 4 * q + 1, ok); f(v[u].z, 4 * q + 2, ok); f(v[u].w, 4 * q + 3, ok);
+    }
+  }
+  const int64_t s = (nq << 2) + tid;
+  f(s < S ? w[s] : 0u, s, s < S);
+}
 
 // smallest digit d with (inclusive prefix count up to d) >= need; returns through shared memory (all threads sync)
 __device__ __forceinline__ void sel_choose(SelShared& sh, int nbins, int need, int tid, int lane, int wid) {
@@ -456,28 +487,27 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
   const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int E = a.E;
   const int64_t S = a.S;
-  if (tid <= SEL_MAX_E) sh.cnt[tid] = 0;
+  const uint32_t* __restrict__ w = a.w;
+  int tn = 0;
+  auto mark = [&](int tag) {
+    if (a.tl && e == 0 && tid == 0) a.tl[tn++] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+  };
+  mark(1);
   if (tid == 0) sh.n_list = 0;
-  __syncthreads();
-  // ---- per-expert totals (all experts: segment starts) + this expert's level-1 histogram ----
-  for (int ee = 0; ee < E; ++ee) {
-    int v = (tid < SEL_HBINS) ? a.hist1[ee * SEL_HBINS + tid] : 0;
-    if (ee == e && tid < SEL_HBINS) sh.hist[tid] = v;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0 && v) atomicAdd(&sh.cnt[ee], v);
+  // ---- per-expert totals (segment starts need all of them) + this expert's level-0 histogram, both from the
+  //      global histogram launch #1 accumulated with fire-and-forget reductions ----
+  for (int ee = wid; ee < E; ee += SEL_THREADS / 32) {
+    int c = 0;
+    for (int i = lane; i < SEL_HBINS; i += 32) {
+      const int v = a.hist0[ee * SEL_HBINS + i];
+      if (ee == e) sh.hist[i] = v;
+      c += v;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) sh.cnt[ee] = c;
   }
   __syncthreads();
-  // the histogram is zeroed again (for the next chunk that uses this workspace set) by the last CTA that has read it
-  if (tid == 0) {
-    __threadfence();
-    sh.last = (atomicAdd(a.ticket, 1) == (int)gridDim.x - 1);
-  }
-  __syncthreads();
-  if (sh.last) {
-    for (int i = tid; i < SEL_MAX_E * SEL_HBINS; i += SEL_THREADS) a.hist1[i] = 0;
-    if (tid == 0) *a.ticket = 0;
-  }
+  mark(2);
   const int cap = capacity_of(S, E, a.cf);
   const int keep_cap = a.no_batch ? 0x7fffffff : cap;
   const int cnt = sh.cnt[e];
@@ -503,29 +533,30 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
     while (true) {
       int dshift, dbits;
       if (level == 0) { dshift = 32 + SEL_L1_SHIFT; dbits = SEL_KEY_BITS - SEL_L1_SHIFT; }
-      else if (level == 1) { dshift = 32 + 8; dbits = SEL_L1_SHIFT - 8; }
-      else if (level == 2) { dshift = 32; dbits = 8; }
+      else if (level == 1) { dshift = 32 + SEL_L2_SHIFT; dbits = SEL_L1_SHIFT - SEL_L2_SHIFT; }
+      else if (level == 2) { dshift = 32; dbits = SEL_L2_SHIFT; }
       else { const int hi = sbits - 9 * (level - 3); dshift = hi > 9 ? hi - 9 : 0; dbits = hi - dshift; }
       const unsigned long long dmask = (1ull << dbits) - 1;
       if (!have_hist) {
-        for (int i = tid; i < SEL_HBINS; i += SEL_THREADS) sh.hist[i] = 0;
+        for (int i = tid; i < 1024; i += SEL_THREADS) sh.hist[i] = 0;
         __syncthreads();
+        // candidates are few here (one digit bucket of the level above): plain shared atomics
         if (from_list) {
           for (int i = tid; i < sh.n_list; i += SEL_THREADS) {
             const unsigned long long c = sh.list[i];
             if ((c & pmask) == pval) atomicAdd(&sh.hist[(int)((c >> dshift) & dmask)], 1);
           }
         } else {
-          for (int64_t s = tid; s < S; s += SEL_THREADS) {
-            const uint32_t wv = a.w[s];
-            if ((int)(wv >> SEL_KEY_BITS) != e) continue;
+          sel_for_each(w, S, tid, [&](uint32_t wv, int64_t s, bool ok) {
+            if (!ok || (int)(wv >> SEL_KEY_BITS) != e) return;
             const unsigned long long c = ((unsigned long long)(wv & SEL_KEY_MASK) << 32) | (unsigned long long)s;
             if ((c & pmask) == pval) atomicAdd(&sh.hist[(int)((c >> dshift) & dmask)], 1);
-          }
+          });
         }
         __syncthreads();
       }
       sel_choose(sh, 1 << dbits, need, tid, lane, wid);
+      mark(10 + level);
       const int d = sh.ch_d, hc = sh.ch_hc;
       need = sh.ch_need;
       pval |= (unsigned long long)d << dshift;
@@ -533,13 +564,25 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
       if (need == hc || dshift == 0) { T = pval | ((1ull << dshift) - 1); break; }   // the whole digit bucket is kept
       if (!from_list && hc <= SEL_LIST) {
         // the undecided bucket fits in shared memory: gather it once, finish the descent there
-        for (int64_t s = tid; s < S; s += SEL_THREADS) {
-          const uint32_t wv = a.w[s];
-          if ((int)(wv >> SEL_KEY_BITS) != e) continue;
+        // (only reached from level 0: the prefix is the level-0 digit of the key)
+        const uint32_t want = (((uint32_t)e << SEL_KEY_BITS) >> SEL_L1_SHIFT) | (uint32_t)(pval >> (32 + SEL_L1_SHIFT));
+        const bool narrow = (pmask == (((1ull << (SEL_KEY_BITS - SEL_L1_SHIFT)) - 1) << (32 + SEL_L1_SHIFT)));
+        sel_for_each(w, S, tid, [&](uint32_t wv, int64_t s, bool ok) {
+          bool hit;
+          if (narrow) hit = ok && (wv >> SEL_L1_SHIFT) == want;
+          else {
+            const unsigned long long c = ((unsigned long long)(wv & SEL_KEY_MASK) << 32) | (unsigned long long)s;
+            hit = ok && (int)(wv >> SEL_KEY_BITS) == e && (c & pmask) == pval;
+          }
           const unsigned long long c = ((unsigned long long)(wv & SEL_KEY_MASK) << 32) | (unsigned long long)s;
-          if ((c & pmask) == pval) sh.list[atomicAdd(&sh.n_list, 1)] = c;
-        }
-        __syncthreads();
+          const unsigned m = __ballot_sync(0xffffffffu, hit);       // one shared atomic per warp, not per candidate
+          if (m) {
+            int base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(&sh.n_list, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (hit) sh.list[base + __popc(m & ((1u << lane) - 1u))] = c;
+          }
+        });
         from_list = true;
       }
       have_hist = false;
@@ -547,76 +590,183 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
       __syncthreads();
     }
   }
-  // ---- ordered pass: rows for the kept samples (index order) and for the dropped ones ----
+  mark(3);
+  // ---- ordered write: rows for the kept samples (index order) and for the dropped ones.  Two sweeps over the words,
+  //      one warp per 128-sample segment and no block barrier inside a sweep: (1) kept / dropped counts per segment,
+  //      (block-wide exclusive scan), (2) rows = segment base + ballot rank.  Chunks larger than SEL_SEG_SMEM
+  //      segments are processed in groups with running bases. ----
   {
-    int run_keep = 0, run_drop = 0;          // block-uniform running totals
     const bool by_rank = !(a.bpr && !a.no_batch);     // plain order: kept iff the index-order rank is below the capacity
-    int parity = 0;
-    for (int64_t base = 0; base < S; base += 4 * SEL_THREADS, parity ^= 1) {
-      const int64_t s0 = base + 4 * (int64_t)tid;
-      uint32_t wv[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    const int64_t nseg = (S + SEL_SEG - 1) / SEL_SEG;
+    int run_keep = 0, run_drop = 0;                   // block-uniform running totals (by_rank: run_keep = rank base)
+    auto load_seg = [&](int64_t g, uint32_t (&wv)[4]) {
+      const int64_t s0 = g * SEL_SEG + 4 * lane;
+      wv[0] = wv[1] = wv[2] = wv[3] = 0xffffffffu;
       if (s0 + 3 < S) {
-        const uint4 q = *reinterpret_cast<const uint4*>(a.w + s0);
+        const uint4 q = *reinterpret_cast<const uint4*>(w + s0);
         wv[0] = q.x; wv[1] = q.y; wv[2] = q.z; wv[3] = q.w;
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (s0 + j < S) wv[j] = a.w[s0 + j];
+        for (int j = 0; j < 4; ++j) if (s0 + j < S) wv[j] = w[s0 + j];
       }
-      int mine[4], kp[4];
-      int packed = 0;
+    };
+    // kept iff mine && (key, sample) <= T.  32-bit form: d = word - (e << 26) is the key when the word is mine and
+    // >= 2^26 otherwise; d < Tk: kept, d > Tk: dropped, d == Tk (ties of the threshold key, rare): by sample index.
+    // Padding words (0xffffffff) are nobody's: the host requires E < 63.
+    const uint32_t ebase = (uint32_t)e << SEL_KEY_BITS;
+    const bool keep_all = by_rank || T == ~0ull;       // no threshold: every word of mine is "kept" at this stage
+    const uint32_t Tk = keep_all ? (SEL_KEY_MASK + 1u) : (uint32_t)(T >> 32);
+    const long long Ts = keep_all ? -1 : (long long)(T & 0xffffffffull);
+    // per lane: bit j of `kp` / `dr` = word j of this lane is mine and kept / mine and dropped
+    auto classify = [&](int g, const uint32_t (&wv)[4], uint32_t& kp, uint32_t& dr) {
+      const long long lim = Ts - ((long long)g * SEL_SEG + 4 * lane);        // tie at sample s0 + j kept iff j <= lim
+      kp = dr = 0u;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        mine[j] = (s0 + j < S) && ((int)(wv[j] >> SEL_KEY_BITS) == e);
-        const unsigned long long c = ((unsigned long long)(wv[j] & SEL_KEY_MASK) << 32) | (unsigned long long)(s0 + j);
-        kp[j] = mine[j] && (by_rank || c <= T);
-        packed += by_rank ? mine[j] : (kp[j] + ((mine[j] && !kp[j]) << 16));
+        const uint32_t d = wv[j] - ebase;
+        const bool k = (d < Tk) || (d == Tk && (long long)j <= lim);
+        kp |= (k ? 1u : 0u) << j;
+        dr |= ((d <= SEL_KEY_MASK && !k) ? 1u : 0u) << j;
       }
-      int inc = warp_incl_scan(packed, lane);
-      if (lane == 31) sh.wsum[parity][wid] = inc;
-      __syncthreads();
-      int wt = warp_incl_scan(sh.wsum[parity][lane], lane);
-      const int total = __shfl_sync(0xffffffffu, wt, 31);
-      const int wbase = __shfl_sync(0xffffffffu, wt, wid > 0 ? wid - 1 : 0);
-      int pre = inc - packed + (wid > 0 ? wbase : 0);          // exclusive prefix of this thread inside the round
+    };
+    // packed (kept | dropped << 16) counts of the lanes below this one, and the segment totals
+    auto lane_prefix = [&](uint32_t kp, uint32_t dr, uint32_t& total) {
+      const uint32_t mine = (uint32_t)__popc(kp) | ((uint32_t)__popc(dr) << 16);
+      uint32_t inc = mine;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (mine[j]) {
-          const int64_t s = s0 + j;
-          int slot, kept;
-          if (by_rank) {
-            const int r = run_keep + pre;
-            kept = r < keep_cap;
-            slot = kept ? r : r - keep_cap;
-            pre += 1;
-          } else {
-            kept = kp[j];
-            slot = kept ? run_keep + (pre & 0xffff) : run_drop + (pre >> 16);
-            pre += kept ? 1 : (1 << 16);
-          }
-          if (a.tt.row2sample) a.tt.row2sample[kept ? seg0 + slot : drop0 + drop_before + slot] = (int)s;
-          if (a.loc) a.loc[s] = kept ? slot : cap + slot;
-          if (a.idx) a.idx[s] = e;
-          if (a.moe_idx) a.moe_idx[s] = e;
-          if (a.gate) a.gate[s] = sel_gate(wv[j]);
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      total = __shfl_sync(0xffffffffu, inc, 31);
+      return inc - mine;
+    };
+    const bool taps = a.loc || a.idx || a.moe_idx || a.gate;
+    constexpr int NW = SEL_THREADS / 32, UF = 4;      // UF segments in flight per warp (independent 16-byte loads)
+    for (int64_t g0 = 0; g0 < nseg; g0 += SEL_SEG_SMEM) {
+      const int ng = (int)min((int64_t)SEL_SEG_SMEM, nseg - g0);
+      for (int gb = wid; gb < ng; gb += NW * UF) {
+        uint32_t wv[UF][4];
+#pragma unroll
+        for (int u = 0; u < UF; ++u) if (gb + u * NW < ng) load_seg(g0 + gb + u * NW, wv[u]);
+#pragma unroll
+        for (int u = 0; u < UF; ++u) {
+          const int g = gb + u * NW;
+          if (g >= ng) break;
+          uint32_t kp, dr, total;
+          classify((int)g0 + g, wv[u], kp, dr);
+          lane_prefix(kp, dr, total);
+          if (lane == 0) sh.seg[g] = total;
         }
       }
-      if (by_rank) run_keep += total;
-      else { run_keep += total & 0xffff; run_drop += total >> 16; }
+      __syncthreads();
+      // exclusive scan of the (<= 2048) packed counts: 2 per thread
+      {
+        const uint32_t v0 = (2 * tid < ng) ? sh.seg[2 * tid] : 0u, v1 = (2 * tid + 1 < ng) ? sh.seg[2 * tid + 1] : 0u;
+        int k = (int)((v0 & 0xffffu) + (v1 & 0xffffu)), d = (int)((v0 >> 16) + (v1 >> 16));
+        int ki = warp_incl_scan(k, lane), di = warp_incl_scan(d, lane);
+        if (lane == 31) { sh.wtot[wid] = ki; sh.hist[wid] = di; }
+        __syncthreads();
+        int kb = 0, db = 0;
+        for (int ww = 0; ww < wid; ++ww) { kb += sh.wtot[ww]; db += sh.hist[ww]; }
+        int ktot = 0, dtot = 0;
+        for (int ww = 0; ww < 32; ++ww) { ktot += sh.wtot[ww]; dtot += sh.hist[ww]; }
+        __syncthreads();
+        const int ke = run_keep + kb + ki - k, de = run_drop + db + di - d;     // exclusive prefixes of segment 2*tid
+        // kept prefix goes back into seg[], dropped prefix into the (now unused) candidate list
+        int* dpre = reinterpret_cast<int*>(sh.list);
+        if (2 * tid < ng) { sh.seg[2 * tid] = (uint32_t)ke; dpre[2 * tid] = de; }
+        if (2 * tid + 1 < ng) { sh.seg[2 * tid + 1] = (uint32_t)(ke + (int)(v0 & 0xffffu)); dpre[2 * tid + 1] = de + (int)(v0 >> 16); }
+        run_keep += ktot;
+        run_drop += dtot;
+        __syncthreads();
+      }
+      const int* dpre = reinterpret_cast<const int*>(sh.list);
+      int* stage = reinterpret_cast<int*>(sh.list) + SEL_SEG_SMEM + wid * SEL_SEG;     // per-warp, behind dpre[]
+      for (int gb = wid; gb < ng; gb += NW * UF) {
+        uint32_t wv[UF][4];
+#pragma unroll
+        for (int u = 0; u < UF; ++u) if (gb + u * NW < ng) load_seg(g0 + gb + u * NW, wv[u]);
+#pragma unroll
+        for (int u = 0; u < UF; ++u) {
+          const int g = gb + u * NW;
+          if (g >= ng) break;
+          uint32_t kp, dr, total;
+          classify((int)g0 + g, wv[u], kp, dr);
+          const uint32_t pre = lane_prefix(kp, dr, total);
+          int kb = (int)sh.seg[g], db = dpre[g];       // first kept / dropped slot of this segment
+          int nk = (int)(total & 0xffffu), nd = (int)(total >> 16);
+          int kl = (int)(pre & 0xffffu), dl = (int)(pre >> 16);     // my first kept / dropped rank inside the segment
+          if (by_rank) {
+            // every word of mine came out as "kept" with its index-order rank kb + kl; the capacity cuts the ranks
+            const int cut = max(0, min(nk, keep_cap - kb));          // ranks [0, cut) of this segment are kept
+            dr = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (((kp >> j) & 1u) && kl + __popc(kp & ((1u << j) - 1u)) >= cut) { dr |= 1u << j; }
+            kp &= ~dr;
+            dl = max(0, kl - cut);
+            kl = min(kl, cut);
+            db = max(kb, keep_cap) - keep_cap;
+            nd = nk - cut;
+            nk = cut;
+          }
+          const int s_lane = ((int)g0 + g) * SEL_SEG + 4 * lane;
+          // rows of one segment are consecutive per class: stage the sample ids in shared memory by rank (kept from
+          // the front, dropped from the back), the warp stores them coalesced below
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if ((kp >> j) & 1u) stage[kl + __popc(kp & ((1u << j) - 1u))] = s_lane + j;
+            if ((dr >> j) & 1u) stage[SEL_SEG - 1 - (dl + __popc(dr & ((1u << j) - 1u)))] = s_lane + j;
+          }
+          if (taps) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool k = (kp >> j) & 1u, d = (dr >> j) & 1u;
+              if (k || d) {
+                const int s = s_lane + j;
+                const int slot = k ? kb + kl + __popc(kp & ((1u << j) - 1u)) : db + dl + __popc(dr & ((1u << j) - 1u));
+                if (a.loc) a.loc[s] = k ? slot : cap + slot;
+                if (a.idx) a.idx[s] = e;
+                if (a.moe_idx) a.moe_idx[s] = e;
+                if (a.gate) a.gate[s] = sel_gate(wv[u][j]);
+              }
+            }
+          }
+          if (a.tt.row2sample) {
+            __syncwarp();
+            if (lane < nk) a.tt.row2sample[seg0 + kb + lane] = stage[lane];
+            for (int i = lane + 32; i < nk; i += 32) a.tt.row2sample[seg0 + kb + i] = stage[i];
+            if (lane < nd) a.tt.row2sample[drop0 + drop_before + db + lane] = stage[SEL_SEG - 1 - lane];
+            for (int i = lane + 32; i < nd; i += 32) a.tt.row2sample[drop0 + drop_before + db + i] = stage[SEL_SEG - 1 - i];
+            __syncwarp();
+          }
+        }
+      }
+      __syncthreads();
     }
   }
+  mark(4);
   // ---- CTA 0: counts, capacity, l_aux and the tile table of launch #2 ----
   if (e == 0) {
     if (tid < E && a.counts) a.counts[tid] = sh.cnt[tid];
-    if (tid == 0) {
-      if (a.cap_dev) *a.cap_dev = cap;
-      if (a.l_aux) {
-        float acc = 0.f;
+    if (tid == 0 && a.cap_dev) *a.cap_dev = cap;
+    if (a.l_aux) {
+      // me[e] = sum of the partial column sums (fixed order, double); lanes e and e+16 of a warp share column e
+      const int col = tid & (SEL_MAX_E - 1);
+      double acc = 0.0;
+      for (int i = tid >> 4; i < a.npm; i += SEL_THREADS / SEL_MAX_E) acc += (double)a.pm[(int64_t)i * SEL_PM_STRIDE + col];
+      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+      if (lane < SEL_MAX_E) sh.red[wid][lane] = acc;
+      __syncthreads();
+      if (tid == 0) {
+        float tot = 0.f;
         for (int ee = 0; ee < E; ++ee) {
           double me = 0.0;
-          for (int i = 0; i < a.npm; ++i) me += (double)a.pm[(int64_t)i * SEL_PM_STRIDE + ee];
-          acc += (float)me * (float)sh.cnt[ee];           // me * ce in fp32 (tutel_fast_dispatch.py:143-145)
+          for (int ww = 0; ww < 32; ++ww) me += sh.red[ww][ee];
+          tot += (float)me * (float)sh.cnt[ee];            // me * ce in fp32 (tutel_fast_dispatch.py:143-145)
         }
-        *a.l_aux = (float)((double)acc * ((double)E / ((double)S * (double)S)));
+        *a.l_aux = (float)((double)tot * ((double)E / ((double)S * (double)S)));
       }
     }
     if (a.tt.n_tiles) {
@@ -639,11 +789,13 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
       if (tid == 0) { *a.tt.n_tiles = nt; *a.tt.drop_counter = 0; }
     }
   }
+  mark(5);
 }
 
 int route_select_launch(const SelectArgs& a, cudaStream_t st) {
   SNB_REQUIRE(a.E >= 1 && a.E <= SEL_MAX_E, "route_select: E=%d out of range [1,%d]", a.E, SEL_MAX_E);
   SNB_REQUIRE(a.S >= 1 && a.S < (1ll << 31), "route_select: S=%lld out of range", (long long)a.S);
+  SNB_REQUIRE((reinterpret_cast<uintptr_t>(a.w) & 15) == 0, "route_select: packed words must be 16-byte aligned");
   k_select<<<a.E, SEL_THREADS, 0, st>>>(a);
   SNB_CHECK_LAUNCH("k_select");
   return SNB_OK;
@@ -651,12 +803,21 @@ int route_select_launch(const SelectArgs& a, cudaStream_t st) {
 
 size_t route_select_workspace_bytes(int64_t S) {
   const int64_t Sx = S > 0 ? S : 1;
-  return align_up((size_t)Sx * 4, 256) + align_up((size_t)(SEL_MAX_E * SEL_HBINS + 64) * 4, 256) +
-         align_up((size_t)cdiv(Sx, 2048) * SEL_PM_STRIDE * 4, 256) + 1024;
+  return align_up((size_t)Sx * 4, 256) + align_up((size_t)cdiv(Sx, 2048) * SEL_PM_STRIDE * 4, 256) +
+         align_up((size_t)SEL_MAX_E * SEL_HBINS * 4, 256) + 1024;
 }
 
-// stand-alone form (gates in global memory): pack + select.  Used by the fp32 path's callers of the select
-// semantics and by the parity tests that compare the kept set with the full-order routing.
+// hist0 must be zero on entry (the caller enqueues the memset)
+int route_pack_top1(const float* gates, int64_t S, int32_t E, uint32_t* w, int* hist0, float* pm, int* npm, cudaStream_t st) {
+  const int nblk = (int)cdiv(S, 2048);
+  k_pack_top1<<<nblk, 256, 0, st>>>(gates, S, E, w, hist0, pm);
+  SNB_CHECK_LAUNCH("k_pack_top1");
+  *npm = nblk;
+  return SNB_OK;
+}
+
+// stand-alone form (gates in global memory): pack + select.  Used by the parity tests that compare the kept set with
+// the full-order routing (snb_route_select through the C ABI).
 int route_select_from_gates(const float* gates, int64_t S, int32_t E, double cf, int32_t bpr, int32_t no_batch,
                             int32_t* idx, int32_t* loc, float* gate, int32_t* counts, int32_t* capacity, float* l_aux,
                             void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -664,15 +825,15 @@ int route_select_from_gates(const float* gates, int64_t S, int32_t E, double cf,
   SNB_REQUIRE(S >= 1 && S < (1ll << 31), "route_select: S=%lld out of range", (long long)S);
   Arena ar(ws, ws_bytes);
   uint32_t* w = ar.take<uint32_t>(S);
-  int* hist = ar.take<int>(SEL_MAX_E * SEL_HBINS + 64);
   const int nblk = (int)cdiv(S, 2048);
   float* pm = ar.take<float>((size_t)nblk * SEL_PM_STRIDE);
+  int* hist0 = ar.take<int>((size_t)SEL_MAX_E * SEL_HBINS);
   if (!ar.ok) { set_error("route_select: workspace too small (%zu bytes given)", ws_bytes); return SNB_EWORKSPACE; }
-  SNB_CHECK_CUDA(cudaMemsetAsync(hist, 0, (SEL_MAX_E * SEL_HBINS + 64) * sizeof(int), st));
-  k_pack_top1<<<nblk, 256, 0, st>>>(gates, S, E, w, hist, pm);
-  SNB_CHECK_LAUNCH("k_pack_top1");
+  SNB_CHECK_CUDA(cudaMemsetAsync(hist0, 0, (size_t)SEL_MAX_E * SEL_HBINS * sizeof(int), st));
   SelectArgs a = {};
-  a.w = w; a.hist1 = hist; a.ticket = hist + SEL_MAX_E * SEL_HBINS; a.pm = pm; a.npm = nblk;
+  int rc = route_pack_top1(gates, S, E, w, hist0, pm, &a.npm, st);
+  if (rc) return rc;
+  a.w = w; a.pm = pm; a.hist0 = hist0;
   a.S = S; a.E = E; a.cf = cf; a.bpr = bpr; a.no_batch = no_batch;
   a.idx = idx; a.loc = loc; a.gate = gate; a.counts = counts; a.cap_dev = capacity; a.l_aux = l_aux;
   return route_select_launch(a, st);

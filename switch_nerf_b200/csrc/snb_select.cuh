@@ -1,4 +1,4 @@
-// Packed routing word shared by launch #1 (k_front_ts writes it), k_select and launch #2 (reads the gate value back):
+// Packed routing word shared by launch #1 (k_front_ts writes it) and k_select (which hands the gate value to launch #2):
 //   w = (expert id << 26) | key,   key = bits(1.0f) - bits(max gate)  (26 bits for E <= 16: max gate >= ~1/E)
 // Ascending key == descending gate, so the batch-prioritised order (tutel_fast_dispatch.py:136-139, 186-188) is the
 // ascending order of (key, sample index).
@@ -11,9 +11,12 @@ namespace snb {
 constexpr int SEL_MAX_E = 16;
 constexpr int SEL_KEY_BITS = 26;
 constexpr uint32_t SEL_KEY_MASK = (1u << SEL_KEY_BITS) - 1u;
-constexpr int SEL_L1_SHIFT = 17;                 // level-1 digit = key bits [17, 26): 512 bins per expert
+constexpr int SEL_L1_SHIFT = 19;                 // level-0 digit = key bits [19, 26): 128 bins per expert
+constexpr int SEL_L2_SHIFT = 9;                  // level-1 digit = key bits [9, 19), level-2 digit = key bits [0, 9)
 constexpr int SEL_HBINS = 1 << (SEL_KEY_BITS - SEL_L1_SHIFT);
 constexpr int SEL_PM_STRIDE = 16;                // floats per partial-column-sum record
+// records a chunk can produce: 4 per CTA of launch #1 (<= 256 CTAs) or one per 2048 samples (k_pack_top1)
+__host__ __device__ inline int64_t SEL_PM_RECORDS(int64_t S) { const int64_t a = (S + 2047) / 2048; return a > 1024 ? a : 1024; }
 
 __host__ __device__ __forceinline__ uint32_t sel_key_bits(uint32_t gate_bits) {
   const uint32_t k = (gate_bits <= 0x3F800000u) ? (0x3F800000u - gate_bits) : 0u;
@@ -24,9 +27,8 @@ __device__ __forceinline__ uint32_t sel_pack(int e, uint32_t key) { return ((uin
 __device__ __forceinline__ float sel_gate(uint32_t w) { return __uint_as_float(0x3F800000u - (w & SEL_KEY_MASK)); }
 
 struct SelectArgs {
-  const uint32_t* w;        // [S] packed words
-  int* hist1;               // [SEL_MAX_E][SEL_HBINS] level-1 histogram; zeroed again by the last CTA that read it
-  int* ticket;              // [1] readers-done counter (self-resetting)
+  const uint32_t* w;        // [S] packed words (16-byte aligned)
+  const int* hist0;         // [SEL_MAX_E][SEL_HBINS] histogram of the top 9 key bits per expert (accumulated by launch #1)
   const float* pm;          // [npm][SEL_PM_STRIDE] partial column sums of the gates (load-balance loss)
   int npm;
   int64_t S;
@@ -42,9 +44,11 @@ struct SelectArgs {
   int* cap_dev;             // [1]
   float* l_aux;             // [1]
   int* moe_idx;             // [S] nullable
+  unsigned long long* tl;   // debug (SNB_TIMELINE): (tag << 48 | clock) marks of CTA 0, nullable
 };
 
 int route_select_launch(const SelectArgs& a, cudaStream_t st);
+int route_pack_top1(const float* gates, int64_t S, int32_t E, uint32_t* w, int* hist0, float* pm, int* npm, cudaStream_t st);
 size_t route_select_workspace_bytes(int64_t S);
 int route_select_from_gates(const float* gates, int64_t S, int32_t E, double cf, int32_t bpr, int32_t no_batch,
                             int32_t* idx, int32_t* loc, float* gate, int32_t* counts, int32_t* capacity, float* l_aux,

@@ -41,9 +41,11 @@
 
 #include "snb_umma.cuh"
 #include "snb_ep.cuh"
+#include "snb_select.cuh"
 
 namespace snb {
 using namespace ptx;
+static_assert(SEL_MAX_E == 16, "k_front_ts keeps one softmax register per possible expert");
 extern unsigned long long* g_timeline;
 
 static constexpr int TILE = 128;            // rows per tile (UMMA M)
@@ -914,7 +916,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, R
         r.e = tt.tile_expert[t];
         if (row < tt.tile_rows[t]) r.sidx = tt.row2sample[tt.tile_row0[t] + row];
         if (r.sidx >= 0) {
-          if (r.e >= 0) r.g = gate[(int64_t)r.sidx * io.g_stride];
+          if (r.e >= 0) r.g = io.wsel ? sel_gate(io.wsel[r.sidx]) : gate[(int64_t)r.sidx * io.g_stride];
           if (ec.cs == 0 && P.recompute_h && r.e >= 0) {
             const float* xr = x + (int64_t)r.sidx * io.x_stride;
             r.x0 = xr[0]; r.x1 = xr[1]; r.x2 = xr[2];
@@ -1132,7 +1134,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, R
 unsigned long long* g_timeline = nullptr;
 int tc_timeline_read(unsigned long long* host, int n) {
   if (!g_timeline) return 0;
-  if (n > 4 * TL_N) n = 4 * TL_N;
+  if (n > 5 * TL_N) n = 5 * TL_N;
   cudaDeviceSynchronize();
   cudaMemcpy(host, g_timeline, (size_t)n * 8, cudaMemcpyDeviceToHost);
   return n;
@@ -1155,6 +1157,9 @@ size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf) {
   b += align_up((size_t)max_rows * 4, 256);          // row2sample
   b += 3 * align_up((size_t)max_tiles * 4, 256);     // tile tables
   b += 4096;                                          // small scalars
+  b += align_up((size_t)S * 4, 256);                  // packed routing words (snb_select.cuh)
+  b += align_up((size_t)SEL_PM_RECORDS(S) * SEL_PM_STRIDE * 4, 256);   // partial column sums of the gates
+  b += align_up((size_t)SEL_MAX_E * SEL_HBINS * 4, 256);               // level-0 key histogram
   b += route_workspace_bytes(S, E);
   return b + 4096;
 }
@@ -1180,6 +1185,12 @@ struct TcChunk {
   int *counts, *cap_dev;
   char* rws;
   size_t rbytes;
+  uint32_t* wsel;           // packed routing words, written by k_front_ts (or k_pack_top1 from `gates`)
+  float* pm;                // partial column sums of the gates
+  int* hist0;               // [SEL_MAX_E][SEL_HBINS] level-0 key histogram per expert
+  int npm;
+  bool front_packed;        // launch #1 wrote wsel / pm itself
+  bool select;              // routing = k_select (kept set only); false = full-order route_top1 (SNB_ROUTE_FULL=1)
   int64_t max_rows, max_tiles;
   PhaseEvents* pe;
   int set;                  // expert-parallel buffer set of this chunk
@@ -1200,10 +1211,10 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
     static int tl_checked = 0;
     if (!tl_checked) {
       tl_checked = 1;
-      if (getenv("SNB_TIMELINE")) { cudaMalloc((void**)&tl_buf, 4 * TL_N * 8); g_timeline = tl_buf; }
+      if (getenv("SNB_TIMELINE")) { cudaMalloc((void**)&tl_buf, 5 * TL_N * 8); g_timeline = tl_buf; }
     }
     if (tl_buf) {
-      cudaMemsetAsync(tl_buf, 0, 4 * TL_N * 8, st);
+      cudaMemsetAsync(tl_buf, 0, 5 * TL_N * 8, st);
       c.Pf.tl = tl_buf;
       c.Pb.tl = tl_buf + 2 * TL_N;
     }
@@ -1231,6 +1242,13 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
   c.tt.tile_row0 = ws.take<int>(c.max_tiles);
   c.tt.tile_rows = ws.take<int>(c.max_tiles);
   int* small = ws.take<int>(1024);
+  c.wsel = ws.take<uint32_t>(S);
+  c.pm = ws.take<float>((size_t)SEL_PM_RECORDS(S) * SEL_PM_STRIDE);
+  c.hist0 = ws.take<int>((size_t)SEL_MAX_E * SEL_HBINS);
+  c.npm = 0;
+  c.front_packed = false;
+  static const bool route_full = getenv("SNB_ROUTE_FULL") != nullptr;
+  c.select = !route_full && E <= SEL_MAX_E;
   c.rbytes = route_workspace_bytes(S, E);
   c.rws = ws.take<char>(c.rbytes);
   if (!ws.ok) { set_error("tc_forward: workspace too small"); return SNB_EWORKSPACE; }
@@ -1266,6 +1284,7 @@ static int tc_front(Model* m, TcChunk& c, cudaStream_t st) {
   const int n_front_tiles = (int)cdiv(c.S, TILE);
   int grid1 = n_front_tiles < c.grid_cap ? n_front_tiles : c.grid_cap;
   if (c.pe) cudaEventRecord(c.pe->e[0], st);
+  if (c.select) SNB_CHECK_CUDA(cudaMemsetAsync(c.hist0, 0, (size_t)SEL_MAX_E * SEL_HBINS * sizeof(int), st));
   if (c.cg == 2) {
     grid1 = (grid1 + 1) & ~1;
     if (grid1 > (c.grid_cap & ~1)) grid1 = c.grid_cap & ~1;
@@ -1280,9 +1299,16 @@ static int tc_front(Model* m, TcChunk& c, cudaStream_t st) {
     // SNB_TS_FRONT=0 / SNB_TS=0: shared-memory A operand (k_front)
     static const bool ts_front = !(getenv("SNB_TS") && atoi(getenv("SNB_TS")) == 0) &&
                                  !(getenv("SNB_TS_FRONT") && atoi(getenv("SNB_TS_FRONT")) == 0);
-    if (ts_front && c.Pf.recompute_h && c.Pf.front[0].K16 <= TS_CAT_COLS)
-      k_front_ts<12><<<grid1, THREADS, TSM_TOTAL, st>>>(c.Pf, c.x, c.S, c.gates);
-    else
+    if (ts_front && c.Pf.recompute_h && c.Pf.front[0].K16 <= TS_CAT_COLS) {
+      // the [S,E] gates only leave the kernel when a caller taps them (or the full-order routing needs them)
+      // the kernel keeps 16-bit row counters per CTA: a CTA must see fewer than 65536 rows (else k_pack_top1 does it)
+      const bool pack = c.select && (int64_t)cdiv(n_front_tiles, grid1) * TILE < 65536;
+      float* gates_out = pack ? c.dbg_gates : c.gates;
+      k_front_ts<12><<<grid1, THREADS, TSM_TOTAL, st>>>(c.Pf, c.x, c.S, gates_out, pack ? c.wsel : nullptr, c.hist0,
+                                                         pack ? c.pm : nullptr, pack ? c.moe_idx : nullptr);
+      c.front_packed = pack;
+      c.npm = 4 * grid1;
+    } else
       k_front<12, 1><<<grid1, THREADS, SM_TOTAL, st>>>(c.Pf, c.x, c.S, c.H, c.gates);
   }
   SNB_CHECK_LAUNCH("k_front");
@@ -1293,8 +1319,35 @@ static int tc_front(Model* m, TcChunk& c, cudaStream_t st) {
 static int tc_route(Model* m, TcChunk& c, cudaStream_t st) {
   const int E = m->d.num_experts;
   if (c.pe) cudaEventRecord(c.pe->e[2], st);
-  int rc = route_top1(c.gates, c.S, E, c.o.capacity_factor, c.o.no_batch ? 0 : c.o.bpr, c.idx, c.loc, c.gate, c.counts,
-                      c.cap_dev, c.l_aux, c.rws, c.rbytes, st);
+  int rc;
+  if (c.select) {
+    // ONE launch: k_select (E CTAs) turns the packed words into the row table + tile plan of launch #2 (and, for
+    // expert parallelism, the per-sample idx / loc / gate the record scatter reads)
+    if (!c.front_packed) {
+      if ((rc = route_pack_top1(c.gates, c.S, E, c.wsel, c.hist0, c.pm, &c.npm, st))) return rc;
+      if (c.dbg_gates) SNB_CHECK_CUDA(cudaMemcpyAsync(c.dbg_gates, c.gates, sizeof(float) * c.S * E, cudaMemcpyDeviceToDevice, st));
+    }
+    SelectArgs a = {};
+    a.w = c.wsel; a.hist0 = c.hist0; a.pm = c.pm; a.npm = c.npm;
+    a.S = c.S; a.E = E; a.cf = c.o.capacity_factor; a.bpr = c.o.no_batch ? 0 : c.o.bpr; a.no_batch = c.o.no_batch;
+    a.pair = c.cg_back == 2;
+    a.counts = c.counts; a.cap_dev = c.cap_dev; a.l_aux = c.l_aux;
+    a.moe_idx = c.front_packed ? nullptr : c.moe_idx;      // k_front_ts already wrote the expert ids
+    a.loc = c.dbg_loc;
+    if (m->ep) { a.idx = c.idx; a.loc = c.loc; a.gate = c.gate; }     // per-sample taps of the record scatter
+    else a.tt = c.tt;                                                  // launch #2 decodes the gate from the packed word
+    if (g_timeline) a.tl = g_timeline + 4 * TL_N;     // debug: phase marks of k_select's CTA 0
+    if ((rc = route_select_launch(a, st))) return rc;
+    if (m->ep) {
+      rc = ep_dispatch_plan(m->ep, c.set, c.x, m->x_cols, c.gate, c.noise, c.idx, c.loc, c.counts, c.cap_dev, c.S,
+                            capacity_of(c.S, E, c.o.capacity_factor), c.cg_back == 2, c.tt, st);
+      if (rc) return rc;
+    }
+    if (c.pe) cudaEventRecord(c.pe->e[3], st);
+    return SNB_OK;
+  }
+  rc = route_top1(c.gates, c.S, E, c.o.capacity_factor, c.o.no_batch ? 0 : c.o.bpr, c.idx, c.loc, c.gate, c.counts,
+                  c.cap_dev, c.l_aux, c.rws, c.rbytes, st);
   if (rc) return rc;
   SNB_CHECK_CUDA(cudaMemsetAsync(c.tt.row2sample, 0xFF, (size_t)c.max_rows * sizeof(int), st));
   if (m->ep) {
@@ -1324,6 +1377,7 @@ static int tc_back(Model* m, TcChunk& c, cudaStream_t st) {
   } else {
     io.x = c.x; io.x_stride = m->x_cols;
     io.gate = c.gate; io.g_stride = 1;
+    io.wsel = c.select ? c.wsel : nullptr;
     io.noise = c.noise; io.n_stride = 1;
     io.out = c.out;
   }
@@ -1391,7 +1445,11 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
   static const int depth_env = getenv("SNB_PIPE_DEPTH") ? atoi(getenv("SNB_PIPE_DEPTH")) : 0;
   static const int route_env = getenv("SNB_ROUTE_SMS") ? atoi(getenv("SNB_ROUTE_SMS")) : -1;
   static const bool back_full = getenv("SNB_BACK_PART") == nullptr;   // launch #2 keeps every SM (tile rounds!)
-  const int route_sms = route_env >= 0 ? route_env : (m->ep ? 36 : 28);
+  // local experts + select routing: k_select is E CTAs of 1024 threads (one per SM); expert-parallel: the routing
+  // stage also scatters records to the peers and waits for theirs (r1q/r1r)
+  static const bool route_full_env = getenv("SNB_ROUTE_FULL") != nullptr;
+  const int sel_sms = m->d.num_experts > 8 ? m->d.num_experts : 8;
+  const int route_sms = route_env >= 0 ? route_env : (m->ep ? 36 : (route_full_env ? 28 : sel_sms));
   int D = depth_env >= 1 ? depth_env : (m->ep ? 3 : 2);
   if (D > nsets - 1) D = nsets - 1;
   if (D > MAXSETS - 1) D = MAXSETS - 1;

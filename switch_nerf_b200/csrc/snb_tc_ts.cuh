@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         if (row < tt.tile_rows[t]) r.sidx = tt.row2sample[tt.tile_row0[t] + row];
         if (r.sidx >= 0) {
           const float* xr = x + (int64_t)r.sidx * io.x_stride;
-          if (r.e >= 0) r.g = gate[(int64_t)r.sidx * io.g_stride];
+          if (r.e >= 0) r.g = io.wsel ? sel_gate(io.wsel[r.sidx]) : gate[(int64_t)r.sidx * io.g_stride];
           if (ec.cs == 0 && r.e >= 0) { r.x0 = xr[0]; r.x1 = xr[1]; r.x2 = xr[2]; }
           if (ec.cs == 1) {
             r.d0 = xr[P.x_cols - 4]; r.d1 = xr[P.x_cols - 3]; r.d2 = xr[P.x_cols - 2];
@@ -529,9 +529,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
 // Launch #1, TS variant: PE -> xyz layer -> external gate MLP -> folded LayerNorm + gate GEMM -> softmax, with the
 // hidden activations packed in tensor memory exactly as in k_back_ts (h is not written: launch #2 recomputes it).
 // ------------------------------------------------------------------------------------------------------------
+// Routing hand-off (snb_select.cuh): the thread that owns a row's softmax writes the packed word
+// (expert id << 26 | key of the max gate) of its sample and counts it in the per-expert histogram of the top 9 key
+// bits (`hist0`, zeroed by the host before the launch), and every CTA leaves the column sums of the gates over its
+// rows (`pm`, 4 records of SEL_PM_STRIDE floats per CTA, one per TMEM lane quarter) for the load-balance loss.
+// `gates` ([S,E] fp32) is only written when a caller asked for it (debug tap).
 template <int FX>
 __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float* __restrict__ x, int64_t S,
-                                                         float* __restrict__ gates) {
+                                                         float* __restrict__ gates, uint32_t* __restrict__ wsel,
+                                                         int* __restrict__ hist0, float* __restrict__ pm,
+                                                         int32_t* __restrict__ moe_idx) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -547,6 +554,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
   if (warp == 1) tmem_alloc<512>(&ctl->tmem_base);
   float* sbias = reinterpret_cast<float*>(smem + TSM_BIAS);
   float* sred = reinterpret_cast<float*>(smem + TSM_RED);
+  float* s_gc = reinterpret_cast<float*>(smem + TSM_VEC);     // [0,16) = c0, [16,32) = c1 of the folded gate GEMM
+  if (threadIdx.x < 2 * MAX_E)
+    s_gc[threadIdx.x] = P.fblob[(threadIdx.x < MAX_E ? P.o_c0 : P.o_c1 - MAX_E) + threadIdx.x];
+  // level-0 key histogram of this CTA's rows: 16-bit counters (a CTA sees < 65536 rows per launch: checked on the host),
+  // two per word; flushed into the global histogram with one reduction per non-zero counter at the end
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_gc + 2 * MAX_E);
+  static_assert((2 * MAX_E + MAX_E * SEL_HBINS / 2) * 4 <= SM_VEC_FLOATS * 4, "histogram fits in the head-vector block");
+  for (int i = threadIdx.x; i < MAX_E * SEL_HBINS / 2; i += THREADS) s_hist[i] = 0u;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -614,6 +629,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
       }
       for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, blk, i, lane, 0);
     };
+    float me_acc[MAX_E];                     // cs == 0 threads: running column sums of the gates (load-balance loss)
+#pragma unroll
+    for (int e = 0; e < MAX_E; ++e) me_acc[e] = 0.f;
     float pn[3];                             // xyz of this thread's row in the NEXT tile (staged one tile ahead)
     load_xyz((int)blockIdx.x, pn);
     if ((int)blockIdx.x < n_tiles) stage_pe(pn, 0);
@@ -677,8 +695,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
         ts_wait_acc(ctl, pp, buf);
         tl_mark(tl, 0, tn, 40);
         {
-          // the four threads of a row (cs = 0..3, different warps) take experts [4cs, 4cs+4): partial max and partial
-          // denominator are exchanged through sred values 2 and 3
+          // every one of the four threads of a row (cs = 0..3, different warps) holds all 32 accumulator columns, so
+          // each computes the whole softmax of its row itself: no exchange rounds.  Thread cs stores gates
+          // [4cs, 4cs+4) (debug tap only); thread 0 owns the routing word and the column sums.
           const float tsum = sred[0 * 128 + row] + sred[1 * 128 + row] + sred[2 * 128 + row] + sred[3 * 128 + row];
           const float tsq = sred[4 * 128 + row] + sred[5 * 128 + row] + sred[6 * 128 + row] + sred[7 * 128 + row];
           const float mean = tsum * (1.f / MW);
@@ -689,37 +708,54 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
           tmem_ld16(tacc, hi);
           tmem_ld16(tacc + 16u, lo);
           tmem_ld_wait();
-          const int e0 = 4 * ec.cs;
-          float lg[4];
+          float lg[MAX_E];
           float mx = -INFINITY;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (ec.cs == q4) {          // static register indices
-                const int e = 4 * q4 + j;
-                lg[j] = rstd * (__uint_as_float(hi[e]) + __uint_as_float(lo[e]) - mean * P.fblob[P.o_c1 + e]) + P.fblob[P.o_c0 + e];
-                if (e < P.E) mx = fmaxf(mx, lg[j]);
-              }
+          for (int e = 0; e < MAX_E; ++e) {
+            lg[e] = rstd * (__uint_as_float(hi[e]) + __uint_as_float(lo[e]) - mean * s_gc[MAX_E + e]) + s_gc[e];
+            if (e < P.E) mx = fmaxf(mx, lg[e]);
           }
-          sred[(2 * 4 + ec.cs) * 128 + row] = mx;
-          epi_bar_sync();
-          mx = fmaxf(fmaxf(sred[8 * 128 + row], sred[9 * 128 + row]), fmaxf(sred[10 * 128 + row], sred[11 * 128 + row]));
           float den = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (e0 + j < P.E) { lg[j] = expf(lg[j] - mx); den += lg[j]; }
-          sred[(3 * 4 + ec.cs) * 128 + row] = den;
-          epi_bar_sync();
-          den = (sred[12 * 128 + row] + sred[13 * 128 + row]) + (sred[14 * 128 + row] + sred[15 * 128 + row]);
-          if (valid) {
-            const float inv = 1.f / den;
-            if ((P.E & 3) == 0 && e0 < P.E) {
-              *reinterpret_cast<float4*>(gates + s * P.E + e0) = make_float4(lg[0] * inv, lg[1] * inv, lg[2] * inv, lg[3] * inv);
-            } else {
+          for (int e = 0; e < MAX_E; ++e) {
+            lg[e] = (e < P.E) ? expf(lg[e] - mx) : 0.f;
+            den += lg[e];
+          }
+          const float inv = 1.f / den;
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (e0 + j < P.E) gates[s * P.E + e0 + j] = lg[j] * inv;
+          for (int e = 0; e < MAX_E; ++e) lg[e] *= inv;
+          if (valid) {
+            if (gates) {
+              const int e0 = 4 * ec.cs;
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4)
+                if (ec.cs == q4) {            // static register indices
+                  if ((P.E & 3) == 0 && e0 < P.E) {
+                    *reinterpret_cast<float4*>(gates + s * P.E + e0) =
+                        make_float4(lg[4 * q4], lg[4 * q4 + 1], lg[4 * q4 + 2], lg[4 * q4 + 3]);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                      if (e0 + j < P.E) gates[s * P.E + e0 + j] = lg[4 * q4 + j];
+                  }
+                }
+            }
+            if (ec.cs == 0) {
+              // argmax of the fp32 gates, lowest expert id on ties (torch.argmax / extract_critical)
+              int best = 0;
+              float bv = lg[0];
+#pragma unroll
+              for (int e = 1; e < MAX_E; ++e)
+                if (e < P.E && lg[e] > bv) { bv = lg[e]; best = e; }
+              if (wsel) {
+                const uint32_t key = sel_key(bv);
+                wsel[s] = sel_pack(best, key);
+                const int bin = best * SEL_HBINS + (int)(key >> SEL_L1_SHIFT);
+                atomicAdd(&s_hist[bin >> 1], 1u << (16 * (bin & 1)));
+                if (moe_idx) moe_idx[s] = best;
+              }
+#pragma unroll
+              for (int e = 0; e < MAX_E; ++e) me_acc[e] += lg[e];
             }
           }
         }
@@ -729,8 +765,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
         ++li;
       }
     }
+    // column sums of the gates over this CTA's rows, one record per lane quarter (fixed order: deterministic l_aux)
+    if (pm && ec.cs == 0) {
+#pragma unroll
+      for (int e = 0; e < MAX_E; ++e) {
+        float v = me_acc[e];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) pm[((int64_t)blockIdx.x * 4 + ec.q) * SEL_PM_STRIDE + e] = v;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (wsel) {
+    for (int i = threadIdx.x; i < MAX_E * SEL_HBINS / 2; i += THREADS) {
+      const uint32_t v = s_hist[i];
+      if (v & 0xffffu) atomicAdd(&hist0[2 * i], (int)(v & 0xffffu));
+      if (v >> 16) atomicAdd(&hist0[2 * i + 1], (int)(v >> 16));
+    }
+  }
 }

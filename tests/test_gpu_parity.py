@@ -95,6 +95,60 @@ def test_route_properties_full_size(built_lib, S, E, bpr):
     assert torch.equal(loc.cpu(), l2) and cap == c2
 
 
+def _route_select(gates, cf, bpr, no_batch=False):
+    from switch_nerf_b200 import _lib as L
+    lib = L.lib()
+    S, E = gates.shape
+    dev = gates.device
+    idx = torch.full((S,), -7, dtype=torch.int32, device=dev)
+    loc = torch.full((S,), -7, dtype=torch.int32, device=dev)
+    gv = torch.zeros(S, dtype=torch.float32, device=dev)
+    counts = torch.zeros(E, dtype=torch.int32, device=dev)
+    cap = torch.zeros(1, dtype=torch.int32, device=dev)
+    l_aux = torch.zeros(1, dtype=torch.float32, device=dev)
+    nb = lib.snb_route_select_workspace_bytes(S)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    L.check(lib.snb_route_select(L.ptr(gates), S, E, float(cf), int(bpr), int(no_batch), L.ptr(idx), L.ptr(loc), L.ptr(gv),
+                                 L.ptr(counts), L.ptr(cap), L.ptr(l_aux), L.ptr(ws), nb, L.stream_handle()))
+    torch.cuda.synchronize()
+    return idx, loc, gv, counts, int(cap), float(l_aux)
+
+
+SELECT_CASES = [c for c in ROUTE_CASES if c[1] > 0 and c[2] <= 16] + [
+    ("sel_ties_heavy", 70001, 8, 1.0, True, 41, 2.0, 0.5, 0.2), ("sel_cf05", 131072, 8, 0.5, True, 42, 1.0, 0.0, 0.0),
+    ("sel_cf2_e16", 100003, 16, 2.0, True, 43, 3.0, 0.05, 0.0), ("sel_nobpr", 131072, 8, 1.0, False, 44, 2.0, 0.01, 0.01),
+    ("sel_tiny", 5, 4, 1.0, True, 45, 1.0, 0.0, 0.0), ("sel_e1", 1000, 1, 0.7, True, 46, 1.0, 0.0, 0.0)]
+
+
+@pytest.mark.parametrize("case", SELECT_CASES, ids=[c[0] for c in SELECT_CASES])
+def test_route_select_kept_set_equals_full_order_routing(built_lib, case):
+    """Routing as the fused path runs it (k_select: one launch, per-expert radix select) vs the full-order routing that
+    is bit-exact against extract_critical: same expert ids, gate values, counts, capacity; the KEPT SET
+    {s : loc < capacity} is identical bit for bit (incl. exact ties and saturated gates); kept locs are a bijection
+    onto [0, kept_e) in sample-index order; dropped locs are >= capacity and distinct."""
+    name, S, E, cf, bpr, seed, temp, tie, sat = case
+    gates = make_gates(S, E, seed, temp, tie, sat).cuda()
+    i0, l0, g0, c0, cap0, a0 = _route(gates, cf, bpr)
+    i1, l1, g1, c1, cap1, a1 = _route_select(gates, cf, bpr)
+    assert cap0 == cap1 and torch.equal(i0, i1) and torch.equal(c0, c1)
+    assert torch.equal(g0, g1), "gate value recovered from the packed routing word differs"
+    assert abs(a0 - a1) <= 1e-6 * max(1.0, abs(a0))
+    kept0, kept1 = l0 < cap0, l1 < cap1
+    assert torch.equal(kept0, kept1), f"kept set differs on {int((kept0 != kept1).sum())} samples"
+    for e in range(E):
+        le = l1[(i1 == e) & kept1]
+        assert torch.equal(le.long(), torch.arange(le.numel(), device=le.device)), "kept locs are not the index-order ranks"
+    for e in range(E):                      # dropped: capacity + a running number per expert
+        d = l1[(i1 == e) & ~kept1]
+        assert torch.equal(torch.sort(d).values.long(), cap1 + torch.arange(d.numel(), device=d.device))
+    # capacity-free mode: nothing dropped, index-order ranks
+    i2, l2, g2, c2, _, _ = _route_select(gates, cf, bpr, no_batch=True)
+    assert torch.equal(i2, i0)
+    for e in range(E):
+        le = l2[i2 == e]
+        assert torch.equal(le.long(), torch.arange(le.numel(), device=le.device))
+
+
 # ----------------------------------------------------------------------------- a10/a12 dispatch + combine
 @pytest.mark.parametrize("nobatch", [False, True])
 def test_dispatch_combine(built_lib, nobatch):
