@@ -408,7 +408,12 @@ def main():
             step_resident()
         ep_out = step_resident()
         torch.cuda.synchronize()
-        eq = all(torch.equal(dp_out[k], ep_out[k]) for k in dp_out)
+        mism = {k: {"mismatched": int((dp_out[k] != ep_out[k]).sum()), "numel": int(dp_out[k].numel()),
+                    "max_abs": float((dp_out[k].double() - ep_out[k].double()).abs().max())}
+                for k in dp_out if not torch.equal(dp_out[k], ep_out[k])}
+        eq = not mism
+        if mism:
+            print(f"[rank {rank}] expert-parallel output differs from the all-local run: {json.dumps(mism)}", file=sys.stderr, flush=True)
         flag = torch.tensor([1 if eq else 0], device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         ms_ep = timed(step_resident, args.steps)

@@ -747,28 +747,42 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
     }
   }
   mark(4);
-  // ---- CTA 0: counts, capacity, l_aux and the tile table of launch #2 ----
+  // ---- load-balance loss: l_aux = E / S^2 * sum_e me_e * ce_e (tutel_fast_dispatch.py:143-145).  Every CTA folds its
+  //      share of the partial column-sum records (fixed order, double); the last CTA to arrive adds the shares in CTA
+  //      order, so the result does not depend on timing or on the grid of launch #1 ----
+  if (a.l_aux) {
+    const int col = tid & (SEL_MAX_E - 1);
+    const int r0 = (int)((int64_t)a.npm * e / E), r1 = (int)((int64_t)a.npm * (e + 1) / E);
+    double acc = 0.0;
+    for (int i = r0 + (tid >> 4); i < r1; i += SEL_THREADS / SEL_MAX_E) acc += (double)a.pm[(int64_t)i * SEL_PM_STRIDE + col];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);         // lanes c and c+16 of a warp share column c
+    if (lane < SEL_MAX_E) sh.red[wid][lane] = acc;
+    __syncthreads();
+    if (tid < SEL_MAX_E) {
+      double me = 0.0;
+      for (int ww = 0; ww < 32; ++ww) me += sh.red[ww][tid];
+      a.lpart[e * SEL_PM_STRIDE + tid] = me;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sh.ch_d = (atomicAdd(a.ticket, 1) == E - 1);
+    __syncthreads();
+    if (sh.ch_d && tid == 0) {
+      __threadfence();
+      float tot = 0.f;
+      for (int ee = 0; ee < E; ++ee) {
+        double me = 0.0;
+        for (int c = 0; c < E; ++c) me += ((volatile double*)a.lpart)[c * SEL_PM_STRIDE + ee];
+        tot += (float)me * (float)sh.cnt[ee];            // me * ce in fp32
+      }
+      *a.l_aux = (float)((double)tot * ((double)E / ((double)S * (double)S)));
+      *a.ticket = 0;
+    }
+  }
+  // ---- CTA 0: counts, capacity and the tile table of launch #2 ----
   if (e == 0) {
     if (tid < E && a.counts) a.counts[tid] = sh.cnt[tid];
     if (tid == 0 && a.cap_dev) *a.cap_dev = cap;
-    if (a.l_aux) {
-      // me[e] = sum of the partial column sums (fixed order, double); lanes e and e+16 of a warp share column e
-      const int col = tid & (SEL_MAX_E - 1);
-      double acc = 0.0;
-      for (int i = tid >> 4; i < a.npm; i += SEL_THREADS / SEL_MAX_E) acc += (double)a.pm[(int64_t)i * SEL_PM_STRIDE + col];
-      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-      if (lane < SEL_MAX_E) sh.red[wid][lane] = acc;
-      __syncthreads();
-      if (tid == 0) {
-        float tot = 0.f;
-        for (int ee = 0; ee < E; ++ee) {
-          double me = 0.0;
-          for (int ww = 0; ww < 32; ++ww) me += sh.red[ww][ee];
-          tot += (float)me * (float)sh.cnt[ee];            // me * ce in fp32 (tutel_fast_dispatch.py:143-145)
-        }
-        *a.l_aux = (float)((double)tot * ((double)E / ((double)S * (double)S)));
-      }
-    }
     if (a.tt.n_tiles) {
       int row = 0, nt = 0, kept_total = 0;
       for (int ee = 0; ee <= E; ++ee) {
@@ -804,7 +818,7 @@ int route_select_launch(const SelectArgs& a, cudaStream_t st) {
 size_t route_select_workspace_bytes(int64_t S) {
   const int64_t Sx = S > 0 ? S : 1;
   return align_up((size_t)Sx * 4, 256) + align_up((size_t)cdiv(Sx, 2048) * SEL_PM_STRIDE * 4, 256) +
-         align_up((size_t)SEL_MAX_E * SEL_HBINS * 4, 256) + 1024;
+         align_up((size_t)SEL_ZERO_INTS * 4, 256) + align_up((size_t)SEL_MAX_E * SEL_PM_STRIDE * 8, 256) + 1024;
 }
 
 // hist0 must be zero on entry (the caller enqueues the memset)
@@ -827,13 +841,14 @@ int route_select_from_gates(const float* gates, int64_t S, int32_t E, double cf,
   uint32_t* w = ar.take<uint32_t>(S);
   const int nblk = (int)cdiv(S, 2048);
   float* pm = ar.take<float>((size_t)nblk * SEL_PM_STRIDE);
-  int* hist0 = ar.take<int>((size_t)SEL_MAX_E * SEL_HBINS);
+  int* hist0 = ar.take<int>((size_t)SEL_ZERO_INTS);
+  double* lpart = ar.take<double>((size_t)SEL_MAX_E * SEL_PM_STRIDE);
   if (!ar.ok) { set_error("route_select: workspace too small (%zu bytes given)", ws_bytes); return SNB_EWORKSPACE; }
-  SNB_CHECK_CUDA(cudaMemsetAsync(hist0, 0, (size_t)SEL_MAX_E * SEL_HBINS * sizeof(int), st));
+  SNB_CHECK_CUDA(cudaMemsetAsync(hist0, 0, (size_t)SEL_ZERO_INTS * sizeof(int), st));
   SelectArgs a = {};
   int rc = route_pack_top1(gates, S, E, w, hist0, pm, &a.npm, st);
   if (rc) return rc;
-  a.w = w; a.pm = pm; a.hist0 = hist0;
+  a.w = w; a.pm = pm; a.hist0 = hist0; a.ticket = hist0 + SEL_MAX_E * SEL_HBINS; a.lpart = lpart;
   a.S = S; a.E = E; a.cf = cf; a.bpr = bpr; a.no_batch = no_batch;
   a.idx = idx; a.loc = loc; a.gate = gate; a.counts = counts; a.cap_dev = capacity; a.l_aux = l_aux;
   return route_select_launch(a, st);

@@ -15,8 +15,9 @@ constexpr int SEL_L1_SHIFT = 19;                 // level-0 digit = key bits [19
 constexpr int SEL_L2_SHIFT = 9;                  // level-1 digit = key bits [9, 19), level-2 digit = key bits [0, 9)
 constexpr int SEL_HBINS = 1 << (SEL_KEY_BITS - SEL_L1_SHIFT);
 constexpr int SEL_PM_STRIDE = 16;                // floats per partial-column-sum record
-// records a chunk can produce: 4 per CTA of launch #1 (<= 256 CTAs) or one per 2048 samples (k_pack_top1)
-__host__ __device__ inline int64_t SEL_PM_RECORDS(int64_t S) { const int64_t a = (S + 2047) / 2048; return a > 1024 ? a : 1024; }
+constexpr int SEL_ZERO_INTS = SEL_MAX_E * SEL_HBINS + 64;   // histogram + ticket: zeroed by the host before launch #1
+// records a chunk can produce: one per 32 rows (launch #1) or one per 2048 samples (k_pack_top1)
+__host__ __device__ inline int64_t SEL_PM_RECORDS(int64_t S) { return 4 * ((S + 127) / 128) + 4; }
 
 __host__ __device__ __forceinline__ uint32_t sel_key_bits(uint32_t gate_bits) {
   const uint32_t k = (gate_bits <= 0x3F800000u) ? (0x3F800000u - gate_bits) : 0u;
@@ -31,6 +32,8 @@ struct SelectArgs {
   const int* hist0;         // [SEL_MAX_E][SEL_HBINS] histogram of the top 9 key bits per expert (accumulated by launch #1)
   const float* pm;          // [npm][SEL_PM_STRIDE] partial column sums of the gates (load-balance loss)
   int npm;
+  double* lpart;            // [SEL_MAX_E][SEL_PM_STRIDE] per-CTA partial column sums (scratch)
+  int* ticket;              // [1] zero on entry: the last CTA to arrive combines the partial sums
   int64_t S;
   int E;
   double cf;

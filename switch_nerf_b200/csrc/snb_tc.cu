@@ -1159,7 +1159,8 @@ size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf) {
   b += 4096;                                          // small scalars
   b += align_up((size_t)S * 4, 256);                  // packed routing words (snb_select.cuh)
   b += align_up((size_t)SEL_PM_RECORDS(S) * SEL_PM_STRIDE * 4, 256);   // partial column sums of the gates
-  b += align_up((size_t)SEL_MAX_E * SEL_HBINS * 4, 256);               // level-0 key histogram
+  b += align_up((size_t)SEL_ZERO_INTS * 4, 256);                        // level-0 key histogram + ticket
+  b += align_up((size_t)SEL_MAX_E * SEL_PM_STRIDE * 8, 256);            // per-CTA partial column sums of k_select
   b += route_workspace_bytes(S, E);
   return b + 4096;
 }
@@ -1187,7 +1188,8 @@ struct TcChunk {
   size_t rbytes;
   uint32_t* wsel;           // packed routing words, written by k_front_ts (or k_pack_top1 from `gates`)
   float* pm;                // partial column sums of the gates
-  int* hist0;               // [SEL_MAX_E][SEL_HBINS] level-0 key histogram per expert
+  int* hist0;               // [SEL_MAX_E][SEL_HBINS] level-0 key histogram per expert (+ the ticket of k_select)
+  double* lpart;
   int npm;
   bool front_packed;        // launch #1 wrote wsel / pm itself
   bool select;              // routing = k_select (kept set only); false = full-order route_top1 (SNB_ROUTE_FULL=1)
@@ -1244,7 +1246,8 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
   int* small = ws.take<int>(1024);
   c.wsel = ws.take<uint32_t>(S);
   c.pm = ws.take<float>((size_t)SEL_PM_RECORDS(S) * SEL_PM_STRIDE);
-  c.hist0 = ws.take<int>((size_t)SEL_MAX_E * SEL_HBINS);
+  c.hist0 = ws.take<int>((size_t)SEL_ZERO_INTS);
+  c.lpart = ws.take<double>((size_t)SEL_MAX_E * SEL_PM_STRIDE);
   c.npm = 0;
   c.front_packed = false;
   static const bool route_full = getenv("SNB_ROUTE_FULL") != nullptr;
@@ -1284,7 +1287,7 @@ static int tc_front(Model* m, TcChunk& c, cudaStream_t st) {
   const int n_front_tiles = (int)cdiv(c.S, TILE);
   int grid1 = n_front_tiles < c.grid_cap ? n_front_tiles : c.grid_cap;
   if (c.pe) cudaEventRecord(c.pe->e[0], st);
-  if (c.select) SNB_CHECK_CUDA(cudaMemsetAsync(c.hist0, 0, (size_t)SEL_MAX_E * SEL_HBINS * sizeof(int), st));
+  if (c.select) SNB_CHECK_CUDA(cudaMemsetAsync(c.hist0, 0, (size_t)SEL_ZERO_INTS * sizeof(int), st));
   if (c.cg == 2) {
     grid1 = (grid1 + 1) & ~1;
     if (grid1 > (c.grid_cap & ~1)) grid1 = c.grid_cap & ~1;
@@ -1307,7 +1310,7 @@ static int tc_front(Model* m, TcChunk& c, cudaStream_t st) {
       k_front_ts<12><<<grid1, THREADS, TSM_TOTAL, st>>>(c.Pf, c.x, c.S, gates_out, pack ? c.wsel : nullptr, c.hist0,
                                                          pack ? c.pm : nullptr, pack ? c.moe_idx : nullptr);
       c.front_packed = pack;
-      c.npm = 4 * grid1;
+      c.npm = 4 * n_front_tiles;
     } else
       k_front<12, 1><<<grid1, THREADS, SM_TOTAL, st>>>(c.Pf, c.x, c.S, c.H, c.gates);
   }
@@ -1329,6 +1332,7 @@ static int tc_route(Model* m, TcChunk& c, cudaStream_t st) {
     }
     SelectArgs a = {};
     a.w = c.wsel; a.hist0 = c.hist0; a.pm = c.pm; a.npm = c.npm;
+    a.ticket = c.hist0 + SEL_MAX_E * SEL_HBINS; a.lpart = c.lpart;
     a.S = c.S; a.E = E; a.cf = c.o.capacity_factor; a.bpr = c.o.no_batch ? 0 : c.o.bpr; a.no_batch = c.o.no_batch;
     a.pair = c.cg_back == 2;
     a.counts = c.counts; a.cap_dev = c.cap_dev; a.l_aux = c.l_aux;

@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
 // Routing hand-off (snb_select.cuh): the thread that owns a row's softmax writes the packed word
 // (expert id << 26 | key of the max gate) of its sample and counts it in the per-expert histogram of the top 9 key
 // bits (`hist0`, zeroed by the host before the launch), and every CTA leaves the column sums of the gates over its
-// rows (`pm`, 4 records of SEL_PM_STRIDE floats per CTA, one per TMEM lane quarter) for the load-balance loss.
+// rows (`pm`, one record of SEL_PM_STRIDE floats per 32 rows = per (tile, TMEM lane quarter)) for the load-balance loss.
 // `gates` ([S,E] fp32) is only written when a caller asked for it (debug tap).
 template <int FX>
 __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float* __restrict__ x, int64_t S,
@@ -629,9 +629,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
       }
       for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, blk, i, lane, 0);
     };
-    float me_acc[MAX_E];                     // cs == 0 threads: running column sums of the gates (load-balance loss)
-#pragma unroll
-    for (int e = 0; e < MAX_E; ++e) me_acc[e] = 0.f;
     float pn[3];                             // xyz of this thread's row in the NEXT tile (staged one tile ahead)
     load_xyz((int)blockIdx.x, pn);
     if ((int)blockIdx.x < n_tiles) stage_pe(pn, 0);
@@ -754,8 +751,47 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
                 atomicAdd(&s_hist[bin >> 1], 1u << (16 * (bin & 1)));
                 if (moe_idx) moe_idx[s] = best;
               }
+            }
+          }
+          if (pm && ec.cs == 0) {
+            // column sums of the gates over the 32 rows of this warp (load-balance loss), in a fixed order that does
+            // not depend on the grid: 16 values x 32 lanes folded by a transpose-reduction (16 shuffles), after which
+            // even lane l holds the sum of expert ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1).
+            if (!valid) {
 #pragma unroll
-              for (int e = 0; e < MAX_E; ++e) me_acc[e] += lg[e];
+              for (int e = 0; e < MAX_E; ++e) lg[e] = 0.f;
+            }
+            float a8[8], b4[4], c2[2];
+            {
+              const bool hi = lane & 16;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float send = hi ? lg[i] : lg[i + 8], keep = hi ? lg[i + 8] : lg[i];
+                a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+            }
+            {
+              const bool hi = lane & 8;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float send = hi ? a8[i] : a8[i + 4], keep = hi ? a8[i + 4] : a8[i];
+                b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+            }
+            {
+              const bool hi = lane & 4;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float send = hi ? b4[i] : b4[i + 2], keep = hi ? b4[i + 2] : b4[i];
+                c2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+            }
+            const bool hi2 = lane & 2;
+            float d1 = (hi2 ? c2[1] : c2[0]) + __shfl_xor_sync(0xffffffffu, hi2 ? c2[0] : c2[1], 2);
+            d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+            if ((lane & 1) == 0) {
+              const int ecol = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+              pm[((int64_t)t * 4 + ec.q) * SEL_PM_STRIDE + ecol] = d1;
             }
           }
         }
@@ -763,16 +799,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
         epi_bar_sync();                       // sred is reused by the next tile
         tl_mark(tl, 0, tn, 41);
         ++li;
-      }
-    }
-    // column sums of the gates over this CTA's rows, one record per lane quarter (fixed order: deterministic l_aux)
-    if (pm && ec.cs == 0) {
-#pragma unroll
-      for (int e = 0; e < MAX_E; ++e) {
-        float v = me_acc[e];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) pm[((int64_t)blockIdx.x * 4 + ec.q) * SEL_PM_STRIDE + e] = v;
       }
     }
   }
