@@ -233,9 +233,12 @@ void snb_model_destroy(snb_model_t* mm) {
   if (!m) return;
   if (m->f32_blob) cudaFree(m->f32_blob);
   tc_release(m);
+  if (m->sel_zero) { cudaFree(m->sel_zero); m->sel_zero = nullptr; }
   if (m->side_stream) {
     cudaStreamDestroy(m->side_stream);
     for (int i = 0; i < 4; ++i) { cudaEventDestroy(m->ev_front[i]); cudaEventDestroy(m->ev_route[i]); }
+    if (m->fin_stream) cudaStreamDestroy(m->fin_stream);
+    for (int i = 0; i < 4; ++i) { if (m->ev_back[i]) cudaEventDestroy(m->ev_back[i]); if (m->ev_fin[i]) cudaEventDestroy(m->ev_fin[i]); }
   }
   delete m;
 }

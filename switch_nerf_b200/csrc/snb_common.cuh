@@ -88,6 +88,9 @@ struct Model {
   int sm_count = 148;
   // software pipelining of render_rays: routing kernels run on this stream
   cudaStream_t side_stream = nullptr;
+  int* sel_zero = nullptr;               // [4 sets][SEL_ZERO_INTS] scratch of k_select that is zero between uses (self-cleaning)
+  cudaStream_t fin_stream = nullptr;     // expert-parallel: waits for the peers' result rows off the main stream
+  cudaEvent_t ev_back[4] = {nullptr, nullptr, nullptr, nullptr}, ev_fin[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_front[4] = {nullptr, nullptr, nullptr, nullptr}, ev_route[4] = {nullptr, nullptr, nullptr, nullptr};
   // expert-parallel group attached by snb_model_attach_a2a (not owned); nullptr = every expert is local
   Ep* ep = nullptr;

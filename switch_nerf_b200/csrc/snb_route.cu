@@ -372,18 +372,12 @@ int route_top1_generic(const float* gates, int64_t S, int32_t E, double cf, int3
 // whose batch-prioritised rank is below the capacity -- not their order.  Input: one packed word per sample
 // (expert id << 26 | key, key = bits(1.0f) - bits(max gate): ascending key == descending gate), written either by
 // launch #1 itself (k_front_ts) or by k_pack_top1 below.
-// One CTA per expert, ONE launch: a counting pass (all experts' totals + this expert's histogram of the top 9 key
-// bits), radix descent to the composite threshold T over the unique 58-bit value (key << 32 | sample) -- ties
-// between equal gates resolve to the lower sample index exactly as the stable sort of the full path does -- then ONE
-// ordered pass that hands every kept sample its row (index order) and every dropped sample a row of the dropped
-// bucket.  No atomics on the output, no memset, deterministic row order; CTA 0 also writes counts, capacity, l_aux
-// and the tile table of launch #2.
+// The threshold of an expert is the composite value (key << 32 | sample) of its capacity-th element: ties between
+// equal gates resolve to the lower sample index exactly as the stable sort of the full path does.  Kept samples get
+// their row in index order, dropped samples a row of the dropped bucket: no atomics on the output, deterministic row
+// order; the kernel also writes counts, capacity, l_aux and the tile table of launch #2.
 // reference: tutel_fast_dispatch.py:136-139, 176-217 (the kept set == {s : locations_s < capacity}).
 // =========================================================================================
-static constexpr int SEL_THREADS = 1024;
-static constexpr int SEL_LIST = 3072;       // candidates of the threshold digit bucket resolved in shared memory
-static_assert(SEL_MAX_E <= 32, "one lane per expert in the count reduction");
-
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -430,329 +424,298 @@ __global__ void __launch_bounds__(256) k_pack_top1(const float* __restrict__ gat
   }
 }
 
-static constexpr int SEL_SEG = 128;          // samples per warp-visit of the ordered passes (4 per lane)
-static constexpr int SEL_SEG_SMEM = 2048;    // segments whose (kept, dropped) counts are scanned in shared memory
-static_assert((SEL_SEG_SMEM + 32 * SEL_SEG) * 4 <= SEL_LIST * 8, "ordered-pass scratch aliases the candidate list");
+// ---------------------------------------------------------------------------------------------------------------
+// k_select: SEL_P CTAs, each owning a contiguous range of the samples (every word is classified ONCE per sweep, by
+// one CTA, for whatever expert it belongs to) -- the ranges' results are combined through a few words of global
+// memory and grid barriers (the CTAs are co-resident: SEL_P <= 16 CTAs, launched on SMs launch #1 leaves free).
+//   1. thresholds, level by level, identically in every CTA: level 0 from the histogram launch #1 accumulated; a deeper
+//      level only for experts whose threshold bucket is still split: every CTA histograms the next digit of ITS
+//      matching words (shared memory, warp-aggregated), adds the non-zero bins to the global level histogram, barrier,
+//      every CTA picks the digit.  Digits: key bits [19,26) [9,19) [0,9), then the sample index 9 bits at a time.
+//   2. per-(CTA, expert, kept|dropped) totals -> global, barrier -> this CTA's first row in every bucket.
+//   3. ordered write: rank inside a 32-sample visit from __match_any_sync, visit prefixes from a shared-memory scan.
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int SEL_THREADS = 1024;
+static constexpr int SEL_P = 8;                      // CTAs
+static constexpr int SEL_CACHE = 16384;              // words of the CTA's range kept in shared memory / per group
+static constexpr int SEL_VIS = SEL_CACHE / 32;       // 32-sample visits per group
+static constexpr int SEL_NLEV = 7;
+static_assert(SEL_LVH_INTS == (SEL_NLEV - 1) * SEL_MAX_E * 1024, "level histograms in the zeroed region");
 
-struct SelShared {
-  int cnt[SEL_MAX_E];
-  int hist[1024];                 // digit histogram of the current level (<= 10 bits)
-  int wtot[32];
+struct SelSmem {
+  uint32_t words[SEL_CACHE];
+  int hist[SEL_MAX_E][1024];
+  uint16_t segcnt[SEL_VIS][32];       // per visit and key (expert * 2 + dropped): count, then exclusive prefix
+  int part[32][33];
   double red[32][SEL_MAX_E];
-  unsigned long long list[SEL_LIST];
-  uint32_t seg[SEL_SEG_SMEM];       // per 128-sample segment: kept count | dropped count << 16, then exclusive prefixes
-  int n_list;
-  int ch_d, ch_need, ch_hc;       // digit chosen by the current level
+  unsigned long long pval[SEL_MAX_E], pmask[SEL_MAX_E];
+  long long Ts[SEL_MAX_E];
+  uint32_t Tk[SEL_MAX_E];
+  int cnt[SEL_MAX_E], need[SEL_MAX_E], done[SEL_MAX_E];
+  int seg0[SEL_MAX_E + 1], dropb[SEL_MAX_E];
+  int tot[32], base[32], run[32];
+  int flag;
 };
 
-// visit the words of this chunk, 4 per 16-byte load, 4 independent loads in flight per thread.  f(word, sample, valid)
-// is called the same number of times by every lane of a warp (warp-collective code is allowed inside f).
-template <typename F>
-__device__ __forceinline__ void sel_for_each(const uint32_t* __restrict__ w, int64_t S, int tid, F&& f) {
-  const int64_t nq = S >> 2;
-  const uint4* w4 = reinterpret_cast<const uint4*>(w);
-  for (int64_t q0 = 0; q0 < nq; q0 += 4 * SEL_THREADS) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t q = q0 + u * SEL_THREADS + tid;
-      v[u] = (q < nq) ? w4[q] : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t q = q0 + u * SEL_THREADS + tid;
-      const bool ok = q < nq;
-      f(v[u].x, 4 * q, ok); f(v[u].y, 4 * q + 1, ok); f(v[u].z, 4 * q + 2, ok); f(v[u].w, 4 * q + 3, ok);
-    }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sel_grid_barrier(int* ctr, int n) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1);
+    while (ld_acquire_gpu(ctr) < n) __nanosleep(32);
+    __threadfence();
   }
-  const int64_t s = (nq << 2) + tid;
-  f(s < S ? w[s] : 0u, s, s < S);
-}
-
-// smallest digit d with (inclusive prefix count up to d) >= need; returns through shared memory (all threads sync)
-__device__ __forceinline__ void sel_choose(SelShared& sh, int nbins, int need, int tid, int lane, int wid) {
-  const int v = (tid < nbins) ? sh.hist[tid] : 0;
-  int inc = warp_incl_scan(v, lane);
-  if (lane == 31) sh.wtot[wid] = inc;
-  __syncthreads();
-  int base = 0;
-  for (int ww = 0; ww < wid; ++ww) base += sh.wtot[ww];
-  inc += base;
-  if (tid < nbins && inc >= need && inc - v < need) { sh.ch_d = tid; sh.ch_need = need - (inc - v); sh.ch_hc = v; }
   __syncthreads();
 }
+__device__ __forceinline__ void sel_level_digit(int lv, int sbits, int& dshift, int& dbits) {
+  if (lv == 0) { dshift = 32 + SEL_L1_SHIFT; dbits = SEL_KEY_BITS - SEL_L1_SHIFT; }
+  else if (lv == 1) { dshift = 32 + SEL_L2_SHIFT; dbits = SEL_L1_SHIFT - SEL_L2_SHIFT; }
+  else if (lv == 2) { dshift = 32; dbits = SEL_L2_SHIFT; }
+  else { const int hi = sbits - 9 * (lv - 3); dshift = hi > 9 ? hi - 9 : 0; dbits = hi - dshift; }
+}
 
-__global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
-  __shared__ SelShared sh;
-  const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+__global__ void __launch_bounds__(SEL_THREADS, 1) k_select(SelectArgs a) {
+  extern __shared__ __align__(16) uint8_t sel_smem_raw[];
+  SelSmem& sh = *reinterpret_cast<SelSmem*>(sel_smem_raw);
+  const int p = blockIdx.x, P = gridDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int E = a.E;
   const int64_t S = a.S;
   const uint32_t* __restrict__ w = a.w;
-  int tn = 0;
+  int* bar = a.zero + SEL_Z_BAR;
+  int tn = 0, nbar = 0, lv_used = 0;
   auto mark = [&](int tag) {
-    if (a.tl && e == 0 && tid == 0) a.tl[tn++] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+    if (a.tl && p == 0 && tid == 0) a.tl[tn++] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
   };
   mark(1);
-  if (tid == 0) sh.n_list = 0;
-  // ---- per-expert totals (segment starts need all of them) + this expert's level-0 histogram, both from the
-  //      global histogram launch #1 accumulated with fire-and-forget reductions ----
-  for (int ee = wid; ee < E; ee += SEL_THREADS / 32) {
-    int c = 0;
-    for (int i = lane; i < SEL_HBINS; i += 32) {
-      const int v = a.hist0[ee * SEL_HBINS + i];
-      if (ee == e) sh.hist[i] = v;
-      c += v;
+  // this CTA's range of 32-sample visits
+  const int64_t nvis = (S + 31) / 32;
+  const int64_t v0 = nvis * p / P, v1 = nvis * (p + 1) / P;
+  const bool cached = (v1 - v0) <= SEL_VIS;
+  if (cached)
+    for (int64_t i = tid; i < (v1 - v0) * 32; i += SEL_THREADS) {
+      const int64_t s = v0 * 32 + i;
+      sh.words[i] = (s < S) ? w[s] : 0xffffffffu;
     }
+  auto word_at = [&](int64_t v) -> uint32_t {       // the word of (visit v, this lane); 0xffffffff past the end
+    if (cached) return sh.words[(v - v0) * 32 + lane];
+    const int64_t s = v * 32 + lane;
+    return (s < S) ? w[s] : 0xffffffffu;
+  };
+  for (int i = tid; i < SEL_MAX_E * 1024; i += SEL_THREADS) (&sh.hist[0][0])[i] = 0;
+  // ---- per-expert totals from the level-0 histogram ----
+  for (int ee = wid; ee < SEL_MAX_E; ee += SEL_THREADS / 32) {
+    int c = 0;
+    if (ee < E)
+      for (int i = lane; i < SEL_HBINS; i += 32) c += __ldcg(&a.zero[ee * SEL_HBINS + i]);
     c = __reduce_add_sync(0xffffffffu, c);
     if (lane == 0) sh.cnt[ee] = c;
   }
   __syncthreads();
-  mark(2);
   const int cap = capacity_of(S, E, a.cf);
   const int keep_cap = a.no_batch ? 0x7fffffff : cap;
-  const int cnt = sh.cnt[e];
-  int seg0 = 0, drop0 = 0, drop_before = 0;        // first row of my segment / of the dropped segment; dropped rows of experts < e
-  {
-    int row = 0;
+  const bool by_rank = !(a.bpr && !a.no_batch);     // plain order: kept iff the index-order rank is below the capacity
+  if (tid < SEL_MAX_E) {
+    const bool thr = !by_rank && tid < E && sh.cnt[tid] > cap;
+    sh.done[tid] = thr ? 0 : 1;
+    sh.need[tid] = cap;
+    sh.pval[tid] = 0; sh.pmask[tid] = 0;
+    sh.Tk[tid] = SEL_KEY_MASK + 1u;      // no threshold: every word of the expert counts as kept
+    sh.Ts[tid] = -1;
+  }
+  if (tid == 0) {
+    int row = 0, db = 0;
     for (int ee = 0; ee < E; ++ee) {
       const int kc = min(sh.cnt[ee], keep_cap);
-      if (ee == e) seg0 = row;
-      if (ee < e) drop_before += sh.cnt[ee] - kc;
+      sh.seg0[ee] = row;
+      sh.dropb[ee] = db;
+      db += sh.cnt[ee] - kc;
       row += (kc + EP_TILE - 1) / EP_TILE * EP_TILE;
     }
-    drop0 = row;
+    sh.seg0[E] = row;
   }
-  // ---- threshold: T = composite value (key << 32 | sample) of the keep_cap-th element in batch-prioritised order ----
-  unsigned long long T = ~0ull;
-  if (a.bpr && !a.no_batch && cnt > cap) {
+  __syncthreads();
+  mark(2);
+  // ---- thresholds: T[e] = composite value (key << 32 | sample) of the capacity-th element in batch-prioritised order ----
+  {
     int sbits = 1;
-    while (sbits < 32 && (1ll << sbits) < S) ++sbits;
-    unsigned long long pmask = 0, pval = 0;
-    int need = cap, level = 0;
-    bool from_list = false, have_hist = true;
-    while (true) {
+    while (sbits < 31 && (1ll << sbits) < S) ++sbits;
+    for (int lv = 0; lv < SEL_NLEV; ++lv) {
       int dshift, dbits;
-      if (level == 0) { dshift = 32 + SEL_L1_SHIFT; dbits = SEL_KEY_BITS - SEL_L1_SHIFT; }
-      else if (level == 1) { dshift = 32 + SEL_L2_SHIFT; dbits = SEL_L1_SHIFT - SEL_L2_SHIFT; }
-      else if (level == 2) { dshift = 32; dbits = SEL_L2_SHIFT; }
-      else { const int hi = sbits - 9 * (level - 3); dshift = hi > 9 ? hi - 9 : 0; dbits = hi - dshift; }
-      const unsigned long long dmask = (1ull << dbits) - 1;
-      if (!have_hist) {
-        for (int i = tid; i < 1024; i += SEL_THREADS) sh.hist[i] = 0;
-        __syncthreads();
-        // candidates are few here (one digit bucket of the level above): plain shared atomics
-        if (from_list) {
-          for (int i = tid; i < sh.n_list; i += SEL_THREADS) {
-            const unsigned long long c = sh.list[i];
-            if ((c & pmask) == pval) atomicAdd(&sh.hist[(int)((c >> dshift) & dmask)], 1);
+      sel_level_digit(lv, sbits, dshift, dbits);
+      const int nb = 1 << dbits;
+      const unsigned long long dmask = (unsigned long long)nb - 1;
+      bool any = false;
+      for (int ee = 0; ee < E; ++ee) any |= !sh.done[ee];
+      if (!any) break;
+      const int* gh = (lv == 0) ? a.zero : a.zero + SEL_Z_LVH + (lv - 1) * SEL_MAX_E * 1024;
+      const int gstride = (lv == 0) ? SEL_HBINS : 1024;
+      if (lv > 0) {
+        lv_used = lv;
+        // histogram of this level's digit over MY words that still match their expert's prefix
+        for (int64_t v = v0 + wid; v < v1; v += SEL_THREADS / 32) {
+          const uint32_t wv = word_at(v);
+          const int ee = (int)(wv >> SEL_KEY_BITS);
+          bool on = false;
+          uint32_t mk = 0x80000000u | (uint32_t)lane;
+          if (ee < E && !sh.done[ee]) {
+            const unsigned long long c = ((unsigned long long)(wv & SEL_KEY_MASK) << 32) | (unsigned long long)(v * 32 + lane);
+            if ((c & sh.pmask[ee]) == sh.pval[ee]) { on = true; mk = ((uint32_t)ee << 10) | (uint32_t)((c >> dshift) & dmask); }
           }
-        } else {
-          sel_for_each(w, S, tid, [&](uint32_t wv, int64_t s, bool ok) {
-            if (!ok || (int)(wv >> SEL_KEY_BITS) != e) return;
-            const unsigned long long c = ((unsigned long long)(wv & SEL_KEY_MASK) << 32) | (unsigned long long)s;
-            if ((c & pmask) == pval) atomicAdd(&sh.hist[(int)((c >> dshift) & dmask)], 1);
-          });
+          if (__any_sync(0xffffffffu, on)) {
+            const unsigned m = __match_any_sync(0xffffffffu, mk);
+            if (on && lane == __ffs(m) - 1) atomicAdd(&sh.hist[mk >> 10][mk & 1023u], __popc(m));
+          }
         }
         __syncthreads();
+        mark(20 + lv);
+        for (int i = tid; i < E * 1024; i += SEL_THREADS) {
+          const int v = (&sh.hist[0][0])[i];
+          if (v) { atomicAdd(&a.zero[SEL_Z_LVH + (lv - 1) * SEL_MAX_E * 1024 + i], v); (&sh.hist[0][0])[i] = 0; }
+        }
+        mark(30 + lv);
+        sel_grid_barrier(&bar[nbar++], P);
+        mark(40 + lv);
       }
-      sel_choose(sh, 1 << dbits, need, tid, lane, wid);
-      mark(10 + level);
-      const int d = sh.ch_d, hc = sh.ch_hc;
-      need = sh.ch_need;
-      pval |= (unsigned long long)d << dshift;
-      pmask |= dmask << dshift;
-      if (need == hc || dshift == 0) { T = pval | ((1ull << dshift) - 1); break; }   // the whole digit bucket is kept
-      if (!from_list && hc <= SEL_LIST) {
-        // the undecided bucket fits in shared memory: gather it once, finish the descent there
-        // (only reached from level 0: the prefix is the level-0 digit of the key)
-        const uint32_t want = (((uint32_t)e << SEL_KEY_BITS) >> SEL_L1_SHIFT) | (uint32_t)(pval >> (32 + SEL_L1_SHIFT));
-        const bool narrow = (pmask == (((1ull << (SEL_KEY_BITS - SEL_L1_SHIFT)) - 1) << (32 + SEL_L1_SHIFT)));
-        sel_for_each(w, S, tid, [&](uint32_t wv, int64_t s, bool ok) {
-          bool hit;
-          if (narrow) hit = ok && (wv >> SEL_L1_SHIFT) == want;
-          else {
-            const unsigned long long c = ((unsigned long long)(wv & SEL_KEY_MASK) << 32) | (unsigned long long)s;
-            hit = ok && (int)(wv >> SEL_KEY_BITS) == e && (c & pmask) == pval;
+      // every CTA picks the digit of every open expert: one warp per expert, bins read 32 at a time (coalesced, all
+      // loads of a warp in flight together), running inclusive scan over the rows of 32
+      for (int ee = wid; ee < E; ee += SEL_THREADS / 32) {
+        if (sh.done[ee]) continue;
+        const int need = sh.need[ee];
+        int carry = 0, d = -1, hc = 0, before = 0;
+        for (int r0 = 0; r0 < nb; r0 += 32 * 8) {
+          int v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = r0 + u * 32 + lane;
+            v[u] = (i < nb) ? __ldcg(&gh[ee * gstride + i]) : 0;
           }
-          const unsigned long long c = ((unsigned long long)(wv & SEL_KEY_MASK) << 32) | (unsigned long long)s;
-          const unsigned m = __ballot_sync(0xffffffffu, hit);       // one shared atomic per warp, not per candidate
-          if (m) {
-            int base = 0;
-            if (lane == __ffs(m) - 1) base = atomicAdd(&sh.n_list, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-            if (hit) sh.list[base + __popc(m & ((1u << lane) - 1u))] = c;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int inc = carry + warp_incl_scan(v[u], lane);
+            const bool here = d < 0 && inc >= need && inc - v[u] < need;
+            const unsigned hm = __ballot_sync(0xffffffffu, here);
+            if (hm) {
+              const int src = __ffs(hm) - 1;
+              d = r0 + u * 32 + src;
+              hc = __shfl_sync(0xffffffffu, v[u], src);
+              before = __shfl_sync(0xffffffffu, inc - v[u], src);
+            }
+            carry = __shfl_sync(0xffffffffu, inc, 31);
           }
-        });
-        from_list = true;
+          if (d >= 0) break;
+        }
+        if (lane == 0) {
+          const int need2 = need - before;
+          const unsigned long long pv = sh.pval[ee] | ((unsigned long long)d << dshift);
+          sh.pval[ee] = pv;
+          sh.pmask[ee] |= dmask << dshift;
+          sh.need[ee] = need2;
+          if (need2 == hc || dshift == 0) {       // the whole digit bucket is kept
+            const unsigned long long T = pv | ((1ull << dshift) - 1ull);
+            sh.Tk[ee] = (uint32_t)(T >> 32);
+            sh.Ts[ee] = (long long)(T & 0xffffffffull);
+            sh.done[ee] = 1;
+          }
+        }
       }
-      have_hist = false;
-      ++level;
       __syncthreads();
+      mark(10 + lv);
     }
   }
   mark(3);
-  // ---- ordered write: rows for the kept samples (index order) and for the dropped ones.  Two sweeps over the words,
-  //      one warp per 128-sample segment and no block barrier inside a sweep: (1) kept / dropped counts per segment,
-  //      (block-wide exclusive scan), (2) rows = segment base + ballot rank.  Chunks larger than SEL_SEG_SMEM
-  //      segments are processed in groups with running bases. ----
-  {
-    const bool by_rank = !(a.bpr && !a.no_batch);     // plain order: kept iff the index-order rank is below the capacity
-    const int64_t nseg = (S + SEL_SEG - 1) / SEL_SEG;
-    int run_keep = 0, run_drop = 0;                   // block-uniform running totals (by_rank: run_keep = rank base)
-    auto load_seg = [&](int64_t g, uint32_t (&wv)[4]) {
-      const int64_t s0 = g * SEL_SEG + 4 * lane;
-      wv[0] = wv[1] = wv[2] = wv[3] = 0xffffffffu;
-      if (s0 + 3 < S) {
-        const uint4 q = *reinterpret_cast<const uint4*>(w + s0);
-        wv[0] = q.x; wv[1] = q.y; wv[2] = q.z; wv[3] = q.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (s0 + j < S) wv[j] = w[s0 + j];
-      }
-    };
-    // kept iff mine && (key, sample) <= T.  32-bit form: d = word - (e << 26) is the key when the word is mine and
-    // >= 2^26 otherwise; d < Tk: kept, d > Tk: dropped, d == Tk (ties of the threshold key, rare): by sample index.
-    // Padding words (0xffffffff) are nobody's: the host requires E < 63.
-    const uint32_t ebase = (uint32_t)e << SEL_KEY_BITS;
-    const bool keep_all = by_rank || T == ~0ull;       // no threshold: every word of mine is "kept" at this stage
-    const uint32_t Tk = keep_all ? (SEL_KEY_MASK + 1u) : (uint32_t)(T >> 32);
-    const long long Ts = keep_all ? -1 : (long long)(T & 0xffffffffull);
-    // per lane: bit j of `kp` / `dr` = word j of this lane is mine and kept / mine and dropped
-    auto classify = [&](int g, const uint32_t (&wv)[4], uint32_t& kp, uint32_t& dr) {
-      const long long lim = Ts - ((long long)g * SEL_SEG + 4 * lane);        // tie at sample s0 + j kept iff j <= lim
-      kp = dr = 0u;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t d = wv[j] - ebase;
-        const bool k = (d < Tk) || (d == Tk && (long long)j <= lim);
-        kp |= (k ? 1u : 0u) << j;
-        dr |= ((d <= SEL_KEY_MASK && !k) ? 1u : 0u) << j;
-      }
-    };
-    // packed (kept | dropped << 16) counts of the lanes below this one, and the segment totals
-    auto lane_prefix = [&](uint32_t kp, uint32_t dr, uint32_t& total) {
-      const uint32_t mine = (uint32_t)__popc(kp) | ((uint32_t)__popc(dr) << 16);
-      uint32_t inc = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      total = __shfl_sync(0xffffffffu, inc, 31);
-      return inc - mine;
-    };
-    const bool taps = a.loc || a.idx || a.moe_idx || a.gate;
-    constexpr int NW = SEL_THREADS / 32, UF = 4;      // UF segments in flight per warp (independent 16-byte loads)
-    for (int64_t g0 = 0; g0 < nseg; g0 += SEL_SEG_SMEM) {
-      const int ng = (int)min((int64_t)SEL_SEG_SMEM, nseg - g0);
-      for (int gb = wid; gb < ng; gb += NW * UF) {
-        uint32_t wv[UF][4];
-#pragma unroll
-        for (int u = 0; u < UF; ++u) if (gb + u * NW < ng) load_seg(g0 + gb + u * NW, wv[u]);
-#pragma unroll
-        for (int u = 0; u < UF; ++u) {
-          const int g = gb + u * NW;
-          if (g >= ng) break;
-          uint32_t kp, dr, total;
-          classify((int)g0 + g, wv[u], kp, dr);
-          lane_prefix(kp, dr, total);
-          if (lane == 0) sh.seg[g] = total;
-        }
-      }
+  // key of a word: expert * 2 + (dropped by the threshold); 63 = nobody's
+  auto key_of = [&](uint32_t wv, int64_t s) -> int {
+    const int ee = (int)(wv >> SEL_KEY_BITS);
+    if (ee >= E || s >= S) return 63;
+    const uint32_t d = wv & SEL_KEY_MASK;
+    const bool kp = (d < sh.Tk[ee]) || (d == sh.Tk[ee] && (long long)s <= sh.Ts[ee]);
+    return 2 * ee + (kp ? 0 : 1);
+  };
+  // ---- totals of my range per key -> global, barrier, my first rank in every bucket ----
+  if (tid < 32) { sh.tot[tid] = 0; sh.run[tid] = 0; }
+  __syncthreads();
+  for (int64_t v = v0 + wid; v < v1; v += SEL_THREADS / 32) {
+    const int k = key_of(word_at(v), v * 32 + lane);
+    const unsigned m = __match_any_sync(0xffffffffu, k);
+    if (k < 32 && lane == __ffs(m) - 1) atomicAdd(&sh.tot[k], __popc(m));
+  }
+  __syncthreads();
+  int* cnt_pe = a.zero + SEL_Z_CNT;
+  if (tid < 32) cnt_pe[p * 32 + tid] = sh.tot[tid];
+  sel_grid_barrier(&bar[nbar++], P);
+  if (tid < 32) {
+    int b = 0;
+    for (int q = 0; q < p; ++q) b += __ldcg(&cnt_pe[q * 32 + tid]);
+    sh.base[tid] = b;
+  }
+  __syncthreads();
+  mark(4);
+  // ---- ordered write, in groups of SEL_VIS visits ----
+  const bool taps = a.loc || a.idx || a.moe_idx || a.gate;
+  for (int64_t g0 = v0; g0 < v1; g0 += SEL_VIS) {
+    const int nv = (int)min((int64_t)SEL_VIS, v1 - g0);
+    for (int i = tid; i < nv * 16; i += SEL_THREADS) reinterpret_cast<uint32_t*>(&sh.segcnt[0][0])[i] = 0u;
+    __syncthreads();
+    for (int v = wid; v < nv; v += SEL_THREADS / 32) {
+      const int k = key_of(word_at(g0 + v), (g0 + v) * 32 + lane);
+      const unsigned m = __match_any_sync(0xffffffffu, k);
+      if (k < 32 && lane == __ffs(m) - 1) sh.segcnt[v][k] = (uint16_t)__popc(m);
+    }
+    __syncthreads();
+    {
+      // exclusive prefix over the visits, per key: thread (key = tid & 31, part = tid >> 5) owns visits [part*per, +per)
+      const int k = tid & 31, part = tid >> 5, per = (nv + 31) / 32;
+      const int a0 = part * per, a1 = min(nv, a0 + per);
+      int sum = 0;
+      for (int v = a0; v < a1; ++v) sum += sh.segcnt[v][k];
+      sh.part[part][k] = sum;
       __syncthreads();
-      // exclusive scan of the (<= 2048) packed counts: 2 per thread
-      {
-        const uint32_t v0 = (2 * tid < ng) ? sh.seg[2 * tid] : 0u, v1 = (2 * tid + 1 < ng) ? sh.seg[2 * tid + 1] : 0u;
-        int k = (int)((v0 & 0xffffu) + (v1 & 0xffffu)), d = (int)((v0 >> 16) + (v1 >> 16));
-        int ki = warp_incl_scan(k, lane), di = warp_incl_scan(d, lane);
-        if (lane == 31) { sh.wtot[wid] = ki; sh.hist[wid] = di; }
-        __syncthreads();
-        int kb = 0, db = 0;
-        for (int ww = 0; ww < wid; ++ww) { kb += sh.wtot[ww]; db += sh.hist[ww]; }
-        int ktot = 0, dtot = 0;
-        for (int ww = 0; ww < 32; ++ww) { ktot += sh.wtot[ww]; dtot += sh.hist[ww]; }
-        __syncthreads();
-        const int ke = run_keep + kb + ki - k, de = run_drop + db + di - d;     // exclusive prefixes of segment 2*tid
-        // kept prefix goes back into seg[], dropped prefix into the (now unused) candidate list
-        int* dpre = reinterpret_cast<int*>(sh.list);
-        if (2 * tid < ng) { sh.seg[2 * tid] = (uint32_t)ke; dpre[2 * tid] = de; }
-        if (2 * tid + 1 < ng) { sh.seg[2 * tid + 1] = (uint32_t)(ke + (int)(v0 & 0xffffu)); dpre[2 * tid + 1] = de + (int)(v0 >> 16); }
-        run_keep += ktot;
-        run_drop += dtot;
-        __syncthreads();
-      }
-      const int* dpre = reinterpret_cast<const int*>(sh.list);
-      int* stage = reinterpret_cast<int*>(sh.list) + SEL_SEG_SMEM + wid * SEL_SEG;     // per-warp, behind dpre[]
-      for (int gb = wid; gb < ng; gb += NW * UF) {
-        uint32_t wv[UF][4];
-#pragma unroll
-        for (int u = 0; u < UF; ++u) if (gb + u * NW < ng) load_seg(g0 + gb + u * NW, wv[u]);
-#pragma unroll
-        for (int u = 0; u < UF; ++u) {
-          const int g = gb + u * NW;
-          if (g >= ng) break;
-          uint32_t kp, dr, total;
-          classify((int)g0 + g, wv[u], kp, dr);
-          const uint32_t pre = lane_prefix(kp, dr, total);
-          int kb = (int)sh.seg[g], db = dpre[g];       // first kept / dropped slot of this segment
-          int nk = (int)(total & 0xffffu), nd = (int)(total >> 16);
-          int kl = (int)(pre & 0xffffu), dl = (int)(pre >> 16);     // my first kept / dropped rank inside the segment
-          if (by_rank) {
-            // every word of mine came out as "kept" with its index-order rank kb + kl; the capacity cuts the ranks
-            const int cut = max(0, min(nk, keep_cap - kb));          // ranks [0, cut) of this segment are kept
-            dr = 0u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (((kp >> j) & 1u) && kl + __popc(kp & ((1u << j) - 1u)) >= cut) { dr |= 1u << j; }
-            kp &= ~dr;
-            dl = max(0, kl - cut);
-            kl = min(kl, cut);
-            db = max(kb, keep_cap) - keep_cap;
-            nd = nk - cut;
-            nk = cut;
-          }
-          const int s_lane = ((int)g0 + g) * SEL_SEG + 4 * lane;
-          // rows of one segment are consecutive per class: stage the sample ids in shared memory by rank (kept from
-          // the front, dropped from the back), the warp stores them coalesced below
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if ((kp >> j) & 1u) stage[kl + __popc(kp & ((1u << j) - 1u))] = s_lane + j;
-            if ((dr >> j) & 1u) stage[SEL_SEG - 1 - (dl + __popc(dr & ((1u << j) - 1u)))] = s_lane + j;
-          }
-          if (taps) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const bool k = (kp >> j) & 1u, d = (dr >> j) & 1u;
-              if (k || d) {
-                const int s = s_lane + j;
-                const int slot = k ? kb + kl + __popc(kp & ((1u << j) - 1u)) : db + dl + __popc(dr & ((1u << j) - 1u));
-                if (a.loc) a.loc[s] = k ? slot : cap + slot;
-                if (a.idx) a.idx[s] = e;
-                if (a.moe_idx) a.moe_idx[s] = e;
-                if (a.gate) a.gate[s] = sel_gate(wv[u][j]);
-              }
-            }
-          }
-          if (a.tt.row2sample) {
-            __syncwarp();
-            if (lane < nk) a.tt.row2sample[seg0 + kb + lane] = stage[lane];
-            for (int i = lane + 32; i < nk; i += 32) a.tt.row2sample[seg0 + kb + i] = stage[i];
-            if (lane < nd) a.tt.row2sample[drop0 + drop_before + db + lane] = stage[SEL_SEG - 1 - lane];
-            for (int i = lane + 32; i < nd; i += 32) a.tt.row2sample[drop0 + drop_before + db + i] = stage[SEL_SEG - 1 - i];
-            __syncwarp();
-          }
+      int pre = 0;
+      for (int q = 0; q < part; ++q) pre += sh.part[q][k];
+      for (int v = a0; v < a1; ++v) { const int c = sh.segcnt[v][k]; sh.segcnt[v][k] = (uint16_t)pre; pre += c; }
+      __syncthreads();
+    }
+    for (int v = wid; v < nv; v += SEL_THREADS / 32) {
+      const int64_t s = (g0 + v) * 32 + lane;
+      const uint32_t wv = word_at(g0 + v);
+      const int k = key_of(wv, s);
+      const unsigned m = __match_any_sync(0xffffffffu, k);
+      if (k < 32) {
+        const int ee = k >> 1;
+        int r = sh.base[k] + sh.run[k] + (int)sh.segcnt[v][k] + __popc(m & ((1u << lane) - 1u));
+        bool kept = !(k & 1);
+        if (by_rank) { kept = r < keep_cap; if (!kept) r -= keep_cap; }
+        if (a.tt.row2sample) a.tt.row2sample[kept ? sh.seg0[ee] + r : sh.seg0[E] + sh.dropb[ee] + r] = (int)s;
+        if (taps) {
+          if (a.loc) a.loc[s] = kept ? r : cap + r;
+          if (a.idx) a.idx[s] = ee;
+          if (a.moe_idx) a.moe_idx[s] = ee;
+          if (a.gate) a.gate[s] = sel_gate(wv);
         }
+      }
+    }
+    __syncthreads();
+    if (g0 + SEL_VIS < v1) {
+      if (tid < 32) {
+        int t = 0;
+        for (int q = 0; q < 32; ++q) t += sh.part[q][tid];
+        sh.run[tid] += t;
       }
       __syncthreads();
     }
   }
-  mark(4);
+  mark(5);
   // ---- load-balance loss: l_aux = E / S^2 * sum_e me_e * ce_e (tutel_fast_dispatch.py:143-145).  Every CTA folds its
   //      share of the partial column-sum records (fixed order, double); the last CTA to arrive adds the shares in CTA
   //      order, so the result does not depend on timing or on the grid of launch #1 ----
   if (a.l_aux) {
     const int col = tid & (SEL_MAX_E - 1);
-    const int r0 = (int)((int64_t)a.npm * e / E), r1 = (int)((int64_t)a.npm * (e + 1) / E);
+    const int r0 = (int)((int64_t)a.npm * p / P), r1 = (int)((int64_t)a.npm * (p + 1) / P);
     double acc = 0.0;
     for (int i = r0 + (tid >> 4); i < r1; i += SEL_THREADS / SEL_MAX_E) acc += (double)a.pm[(int64_t)i * SEL_PM_STRIDE + col];
     acc += __shfl_xor_sync(0xffffffffu, acc, 16);         // lanes c and c+16 of a warp share column c
@@ -761,26 +724,11 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
     if (tid < SEL_MAX_E) {
       double me = 0.0;
       for (int ww = 0; ww < 32; ++ww) me += sh.red[ww][tid];
-      a.lpart[e * SEL_PM_STRIDE + tid] = me;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) sh.ch_d = (atomicAdd(a.ticket, 1) == E - 1);
-    __syncthreads();
-    if (sh.ch_d && tid == 0) {
-      __threadfence();
-      float tot = 0.f;
-      for (int ee = 0; ee < E; ++ee) {
-        double me = 0.0;
-        for (int c = 0; c < E; ++c) me += ((volatile double*)a.lpart)[c * SEL_PM_STRIDE + ee];
-        tot += (float)me * (float)sh.cnt[ee];            // me * ce in fp32
-      }
-      *a.l_aux = (float)((double)tot * ((double)E / ((double)S * (double)S)));
-      *a.ticket = 0;
+      a.lpart[p * SEL_PM_STRIDE + tid] = me;
     }
   }
   // ---- CTA 0: counts, capacity and the tile table of launch #2 ----
-  if (e == 0) {
+  if (p == 0) {
     if (tid < E && a.counts) a.counts[tid] = sh.cnt[tid];
     if (tid == 0 && a.cap_dev) *a.cap_dev = cap;
     if (a.tt.n_tiles) {
@@ -803,14 +751,40 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
       if (tid == 0) { *a.tt.n_tiles = nt; *a.tt.drop_counter = 0; }
     }
   }
-  mark(5);
+  // ---- the last CTA to get here combines the l_aux shares and cleans the zero-between-uses region ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) sh.flag = (atomicAdd(&a.zero[SEL_Z_TICKET], 1) == P - 1);
+  __syncthreads();
+  if (sh.flag) {
+    __threadfence();
+    if (a.l_aux && tid == 0) {
+      float tot = 0.f;
+      for (int ee = 0; ee < E; ++ee) {
+        double me = 0.0;
+        for (int c = 0; c < P; ++c) me += ((volatile double*)a.lpart)[c * SEL_PM_STRIDE + ee];
+        tot += (float)me * (float)sh.cnt[ee];            // me * ce in fp32
+      }
+      *a.l_aux = (float)((double)tot * ((double)E / ((double)S * (double)S)));
+    }
+    if (a.self_clean) {
+      for (int i = tid; i < SEL_Z_LVH + lv_used * SEL_MAX_E * 1024; i += SEL_THREADS) a.zero[i] = 0;
+    }
+  }
+  mark(6);
 }
 
 int route_select_launch(const SelectArgs& a, cudaStream_t st) {
   SNB_REQUIRE(a.E >= 1 && a.E <= SEL_MAX_E, "route_select: E=%d out of range [1,%d]", a.E, SEL_MAX_E);
   SNB_REQUIRE(a.S >= 1 && a.S < (1ll << 31), "route_select: S=%lld out of range", (long long)a.S);
-  SNB_REQUIRE((reinterpret_cast<uintptr_t>(a.w) & 15) == 0, "route_select: packed words must be 16-byte aligned");
-  k_select<<<a.E, SEL_THREADS, 0, st>>>(a);
+  static bool attr_done_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done_dev[dev & 63]) {
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
+    attr_done_dev[dev & 63] = true;
+  }
+  k_select<<<SEL_P, SEL_THREADS, sizeof(SelSmem), st>>>(a);
   SNB_CHECK_LAUNCH("k_select");
   return SNB_OK;
 }
@@ -848,7 +822,7 @@ int route_select_from_gates(const float* gates, int64_t S, int32_t E, double cf,
   SelectArgs a = {};
   int rc = route_pack_top1(gates, S, E, w, hist0, pm, &a.npm, st);
   if (rc) return rc;
-  a.w = w; a.pm = pm; a.hist0 = hist0; a.ticket = hist0 + SEL_MAX_E * SEL_HBINS; a.lpart = lpart;
+  a.w = w; a.pm = pm; a.zero = hist0; a.lpart = lpart;
   a.S = S; a.E = E; a.cf = cf; a.bpr = bpr; a.no_batch = no_batch;
   a.idx = idx; a.loc = loc; a.gate = gate; a.counts = counts; a.cap_dev = capacity; a.l_aux = l_aux;
   return route_select_launch(a, st);

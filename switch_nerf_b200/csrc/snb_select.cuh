@@ -15,7 +15,13 @@ constexpr int SEL_L1_SHIFT = 19;                 // level-0 digit = key bits [19
 constexpr int SEL_L2_SHIFT = 9;                  // level-1 digit = key bits [9, 19), level-2 digit = key bits [0, 9)
 constexpr int SEL_HBINS = 1 << (SEL_KEY_BITS - SEL_L1_SHIFT);
 constexpr int SEL_PM_STRIDE = 16;                // floats per partial-column-sum record
-constexpr int SEL_ZERO_INTS = SEL_MAX_E * SEL_HBINS + 64;   // histogram + ticket: zeroed by the host before launch #1
+// region zeroed by the host (one memset) before launch #1 of a chunk, in ints:
+constexpr int SEL_Z_TICKET = SEL_MAX_E * SEL_HBINS;          // [0, SEL_Z_TICKET) = level-0 histogram; then the l_aux ticket,
+constexpr int SEL_Z_BAR = SEL_Z_TICKET + 16;                 // the grid-barrier counters of k_select,
+constexpr int SEL_Z_CNT = SEL_Z_BAR + 16;                    // the per-(CTA, key) totals [16][32],
+constexpr int SEL_Z_LVH = SEL_Z_CNT + 16 * 32;               // the level histograms [6][SEL_MAX_E][1024]
+constexpr int SEL_LVH_INTS = 6 * SEL_MAX_E * 1024;
+constexpr int SEL_ZERO_INTS = SEL_Z_LVH + SEL_LVH_INTS;
 // records a chunk can produce: one per 32 rows (launch #1) or one per 2048 samples (k_pack_top1)
 __host__ __device__ inline int64_t SEL_PM_RECORDS(int64_t S) { return 4 * ((S + 127) / 128) + 4; }
 
@@ -29,11 +35,11 @@ __device__ __forceinline__ float sel_gate(uint32_t w) { return __uint_as_float(0
 
 struct SelectArgs {
   const uint32_t* w;        // [S] packed words (16-byte aligned)
-  const int* hist0;         // [SEL_MAX_E][SEL_HBINS] histogram of the top 9 key bits per expert (accumulated by launch #1)
+  int* zero;                // the zeroed region (SEL_Z_*): level-0 key histogram per expert accumulated by launch #1 first
+  int self_clean;           // 1: the last CTA zeroes what this chunk dirtied (the region is zero again when the kernel ends)
   const float* pm;          // [npm][SEL_PM_STRIDE] partial column sums of the gates (load-balance loss)
   int npm;
-  double* lpart;            // [SEL_MAX_E][SEL_PM_STRIDE] per-CTA partial column sums (scratch)
-  int* ticket;              // [1] zero on entry: the last CTA to arrive combines the partial sums
+  double* lpart;            // [16][SEL_PM_STRIDE] per-CTA partial column sums (scratch)
   int64_t S;
   int E;
   double cf;

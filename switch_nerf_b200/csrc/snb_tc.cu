@@ -100,6 +100,7 @@ struct TcParams {
   int E, skip_layer, pos_xyz_freqs, pos_dir_freqs, appearance_dim, appearance_count, hidden2, x_cols;
   const float* emb_a;       // fp32 [count, A]
   unsigned long long* tl;   // debug timeline (nullable): [role][TL_N] (tag<<48 | clock) marks of CTA 0
+  int ab;                   // debug A/B switches (SNB_FRONT_AB): 1 = no level-0 histogram, 2 = no column sums
 };
 
 // canonical image: slices of 64 k; inside a slice (n/8)*(klen*16) + (kk/8)*128 + (n%8)*16 + (kk%8)*2 bytes
@@ -1159,7 +1160,6 @@ size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf) {
   b += 4096;                                          // small scalars
   b += align_up((size_t)S * 4, 256);                  // packed routing words (snb_select.cuh)
   b += align_up((size_t)SEL_PM_RECORDS(S) * SEL_PM_STRIDE * 4, 256);   // partial column sums of the gates
-  b += align_up((size_t)SEL_ZERO_INTS * 4, 256);                        // level-0 key histogram + ticket
   b += align_up((size_t)SEL_MAX_E * SEL_PM_STRIDE * 8, 256);            // per-CTA partial column sums of k_select
   b += route_workspace_bytes(S, E);
   return b + 4096;
@@ -1203,7 +1203,7 @@ struct TcChunk {
 
 static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const float* sigma_noise,
                          const snb_route_opts* o, float* out, int32_t* moe_idx, float* l_aux, float* dbg_gates,
-                         int32_t* dbg_loc, Arena& ws, cudaStream_t st) {
+                         int32_t* dbg_loc, Arena& ws, cudaStream_t st, int set = 0) {
   SNB_REQUIRE(m->tc_blob, "tc_forward: weights were not packed");
   c.Pf = ((TcOwner*)m->tc_blob)->h.p;
   c.Pb = c.Pf;
@@ -1246,7 +1246,13 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
   int* small = ws.take<int>(1024);
   c.wsel = ws.take<uint32_t>(S);
   c.pm = ws.take<float>((size_t)SEL_PM_RECORDS(S) * SEL_PM_STRIDE);
-  c.hist0 = ws.take<int>((size_t)SEL_ZERO_INTS);
+  // zero-between-uses scratch of the routing (level-0 histogram written by launch #1, barrier counters, level
+  // histograms): owned by the model, zeroed once here and cleaned by k_select itself after every use
+  if (!m->sel_zero) {
+    SNB_CHECK_CUDA(cudaMalloc((void**)&m->sel_zero, (size_t)4 * SEL_ZERO_INTS * sizeof(int)));
+    SNB_CHECK_CUDA(cudaMemsetAsync(m->sel_zero, 0, (size_t)4 * SEL_ZERO_INTS * sizeof(int), st));
+  }
+  c.hist0 = m->sel_zero + (size_t)(set & 3) * SEL_ZERO_INTS;
   c.lpart = ws.take<double>((size_t)SEL_MAX_E * SEL_PM_STRIDE);
   c.npm = 0;
   c.front_packed = false;
@@ -1287,7 +1293,6 @@ static int tc_front(Model* m, TcChunk& c, cudaStream_t st) {
   const int n_front_tiles = (int)cdiv(c.S, TILE);
   int grid1 = n_front_tiles < c.grid_cap ? n_front_tiles : c.grid_cap;
   if (c.pe) cudaEventRecord(c.pe->e[0], st);
-  if (c.select) SNB_CHECK_CUDA(cudaMemsetAsync(c.hist0, 0, (size_t)SEL_ZERO_INTS * sizeof(int), st));
   if (c.cg == 2) {
     grid1 = (grid1 + 1) & ~1;
     if (grid1 > (c.grid_cap & ~1)) grid1 = c.grid_cap & ~1;
@@ -1306,6 +1311,8 @@ static int tc_front(Model* m, TcChunk& c, cudaStream_t st) {
       // the [S,E] gates only leave the kernel when a caller taps them (or the full-order routing needs them)
       // the kernel keeps 16-bit row counters per CTA: a CTA must see fewer than 65536 rows (else k_pack_top1 does it)
       const bool pack = c.select && (int64_t)cdiv(n_front_tiles, grid1) * TILE < 65536;
+      static const int ab_env = getenv("SNB_FRONT_AB") ? atoi(getenv("SNB_FRONT_AB")) : 0;
+      c.Pf.ab = ab_env;
       float* gates_out = pack ? c.dbg_gates : c.gates;
       k_front_ts<12><<<grid1, THREADS, TSM_TOTAL, st>>>(c.Pf, c.x, c.S, gates_out, pack ? c.wsel : nullptr, c.hist0,
                                                          pack ? c.pm : nullptr, pack ? c.moe_idx : nullptr);
@@ -1331,8 +1338,7 @@ static int tc_route(Model* m, TcChunk& c, cudaStream_t st) {
       if (c.dbg_gates) SNB_CHECK_CUDA(cudaMemcpyAsync(c.dbg_gates, c.gates, sizeof(float) * c.S * E, cudaMemcpyDeviceToDevice, st));
     }
     SelectArgs a = {};
-    a.w = c.wsel; a.hist0 = c.hist0; a.pm = c.pm; a.npm = c.npm;
-    a.ticket = c.hist0 + SEL_MAX_E * SEL_HBINS; a.lpart = c.lpart;
+    a.w = c.wsel; a.zero = c.hist0; a.pm = c.pm; a.npm = c.npm; a.lpart = c.lpart; a.self_clean = 1;
     a.S = c.S; a.E = E; a.cf = c.o.capacity_factor; a.bpr = c.o.no_batch ? 0 : c.o.bpr; a.no_batch = c.o.no_batch;
     a.pair = c.cg_back == 2;
     a.counts = c.counts; a.cap_dev = c.cap_dev; a.l_aux = c.l_aux;
@@ -1373,7 +1379,7 @@ static int tc_route(Model* m, TcChunk& c, cudaStream_t st) {
   return SNB_OK;
 }
 
-static int tc_back(Model* m, TcChunk& c, cudaStream_t st) {
+static int tc_back(Model* m, TcChunk& c, cudaStream_t st, bool finish_inline = true) {
   int grid2 = (int)(c.max_tiles < c.grid_cap ? c.max_tiles : c.grid_cap);
   RowIO io = {};
   if (m->ep) {
@@ -1406,7 +1412,7 @@ static int tc_back(Model* m, TcChunk& c, cudaStream_t st) {
     k_back<4, 1><<<grid2, THREADS, SM_TOTAL, st>>>(c.Pb, c.tt, io, c.H);
   }
   SNB_CHECK_LAUNCH("k_back");
-  if (m->ep) {
+  if (m->ep && finish_inline) {
     int rc = ep_finish(m->ep, c.set, c.out, c.S, st);
     if (rc) return rc;
   }
@@ -1463,12 +1469,39 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
   TcChunk cc[MAXSETS];
   int ci = 0;
   int rc;
+  // expert parallelism: the wait for the peers' result rows of chunk c (flag B of every peer) and the copy of the rows
+  // into `out` run on a third stream, so a slower peer never stalls this rank's launches; the main stream only joins
+  // at the end of the pass (the routing stream joins before the buffer set is reused, NS chunks later)
+  const bool fin_async = m->ep != nullptr;
+  bool fin_pending[MAXSETS] = {false, false, false, false};
+  if (fin_async && !m->fin_stream) {
+    int prio_lo = 0, prio_hi = 0;
+    SNB_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    SNB_CHECK_CUDA(cudaStreamCreateWithPriority(&m->fin_stream, cudaStreamNonBlocking, prio_hi));
+    for (int i = 0; i < MAXSETS; ++i) {
+      SNB_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_back[i], cudaEventDisableTiming));
+      SNB_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_fin[i], cudaEventDisableTiming));
+    }
+  }
+  auto back_of = [&](int kb) -> int {
+    SNB_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_route[kb], 0));
+    int r = tc_back(m, cc[kb], st, !fin_async);
+    if (r) return r;
+    if (fin_async) {
+      SNB_CHECK_CUDA(cudaEventRecord(m->ev_back[kb], st));
+      SNB_CHECK_CUDA(cudaStreamWaitEvent(m->fin_stream, m->ev_back[kb], 0));
+      if ((r = ep_finish(m->ep, cc[kb].set, cc[kb].out, cc[kb].S, m->fin_stream))) return r;
+      SNB_CHECK_CUDA(cudaEventRecord(m->ev_fin[kb], m->fin_stream));
+      fin_pending[kb] = true;
+    }
+    return SNB_OK;
+  };
   for (int64_t i = 0; i < B; i += chunk, ++ci) {
     const int64_t rows = (B - i < chunk) ? (B - i) : chunk;
     const int k = ci % NS;
     Arena a((char*)ws_base + (size_t)k * ws_stride, ws_stride);
     if ((rc = tc_chunk_init(m, cc[k], x + i * m->x_cols, rows, nullptr, o, out + i * 4, moe_idx ? moe_idx + i : nullptr,
-                            l_aux ? l_aux + ci : nullptr, nullptr, nullptr, a, st)))
+                            l_aux ? l_aux + ci : nullptr, nullptr, nullptr, a, st, k)))
       return rc;
     cc[k].set = k;
     cc[k].grid_cap = grid_cap;
@@ -1476,19 +1509,21 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
     if (back_full) cc[k].grid_cap = m->sm_count;
     SNB_CHECK_CUDA(cudaEventRecord(m->ev_front[k], st));
     SNB_CHECK_CUDA(cudaStreamWaitEvent(sr, m->ev_front[k], 0));
+    if (fin_pending[k]) {
+      // the expert-parallel buffers of this set are about to be reused: this rank may only send the records of the
+      // new chunk after every peer finished the old one (flag B seen => the peers no longer read rx[k]) and the old
+      // result rows were copied out of ret[k].  Only the routing stream waits; launch #1 above does not.
+      SNB_CHECK_CUDA(cudaStreamWaitEvent(sr, m->ev_fin[k], 0));
+      fin_pending[k] = false;
+    }
     if ((rc = tc_route(m, cc[k], sr))) return rc;
     SNB_CHECK_CUDA(cudaEventRecord(m->ev_route[k], sr));
-    if (ci >= D) {
-      const int kb = (ci - D) % NS;
-      SNB_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_route[kb], 0));
-      if ((rc = tc_back(m, cc[kb], st))) return rc;
-    }
+    if (ci >= D && (rc = back_of((ci - D) % NS))) return rc;
   }
-  for (int j = (ci - D > 0 ? ci - D : 0); j < ci; ++j) {
-    const int kb = j % NS;
-    SNB_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_route[kb], 0));
-    if ((rc = tc_back(m, cc[kb], st))) return rc;
-  }
+  for (int j = (ci - D > 0 ? ci - D : 0); j < ci; ++j)
+    if ((rc = back_of(j % NS))) return rc;
+  for (int k = 0; k < MAXSETS; ++k)
+    if (fin_pending[k]) SNB_CHECK_CUDA(cudaStreamWaitEvent(st, m->ev_fin[k], 0));
   return SNB_OK;
 }
 

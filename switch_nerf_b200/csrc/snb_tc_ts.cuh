@@ -748,12 +748,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
                 const uint32_t key = sel_key(bv);
                 wsel[s] = sel_pack(best, key);
                 const int bin = best * SEL_HBINS + (int)(key >> SEL_L1_SHIFT);
-                atomicAdd(&s_hist[bin >> 1], 1u << (16 * (bin & 1)));
+                if (!(P.ab & 1)) atomicAdd(&s_hist[bin >> 1], 1u << (16 * (bin & 1)));
                 if (moe_idx) moe_idx[s] = best;
               }
             }
           }
-          if (pm && ec.cs == 0) {
+          if (pm && ec.cs == 0 && !(P.ab & 2)) {
             // column sums of the gates over the 32 rows of this warp (load-balance loss), in a fixed order that does
             // not depend on the grid: 16 values x 32 lanes folded by a transpose-reduction (16 shuffles), after which
             // even lane l holds the sum of expert ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1).
