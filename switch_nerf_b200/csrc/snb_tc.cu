@@ -1458,8 +1458,10 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
   // local experts + select routing: k_select is E CTAs of 1024 threads (one per SM); expert-parallel: the routing
   // stage also scatters records to the peers and waits for theirs (r1q/r1r)
   static const bool route_full_env = getenv("SNB_ROUTE_FULL") != nullptr;
-  const int sel_sms = m->d.num_experts > 8 ? m->d.num_experts : 8;
-  const int route_sms = route_env >= 0 ? route_env : (m->ep ? 36 : (route_full_env ? 28 : sel_sms));
+  const int sel_sms = 8;      // k_select: SEL_P = 8 CTAs of 1024 threads, one per SM
+  // (r2t, N=2 expert-parallel: 8 / 16 / 36 SMs -> 729 / 726 / 682 M samples/s: the record scatter and the plan kernel are
+  // short and follow k_select on the same SMs)
+  const int route_sms = route_env >= 0 ? route_env : (route_full_env ? (m->ep ? 36 : 28) : sel_sms);
   int D = depth_env >= 1 ? depth_env : (m->ep ? 3 : 2);
   if (D > nsets - 1) D = nsets - 1;
   if (D > MAXSETS - 1) D = MAXSETS - 1;
