@@ -341,7 +341,8 @@ int snb_moe_forward(snb_model_t* mm, const float* x, int64_t S, const float* sig
     return fp32_forward(m, x, S, sigma_noise, opts, out, moe_idx, l_aux, dbg_gates, dbg_loc, ws, st);
   if (precision == SNB_PREC_BF16) {
     if (!tc_supported(m)) {
-      set_error("SNB_PREC_BF16 (tcgen05) supports width 256/512 topologies only (got width=%d, hidden2=%d)",
+      set_error("SNB_PREC_BF16 (tcgen05) supports the Building / Mission-Bay topologies only: width 256 or 512, hidden2 <= 256, "
+                "pos_xyz_dim 12, pos_dir_dim 4, a skip layer for width 512 / mip (got width=%d, hidden2=%d)",
                 m->d.width, m->d.hidden2);
       return SNB_EUNSUPPORTED;
     }
@@ -482,7 +483,7 @@ static size_t render_mip_ws_layout(const Model* m, int64_t N, const snb_render_o
   if (chunk < 1) chunk = 1;
   size_t mw = align_up(snb_workspace_bytes((const snb_model_t*)m, chunk, o->route.capacity_factor), 256);
   if (model_ws) *model_ws = mw;
-  size_t b = mw;
+  size_t b = 4 * mw;                         // workspace sets of the chunk pipeline (tc_forward_chunks)
   auto add = [&](size_t n) { b += align_up(n * sizeof(float), 256); };
   add((size_t)N * Sc);                       // coarse edges
   add((size_t)N * (Sf > 0 ? Sf : 1));        // fine edges
@@ -516,7 +517,7 @@ int snb_render_rays_mip(snb_model_t* mm, const float* rays, const float* radii, 
   size_t need = render_mip_ws_layout(m, N, o, &model_ws);
   if (workspace_bytes < need) { set_error("snb_render_rays_mip: workspace %zu < required %zu", workspace_bytes, need); return SNB_EWORKSPACE; }
   Arena a(workspace, workspace_bytes);
-  char* mws = a.take<char>(model_ws);
+  char* mws = a.take<char>(4 * model_ws);
   float* zc = a.take<float>((size_t)N * Sc);
   float* zf = a.take<float>((size_t)N * (Sf > 0 ? Sf : 1));
   float* wc = a.take<float>((size_t)N * (Sc - 1));
@@ -534,6 +535,8 @@ int snb_render_rays_mip(snb_model_t* mm, const float* rays, const float* radii, 
     int rc = mip_fill_x_launch(rays, radii, image_indices, ze, N, Se, x, st);
     if (rc) return rc;
     const int64_t B = N * (Se - 1);
+    if (o->precision == SNB_PREC_BF16 && tc_supported(m))
+      return tc_forward_chunks(m, x, B, o->model_chunk_size, &o->route, raw, gates_out, loss_out, mws, model_ws, 4, st);
     int ci = 0;
     for (int64_t i = 0; i < B; i += o->model_chunk_size, ++ci) {       // rendering_mip.py:327
       const int64_t rows = (B - i < o->model_chunk_size) ? (B - i) : o->model_chunk_size;

@@ -77,6 +77,7 @@ __device__ __forceinline__ uint64_t op_desc(uint32_t addr, uint32_t k_stride, ui
 // packed weights
 // ------------------------------------------------------------------------------------------
 struct TcLayer {
+  uint32_t w_off_w; // byte offset of the wide image (snb_tc_wide.cuh) inside wblob_w
   uint32_t w_off;   // byte offset of the packed bf16 image inside tc_blob
   uint32_t K16;     // K rounded up to 16
   uint32_t N;       // output features (<= 256)
@@ -84,6 +85,9 @@ struct TcLayer {
 };
 
 struct TcParams {
+  const uint8_t* wblob_w;   // packed bf16 weights, wide images (per layer half and 32-wide K-slice); nullptr unless used
+  uint32_t expert_w_stride_w;
+  int mip;                  // MipNeRFMoE: x = [mean3, cov3, dir3, idx], integrated positional encoding
   const uint8_t* wblob;     // packed bf16 weights
   const float* fblob;       // fp32 side table: biases (bf16-rounded), gate constants, sigma/colour heads
   TcLayer front[5];         // xyz, gate fcs
@@ -165,6 +169,10 @@ __global__ void k_round_copy(const float* __restrict__ src, int n, int round_bf1
   if (i < n) dst[i] = round_bf16 ? bf16_round(src[i]) : src[i];
 }
 
+__global__ void k_pack_layer_wide(const float* __restrict__ w, int N, int K, int K16, __nv_bfloat16* __restrict__ dst);
+__global__ void k_pack_gate_wide(const float* __restrict__ ln_w, const float* __restrict__ wg, int E, int K,
+                                 __nv_bfloat16* __restrict__ dst);
+
 struct TcHost {
   TcParams p;
   float* fblob;
@@ -173,17 +181,26 @@ struct TcHost {
 
 bool tc_supported(const Model* m) {
   const snb_model_desc& d = m->d;
-  return d.width == MW && d.num_experts <= MAX_E && d.hidden2 <= 256 && d.hidden2 % 64 == 0 && d.gate_layers <= 4 &&
-         !d.mip && m->xyz_in <= 128 && ((m->cat_in + 15) / 16 * 16) <= KA_MAX && d.expert_layers <= 16 &&
-         d.appearance_dim % 4 == 0 && d.pos_xyz_freqs == 12 && d.pos_dir_freqs == 4;
+  // width 256: TS kernels (hidden activations in tensor memory); width 512 and every mip model: wide kernels
+  // (snb_tc_wide.cuh: A operand in shared memory, a layer's accumulators own all of tensor memory)
+  return (d.width == 256 || d.width == 512) && d.num_experts <= MAX_E && d.hidden2 <= 256 && d.hidden2 % 64 == 0 &&
+         d.gate_layers >= 1 && d.gate_layers <= 4 && m->xyz_in <= 80 && m->cat_in - d.width <= 80 && d.expert_layers <= 16 &&
+         d.expert_layers >= 1 && d.appearance_dim % 4 == 0 && d.pos_xyz_freqs == 12 && d.pos_dir_freqs == 4 &&
+         (d.skip_layer >= 0 || (d.width == 256 && !d.mip));
 }
 
-struct TcOwner { TcHost h; uint8_t* wblob; };
+struct TcOwner { TcHost h; uint8_t* wblob; uint8_t* wblob_w; };
+// which kernel family evaluates a model: wide for width 512 and mip models (SNB_WIDE=1 forces it for A/B tests)
+static bool tc_use_wide(const Model* m) {
+  static const bool force = getenv("SNB_WIDE") && atoi(getenv("SNB_WIDE")) != 0;
+  return m->d.width != 256 || m->d.mip || force;
+}
 
 void tc_release(Model* m) {
   TcOwner* own = (TcOwner*)m->tc_blob;
   if (!own) return;
   if (own->wblob) cudaFree(own->wblob);
+  if (own->wblob_w) cudaFree(own->wblob_w);
   if (own->h.fblob) cudaFree(own->h.fblob);
   delete own;
   m->tc_blob = nullptr;
@@ -191,7 +208,8 @@ void tc_release(Model* m) {
 
 int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
   const snb_model_desc& d = m->d;
-  const int E = d.num_experts, L = d.expert_layers, H2 = d.hidden2;
+  const int E = d.num_experts, L = d.expert_layers, H2 = d.hidden2, MW = d.width;
+  const bool wide = tc_use_wide(m), narrow = (d.width == 256 && !d.mip);
   TcOwner* own = nullptr;
   if (m->tc_blob == nullptr) {
     own = new TcOwner();
@@ -201,7 +219,7 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
     auto add_layer = [&](TcLayer& l, int N, int K) {
       l.K16 = (uint32_t)((K + 15) / 16 * 16);
       l.N = (uint32_t)N;
-      l.w_off = (uint32_t)wbytes;
+      l.w_off = l.w_off_w = (uint32_t)wbytes;      // both image kinds have the same size: one offset table
       wbytes += (size_t)N * l.K16 * 2;
       wbytes = align_up(wbytes, 128);
       l.b_off = (uint32_t)nf;
@@ -216,7 +234,7 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
     p.n_expert = L;
     size_t e0_w = wbytes, e0_f = nf;
     for (int j = 0; j < L; ++j) add_layer(p.expert[j], MW, MW);
-    p.expert_w_stride = (uint32_t)(wbytes - e0_w);
+    p.expert_w_stride = p.expert_w_stride_w = (uint32_t)(wbytes - e0_w);
     p.expert_b_stride = (uint32_t)(nf - e0_f);
     wbytes = e0_w + (size_t)p.expert_w_stride * E;
     nf = e0_f + (size_t)p.expert_b_stride * E;
@@ -225,12 +243,15 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
     p.o_wsig = addf(MW); p.o_bsig = addf(1); p.o_wcol = addf((size_t)3 * H2); p.o_bcol = addf(3);
     p.o_b3x = addf((size_t)E * MW);
     p.recompute_h = (getenv("SNB_GATHER_H") == nullptr && d.skip_layer >= 0) ? 1 : 0;
+    p.mip = d.mip;
     p.E = E; p.skip_layer = d.skip_layer; p.pos_xyz_freqs = d.pos_xyz_freqs; p.pos_dir_freqs = d.pos_dir_freqs;
     p.appearance_dim = d.appearance_dim; p.appearance_count = d.appearance_count; p.hidden2 = H2; p.x_cols = m->x_cols;
-    SNB_CHECK_CUDA(cudaMalloc((void**)&own->wblob, wbytes));
+    if (narrow) SNB_CHECK_CUDA(cudaMalloc((void**)&own->wblob, wbytes));
+    if (wide) SNB_CHECK_CUDA(cudaMalloc((void**)&own->wblob_w, wbytes));
     SNB_CHECK_CUDA(cudaMalloc((void**)&own->h.fblob, nf * sizeof(float)));
     own->h.fblob_floats = nf;
     p.wblob = own->wblob;
+    p.wblob_w = own->wblob_w;
     p.fblob = own->h.fblob;
     p.emb_a = m->emb_a;
     m->tc_blob = own;
@@ -241,8 +262,14 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
   TcParams& p = own->h.p;
   SNB_CHECK_CUDA(cudaMemsetAsync(own->h.fblob, 0, own->h.fblob_floats * sizeof(float), st));
   auto pack = [&](const TcLayer& l, const float* wsrc, int K, size_t extra_w, const float* bsrc, size_t extra_b) -> int {
-    k_pack_layer<<<256, 256, 0, st>>>(wsrc, (int)l.N, K, (int)l.K16, (__nv_bfloat16*)(own->wblob + l.w_off + extra_w));
-    SNB_CHECK_LAUNCH("k_pack_layer");
+    if (own->wblob) {
+      k_pack_layer<<<256, 256, 0, st>>>(wsrc, (int)l.N, K, (int)l.K16, (__nv_bfloat16*)(own->wblob + l.w_off + extra_w));
+      SNB_CHECK_LAUNCH("k_pack_layer");
+    }
+    if (own->wblob_w) {
+      k_pack_layer_wide<<<256, 256, 0, st>>>(wsrc, (int)l.N, K, (int)l.K16, (__nv_bfloat16*)(own->wblob_w + l.w_off_w + extra_w));
+      SNB_CHECK_LAUNCH("k_pack_layer_wide");
+    }
     k_round_copy<<<(unsigned)cdiv(l.N, 256), 256, 0, st>>>(bsrc, (int)l.N, 1, own->h.fblob + l.b_off + extra_b);
     SNB_CHECK_LAUNCH("k_round_copy");
     return SNB_OK;
@@ -259,8 +286,14 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
       if ((rc = pack(p.expert[j], m->exp_w[j] + (size_t)e * MW * MW, MW, (size_t)e * p.expert_w_stride,
                      m->exp_b[j] + (size_t)e * MW, (size_t)e * p.expert_b_stride)))
         return rc;
-  k_pack_gate<<<32, 256, 0, st>>>(m->ln_w, m->wg, E, MW, (__nv_bfloat16*)(own->wblob + p.gate.w_off));
-  SNB_CHECK_LAUNCH("k_pack_gate");
+  if (own->wblob) {
+    k_pack_gate<<<32, 256, 0, st>>>(m->ln_w, m->wg, E, MW, (__nv_bfloat16*)(own->wblob + p.gate.w_off));
+    SNB_CHECK_LAUNCH("k_pack_gate");
+  }
+  if (own->wblob_w) {
+    k_pack_gate_wide<<<32, 256, 0, st>>>(m->ln_w, m->wg, E, MW, (__nv_bfloat16*)(own->wblob_w + p.gate.w_off_w));
+    SNB_CHECK_LAUNCH("k_pack_gate_wide");
+  }
   k_gate_consts<<<E, 32, 0, st>>>(m->ln_w, m->ln_b, m->wg, E, MW, own->h.fblob + p.o_c0, own->h.fblob + p.o_c1);
   SNB_CHECK_LAUNCH("k_gate_consts");
   auto cpf = [&](uint32_t off, const float* src, int n, int round) -> int {
@@ -1128,6 +1161,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back(TcParams P, TileTable tt, R
 }
 
 #include "snb_tc_ts.cuh"
+#include "snb_tc_wide.cuh"
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -1191,6 +1225,7 @@ struct TcChunk {
   int* hist0;               // [SEL_MAX_E][SEL_HBINS] level-0 key histogram per expert (+ the ticket of k_select)
   double* lpart;
   int npm;
+  bool wide;                // wide kernels (width 512 / mip models)
   bool front_packed;        // launch #1 wrote wsel / pm itself
   bool select;              // routing = k_select (kept set only); false = full-order route_top1 (SNB_ROUTE_FULL=1)
   int64_t max_rows, max_tiles;
@@ -1227,6 +1262,11 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
   c.max_rows = S + (int64_t)TILE * (E + 2);
   c.max_tiles = cdiv(S, TILE) + 2 * (E + 2);
   c.set = 0;
+  c.wide = tc_use_wide(m);
+  if (c.wide) {
+    SNB_REQUIRE(((TcOwner*)m->tc_blob)->wblob_w, "tc_forward: the wide weight images were not packed");
+    SNB_REQUIRE(!m->ep, "expert parallelism is implemented for the width-256 NeRFMoE kernels only");
+  }
   if (m->ep) {
     SNB_REQUIRE(c.Pf.recompute_h, "expert-parallel launch #2 recomputes h (SNB_GATHER_H is a single-GPU debug switch)");
     SNB_REQUIRE(!o->no_batch, "expert-parallel mode implements the capacity (batched) dispatch only");
@@ -1277,13 +1317,17 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front_ts<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_ts<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_ts<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSM_TOTAL));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front_wide<1, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes<1>()));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_wide<1, 12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes<1>()));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front_wide<2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes<2>()));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_wide<2, 12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes<2>()));
     attr_done = true;
   }
   static const int cg_env = getenv("SNB_CG") ? atoi(getenv("SNB_CG")) : 1;
   static const int cg_front_env = getenv("SNB_CG_FRONT") ? atoi(getenv("SNB_CG_FRONT")) : cg_env;
   static const int cg_back_env = getenv("SNB_CG_BACK") ? atoi(getenv("SNB_CG_BACK")) : cg_env;
-  c.cg = (cg_front_env == 2) ? 2 : 1;
-  c.cg_back = (cg_back_env == 2) ? 2 : 1;
+  c.cg = (cg_front_env == 2 && !c.wide) ? 2 : 1;
+  c.cg_back = (cg_back_env == 2 && !c.wide) ? 2 : 1;
   c.pe = profile_next();
   c.grid_cap = m->sm_count;
   return SNB_OK;
@@ -1293,7 +1337,18 @@ static int tc_front(Model* m, TcChunk& c, cudaStream_t st) {
   const int n_front_tiles = (int)cdiv(c.S, TILE);
   int grid1 = n_front_tiles < c.grid_cap ? n_front_tiles : c.grid_cap;
   if (c.pe) cudaEventRecord(c.pe->e[0], st);
-  if (c.cg == 2) {
+  if (c.wide) {
+    const bool pack = c.select && (int64_t)cdiv(n_front_tiles, grid1) * TILE < 65536;
+    float* gates_out = pack ? c.dbg_gates : c.gates;
+    if (m->d.width == 512)
+      k_front_wide<2, 12><<<grid1, THREADS, wide_smem_bytes<2>(), st>>>(c.Pf, c.x, c.S, gates_out, pack ? c.wsel : nullptr,
+                                                                        c.hist0, pack ? c.pm : nullptr, pack ? c.moe_idx : nullptr);
+    else
+      k_front_wide<1, 12><<<grid1, THREADS, wide_smem_bytes<1>(), st>>>(c.Pf, c.x, c.S, gates_out, pack ? c.wsel : nullptr,
+                                                                        c.hist0, pack ? c.pm : nullptr, pack ? c.moe_idx : nullptr);
+    c.front_packed = pack;
+    c.npm = 4 * n_front_tiles;
+  } else if (c.cg == 2) {
     grid1 = (grid1 + 1) & ~1;
     if (grid1 > (c.grid_cap & ~1)) grid1 = c.grid_cap & ~1;
     cudaLaunchConfig_t cfg = {};
@@ -1396,7 +1451,10 @@ static int tc_back(Model* m, TcChunk& c, cudaStream_t st, bool finish_inline = t
   static const bool use_ts = !(getenv("SNB_TS") && atoi(getenv("SNB_TS")) == 0);
   const bool ts_ok = use_ts && c.Pb.recompute_h && c.Pb.back[1].K16 > MW && c.Pb.back[1].K16 - MW <= TS_CAT_COLS &&
                      c.Pb.front[0].K16 <= TS_CAT_COLS;
-  if (c.cg_back == 2) {
+  if (c.wide) {
+    if (m->d.width == 512) k_back_wide<2, 12, 4><<<grid2, THREADS, wide_smem_bytes<2>(), st>>>(c.Pb, c.tt, io);
+    else k_back_wide<1, 12, 4><<<grid2, THREADS, wide_smem_bytes<1>(), st>>>(c.Pb, c.tt, io);
+  } else if (c.cg_back == 2) {
     grid2 &= ~1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid2); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = ts_ok ? TSM_TOTAL : SM_TOTAL; cfg.stream = st;

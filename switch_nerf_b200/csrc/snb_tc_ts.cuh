@@ -525,6 +525,117 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
   }
 }
 
+// ---- softmax of the gate logits + routing hand-off, shared by the front kernels -------------------------------------
+// logits = rstd * (G_hi + G_lo - mean * c1) + c0 from the folded LayerNorm + gate GEMM accumulator (32 columns at
+// `tacc`); LayerNorm partial sums in sred[0..7]; s_gc = [c0 | c1]; s_hist = the CTA's level-0 key histogram.
+__device__ __forceinline__ void front_softmax_select(const TcParams& P, const float* sred, const float* s_gc,
+                                                     uint32_t* s_hist, uint32_t tacc, const EpiCtx& ec, int row, int lane,
+                                                     bool valid, int64_t s, int t, float inv_w,
+                                                     float* __restrict__ gates, uint32_t* __restrict__ wsel,
+                                                     float* __restrict__ pm, int32_t* __restrict__ moe_idx) {
+  // every one of the four threads of a row (cs = 0..3, different warps) holds all 32 accumulator columns, so
+  // each computes the whole softmax of its row itself: no exchange rounds.  Thread cs stores gates
+  // [4cs, 4cs+4) (debug tap only); thread 0 owns the routing word and the column sums.
+  const float tsum = sred[0 * 128 + row] + sred[1 * 128 + row] + sred[2 * 128 + row] + sred[3 * 128 + row];
+  const float tsq = sred[4 * 128 + row] + sred[5 * 128 + row] + sred[6 * 128 + row] + sred[7 * 128 + row];
+  const float mean = tsum * inv_w;
+  const float var = fmaxf(tsq * inv_w - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+    uint32_t hi[16], lo[16];
+  tmem_ld16(tacc, hi);
+  tmem_ld16(tacc + 16u, lo);
+  tmem_ld_wait();
+  float lg[MAX_E];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < MAX_E; ++e) {
+    lg[e] = rstd * (__uint_as_float(hi[e]) + __uint_as_float(lo[e]) - mean * s_gc[MAX_E + e]) + s_gc[e];
+    if (e < P.E) mx = fmaxf(mx, lg[e]);
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int e = 0; e < MAX_E; ++e) {
+    lg[e] = (e < P.E) ? expf(lg[e] - mx) : 0.f;
+    den += lg[e];
+  }
+  const float inv = 1.f / den;
+#pragma unroll
+  for (int e = 0; e < MAX_E; ++e) lg[e] *= inv;
+  if (valid) {
+    if (gates) {
+      const int e0 = 4 * ec.cs;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4)
+        if (ec.cs == q4) {            // static register indices
+          if ((P.E & 3) == 0 && e0 < P.E) {
+            *reinterpret_cast<float4*>(gates + s * P.E + e0) =
+                make_float4(lg[4 * q4], lg[4 * q4 + 1], lg[4 * q4 + 2], lg[4 * q4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (e0 + j < P.E) gates[s * P.E + e0 + j] = lg[4 * q4 + j];
+          }
+        }
+    }
+    if (ec.cs == 0) {
+      // argmax of the fp32 gates, lowest expert id on ties (torch.argmax / extract_critical)
+      int best = 0;
+      float bv = lg[0];
+#pragma unroll
+      for (int e = 1; e < MAX_E; ++e)
+        if (e < P.E && lg[e] > bv) { bv = lg[e]; best = e; }
+      if (wsel) {
+        const uint32_t key = sel_key(bv);
+        wsel[s] = sel_pack(best, key);
+        const int bin = best * SEL_HBINS + (int)(key >> SEL_L1_SHIFT);
+        if (!(P.ab & 1)) atomicAdd(&s_hist[bin >> 1], 1u << (16 * (bin & 1)));
+        if (moe_idx) moe_idx[s] = best;
+      }
+    }
+  }
+  if (pm && ec.cs == 0 && !(P.ab & 2)) {
+    // column sums of the gates over the 32 rows of this warp (load-balance loss), in a fixed order that does
+    // not depend on the grid: 16 values x 32 lanes folded by a transpose-reduction (16 shuffles), after which
+    // even lane l holds the sum of expert ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1).
+    if (!valid) {
+#pragma unroll
+      for (int e = 0; e < MAX_E; ++e) lg[e] = 0.f;
+    }
+    float a8[8], b4[4], c2[2];
+    {
+      const bool hi = lane & 16;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float send = hi ? lg[i] : lg[i + 8], keep = hi ? lg[i + 8] : lg[i];
+        a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+    }
+    {
+      const bool hi = lane & 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float send = hi ? a8[i] : a8[i + 4], keep = hi ? a8[i + 4] : a8[i];
+        b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+    }
+    {
+      const bool hi = lane & 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float send = hi ? b4[i] : b4[i + 2], keep = hi ? b4[i + 2] : b4[i];
+        c2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+    }
+    const bool hi2 = lane & 2;
+    float d1 = (hi2 ? c2[1] : c2[0]) + __shfl_xor_sync(0xffffffffu, hi2 ? c2[0] : c2[1], 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+    if ((lane & 1) == 0) {
+      const int ecol = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+      pm[((int64_t)t * 4 + ec.q) * SEL_PM_STRIDE + ecol] = d1;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Launch #1, TS variant: PE -> xyz layer -> external gate MLP -> folded LayerNorm + gate GEMM -> softmax, with the
 // hidden activations packed in tensor memory exactly as in k_back_ts (h is not written: launch #2 recomputes it).
@@ -691,110 +802,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
         epi_bar_sync();                       // LayerNorm partial sums of all 4 column sub-slices are in sred
         ts_wait_acc(ctl, pp, buf);
         tl_mark(tl, 0, tn, 40);
-        {
-          // every one of the four threads of a row (cs = 0..3, different warps) holds all 32 accumulator columns, so
-          // each computes the whole softmax of its row itself: no exchange rounds.  Thread cs stores gates
-          // [4cs, 4cs+4) (debug tap only); thread 0 owns the routing word and the column sums.
-          const float tsum = sred[0 * 128 + row] + sred[1 * 128 + row] + sred[2 * 128 + row] + sred[3 * 128 + row];
-          const float tsq = sred[4 * 128 + row] + sred[5 * 128 + row] + sred[6 * 128 + row] + sred[7 * 128 + row];
-          const float mean = tsum * (1.f / MW);
-          const float var = fmaxf(tsq * (1.f / MW) - mean * mean, 0.f);
-          const float rstd = rsqrtf(var + 1e-5f);
-          const uint32_t tacc = tbuf_of(li);
-          uint32_t hi[16], lo[16];
-          tmem_ld16(tacc, hi);
-          tmem_ld16(tacc + 16u, lo);
-          tmem_ld_wait();
-          float lg[MAX_E];
-          float mx = -INFINITY;
-#pragma unroll
-          for (int e = 0; e < MAX_E; ++e) {
-            lg[e] = rstd * (__uint_as_float(hi[e]) + __uint_as_float(lo[e]) - mean * s_gc[MAX_E + e]) + s_gc[e];
-            if (e < P.E) mx = fmaxf(mx, lg[e]);
-          }
-          float den = 0.f;
-#pragma unroll
-          for (int e = 0; e < MAX_E; ++e) {
-            lg[e] = (e < P.E) ? expf(lg[e] - mx) : 0.f;
-            den += lg[e];
-          }
-          const float inv = 1.f / den;
-#pragma unroll
-          for (int e = 0; e < MAX_E; ++e) lg[e] *= inv;
-          if (valid) {
-            if (gates) {
-              const int e0 = 4 * ec.cs;
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4)
-                if (ec.cs == q4) {            // static register indices
-                  if ((P.E & 3) == 0 && e0 < P.E) {
-                    *reinterpret_cast<float4*>(gates + s * P.E + e0) =
-                        make_float4(lg[4 * q4], lg[4 * q4 + 1], lg[4 * q4 + 2], lg[4 * q4 + 3]);
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                      if (e0 + j < P.E) gates[s * P.E + e0 + j] = lg[4 * q4 + j];
-                  }
-                }
-            }
-            if (ec.cs == 0) {
-              // argmax of the fp32 gates, lowest expert id on ties (torch.argmax / extract_critical)
-              int best = 0;
-              float bv = lg[0];
-#pragma unroll
-              for (int e = 1; e < MAX_E; ++e)
-                if (e < P.E && lg[e] > bv) { bv = lg[e]; best = e; }
-              if (wsel) {
-                const uint32_t key = sel_key(bv);
-                wsel[s] = sel_pack(best, key);
-                const int bin = best * SEL_HBINS + (int)(key >> SEL_L1_SHIFT);
-                if (!(P.ab & 1)) atomicAdd(&s_hist[bin >> 1], 1u << (16 * (bin & 1)));
-                if (moe_idx) moe_idx[s] = best;
-              }
-            }
-          }
-          if (pm && ec.cs == 0 && !(P.ab & 2)) {
-            // column sums of the gates over the 32 rows of this warp (load-balance loss), in a fixed order that does
-            // not depend on the grid: 16 values x 32 lanes folded by a transpose-reduction (16 shuffles), after which
-            // even lane l holds the sum of expert ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1).
-            if (!valid) {
-#pragma unroll
-              for (int e = 0; e < MAX_E; ++e) lg[e] = 0.f;
-            }
-            float a8[8], b4[4], c2[2];
-            {
-              const bool hi = lane & 16;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float send = hi ? lg[i] : lg[i + 8], keep = hi ? lg[i + 8] : lg[i];
-                a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-              }
-            }
-            {
-              const bool hi = lane & 8;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float send = hi ? a8[i] : a8[i + 4], keep = hi ? a8[i + 4] : a8[i];
-                b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-              }
-            }
-            {
-              const bool hi = lane & 4;
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const float send = hi ? b4[i] : b4[i + 2], keep = hi ? b4[i + 2] : b4[i];
-                c2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-              }
-            }
-            const bool hi2 = lane & 2;
-            float d1 = (hi2 ? c2[1] : c2[0]) + __shfl_xor_sync(0xffffffffu, hi2 ? c2[0] : c2[1], 2);
-            d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
-            if ((lane & 1) == 0) {
-              const int ecol = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-              pm[((int64_t)t * 4 + ec.q) * SEL_PM_STRIDE + ecol] = d1;
-            }
-          }
-        }
+        front_softmax_select(P, sred, s_gc, s_hist, tbuf_of(li), ec, row, lane, valid, s, t, 1.f / MW, gates, wsel, pm, moe_idx);
         tc_fence_before();
         epi_bar_sync();                       // sred is reused by the next tile
         tl_mark(tl, 0, tn, 41);

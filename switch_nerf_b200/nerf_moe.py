@@ -446,7 +446,7 @@ class MipNeRFMoE(NeRFMoE):
     def __init__(self, *a, **k):
         super().__init__(*a, mip=True, **k)
         self.xyz_dim = 6          # x = [mean(3), cov_diag(3), dir(3), image_index]
-        self.precision = "fp32"   # the tcgen05 path is specialised for NeRFMoE; mip chunks run on the fp32 CUDA path
+        # precision follows hparams.amp_use_bfloat16 like NeRFMoE: bf16 = the wide tcgen05 kernels (csrc/snb_tc_wide.cuh)
 
 
 def get_nerf_moe_inner(hparams, appearance_count: int, xyz_dim: int, model_cfg_name="model") -> nn.Module:

@@ -30,7 +30,7 @@ def render_rays(nerf, rays: torch.Tensor, radii: torch.Tensor, image_indices: Op
     opts.coarse_samples, opts.fine_samples, opts.model_chunk_size = Sc, Sf, chunk
     opts.perturb, opts.seed = 0.0, 0
     opts.white_bkgd = int(bool(getattr(hparams, "white_bkgd", False)))
-    opts.precision = L.SNB_PREC_FP32
+    opts.precision = L.PRECISIONS[model.precision]
     opts.route = model.route_opts()
     f32 = dict(dtype=torch.float32, device=dev)
     typ = "fine" if Sf > 0 else "coarse"

@@ -11,8 +11,8 @@ import torch
 
 from oracle import switch_nerf_oracle as O
 from oracle.make_golden import ROUTE_CASES, make_gates
-from tests.util import (CUDA_MODEL_GOLDENS, bf16_contract_check, cuda_golden_case, golden_sd, load_golden,
-                        make_model)
+from tests.util import (CUDA_MIP_GOLDENS, CUDA_MODEL_GOLDENS, bf16_contract_check, cuda_golden_case, golden_sd,
+                        load_golden, make_model)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3  # BASELINE.json north_star: "within 1e-3 abs on RGB/sigma"
@@ -322,6 +322,59 @@ def test_model_bf16_tcgen05_vs_reference_cuda_golden(built_lib, tag):
         assert float(torch.from_numpy(c["g"]["gate_margin"].astype(np.float32))[flip].max()) < 2e-2
 
 
+@pytest.mark.parametrize("tag", CUDA_MIP_GOLDENS)
+def test_model_bf16_mip_wide_vs_reference_cuda_golden(built_lib, tag):
+    """MipNeRFMoE on the wide tcgen05 kernels (width 256 and the Mission-Bay width 512, mission_bay.yaml) vs the UNMODIFIED
+    reference's MipNeRFMoE run on a B200 under cuda autocast: the same contract C1-C3 as the Building topology."""
+    c = cuda_golden_case(tag)
+    hp = __import__("oracle.ref_shims", fromlist=["x"]).make_hparams(
+        num_experts=c["E"], capacity_factor=c["cf"], bpr=c["bpr"], width=c["width"], amp_bf16=True,
+        nerfmoe_class_name="MipNeRFMoE", moe_return_gates=True)
+    from switch_nerf_b200.nerf_moe import get_nerf_moe_inner
+    model = get_nerf_moe_inner(hp, c["count"], 3)
+    model.load_state_dict(c["sd"])
+    model = model.cuda().eval()
+    assert model.precision == "bf16"
+    with torch.no_grad():
+        r = model(c["x"].cuda(), return_debug=True)
+    torch.cuda.synchronize()
+    st = bf16_contract_check(r["outputs"].cpu(), r["extras"]["moe_gates"][0].view(-1).cpu(),
+                             r["extras"]["debug_loc"].cpu() < c["cap"], c)
+    assert abs(float(r["extras"]["moe_loss"][0]) - float(c["g"]["l_aux"][0])) < 2e-3 * abs(float(c["g"]["l_aux"][0])), st
+
+
+@pytest.mark.parametrize("tag", ["mip_w256", "mip_mission_bay_w512"])
+def test_render_mip_bf16_vs_reference_cuda_golden(built_lib, tag):
+    """rendering_mip.render_rays on the bf16 wide kernels (chunk pipeline) vs the unmodified reference's
+    rendering_mip.render_rays + MipNeRFMoE on a B200 under cuda autocast: per-ray rgb within one bf16 output ulp,
+    >= 97 % within 1e-3, PSNR >= 60 dB."""
+    from switch_nerf_b200.nerf_moe import get_nerf_moe_inner
+    from switch_nerf_b200.rendering_mip import render_rays as render_rays_mip
+    from oracle import ref_shims as R
+    g = load_golden(f"render_{tag}_bf16cuda.npz")
+    E, width, n_rays, cs, fs, chunk, seed, gs, count = g["params"]
+    sd = O.synthetic_state_dict(num_experts=int(E), appearance_count=int(count), seed=int(seed), gate_scale=float(gs), width=int(width))
+    hp = R.make_hparams(num_experts=int(E), model_chunk_size=int(chunk), coarse_samples=int(cs), fine_samples=int(fs),
+                        width=int(width), nerfmoe_class_name="MipNeRFMoE", amp_bf16=True)
+    hp.perturb = 0
+    model = get_nerf_moe_inner(hp, int(count), 3)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        res, _ = render_rays_mip(model, torch.from_numpy(g["rays"]).cuda(), torch.from_numpy(g["radii"]).cuda(),
+                                 torch.from_numpy(g["image_indices"]).cuda(), hp, True, True)
+    torch.cuda.synchronize()
+    for k in ("rgb_coarse", "rgb_fine"):
+        err = (res[k].cpu() - torch.from_numpy(g[k])).abs()
+        stats = {"max": float(err.max()), "mean": float(err.mean()), "frac_le_1e-3": float((err <= 1e-3).float().mean()),
+                 "psnr": O.psnr(res[k].cpu(), torch.from_numpy(g[k]))}
+        print(tag, k, stats)
+        # (64 - 128 rays: a handful of values decide the fraction)
+        assert stats["max"] <= RENDER_BF16_RGB_MAX and stats["frac_le_1e-3"] >= 0.97 and stats["psnr"] >= 60.0, (k, stats)
+    d = (res["depth_fine"].cpu() - torch.from_numpy(g["depth_fine"])).abs() / torch.from_numpy(g["depth_fine"]).abs().clamp_min(1e-3)
+    assert float(d.max()) <= RENDER_BF16_DEPTH_REL
+
+
 def test_model_bf16_vs_fp32_reference_golden(built_lib):
     """bf16 path vs the reference's FP32 output: no worse than the reference's own autocast run is (mean error ratio
     <= 1.25), routing >= 97 % identical to the fp32 routing."""
@@ -491,10 +544,13 @@ def test_model_bf16_cta_pair_and_gather_variants(built_lib, tmp_path):
     """Launch #2 has variants selected by environment switches read once per process.  Default: hidden activations in
     tensor memory (tcgen05.st by the epilogue, A operand of tcgen05.mma taken from TMEM, csrc/snb_tc_ts.cuh).
     SNB_CG=2: tcgen05 cta_group::2 CTA pairs (M=256 MMAs issued by the leader CTA of a 2-CTA cluster).
+    SNB_WIDE=1: the wide kernels (snb_tc_wide.cuh, the width-512 / mip data flow) instantiated at width 256.
+    SNB_ROUTE_FULL=1: full-order routing (route_top1 + tile plan) instead of k_select.
     SNB_TS=0: A operand staged in shared memory (k_back).  SNB_GATHER_H=1: launch #2 gathers h from HBM instead of
     recomputing it (shared-memory kernel only).  Each must agree with the default on the same inputs (same rounding
     points; only the fp32 accumulation order inside a layer differs)."""
-    _check_bf16_variants(tmp_path, (("ts_pair", {"SNB_CG": "2"}), ("smem", {"SNB_TS": "0"}), ("smem_front", {"SNB_TS_FRONT": "0"}),
+    _check_bf16_variants(tmp_path, (("wide", {"SNB_WIDE": "1"}), ("route_full", {"SNB_ROUTE_FULL": "1"}),
+                                    ("ts_pair", {"SNB_CG": "2"}), ("smem", {"SNB_TS": "0"}), ("smem_front", {"SNB_TS_FRONT": "0"}),
                                     ("smem_pair", {"SNB_TS": "0", "SNB_CG": "2"}), ("gather", {"SNB_GATHER_H": "1"}),
                                     ("pair_gather", {"SNB_CG": "2", "SNB_GATHER_H": "1"})))
 
