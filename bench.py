@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-comparator", action="store_true")
     ap.add_argument("--no-ep", action="store_true", help="N > 1: skip the expert-parallel leg (`ep` key)")
+    ap.add_argument("--workload", default="building", choices=["building", "mission_bay"],
+                    help="building (default, BASELINE.json configs[1], the line the driver records) or mission_bay "
+                         "(configs[3]: MipNeRFMoE width 512, 13312 rays x (256+256) intervals, chunk 212992)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--parallelism", default="dp", choices=["dp", "ep"],
                     help="dp: every expert on every GPU, rays sharded (the reference's shipped mode). "
@@ -303,6 +306,175 @@ def gpu_comparator(device):
         return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# --workload mission_bay: BASELINE.json configs[3] (mission_bay.yaml: MipNeRFMoE, width 512; README recipe: 13312 rays per
+# iteration, coarse / fine 257 edges = 256 + 256 intervals, model_chunk_size 212992).  Same JSON contract; rays shard
+# over the ranks with no data-path collective.
+# ---------------------------------------------------------------------------------------------------------------
+MB_RAYS, MB_EDGES, MB_CHUNK = 13312, 257, 212992
+MB_FLOPS_PER_SAMPLE = 5_479_936
+MB_FLOPS_BACK_KEPT = 3_670_016 + 1_024 + 524_288 + 150_272 + 768
+MB_FLOPS_BACK_DROPPED = 1_024 + 524_288 + 150_272 + 768
+MB_WORKLOAD = "mission_bay: 13312 rays x (256+256) intervals, MipNeRFMoE width 512, 8 experts, chunk 212992, cf=1.0, BPR"
+
+
+def mission_bay_inputs(rank, device):
+    from switch_nerf_b200 import synthetic as SY
+    from switch_nerf_b200.configs import make_hparams
+    from switch_nerf_b200.nerf_moe import get_nerf_moe_inner
+    sd = SY.mission_bay_state_dict(num_experts=EXPERTS, appearance_count=2048, seed=0, n_rays=MB_RAYS, coarse=MB_EDGES)
+    hp = make_hparams(num_experts=EXPERTS, capacity_factor=1.0, bpr=True, model_chunk_size=MB_CHUNK, coarse_samples=MB_EDGES,
+                      fine_samples=MB_EDGES, width=512, amp_bf16=True, moe_return_gates=False, nerfmoe_class_name="MipNeRFMoE")
+    hp.perturb = 0
+    model = get_nerf_moe_inner(hp, 2048, 3)
+    model.load_state_dict(sd)
+    model = model.to(device).eval()
+    rays, radii, idx = SY.mission_bay_rays(MB_RAYS, 2048, seed=100 + rank)
+    return model, hp, rays, radii, idx, sd
+
+
+def mission_bay_oracle(sd, rays, radii, idx, n, mode):
+    from oracle import switch_nerf_oracle as O
+    cfg = O.default_cfg(sd, 1.0, True, mip=True)
+    with torch.no_grad():
+        return O.render_rays_mip(sd, cfg, rays[:n], radii[:n], idx[:n], coarse_samples=MB_EDGES, fine_samples=MB_EDGES,
+                                 model_chunk_size=MB_CHUNK, mode=mode, flavor="cuda")
+
+
+def main_mission_bay(args, rank, local_rank, world):
+    import ctypes as C
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    from switch_nerf_b200 import _lib as L
+    from switch_nerf_b200.rendering_mip import render_rays as render_rays_mip
+    model, hp, rays_h, radii_h, idx_h, sd = mission_bay_inputs(rank, device)
+    model.precision = args.precision
+    lib = L.lib()
+    rays_pin, radii_pin, idx_pin = rays_h.pin_memory(), radii_h.pin_memory(), idx_h.to(torch.int32).pin_memory()
+    rays_d, radii_d, idx_d = rays_pin.to(device), radii_pin.to(device), idx_pin.to(device)
+    samples_per_step = MB_RAYS * 2 * (MB_EDGES - 1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def step_resident():
+        return render_rays_mip(model, rays_d, radii_d, idx_d, hp, True, True)[0]
+
+    def step_e2e():
+        res = render_rays_mip(model, rays_pin.to(device, non_blocking=True), radii_pin.to(device, non_blocking=True),
+                              idx_pin.to(device, non_blocking=True), hp, True, True)[0]
+        return res["rgb_fine"].cpu(), res["depth_fine"].cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        evs = []
+        barrier()
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    step_e2e()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.snb_profile_enable(1)
+    launches0 = lib.snb_launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = lib.snb_launch_count() - launches0
+    prof = (C.c_double * 4)()
+    L.check(lib.snb_profile_collect(prof))
+    lib.snb_profile_enable(0)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        hp2 = __import__("copy").copy(hp)
+        hp2.moe_return_gates = True
+        model.args.moe_return_gates = True
+        res = render_rays_mip(model, rays_d, radii_d, idx_d, hp2, True, True)[0]
+        model.args.moe_return_gates = False
+        dropped, total, hist = 0, 0, torch.zeros(EXPERTS, dtype=torch.float64)
+        for key in ("moe_gates_coarse", "moe_gates_fine"):
+            g = res[key].view(-1).cpu()
+            for i in range(0, g.numel(), MB_CHUNK):
+                c = torch.bincount(g[i:i + MB_CHUNK], minlength=EXPERTS)
+                capc = int(1.0 * ((min(MB_CHUNK, g.numel() - i) + EXPERTS - 1) // EXPERTS))
+                dropped += int(torch.clamp(c - capc, min=0).sum())
+                total += int(c.sum())
+                hist += c.double()
+        kept_frac = 1.0 - dropped / max(total, 1)
+        shares = [round(float(v), 4) for v in (hist / hist.sum())]
+        ms_per_step = ms_total / args.steps
+        peak_tf, _, which = measured_peaks(clocks)
+        front_ms, route_ms, back_ms, n_chunks = prof[0], prof[1], prof[2], prof[3]
+        roof = None
+        if n_chunks > 0 and back_ms > 0:
+            per_launch = samples_per_step * args.steps / n_chunks
+            flops_back = kept_frac * MB_FLOPS_BACK_KEPT + (1.0 - kept_frac) * MB_FLOPS_BACK_DROPPED
+            tf = per_launch * flops_back / (back_ms / n_chunks * 1e-3) / 1e12
+            roof = {"kernel": "k_back_wide<2> (recompute h + 7 expert layers of 512x512 + combine + sigma/colour heads)",
+                    "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                    "peak_source": which, "avg_launch_ms": back_ms / n_chunks, "traffic": None,
+                    "algorithmic_gflop_per_launch": per_launch * flops_back / 1e9,
+                    "phase_ms_per_step": {"front": front_ms / args.steps, "route": route_ms / args.steps, "back": back_ms / args.steps},
+                    "step_tflops_per_gpu": samples_per_step * (MB_FLOPS_PER_SAMPLE - (1.0 - kept_frac) * 3_670_016) / (ms_per_step * 1e-3) / 1e12}
+        out = {"metric": "point-samples/sec", "value": world * samples_per_step / (ms_per_step * 1e-3), "unit": "samples/s",
+               "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+               "config": {"workload": MB_WORKLOAD, "rays_per_gpu": MB_RAYS, "l2": "256 MiB buffer written between timed steps",
+                          "weights": "seeded random init, gate LayerNorm bias balanced on the ray batch",
+                          "expert_shares": shares, "kept_fraction": round(kept_frac, 4),
+                          "parallelism": f"dp{world} over rays, no data-path collective"},
+               "clocks": clocks,
+               "e2e": {"value": world * samples_per_step * args.steps / e2e_s, "unit": "samples/s",
+                       "h2d_bytes_per_step": int((rays_pin.numel() + radii_pin.numel() + idx_pin.numel()) * 4),
+                       "d2h_bytes_per_step": int(MB_RAYS * 4 * 4)},
+               "gpu_launches": int(launches), "roofline": roof}
+        if world == 1 and not args.no_cpu_baseline:
+            n = 1024
+            mission_bay_oracle(sd, rays_h, radii_h, idx_h, 8, "fp32")
+            cores = pick_cpu_threads(lambda: mission_bay_oracle(sd, rays_h, radii_h, idx_h, 8, "fp32"))
+            t0 = time.perf_counter()
+            ref = mission_bay_oracle(sd, rays_h, radii_h, idx_h, n, "fp32")
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": n * 2 * (MB_EDGES - 1) / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+                                   "sample": f"{n} of {MB_RAYS} rays x {2 * (MB_EDGES - 1)} intervals, one pass, fp32 oracle port"}
+            with torch.no_grad():
+                mine = render_rays_mip(model, rays_d[:n].contiguous(), radii_d[:n].contiguous(), idx_d[:n].contiguous(), hp, True, True)[0]
+            rgb = mine["rgb_fine"].cpu()
+            out["parity"] = {"vs": f"oracle fp32 restatement of rendering_mip + MipNeRFMoE, first {n} rays",
+                             "max_abs": float((rgb - ref["rgb_fine"]).abs().max()), "mean_abs": float((rgb - ref["rgb_fine"]).abs().mean()),
+                             "psnr_db": psnr_db(rgb, ref["rgb_fine"])}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -313,6 +485,8 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: switch_nerf_b200 has no CPU path")
+    if args.workload == "mission_bay":
+        return main_mission_bay(args, rank, local_rank, world)
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)

@@ -117,7 +117,10 @@ def _route_select(gates, cf, bpr, no_batch=False):
 SELECT_CASES = [c for c in ROUTE_CASES if c[1] > 0 and c[2] <= 16] + [
     ("sel_ties_heavy", 70001, 8, 1.0, True, 41, 2.0, 0.5, 0.2), ("sel_cf05", 131072, 8, 0.5, True, 42, 1.0, 0.0, 0.0),
     ("sel_cf2_e16", 100003, 16, 2.0, True, 43, 3.0, 0.05, 0.0), ("sel_nobpr", 131072, 8, 1.0, False, 44, 2.0, 0.01, 0.01),
-    ("sel_tiny", 5, 4, 1.0, True, 45, 1.0, 0.0, 0.0), ("sel_e1", 1000, 1, 0.7, True, 46, 1.0, 0.0, 0.0)]
+    ("sel_tiny", 5, 4, 1.0, True, 45, 1.0, 0.0, 0.0), ("sel_e1", 1000, 1, 0.7, True, 46, 1.0, 0.0, 0.0),
+    # Mission-Bay chunk (more samples per CTA than the shared-memory word cache: grouped path), heavy ties, saturation
+    ("sel_mission_bay", 212992, 8, 1.0, True, 47, 2.0, 0.02, 0.01), ("sel_big_ties", 400003, 8, 0.5, True, 48, 3.0, 0.3, 0.3),
+    ("sel_big_nobpr", 300000, 16, 1.0, False, 49, 1.0, 0.0, 0.0)]
 
 
 @pytest.mark.parametrize("case", SELECT_CASES, ids=[c[0] for c in SELECT_CASES])
