@@ -221,6 +221,11 @@ typedef struct snb_render_opts {
   int32_t white_bkgd;       /* hparams.white_bkgd                                              */
   int32_t precision;        /* SNB_PREC_*                                                      */
   snb_route_opts route;
+  /* rendering.py:316-322 (`sigma_noise = randn * sigma_noise_std` per chunk when hparams.use_sigma_noise and
+   * nerf.training): caller-drawn noise added to the raw sigma before the softplus, one value per point-sample
+   * in ray-major order; device pointers, nullable (= no noise). */
+  const float* sigma_noise_coarse; /* [N * coarse_samples] */
+  const float* sigma_noise_fine;   /* [N * fine_samples]   */
 } snb_render_opts;
 
 /* Per-ray outputs (all nullable; device pointers). Keys of the reference `results` dict

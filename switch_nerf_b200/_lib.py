@@ -46,7 +46,7 @@ class RouteOpts(C.Structure):
 class RenderOpts(C.Structure):
     _fields_ = [("coarse_samples", C.c_int32), ("fine_samples", C.c_int32), ("model_chunk_size", C.c_int64),
                 ("perturb", C.c_float), ("seed", C.c_uint64), ("white_bkgd", C.c_int32), ("precision", C.c_int32),
-                ("route", RouteOpts)]
+                ("route", RouteOpts), ("sigma_noise_coarse", C.c_void_p), ("sigma_noise_fine", C.c_void_p)]
 
 
 class RenderOut(C.Structure):

@@ -440,16 +440,16 @@ int snb_render_rays(snb_model_t* mm, const float* rays, const int32_t* image_ind
   if (out->raw_fine && Sf > 0) raw_f = out->raw_fine;
   if (out->z_fine && Sf > 0) zf = out->z_fine;
 
-  auto run_pass = [&](const float* z, int Sn, float* raw, int32_t* gates_out, float* loss_out) -> int {
+  auto run_pass = [&](const float* z, int Sn, float* raw, int32_t* gates_out, float* loss_out, const float* noise) -> int {
     int rc = fill_x_launch(rays, image_indices, z, N, Sn, x, st);
     if (rc) return rc;
     const int64_t B = N * Sn;
     if (o->precision == SNB_PREC_BF16 && tc_supported(m))
-      return tc_forward_chunks(m, x, B, o->model_chunk_size, &o->route, raw, gates_out, loss_out, mws, model_ws, 4, st);
+      return tc_forward_chunks(m, x, B, o->model_chunk_size, &o->route, raw, gates_out, loss_out, mws, model_ws, 4, st, noise);
     int ci = 0;
     for (int64_t i = 0; i < B; i += o->model_chunk_size, ++ci) {       // rendering.py:354
       const int64_t rows = (B - i < o->model_chunk_size) ? (B - i) : o->model_chunk_size;
-      rc = snb_moe_forward(mm, x + i * m->x_cols, rows, nullptr, &o->route, o->precision, raw + i * 4,
+      rc = snb_moe_forward(mm, x + i * m->x_cols, rows, noise ? noise + i : nullptr, &o->route, o->precision, raw + i * 4,
                            gates_out ? gates_out + i : nullptr, loss_out ? loss_out + ci : nullptr, nullptr, nullptr,
                            mws, model_ws, st);
       if (rc) return rc;
@@ -459,7 +459,7 @@ int snb_render_rays(snb_model_t* mm, const float* rays, const int32_t* image_ind
 
   int rc;
   if ((rc = coarse_z_launch(rays, N, Sc, o->perturb, o->seed, zc, st))) return rc;
-  if ((rc = run_pass(zc, Sc, raw_c, out->moe_gates_coarse, out->gate_loss_coarse))) return rc;
+  if ((rc = run_pass(zc, Sc, raw_c, out->moe_gates_coarse, out->gate_loss_coarse, o->sigma_noise_coarse))) return rc;
   if (Sf == 0) {
     return composite_launch(zc, raw_c, last_delta, N, Sc, o->white_bkgd, out->rgb, out->depth, out->depth_variance,
                             out->bg_lambda, nullptr, st);
@@ -468,7 +468,7 @@ int snb_render_rays(snb_model_t* mm, const float* rays, const int32_t* image_ind
   if ((rc = composite_launch(zc, raw_c, last_delta, N, Sc, 0, nullptr, nullptr, nullptr, nullptr, wc, st))) return rc;
   if ((rc = zmid_launch(zc, N, Sc, zmid, st))) return rc;
   if ((rc = sample_pdf_launch(zmid, Sc - 1, wc, Sc, 1, nullptr, N, Sc - 2, Sf, o->seed, o->perturb == 0.f, zf, st))) return rc;
-  if ((rc = run_pass(zf, Sf, raw_f, out->moe_gates_fine, out->gate_loss_fine))) return rc;
+  if ((rc = run_pass(zf, Sf, raw_f, out->moe_gates_fine, out->gate_loss_fine, o->sigma_noise_fine))) return rc;
   // perturb == 0: z_fine comes from an ascending u through a monotone cdf, z_coarse is a linspace -> both sorted
   return merge_composite_launch(zf, zc, raw_f, raw_c, last_delta, N, Sf, Sc, o->perturb == 0.f, o->white_bkgd, out->rgb, out->depth,
                                 out->depth_variance, out->bg_lambda, st);

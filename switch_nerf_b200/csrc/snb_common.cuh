@@ -111,7 +111,8 @@ int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, co
                Arena& ws, cudaStream_t st);
 size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf);
 int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const snb_route_opts* o, float* out,
-                      int32_t* moe_idx, float* l_aux, void* ws_base, size_t ws_stride, int nsets, cudaStream_t st);
+                      int32_t* moe_idx, float* l_aux, void* ws_base, size_t ws_stride, int nsets, cudaStream_t st,
+                      const float* sigma_noise = nullptr);
 bool tc_supported(const Model* m);
 void tc_release(Model* m);
 

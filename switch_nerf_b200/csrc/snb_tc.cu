@@ -1492,7 +1492,8 @@ int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, co
 // side stream: st = front(0) front(1) back(0) front(2) back(1) ... ; side = route(0) route(1) ...
 // Two workspace sets alternate between consecutive chunks.
 int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const snb_route_opts* o, float* out,
-                      int32_t* moe_idx, float* l_aux, void* ws_base, size_t ws_stride, int nsets, cudaStream_t st) {
+                      int32_t* moe_idx, float* l_aux, void* ws_base, size_t ws_stride, int nsets, cudaStream_t st,
+                      const float* sigma_noise) {
   if (B <= 0) return SNB_OK;
   constexpr int MAXSETS = 4;
   static_assert(MAXSETS <= EP_SETS, "one expert-parallel buffer set per workspace set");
@@ -1560,7 +1561,8 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
     const int64_t rows = (B - i < chunk) ? (B - i) : chunk;
     const int k = ci % NS;
     Arena a((char*)ws_base + (size_t)k * ws_stride, ws_stride);
-    if ((rc = tc_chunk_init(m, cc[k], x + i * m->x_cols, rows, nullptr, o, out + i * 4, moe_idx ? moe_idx + i : nullptr,
+    if ((rc = tc_chunk_init(m, cc[k], x + i * m->x_cols, rows, sigma_noise ? sigma_noise + i : nullptr, o, out + i * 4,
+                            moe_idx ? moe_idx + i : nullptr,
                             l_aux ? l_aux + ci : nullptr, nullptr, nullptr, a, st, k)))
       return rc;
     cc[k].set = k;

@@ -68,6 +68,17 @@ def render_rays(nerf, bg_nerf, rays: torch.Tensor, image_indices: Optional[torch
     opts.white_bkgd = int(bool(getattr(hparams, "white_bkgd", False)))
     opts.precision = L.PRECISIONS[model.precision]
     opts.route = model.route_opts()
+    # rendering.py:316-322: sigma noise is drawn per chunk in training mode (torch's generator, like the reference)
+    noise_c = noise_f = None
+    if model.training and getattr(hparams, "use_sigma_noise", False) and float(getattr(hparams, "sigma_noise_std", 0.0)) > 0:
+        std = float(hparams.sigma_noise_std)
+        noise_c = torch.randn(N * Sc, dtype=torch.float32, device=dev) * std
+        noise_f = torch.randn(N * Sf, dtype=torch.float32, device=dev) * std if Sf > 0 else None
+    opts.sigma_noise_coarse, opts.sigma_noise_fine = L.ptr(noise_c), L.ptr(noise_f)
+    for flag in ("use_random_background_color", "return_pts", "return_pts_rgb", "return_pts_alpha", "return_sigma", "return_alpha"):
+        if getattr(hparams, flag, False):
+            raise NotImplementedError(f"hparams.{flag} is not implemented by switch_nerf_b200.rendering.render_rays "
+                                      "(debug / visualisation outputs of rendering.py:385-409 outside the hot path)")
 
     f32 = dict(dtype=torch.float32, device=dev)
     n_chunks_c = -(-N * Sc // chunk) if N > 0 else 0

@@ -295,6 +295,38 @@ def test_render_perturb_is_stratified(built_lib):
     assert (res["rgb_fine"] >= 0).all() and (res["rgb_fine"] <= 1.0 + 1e-5).all()
 
 
+def test_render_sigma_noise_training_mode(built_lib):
+    """rendering.py:316-322: in training mode with hparams.use_sigma_noise the per-sample noise randn * sigma_noise_std is
+    added to the raw sigma before the shifted softplus.  The mirror draws it from torch's generator: with the same seed
+    the coarse raw sigma must equal softplus(softplus^-1(sigma without noise) + noise) sample by sample (fp32 path)."""
+    from switch_nerf_b200.rendering import render_rays
+    g = load_golden("render_config1.npz")
+    model, hp = make_model(golden_sd(g), 1.0, True)
+    hp.coarse_samples, hp.fine_samples, hp.model_chunk_size, hp.perturb = 32, 0, 4096, 0.0
+    rays, idx = torch.from_numpy(g["rays"]).cuda(), torch.from_numpy(g["image_indices"]).cuda()
+    N = rays.shape[0]
+    base, _ = render_rays(model, None, rays, idx, hp, None, None, True, True, False, debug_taps=True)
+    model.train()
+    hp.use_sigma_noise, hp.sigma_noise_std = True, 0.7
+    torch.manual_seed(11)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        noisy, _ = render_rays(model, None, rays, idx, hp, None, None, True, True, False, debug_taps=True)
+    torch.manual_seed(11)
+    noise = (torch.randn(N * 32, dtype=torch.float32, device="cuda") * 0.7).view(N, 32)
+    s0 = base["_raw_coarse"][..., 3].double()
+    pre = torch.log(torch.expm1(s0))                                   # raw sigma - 1
+    expect = torch.nn.functional.softplus(pre + noise.double())
+    ok = s0 > 1e-3                                                     # the inverse is ill-conditioned for sigma -> 0
+    err = (noisy["_raw_coarse"][..., 3].double() - expect).abs()[ok]
+    assert ok.float().mean() > 0.9 and float(err.max()) < 1e-4, float(err.max())
+    assert torch.equal(noisy["_raw_coarse"][..., :3], base["_raw_coarse"][..., :3])
+    hp.return_sigma = True
+    with pytest.raises(NotImplementedError):
+        render_rays(model, None, rays, idx, hp, None, None, True, True, False)
+
+
 # ----------------------------------------------------------------------------- bf16 tcgen05 path
 def _run_bf16(c, chunked=False):
     model, _ = make_model(c["sd"], c["cf"], c["bpr"], c["no_batch"], "bf16")
