@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--workload", default="building", choices=["building", "mission_bay"],
                     help="building (default, BASELINE.json configs[1], the line the driver records) or mission_bay "
                          "(configs[3]: MipNeRFMoE width 512, 13312 rays x (256+256) intervals, chunk 212992)")
+    ap.add_argument("--sweep", default=None, choices=["cf"],
+                    help="cf: BASELINE.json configs[4] -- capacity factor 0.5/1/2 x batch_prioritized_routing on/off x gate "
+                         "balance (raw random init ... balanced) on the Building workload, one JSON line with every point")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--parallelism", default="dp", choices=["dp", "ep"],
                     help="dp: every expert on every GPU, rays sharded (the reference's shipped mode). "
@@ -475,6 +478,60 @@ def main_mission_bay(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def main_sweep_cf(args, local_rank):
+    """BASELINE.json configs[4]: the routing-imbalance throughput curve on the current kernels (single GPU)."""
+    from switch_nerf_b200 import synthetic as SY
+    from switch_nerf_b200.configs import make_hparams
+    from switch_nerf_b200.nerf_moe import get_nerf_moe_inner
+    from switch_nerf_b200.rendering import render_rays
+    torch.cuda.set_device(local_rank)
+    rays_c, idx_c = SY.synthetic_rays(N_RAYS, 2048, seed=100)
+    rays, idx = rays_c.cuda(), idx_c.cuda()
+    base_sd = SY.synthetic_state_dict(num_experts=EXPERTS, appearance_count=2048, seed=0, gate_scale=4.0)
+    pick = torch.randperm(N_RAYS, generator=torch.Generator().manual_seed(7))[:512]
+    tt = torch.linspace(0, 1, 64)
+    zz = rays_c[pick, 6:7] * (1 - tt) + rays_c[pick, 7:8] * tt
+    pts = (rays_c[pick, None, 0:3] + rays_c[pick, None, 3:6] * zz[..., None]).reshape(-1, 3)
+    rows = []
+    # gate skew: 0 balance iterations = raw random init (3 experts take ~95 %), 3 / 8 = partially, 60 = balanced
+    for iters in (0, 3, 8, 60):
+        sd = SY.balance_gate(base_sd, pts, iters=iters) if iters > 0 else base_sd
+        for cf in (0.5, 1.0, 2.0):
+            for bpr in (True, False):
+                hp = make_hparams(num_experts=EXPERTS, capacity_factor=cf, bpr=bpr, model_chunk_size=CHUNK, coarse_samples=COARSE,
+                                  fine_samples=FINE, amp_bf16=True, moe_return_gates=True)
+                model = get_nerf_moe_inner(hp, 2048, 3)
+                model.load_state_dict(sd)
+                model = model.cuda().eval()
+                for _ in range(3):
+                    res = render_rays(model, None, rays, idx, hp, None, None, True, True, False)[0]
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(max(args.steps, 3)):
+                    res = render_rays(model, None, rays, idx, hp, None, None, True, True, False)[0]
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / max(args.steps, 3)
+                gates = torch.cat([res["moe_gates_coarse"].view(-1), res["moe_gates_fine"].view(-1)])
+                share = torch.bincount(gates, minlength=EXPERTS).float() / gates.numel()
+                dropped_n, total_n = 0, 0
+                for key in ("moe_gates_coarse", "moe_gates_fine"):
+                    gk = res[key].view(-1)
+                    for i in range(0, gk.numel(), CHUNK):
+                        c = torch.bincount(gk[i:i + CHUNK], minlength=EXPERTS)
+                        capc = int(cf * ((min(CHUNK, gk.numel() - i) + EXPERTS - 1) // EXPERTS))
+                        dropped_n += int(torch.clamp(c - capc, min=0).sum())
+                        total_n += int(c.sum())
+                rows.append({"balance_iters": iters, "capacity_factor": cf, "bpr": bpr, "ms_per_step": round(ms, 4),
+                             "msamples_per_s": round(N_RAYS * (COARSE + FINE) / ms / 1e3, 2),
+                             "max_expert_share": round(float(share.max()), 4), "dropped_fraction": round(dropped_n / total_n, 4)})
+                model.release()
+    print(json.dumps({"sweep": "cf", "metric": "point-samples/sec", "unit": "M samples/s", "n_gpus": 1, "dtype": "bf16",
+                      "data": "synthetic", "config": {"workload": WORKLOAD.replace("cf=1.0, BPR", "cf x BPR x gate balance sweep")},
+                      "rows": rows}))
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -487,6 +544,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: switch_nerf_b200 has no CPU path")
     if args.workload == "mission_bay":
         return main_mission_bay(args, rank, local_rank, world)
+    if args.sweep == "cf":
+        if rank == 0:
+            main_sweep_cf(args, local_rank)
+        return
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)

@@ -211,6 +211,14 @@ int snb_moe_forward(snb_model_t* m, const float* x, int64_t S, const float* sigm
                     float* l_aux, float* dbg_gates, int32_t* dbg_loc, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* ---- f2: ray generation ------------------------------------------------------------------- */
+/* Replaces ray_utils.get_ray_directions + get_rays (ray_utils.py:6-84) for one image: rays [H*W, 8] fp32 =
+ * [origin(3), unit direction(3), near, far], pixel (row j, column i) at index j*W + i.
+ * c2w: DEVICE pointer to the 3x4 camera-to-world matrix (row-major); altitude_range: HOST pointer to
+ * [max_altitude, min_altitude] (hparams.ray_altitude_range) or NULL. */
+int snb_get_rays(int32_t W, int32_t H, float fx, float fy, float cx, float cy, int32_t center_pixels,
+                 const float* c2w, float near, float far, const float* altitude_range, float* rays, void* stream);
+
 /* ---- a1..a3: rendering.render_rays ------------------------------------------------------- */
 typedef struct snb_render_opts {
   int32_t coarse_samples;   /* hparams.coarse_samples                                          */

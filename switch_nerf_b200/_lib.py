@@ -80,6 +80,8 @@ _SIGNATURES = {
     "snb_route_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "snb_route_top1": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snb_get_rays": (C.c_int, [C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p,
+                               C.c_float, C.c_float, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
     "snb_route_select_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "snb_route_select": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

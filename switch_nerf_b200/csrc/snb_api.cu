@@ -53,6 +53,8 @@ int composite_launch(const float* z, const float* raw, const float* last_delta, 
 int sample_pdf_launch(const float* bins, int ld_bins, const float* weights, int ld_w, int w_off, const float* u,
                       int64_t N, int nb, int nf, uint64_t seed, int det, float* zf, cudaStream_t st);
 int coarse_z_launch(const float* rays, int64_t N, int Sc, float perturb, uint64_t seed, float* z, cudaStream_t st);
+int get_rays_launch(int W, int H, float fx, float fy, float cx, float cy, int center_pixels, const float* c2w, float near,
+                    float far, const float* alt, float* rays, cudaStream_t st);
 int fill_x_launch(const float* rays, const int* image_indices, const float* z, int64_t N, int Sn, float* x,
                   cudaStream_t st);
 int zmid_launch(const float* z, int64_t N, int S, float* mid, cudaStream_t st);
@@ -404,6 +406,14 @@ static size_t render_ws_layout(const Model* m, int64_t N, const snb_render_opts*
   return b + 4096;
 }
 
+int snb_get_rays(int32_t W, int32_t H, float fx, float fy, float cx, float cy, int32_t center_pixels, const float* c2w,
+                 float near, float far, const float* altitude_range, float* rays, void* stream) {
+  SNB_REQUIRE(W >= 0 && H >= 0 && (int64_t)W * H < (1ll << 31), "snb_get_rays: bad image size %d x %d", W, H);
+  SNB_REQUIRE(W == 0 || H == 0 || (c2w && rays), "snb_get_rays: NULL pointer");
+  SNB_REQUIRE(fx != 0.f && fy != 0.f, "snb_get_rays: zero focal length");
+  return get_rays_launch(W, H, fx, fy, cx, cy, center_pixels, c2w, near, far, altitude_range, rays, (cudaStream_t)stream);
+}
+
 size_t snb_render_workspace_bytes(const snb_model_t* mm, int64_t n_rays, const snb_render_opts* o) {
   if (!mm || !o) return 0;
   return render_ws_layout((const Model*)mm, n_rays, o, nullptr);
@@ -441,9 +451,16 @@ int snb_render_rays(snb_model_t* mm, const float* rays, const int32_t* image_ind
   if (out->z_fine && Sf > 0) zf = out->z_fine;
 
   auto run_pass = [&](const float* z, int Sn, float* raw, int32_t* gates_out, float* loss_out, const float* noise) -> int {
-    int rc = fill_x_launch(rays, image_indices, z, N, Sn, x, st);
-    if (rc) return rc;
     const int64_t B = N * Sn;
+    int rc;
+    if (o->precision == SNB_PREC_BF16 && tc_supported(m) && tc_ray_source_ok(m)) {
+      // the [N*Sn, 7] point tensor of rendering.py:357-362 is never built: both fused kernels rebuild a row from its ray
+      // (32 B, cached) and its depth (4 B) where they consume it
+      const RaySource rs = {rays, z, image_indices, Sn};
+      return tc_forward_chunks(m, nullptr, B, o->model_chunk_size, &o->route, raw, gates_out, loss_out, mws, model_ws, 4, st,
+                               noise, &rs);
+    }
+    if ((rc = fill_x_launch(rays, image_indices, z, N, Sn, x, st))) return rc;
     if (o->precision == SNB_PREC_BF16 && tc_supported(m))
       return tc_forward_chunks(m, x, B, o->model_chunk_size, &o->route, raw, gates_out, loss_out, mws, model_ws, 4, st, noise);
     int ci = 0;

@@ -110,9 +110,18 @@ int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, co
                float* out, int32_t* moe_idx, float* l_aux, float* dbg_gates, int32_t* dbg_loc,
                Arena& ws, cudaStream_t st);
 size_t tc_workspace_bytes(const Model* m, int64_t S, double max_cf);
+// rows of a render pass given as rays + depths instead of the materialised [S,7] tensor (x may then be NULL)
+struct RaySource {
+  const float* rays;   // [N,8]
+  const float* z;      // [N*Sn] ray-major
+  const int* img;      // [N] nullable
+  int Sn;
+};
 int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const snb_route_opts* o, float* out,
                       int32_t* moe_idx, float* l_aux, void* ws_base, size_t ws_stride, int nsets, cudaStream_t st,
-                      const float* sigma_noise = nullptr);
+                      const float* sigma_noise = nullptr, const RaySource* rs = nullptr);
+// true when the kernels that will run for this model can take a RaySource (the TS kernels, all experts local)
+bool tc_ray_source_ok(const Model* m);
 bool tc_supported(const Model* m);
 void tc_release(Model* m);
 

@@ -329,6 +329,61 @@ int sample_pdf_launch(const float* bins, int ld_bins, const float* weights, int 
   return SNB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// camera rays of one image: ray_utils.py:6-84 (get_ray_directions + get_rays + _get_rays_inner +
+// _truncate_with_plane_intersection), one thread per pixel.  rays [H*W, 8] = [o, d, near, far].
+// ------------------------------------------------------------------------------------------
+__global__ void k_get_rays(int W, int H, float fx, float fy, float cx, float cy, int center_pixels, const float* __restrict__ c2w,
+                           float near, float far, int has_alt, float alt0, float alt1, float* __restrict__ rays) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (int64_t)W * H) return;
+  const int i = (int)(p % W), j = (int)(p / W);                  // meshgrid(indexing='xy'): i = column, j = row
+  const float fi = (float)i + (center_pixels ? 0.5f : 0.f), fj = (float)j + (center_pixels ? 0.5f : 0.f);
+  float dx = __fdiv_rn(fi - cx, fx), dy = -__fdiv_rn(fj - cy, fy), dz = -1.f;      // ray_utils.py:14-15
+  float n = sqrtf(dx * dx + dy * dy + dz * dz);
+  dx = __fdiv_rn(dx, n); dy = __fdiv_rn(dy, n); dz = __fdiv_rn(dz, n);            // :16
+  float r[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) r[a] = dx * c2w[a * 4 + 0] + dy * c2w[a * 4 + 1] + dz * c2w[a * 4 + 2];   // directions @ c2w[:, :3].T
+  n = sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) r[a] = __fdiv_rn(r[a], n);                                              // :25
+  const float o[3] = {c2w[3], c2w[7], c2w[11]};
+  float nb = near, fb = far;
+  if (has_alt) {
+    // _truncate_with_plane_intersection (:69-90): plane x = altitude, normal (-1, 0, 0); only for rays that start
+    // before the plane and head towards it
+    if (o[0] < alt0 && r[0] > 0.f) {
+      const float w0 = o[0] - alt0, si = __fdiv_rn(w0, -r[0]);       // si = -w.n / (d.n) with n = (-1,0,0)
+      const float q0 = w0 + si * r[0], q1 = o[1] + si * r[1], q2 = o[2] + si * r[2];   // plane_intersection - plane_point (+ plane_point)
+      const float e0 = o[0] - (q0 + alt0), e1 = o[1] - q1, e2 = o[2] - q2;
+      nb = sqrtf(e0 * e0 + e1 * e1 + e2 * e2);
+    }
+    nb = fmaxf(nb, near);                                                                             // :52
+    if (o[0] < alt1 && r[0] > 0.f) {
+      const float w0 = o[0] - alt1, si = __fdiv_rn(w0, -r[0]);
+      const float q0 = w0 + si * r[0], q1 = o[1] + si * r[1], q2 = o[2] + si * r[2];
+      const float e0 = o[0] - (q0 + alt1), e1 = o[1] - q1, e2 = o[2] - q2;
+      fb = sqrtf(e0 * e0 + e1 * e1 + e2 * e2);
+    }
+    fb = fminf(fb, far);                                                                              // :55
+    fb = fmaxf(nb, fb);                                                                               // :56
+  }
+  float* out = rays + p * 8;
+  out[0] = o[0]; out[1] = o[1]; out[2] = o[2];
+  out[3] = r[0]; out[4] = r[1]; out[5] = r[2];
+  out[6] = nb; out[7] = fb;
+}
+
+int get_rays_launch(int W, int H, float fx, float fy, float cx, float cy, int center_pixels, const float* c2w, float near,
+                    float far, const float* alt, float* rays, cudaStream_t st) {
+  if (W <= 0 || H <= 0) return SNB_OK;
+  k_get_rays<<<(unsigned)cdiv((int64_t)W * H, 256), 256, 0, st>>>(W, H, fx, fy, cx, cy, center_pixels, c2w, near, far,
+                                                                   alt != nullptr, alt ? alt[0] : 0.f, alt ? alt[1] : 0.f, rays);
+  SNB_CHECK_LAUNCH("k_get_rays");
+  return SNB_OK;
+}
+
 int coarse_z_launch(const float* rays, int64_t N, int Sc, float perturb, uint64_t seed, float* z, cudaStream_t st) {
   if (N == 0) return SNB_OK;
   k_coarse_z<<<(unsigned)cdiv(N * Sc, 256), 256, 0, st>>>(rays, N, Sc, perturb, seed, z);

@@ -105,7 +105,30 @@ struct TcParams {
   const float* emb_a;       // fp32 [count, A]
   unsigned long long* tl;   // debug timeline (nullable): [role][TL_N] (tag<<48 | clock) marks of CTA 0
   int ab;                   // debug A/B switches (SNB_FRONT_AB): 1 = no level-0 histogram, 2 = no column sums
+  // ray source (render passes on the TS kernels): the [S,7] rows [o + d z, d, image index] of rendering.py:357-362 are
+  // never materialised -- a row is rebuilt from its 32-byte ray and its 4-byte depth where it is consumed
+  const float* ray_src;     // [N,8] rays (nullptr: rows come from x)
+  const float* ray_z;       // [N * ray_sn] depths of the pass, ray-major
+  const int* ray_img;       // [N] image indices (nullable)
+  int ray_sn;               // samples per ray of the pass
+  int64_t ray_s0;           // first sample of this chunk inside the pass
 };
+
+// row `s` of the chunk from the ray source: xyz = o + d * z with separate multiply and add (torch: rays_o + rays_d * z)
+__device__ __forceinline__ void ray_row_xyz(const TcParams& P, int64_t s, float& x0, float& x1, float& x2) {
+  const uint32_t g = (uint32_t)(P.ray_s0 + s);
+  const float* ray = P.ray_src + (size_t)(g / (uint32_t)P.ray_sn) * 8;
+  const float zv = P.ray_z[g];
+  x0 = __fadd_rn(ray[0], __fmul_rn(ray[3], zv));
+  x1 = __fadd_rn(ray[1], __fmul_rn(ray[4], zv));
+  x2 = __fadd_rn(ray[2], __fmul_rn(ray[5], zv));
+}
+__device__ __forceinline__ void ray_row_dir(const TcParams& P, int64_t s, float& d0, float& d1, float& d2, int& img) {
+  const uint32_t r = (uint32_t)(P.ray_s0 + s) / (uint32_t)P.ray_sn;
+  const float* ray = P.ray_src + (size_t)r * 8;
+  d0 = ray[3]; d1 = ray[4]; d2 = ray[5];
+  img = P.ray_img ? P.ray_img[r] : 0;
+}
 
 // canonical image: slices of 64 k; inside a slice (n/8)*(klen*16) + (kk/8)*128 + (n%8)*16 + (kk%8)*2 bytes
 __device__ __forceinline__ size_t packed_index(int n, int k, int N, int K16) {
@@ -190,6 +213,7 @@ bool tc_supported(const Model* m) {
 }
 
 struct TcOwner { TcHost h; uint8_t* wblob; uint8_t* wblob_w; };
+static bool env_is(const char* name, int v) { const char* e = getenv(name); return e && atoi(e) == v; }
 // which kernel family evaluates a model: wide for width 512 and mip models (SNB_WIDE=1 forces it for A/B tests)
 static bool tc_use_wide(const Model* m) {
   static const bool force = getenv("SNB_WIDE") && atoi(getenv("SNB_WIDE")) != 0;
@@ -1478,6 +1502,15 @@ static int tc_back(Model* m, TcChunk& c, cudaStream_t st, bool finish_inline = t
   return SNB_OK;
 }
 
+bool tc_ray_source_ok(const Model* m) {
+  if (!m->tc_blob || m->ep || tc_use_wide(m)) return false;
+  const TcParams& p = ((TcOwner*)m->tc_blob)->h.p;
+  static const bool ts_off = env_is("SNB_TS", 0) || env_is("SNB_TS_FRONT", 0) || env_is("SNB_CG", 2) ||
+                             env_is("SNB_CG_FRONT", 2) || env_is("SNB_CG_BACK", 2) || getenv("SNB_NO_RAY_SOURCE");
+  return !ts_off && p.recompute_h && p.front[0].K16 <= TS_CAT_COLS && p.back[1].K16 > (uint32_t)MW &&
+         p.back[1].K16 - MW <= TS_CAT_COLS;
+}
+
 int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* o, float* out,
                int32_t* moe_idx, float* l_aux, float* dbg_gates, int32_t* dbg_loc, Arena& ws, cudaStream_t st) {
   TcChunk c;
@@ -1493,7 +1526,9 @@ int tc_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, co
 // Two workspace sets alternate between consecutive chunks.
 int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const snb_route_opts* o, float* out,
                       int32_t* moe_idx, float* l_aux, void* ws_base, size_t ws_stride, int nsets, cudaStream_t st,
-                      const float* sigma_noise) {
+                      const float* sigma_noise, const RaySource* rs) {
+  SNB_REQUIRE(x || rs, "tc_forward_chunks: neither rows nor a ray source");
+  SNB_REQUIRE(!rs || tc_ray_source_ok(m), "tc_forward_chunks: the kernels selected for this model read materialised rows");
   if (B <= 0) return SNB_OK;
   constexpr int MAXSETS = 4;
   static_assert(MAXSETS <= EP_SETS, "one expert-parallel buffer set per workspace set");
@@ -1561,12 +1596,18 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
     const int64_t rows = (B - i < chunk) ? (B - i) : chunk;
     const int k = ci % NS;
     Arena a((char*)ws_base + (size_t)k * ws_stride, ws_stride);
-    if ((rc = tc_chunk_init(m, cc[k], x + i * m->x_cols, rows, sigma_noise ? sigma_noise + i : nullptr, o, out + i * 4,
+    if ((rc = tc_chunk_init(m, cc[k], x ? x + i * m->x_cols : nullptr, rows, sigma_noise ? sigma_noise + i : nullptr, o, out + i * 4,
                             moe_idx ? moe_idx + i : nullptr,
                             l_aux ? l_aux + ci : nullptr, nullptr, nullptr, a, st, k)))
       return rc;
     cc[k].set = k;
     cc[k].grid_cap = grid_cap;
+    if (rs) {
+      for (TcParams* P : {&cc[k].Pf, &cc[k].Pb}) {
+        P->ray_src = rs->rays; P->ray_z = rs->z; P->ray_img = rs->img; P->ray_sn = rs->Sn; P->ray_s0 = i;
+      }
+      cc[k].x = nullptr;
+    }
     if ((rc = tc_front(m, cc[k], st))) return rc;
     if (back_full) cc[k].grid_cap = m->sm_count;
     SNB_CHECK_CUDA(cudaEventRecord(m->ev_front[k], st));

@@ -320,10 +320,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         if (r.sidx >= 0) {
           const float* xr = x + (int64_t)r.sidx * io.x_stride;
           if (r.e >= 0) r.g = io.wsel ? sel_gate(io.wsel[r.sidx]) : gate[(int64_t)r.sidx * io.g_stride];
-          if (ec.cs == 0 && r.e >= 0) { r.x0 = xr[0]; r.x1 = xr[1]; r.x2 = xr[2]; }
-          if (ec.cs == 1) {
-            r.d0 = xr[P.x_cols - 4]; r.d1 = xr[P.x_cols - 3]; r.d2 = xr[P.x_cols - 2];
-            r.ai = min(max((int)xr[P.x_cols - 1], 0), P.appearance_count - 1);
+          if (P.ray_src) {
+            if (ec.cs == 0 && r.e >= 0) ray_row_xyz(P, r.sidx, r.x0, r.x1, r.x2);
+            if (ec.cs == 1) {
+              ray_row_dir(P, r.sidx, r.d0, r.d1, r.d2, r.ai);
+              r.ai = min(max(r.ai, 0), P.appearance_count - 1);
+            }
+          } else {
+            if (ec.cs == 0 && r.e >= 0) { r.x0 = xr[0]; r.x1 = xr[1]; r.x2 = xr[2]; }
+            if (ec.cs == 1) {
+              r.d0 = xr[P.x_cols - 4]; r.d1 = xr[P.x_cols - 3]; r.d2 = xr[P.x_cols - 2];
+              r.ai = min(max((int)xr[P.x_cols - 1], 0), P.appearance_count - 1);
+            }
           }
         }
       }
@@ -727,7 +735,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
     auto load_xyz = [&](int tile, float (&p)[3]) {
       p[0] = p[1] = p[2] = 0.f;
       const int64_t sr = (int64_t)tile * TILE + row;
-      if (ec.cs == 0 && tile < n_tiles && sr < S) { p[0] = x[sr * P.x_cols]; p[1] = x[sr * P.x_cols + 1]; p[2] = x[sr * P.x_cols + 2]; }
+      if (ec.cs == 0 && tile < n_tiles && sr < S) {
+        if (P.ray_src) ray_row_xyz(P, sr, p[0], p[1], p[2]);
+        else { p[0] = x[sr * P.x_cols]; p[1] = x[sr * P.x_cols + 1]; p[2] = x[sr * P.x_cols + 2]; }
+      }
     };
     // PE(xyz) of a tile -> cat block `blk` (cs == 0 threads) + release of its chunks to the MMA issuer
     auto stage_pe = [&](const float (&p)[3], int blk) {

@@ -147,3 +147,29 @@ def test_import_surface_aliases(built_lib):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+@pytest.mark.parametrize("alt", [None, [0.3, 1.2]])
+@pytest.mark.parametrize("center", [False, True])
+def test_get_rays_equals_reference_ray_utils(built_lib, alt, center):
+    """snb_get_rays (one kernel per image) == the unmodified switch_nerf.ray_utils.get_ray_directions + get_rays
+    (ray_utils.py:6-84) run on the same GPU, incl. the altitude-plane truncation of near / far."""
+    R.install_shims()
+    from switch_nerf import ray_utils as ref
+    from switch_nerf_b200.ray_utils import get_rays_for_image
+    W, H, fx, fy, cx, cy = 61, 37, 55.0, 57.5, 30.2, 18.9
+    g = torch.Generator().manual_seed(3)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    c2w = torch.cat([q, torch.tensor([[-0.4], [0.1], [0.2]])], 1).cuda()
+    dev = c2w.device
+    d = ref.get_ray_directions(W, H, fx, fy, cx, cy, center, dev)
+    want = ref.get_rays(d, c2w, 0.05, 2.0, alt)
+    mine = get_rays_for_image(W, H, fx, fy, cx, cy, center, c2w, 0.05, 2.0, alt)
+    torch.cuda.synchronize()
+    assert mine.shape == want.shape == (H, W, 8)
+    assert torch.equal(mine[..., :3], want[..., :3])
+    assert float((mine[..., 3:6] - want[..., 3:6]).abs().max()) < 5e-7          # fp32 matmul accumulation order
+    err = (mine[..., 6:] - want[..., 6:]).abs() / want[..., 6:].abs().clamp_min(1e-3)
+    assert float(err.max()) < 1e-5, float(err.max())
+    if alt is not None:
+        assert float((want[..., 6] > 0.05).float().mean()) > 0.05, "the case must exercise the near-plane truncation"
