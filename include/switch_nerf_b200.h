@@ -104,7 +104,10 @@ int snb_profile_collect(double* out4);
  * 64-bit words copied (0 when disabled).  Synchronises the device. */
 int snb_debug_timeline(uint64_t* host_out, int32_t n);
 
-/* ---- model object ----------------------------------------------------------------------- */
+/* ---- model object -----------------------------------------------------------------------
+ * Concurrency: every entry point only enqueues on the caller's stream, but a model object owns the side streams /
+ * events of its chunk pipeline and the zero-between-uses scratch of the routing kernel, so ONE caller stream may use a
+ * given model at a time (serialise host threads that share a model; different models are independent). */
 /* Replaces models/nerf_moe.py:1004-1041 get_nerf_moe_inner + load_state_dict: copies/packs the
  * caller's fp32 weights into kernel-native layouts (fp32 [N,K] for the CUDA-core path; bf16
  * UMMA canonical K-major core-matrix tiles for the tcgen05 path).  Call again after an
