@@ -98,9 +98,14 @@ __global__ void __launch_bounds__(256) k_ep_dispatch(EpDev d, const float* __res
   }
 }
 
-__global__ void __launch_bounds__(1024) k_ep_plan(EpDev d, TileTable tt, int pair, uint32_t epoch) {
+// Several small CTAs (256 threads, 32 registers: they fit next to a resident launch-#2 CTA, so the plan never has to wait
+// for a free SM): every CTA waits for the peers' flag A and derives the same segment table; the rows are filled with a
+// grid-stride loop; the last CTA to finish resets the per-set scratch.  local[3] = CTA ticket.
+constexpr int EP_PLAN_CTAS = 32;
+__global__ void __launch_bounds__(256) k_ep_plan(EpDev d, TileTable tt, int pair, uint32_t epoch) {
   __shared__ int s_row[MAX_LOCAL_EXPERTS_PLUS], s_tile[MAX_LOCAL_EXPERTS_PLUS], s_kc[MAX_LOCAL_EXPERTS_PLUS],
       s_nt[MAX_LOCAL_EXPERTS_PLUS];
+  __shared__ int s_last;
   char* mine = d.peer[d.rank];
   if ((int)threadIdx.x < d.world) wait_flag(reinterpret_cast<const uint32_t*>(mine + d.o_flag) + threadIdx.x, epoch);
   __syncthreads();
@@ -112,21 +117,21 @@ __global__ void __launch_bounds__(1024) k_ep_plan(EpDev d, TileTable tt, int pai
     for (int el = 0; el <= EL; ++el) {
       int kc = 0;
       if (el < EL) for (int w = 0; w < d.world; ++w) kc += cnt[w * EL + el];
-      else kc = local[0];                                            // dropped bucket (local samples only)
+      else kc = *reinterpret_cast<volatile int*>(&local[0]);         // dropped bucket (local samples only)
       int n = (kc + EP_TILE - 1) / EP_TILE;
       if (pair) n = (n + 1) & ~1;
       s_row[el] = row; s_tile[el] = nt; s_kc[el] = kc; s_nt[el] = n;
-      tt.seg_start[el] = row;
+      if (blockIdx.x == 0) tt.seg_start[el] = row;
       row += (kc + EP_TILE - 1) / EP_TILE * EP_TILE;
       nt += n;
     }
-    *tt.n_tiles = nt;
-    *tt.drop_counter = 0;
+    if (blockIdx.x == 0) { *tt.n_tiles = nt; *tt.drop_counter = 0; }
   }
   __syncthreads();
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
   for (int el = 0; el <= EL; ++el) {
     const int t0 = s_tile[el], nt = s_nt[el];
-    for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+    for (int i = gtid; i < nt; i += gsz) {
       tt.tile_expert[t0 + i] = (el < EL) ? d.rank * EL + el : -1;
       tt.tile_row0[t0 + i] = s_row[el] + i * EP_TILE;
       tt.tile_rows[t0 + i] = max(0, min(EP_TILE, s_kc[el] - i * EP_TILE));
@@ -136,16 +141,19 @@ __global__ void __launch_bounds__(1024) k_ep_plan(EpDev d, TileTable tt, int pai
       for (int w = 0; w < d.world; ++w) {
         const int kcw = cnt[w * EL + el];
         const int slot0 = (w * EL + el) * d.capmax;
-        for (int l = threadIdx.x; l < kcw; l += blockDim.x) tt.row2sample[off + l] = slot0 + l;
+        for (int l = gtid; l < kcw; l += gsz) tt.row2sample[off + l] = slot0 + l;
         off += kcw;
       }
     } else {
       const int slot0 = d.world * EL * d.capmax;
-      for (int j = threadIdx.x; j < s_kc[el]; j += blockDim.x) tt.row2sample[s_row[el] + j] = slot0 + j;
+      for (int j = gtid; j < s_kc[el]; j += gsz) tt.row2sample[s_row[el] + j] = slot0 + j;
     }
   }
+  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) local[0] = 0;          // drop counter of the next chunk that uses this set
+  if (threadIdx.x == 0) s_last = (atomicAdd(&local[3], 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) { local[0] = 0; local[3] = 0; }     // drop counter / ticket of the next chunk that uses this set
 }
 
 __global__ void k_ep_wait(EpDev d, uint32_t epoch) {
@@ -289,7 +297,7 @@ int ep_dispatch_plan(Ep* ep, int set, const float* x, int x_cols, const float* g
   const EpDev d = dev_view(ep, set);
   k_ep_dispatch<<<(unsigned)cdiv(S, 256), 256, 0, st>>>(d, x, x_cols, gate, noise, idx, loc, counts, cap_dev, S, epoch);
   SNB_CHECK_LAUNCH("k_ep_dispatch");
-  k_ep_plan<<<1, 1024, 0, st>>>(d, tt, pair, epoch);
+  k_ep_plan<<<EP_PLAN_CTAS, 256, 0, st>>>(d, tt, pair, epoch);
   SNB_CHECK_LAUNCH("k_ep_plan");
   return SNB_OK;
 }
