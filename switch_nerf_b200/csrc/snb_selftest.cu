@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(192) k_umma_bench(int N, int ts, int flags, in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* sA = smem;                       // 128 x 64 bf16 canonical (16 KB)
   uint8_t* sB = smem + 16384;               // 256 x 64 bf16 canonical (32 KB)
-  uint8_t* sL = smem + 49152;               // landing zone 4 x 8 KB
+  uint8_t* sL = smem + 49152;               // landing zone 4 x (8 KB << ((flags >> 4) & 3))
+  const uint32_t cbytes = 8192u << ((flags >> 4) & 3);
   if (threadIdx.x == 0) {
     mbar_init(&bar_mma, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bar_full[i], 1);
@@ -185,29 +186,29 @@ __global__ void __launch_bounds__(192) k_umma_bench(int N, int ts, int flags, in
       umma_commit(&bar_mma);
       mbar_wait(&bar_mma, 0);
       const unsigned long long t1 = clock64();
-      out[0] = t1 - t0;
+      if (blockIdx.x == 0) out[0] = t1 - t0;
       done = 1;
     }
   } else if (warp == 1) {
     if (lane == 0 && (flags & 1)) {
-      // keep four 8 KB copies in flight (one per landing slot), like the weight ring of the fused kernels
+      // keep four copies in flight (one per landing slot), like the weight ring of the fused kernels
       uint32_t n = 0;
       for (uint32_t s2 = 0; s2 < 4; ++s2) {
-        mbar_arrive_expect_tx(&bar_full[s2], 8192);
-        bulk_g2s(sL + s2 * 8192, src + (size_t)s2 * 8192, 8192, &bar_full[s2]);
+        mbar_arrive_expect_tx(&bar_full[s2], cbytes);
+        bulk_g2s(sL + s2 * cbytes, src + (size_t)s2 * cbytes, cbytes, &bar_full[s2]);
       }
       while (!done) {
         const uint32_t s2 = n & 3, ph = (n >> 2) & 1;
         mbar_wait(&bar_full[s2], ph);
         ++n;
-        mbar_arrive_expect_tx(&bar_full[s2], 8192);
-        bulk_g2s(sL + s2 * 8192, src + (size_t)((n + 3) & 1023) * 8192, 8192, &bar_full[s2]);
+        mbar_arrive_expect_tx(&bar_full[s2], cbytes);
+        bulk_g2s(sL + s2 * cbytes, src + (size_t)((n + 3 + 7 * blockIdx.x) & 127) * cbytes, cbytes, &bar_full[s2]);
       }
       for (uint32_t k = 0; k < 4; ++k) {            // drain what is still in flight before the CTA exits
         const uint32_t s2 = (n + k) & 3, ph = ((n + k) >> 2) & 1;
         mbar_wait(&bar_full[s2], ph);
       }
-      out[1] = n;
+      if (blockIdx.x == 0) out[1] = n;
     }
   } else if (flags & 2) {
     unsigned long long n = 0;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(192) k_umma_bench(int N, int ts, int flags, in
       acc ^= v[0];
       ++n;
     }
-    if (lane == 0) out[2 + (warp - 2)] = n + (acc == 0x12345u);
+    if (lane == 0 && blockIdx.x == 0) out[2 + (warp - 2)] = n + (acc == 0x12345u);
   }
   tc_fence_before();
   __syncthreads();
@@ -269,11 +270,11 @@ __global__ void __launch_bounds__(192) k_umma_bench_pair(int N, int ts, int reps
 int umma_microbench(int N, int ts, int flags, int reps, unsigned long long* host_out6, cudaStream_t st) {
   SNB_REQUIRE(N == 64 || N == 128 || N == 256, "microbench: N must be 64, 128 or 256");
   SNB_REQUIRE(reps > 0 && reps <= (1 << 20), "microbench: bad reps");
-  const size_t smem = 49152 + 4 * 8192 + 1024;
+  const size_t smem = 49152 + 4 * (8192u << ((flags >> 4) & 3)) + 1024;
   SNB_CHECK_CUDA(cudaFuncSetAttribute(k_umma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   uint8_t* src = nullptr;
   unsigned long long* out = nullptr;
-  SNB_CHECK_CUDA(cudaMalloc((void**)&src, (size_t)1024 * 8192));
+  SNB_CHECK_CUDA(cudaMalloc((void**)&src, (size_t)1024 * 8192));      // 8 MB: 128 slots of up to 64 KB
   SNB_CHECK_CUDA(cudaMalloc((void**)&out, 6 * sizeof(unsigned long long)));
   SNB_CHECK_CUDA(cudaMemsetAsync(out, 0, 6 * sizeof(unsigned long long), st));
   if (flags & 4) {
@@ -286,7 +287,10 @@ int umma_microbench(int N, int ts, int flags, int reps, unsigned long long* host
     cfg.attrs = at; cfg.numAttrs = 1;
     SNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_umma_bench_pair, N, ts, reps, out));
   } else {
-    k_umma_bench<<<1, 192, smem, st>>>(N, ts, flags, reps, src, out);
+    // flags & 0x100: one CTA on every SM (full-chip L2 load), CTA 0 reports
+    int grid = 1;
+    if (flags & 0x100) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&grid, cudaDevAttrMultiProcessorCount, dev); }
+    k_umma_bench<<<grid, 192, smem, st>>>(N, ts, flags, reps, src, out);
   }
   SNB_CHECK_LAUNCH("k_umma_bench");
   SNB_CHECK_CUDA(cudaMemcpyAsync(host_out6, out, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
