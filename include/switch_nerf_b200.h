@@ -214,6 +214,35 @@ int snb_moe_forward(snb_model_t* m, const float* x, int64_t S, const float* sigm
                     float* l_aux, float* dbg_gates, int32_t* dbg_loc, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* ---- f1: backward ------------------------------------------------------------------------- */
+/* Gradient buffers, fp32 device pointers in the reference's state_dict layouts (same fields as snb_weights; experts
+ * [E, in, out] / [E, 1, out]); every pointer nullable (that gradient is skipped).  Gradients are ACCUMULATED. */
+typedef struct snb_grads {
+  float* xyz_w; float* xyz_b;
+  float* gate_w[4]; float* gate_b[4];
+  float* ln_w; float* ln_b;
+  float* wg;
+  float* exp_w[16]; float* exp_b[16];
+  float* l1_w; float* l1_b; float* l2_w; float* l2_b;
+  float* sigma_w; float* sigma_b; float* color_w; float* color_b;
+  float* emb_a;
+} snb_grads;
+
+/* Parameter gradients of one model chunk: backward of snb_moe_forward (NeRFMoE.forward, models/nerf_moe.py:320-455, with
+ * GatingEncoder/Decoder.backward of tutel_fast_dispatch.py:30-45, 65-78 and the ExpertMLP dgrad / wgrad,
+ * tutel_moe_layer_nobatch.py:887-924; the caller is runner.py:677-690).  fp32, capacity (batched) dispatch; the forward
+ * intermediates are recomputed inside.  d_out [S,4] = dL/d[rgb, sigma]; d_l_aux: DEVICE scalar dL/d(l_aux of this
+ * chunk) or NULL.  Nothing flows into x. */
+size_t snb_moe_backward_workspace_bytes(const snb_model_t* m, int64_t S, double capacity_factor);
+int snb_moe_backward(snb_model_t* m, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* opts,
+                     const float* d_out, const float* d_l_aux, const snb_grads* grads, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* Backward of the volumetric composite (rendering.py:436-494; depth / variance are computed under no_grad there):
+ * z [N,S] sorted depths, raw [N,S,4] = [rgb, sigma] in the same order, last_delta [N] or NULL (1e10), d_rgb [N,3];
+ * writes d_raw [N,S,4]. */
+int snb_composite_backward(const float* z, const float* raw, const float* last_delta, int64_t n_rays, int32_t n_samples,
+                           const float* d_rgb, float* d_raw, void* stream);
+
 /* ---- f2: ray generation ------------------------------------------------------------------- */
 /* Replaces ray_utils.get_ray_directions + get_rays (ray_utils.py:6-84) for one image: rays [H*W, 8] fp32 =
  * [origin(3), unit direction(3), near, far], pixel (row j, column i) at index j*W + i.
@@ -254,6 +283,7 @@ typedef struct snb_render_out {
   float* raw_coarse;     /* tap: per-sample [rgb,sigma]  [N, coarse, 4] */
   float* raw_fine;       /* tap: per-sample [rgb,sigma]  [N, fine, 4]   */
   float* rgb_coarse;     /* mip renderer only: rgb_coarse [N,3] (rendering_mip.py composites both levels) */
+  float* z_coarse;       /* tap: coarse z values (after perturb) [N, coarse]; the backward needs them */
 } snb_render_out;
 
 size_t snb_render_workspace_bytes(const snb_model_t* m, int64_t n_rays, const snb_render_opts* o);

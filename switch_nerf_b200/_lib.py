@@ -52,7 +52,7 @@ class RenderOpts(C.Structure):
 class RenderOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "rgb", "depth", "depth_variance", "bg_lambda", "gate_loss_coarse", "gate_loss_fine",
-        "moe_gates_coarse", "moe_gates_fine", "z_fine", "raw_coarse", "raw_fine", "rgb_coarse")]
+        "moe_gates_coarse", "moe_gates_fine", "z_fine", "raw_coarse", "raw_fine", "rgb_coarse", "z_coarse")]
 
 
 # name -> (restype, argtypes); mirrors include/switch_nerf_b200.h one to one
@@ -80,6 +80,11 @@ _SIGNATURES = {
     "snb_route_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "snb_route_top1": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snb_moe_backward_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_double]),
+    "snb_moe_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(RouteOpts), C.c_void_p, C.c_void_p,
+                                   C.POINTER(Weights), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snb_composite_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
     "snb_get_rays": (C.c_int, [C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p,
                                C.c_float, C.c_float, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
     "snb_route_select_workspace_bytes": (C.c_size_t, [C.c_int64]),
@@ -160,8 +165,8 @@ class Workspace:
     _cache = {}
 
     @classmethod
-    def get(cls, nbytes, device):
-        key = (device.type, device.index)
+    def get(cls, nbytes, device, tag=None):
+        key = (device.type, device.index, tag)
         buf = cls._cache.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = None

@@ -406,6 +406,31 @@ static size_t render_ws_layout(const Model* m, int64_t N, const snb_render_opts*
   return b + 4096;
 }
 
+size_t snb_moe_backward_workspace_bytes(const snb_model_t* mm, int64_t S, double capacity_factor) {
+  if (!mm) return 0;
+  return fp32_backward_workspace_bytes((const Model*)mm, S, capacity_factor) + 4096;
+}
+
+int snb_moe_backward(snb_model_t* mm, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* opts,
+                     const float* d_out, const float* d_l_aux, const snb_grads* grads, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  Model* m = (Model*)mm;
+  SNB_REQUIRE(m && opts && grads && workspace, "snb_moe_backward: NULL argument");
+  SNB_REQUIRE(S >= 0 && (S == 0 || (x && d_out)), "snb_moe_backward: NULL input");
+  SNB_REQUIRE(opts->capacity_factor > 0, "capacity_factor must be > 0");
+  SNB_REQUIRE(!m->d.mip, "snb_moe_backward: MipNeRFMoE backward is not implemented");
+  SNB_REQUIRE(!m->ep, "snb_moe_backward: expert-parallel backward is not implemented");
+  Arena ws(workspace, workspace_bytes);
+  return fp32_backward(m, x, S, sigma_noise, opts, d_out, d_l_aux, grads, ws, (cudaStream_t)stream);
+}
+
+int snb_composite_backward(const float* z, const float* raw, const float* last_delta, int64_t n_rays, int32_t n_samples,
+                           const float* d_rgb, float* d_raw, void* stream) {
+  SNB_REQUIRE(n_rays >= 0 && n_samples >= 0, "snb_composite_backward: bad sizes");
+  SNB_REQUIRE(n_rays == 0 || n_samples == 0 || (z && raw && d_rgb && d_raw), "snb_composite_backward: NULL pointer");
+  return composite_backward_launch(z, raw, last_delta, n_rays, n_samples, d_rgb, d_raw, (cudaStream_t)stream);
+}
+
 int snb_get_rays(int32_t W, int32_t H, float fx, float fy, float cx, float cy, int32_t center_pixels, const float* c2w,
                  float near, float far, const float* altitude_range, float* rays, void* stream) {
   SNB_REQUIRE(W >= 0 && H >= 0 && (int64_t)W * H < (1ll << 31), "snb_get_rays: bad image size %d x %d", W, H);
@@ -449,6 +474,7 @@ int snb_render_rays(snb_model_t* mm, const float* rays, const int32_t* image_ind
   if (out->raw_coarse) raw_c = out->raw_coarse;
   if (out->raw_fine && Sf > 0) raw_f = out->raw_fine;
   if (out->z_fine && Sf > 0) zf = out->z_fine;
+  if (out->z_coarse) zc = out->z_coarse;
 
   auto run_pass = [&](const float* z, int Sn, float* raw, int32_t* gates_out, float* loss_out, const float* noise) -> int {
     const int64_t B = N * Sn;

@@ -96,6 +96,21 @@ struct Model {
   Ep* ep = nullptr;
 };
 
+// forward intermediates of one model chunk kept for the backward sweep (snb_fp32.cu fills it, snb_backward.cu reads it)
+struct Fp32Saved {
+  float *pe, *h, *ga[5], *g, *gates, *gate, *bufx, *act[16], *out_rows, *hr, *sig_pre, *cat, *h2, *rgb;
+  int *idx, *loc, *counts, *cap_dev, *ebase, *erows;
+  int64_t rows, cap_host;
+};
+int fp32_forward_saved(Model* m, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* o,
+                       Fp32Saved* sv, Arena& ws, cudaStream_t st);
+int ln_forward_launch(const float* g, int64_t S, int M, const float* w, const float* b, float* out, cudaStream_t st);
+int fp32_backward(Model* m, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* o, const float* d_out,
+                  const float* d_l_aux, const snb_grads* G, Arena& ws, cudaStream_t st);
+size_t fp32_backward_workspace_bytes(const Model* m, int64_t S, double max_cf);
+int composite_backward_launch(const float* z, const float* raw, const float* last_delta, int64_t N, int S, const float* d_rgb,
+                              float* d_raw, cudaStream_t st);
+
 // ---- entry points implemented in the individual .cu files ----
 int fp32_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* o,
                  float* out, int32_t* moe_idx, float* l_aux, float* dbg_gates, int32_t* dbg_loc,

@@ -485,4 +485,114 @@ int fp32_forward(Model* m, const float* x, int64_t S, const float* sigma_noise, 
   return SNB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward recomputation for the backward pass (snb_backward.cu): the same kernels as fp32_forward, but every
+// intermediate the backward sweep needs stays in its own buffer
+// ---------------------------------------------------------------------------------------------------------------
+
+// gate input of the reference: LayerNorm(g) (eps 1e-5, biased variance), one warp per row
+__global__ void __launch_bounds__(256) k_ln_fwd(const float* __restrict__ g, int64_t S, int M, const float* __restrict__ w,
+                                                const float* __restrict__ b, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= S) return;
+  const float* row = g + s * M;
+  float sum = 0.f;
+  for (int k = lane; k < M; k += 32) sum += row[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)M;
+  float var = 0.f;
+  for (int k = lane; k < M; k += 32) { const float d = row[k] - mean; var += d * d; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / (float)M + 1e-5f);
+  for (int k = lane; k < M; k += 32) out[s * M + k] = (row[k] - mean) * rstd * w[k] + b[k];
+}
+int ln_forward_launch(const float* g, int64_t S, int M, const float* w, const float* b, float* out, cudaStream_t st) {
+  k_ln_fwd<<<(unsigned)cdiv(S, 8), 256, 0, st>>>(g, S, M, w, b, out);
+  SNB_CHECK_LAUNCH("k_ln_fwd");
+  return SNB_OK;
+}
+
+int fp32_forward_saved(Model* m, const float* x, int64_t S, const float* sigma_noise, const snb_route_opts* o, Fp32Saved* sv,
+                       Arena& ws, cudaStream_t st) {
+  const int M = m->d.width, E = m->d.num_experts, L = m->d.expert_layers, H2 = m->d.hidden2, NG = m->d.gate_layers;
+  const double cf = o->capacity_factor;
+  const int64_t cap_host = capacity_of(S, E, cf);
+  int64_t rows = (int64_t)E * cap_host;
+  if (rows < 1) rows = 1;
+  sv->rows = rows; sv->cap_host = cap_host;
+  sv->pe = ws.take<float>((size_t)S * m->xyz_in);
+  sv->h = ws.take<float>((size_t)S * M);
+  sv->ga[0] = sv->h;
+  for (int i = 1; i < NG; ++i) sv->ga[i] = ws.take<float>((size_t)S * M);
+  sv->g = ws.take<float>((size_t)S * M);
+  sv->gates = ws.take<float>((size_t)S * E);
+  sv->idx = ws.take<int>(S);
+  sv->loc = ws.take<int>(S);
+  sv->gate = ws.take<float>(S);
+  sv->bufx = ws.take<float>((size_t)rows * M);
+  for (int j = 1; j < L; ++j) sv->act[j] = ws.take<float>((size_t)rows * M);
+  sv->act[0] = sv->bufx;
+  sv->out_rows = ws.take<float>((size_t)rows * M);
+  sv->hr = ws.take<float>((size_t)S * M);
+  sv->sig_pre = ws.take<float>(S);
+  sv->cat = ws.take<float>((size_t)S * m->cat_in);
+  sv->h2 = ws.take<float>((size_t)S * H2);
+  sv->rgb = ws.take<float>((size_t)S * 3);
+  int* small = ws.take<int>(1024);
+  float* l_aux = ws.take<float>(64);
+  const size_t rbytes = route_workspace_bytes(S, E);
+  char* rws = ws.take<char>(rbytes);
+  if (!ws.ok) { set_error("snb_moe_backward: workspace too small"); return SNB_EWORKSPACE; }
+  int *counts = small, *cap_dev = small + E, *ebase = small + E + 1, *erows = ebase + E, *begin = erows + E;
+  sv->counts = counts; sv->cap_dev = cap_dev; sv->ebase = ebase; sv->erows = erows;
+  {
+    dim3 blk(32, 8);
+    k_encode<<<(unsigned)cdiv(S, 8), blk, 0, st>>>(x, S, m->x_cols, m->d.mip, m->d.pos_xyz_freqs, m->d.pos_dir_freqs,
+                                                   m->d.appearance_dim, m->d.appearance_count, m->emb_a, sv->pe, m->xyz_in,
+                                                   sv->cat, m->cat_in, M);
+    SNB_CHECK_LAUNCH("k_encode");
+  }
+  int rc;
+  if ((rc = launch_linear(ACT_NONE, sv->pe, m->xyz_in, m->xyz_w, m->xyz_b, nullptr, 0, sv->h, M, S, M, m->xyz_in, 1, nullptr, nullptr, nullptr, st))) return rc;
+  for (int i = 0; i < NG; ++i) {
+    float* outp = (i < NG - 1) ? sv->ga[i + 1] : sv->g;
+    if ((rc = launch_linear(i < NG - 1 ? ACT_RELU : ACT_NONE, sv->ga[i], M, m->gate_w[i], m->gate_b[i], nullptr, 0, outp, M, S, M, M, 1, nullptr, nullptr, nullptr, st))) return rc;
+  }
+  {
+    const size_t smem = (size_t)E * M * sizeof(float);
+    SNB_REQUIRE(smem <= 200 * 1024, "wg too large for shared memory");
+    if (smem > 48 * 1024) SNB_CHECK_CUDA(cudaFuncSetAttribute(k_ln_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ln_gate<<<(unsigned)cdiv(S, 8), 256, smem, st>>>(sv->g, S, M, E, m->ln_w, m->ln_b, m->wg, sv->gates);
+    SNB_CHECK_LAUNCH("k_ln_gate");
+  }
+  if ((rc = route_top1(sv->gates, S, E, cf, o->bpr, sv->idx, sv->loc, sv->gate, counts, cap_dev, l_aux, rws, rbytes, st))) return rc;
+  k_expert_ranges<<<1, 32, 0, st>>>(counts, cap_dev, E, 0, ebase, erows, begin);
+  SNB_CHECK_LAUNCH("k_expert_ranges");
+  // the padded dispatch buffer is zero where no sample landed (the skip connection reads it)
+  if ((rc = snb_dispatch_impl(sv->h, sv->idx, sv->loc, nullptr, cap_dev, 0, S, M, rows, sv->bufx, true, st))) return rc;
+  for (int j = 0; j < L; ++j) {
+    const bool skip = (j == m->d.skip_layer);
+    float* outb = (j < L - 1) ? sv->act[j + 1] : sv->out_rows;
+    if (cap_host > 0) {
+      dim3 grid((unsigned)cdiv(cap_host, 64), (unsigned)cdiv(M, 64), (unsigned)E);
+      if (j < L - 1)
+        k_linear<ACT_RELU><<<grid, 256, 0, st>>>(sv->act[j], M, m->exp_w[j], m->exp_b[j], skip ? sv->bufx : nullptr, M, outb, M, 0, M, M, ebase, erows, nullptr);
+      else
+        k_linear<ACT_NONE><<<grid, 256, 0, st>>>(sv->act[j], M, m->exp_w[j], m->exp_b[j], skip ? sv->bufx : nullptr, M, outb, M, 0, M, M, ebase, erows, nullptr);
+      SNB_CHECK_LAUNCH("k_linear(expert)");
+    }
+  }
+  if ((rc = snb_combine_impl(sv->out_rows, sv->idx, sv->loc, nullptr, sv->gate, cap_dev, 0, S, M, rows, sv->hr, true, st))) return rc;
+  if ((rc = launch_linear(ACT_NONE, sv->hr, M, m->sigma_w, m->sigma_b, nullptr, 0, sv->sig_pre, 1, S, 1, M, 1, nullptr, nullptr, nullptr, st))) return rc;
+  if ((rc = launch_linear(ACT_NONE, sv->hr, M, m->l1_w, m->l1_b, nullptr, 0, sv->cat, m->cat_in, S, M, M, 1, nullptr, nullptr, nullptr, st))) return rc;
+  if ((rc = launch_linear(ACT_RELU, sv->cat, m->cat_in, m->l2_w, m->l2_b, nullptr, 0, sv->h2, H2, S, H2, m->cat_in, 1, nullptr, nullptr, nullptr, st))) return rc;
+  if ((rc = launch_linear(ACT_SIGMOID, sv->h2, H2, m->color_w, m->color_b, nullptr, 0, sv->rgb, 3, S, 3, H2, 1, nullptr, nullptr, nullptr, st))) return rc;
+  (void)sigma_noise;
+  return SNB_OK;
+}
+
 }  // namespace snb

@@ -12,7 +12,8 @@ layer tags [0, 1, 2, xyz, sigma, color, moe_external_gate, gate_input_norm]; exp
 `seeds=(1, rank+1, 1)`, nerf_moe.py:284, tutel_moe_layer_nobatch.py:636-703), so the same
 `torch.manual_seed` gives bit-identical initial weights.
 
-Scope: forward only (inference / evaluation and the forward half of a training step).  The
+Scope: forward on the fused kernels; the backward for the parameters is attached by rendering.render_rays
+(csrc/snb_backward.cu, fp32 kernels).  The
 backward of the fused path is SURVEY.md 8f rank 1 ("next").
 """
 import ctypes as C
@@ -347,6 +348,23 @@ class NeRFMoE(nn.Module):
         w.color_w, w.color_b = p(lay["color"].fcs[0].weight), p(lay["color"].fcs[0].bias)
         w.emb_a = p(self.embedding_a.weight)
         return w, keep
+
+    def _grad_params(self):
+        """The parameters in the field order of snb_weights / snb_grads: [(field, index or None, parameter)]."""
+        lay, moe = self.layers, self.layers["0"]
+        out = [("xyz_w", None, lay["xyz"].fcs[0].weight), ("xyz_b", None, lay["xyz"].fcs[0].bias)]
+        for i, fc in enumerate(lay["moe_external_gate"].fcs):
+            out += [("gate_w", i, fc.weight), ("gate_b", i, fc.bias)]
+        out += [("ln_w", None, lay["gate_input_norm"].weight), ("ln_b", None, lay["gate_input_norm"].bias),
+                ("wg", None, moe.gates[0].wg.weight)]
+        for j in range(moe.experts[0].layer_num):
+            out += [("expert_w", j, moe.experts[0].weights[j]), ("expert_b", j, moe.experts[0].bias[j])]
+        out += [("l1_w", None, lay["1"].fcs[0].weight), ("l1_b", None, lay["1"].fcs[0].bias),
+                ("l2_w", None, lay["2"].fcs[0].weight), ("l2_b", None, lay["2"].fcs[0].bias),
+                ("sigma_w", None, lay["sigma"].fcs[0].weight), ("sigma_b", None, lay["sigma"].fcs[0].bias),
+                ("color_w", None, lay["color"].fcs[0].weight), ("color_b", None, lay["color"].fcs[0].bias),
+                ("emb_a", None, self.embedding_a.weight)]
+        return out
 
     def _desc(self):
         lay = self.layer_cfg["layers"]

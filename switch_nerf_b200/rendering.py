@@ -20,20 +20,6 @@ from . import _lib as L
 from .nerf_moe import NeRFMoE
 
 
-_WARNED = False
-
-
-def _warn_forward_only(model):
-    """The fused path has no backward yet: say so once instead of letting loss.backward() fail later
-    with an unrelated-looking autograd error."""
-    global _WARNED
-    if not _WARNED and model.training and torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
-        import warnings
-        warnings.warn("switch_nerf_b200.render_rays is forward-only: the results carry no autograd graph "
-                      "(backward of the fused path is the next scope row)", RuntimeWarning, stacklevel=3)
-        _WARNED = True
-
-
 def _unwrap(nerf):
     return nerf.module if hasattr(nerf, "module") and isinstance(nerf.module, NeRFMoE) else nerf
 
@@ -58,8 +44,8 @@ def render_rays(nerf, bg_nerf, rays: torch.Tensor, image_indices: Optional[torch
     if image_indices is not None:
         idx32 = image_indices.to(device=dev, dtype=torch.int32).contiguous()
     perturb = float(hparams.perturb) if model.training else 0.0          # rendering.py:32
-    _warn_forward_only(model)
     typ = "fine" if Sf > 0 else "coarse"
+    want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
 
     opts = L.RenderOpts()
     opts.coarse_samples, opts.fine_samples, opts.model_chunk_size = Sc, Sf, chunk
@@ -97,7 +83,9 @@ def render_rays(nerf, bg_nerf, rays: torch.Tensor, image_indices: Optional[torch
     out.gate_loss_coarse, out.gate_loss_fine = L.ptr(gl_c), L.ptr(gl_f)
     out.moe_gates_coarse, out.moe_gates_fine = L.ptr(mg_c), L.ptr(mg_f)
     taps = {}
-    if debug_taps:
+    if debug_taps or want_grad:
+        taps["z_coarse"] = torch.empty(N, Sc, **f32)
+        out.z_coarse = L.ptr(taps["z_coarse"])
         taps["raw_coarse"] = torch.empty(N, Sc, 4, **f32)
         out.raw_coarse = L.ptr(taps["raw_coarse"])
         if Sf > 0:
@@ -113,6 +101,18 @@ def render_rays(nerf, bg_nerf, rays: torch.Tensor, image_indices: Optional[torch
         L.check(lib.snb_render_rays(h, L.ptr(rays), L.ptr(idx32), None, N, C.byref(opts), C.byref(out), L.ptr(ws),
                                     ws.numel(), L.stream_handle()))
 
+    if want_grad:
+        # attach the autograd graph: rgb and the per-chunk gate losses are functions of the parameters (depth and its
+        # variance are computed under no_grad in the reference too, rendering.py:479-494)
+        if getattr(hparams, "white_bkgd", False):
+            raise NotImplementedError("backward with white_bkgd is not implemented")
+        if model.layers["0"].moe_no_batch:
+            raise NotImplementedError("backward implements the capacity (batched) dispatch, the reference's training mode")
+        plist = [p for _, _, p in model._grad_params()]
+        saved = dict(model=model, rays=rays, idx32=idx32, N=N, Sc=Sc, Sf=Sf, chunk=chunk, taps=taps, noise_c=noise_c, noise_f=noise_f)
+        rgb, gl_c, gl_f_t = _RenderGrad.apply(saved, rgb, gl_c, gl_f if gl_f is not None else gl_c.new_zeros(0), *plist)
+        if gl_f is not None:
+            gl_f = gl_f_t
     # result keys of rendering.py:385-409, 466-494
     res["gate_loss_coarse"] = gl_c
     if want_gates:
@@ -126,6 +126,77 @@ def render_rays(nerf, bg_nerf, rays: torch.Tensor, image_indices: Optional[torch
         res[f"depth_{typ}"] = depth
     if get_depth_variance:
         res[f"depth_variance_{typ}"] = var
-    for k, v in taps.items():
-        res[f"_{k}"] = v
+    if debug_taps:
+        for k, v in taps.items():
+            res[f"_{k}"] = v
     return res, False
+
+
+class _RenderGrad(torch.autograd.Function):
+    """Backward of render_rays for the parameters (what runner.py:677-690 calls through loss.backward()):
+    composite^T (snb_composite_backward; the fine pass through the sorted merge of rendering.py:419-431), then the
+    model-chunk backward of every chunk of both passes (snb_moe_backward: heads, combine^T + gate-value gradient, expert
+    dgrad / wgrad with the skip, dispatch^T, l_aux term, softmax / LayerNorm / gate MLP / xyz layer, embedding
+    scatter).  fp32 CUDA kernels that recompute the forward intermediates of a chunk; with a bf16 forward this is an
+    fp32 backward of the same function.  The fine sample positions come from detached coarse weights (rendering.py:240),
+    so nothing flows through them."""
+
+    @staticmethod
+    def forward(ctx, saved, rgb, gl_c, gl_f, *params):
+        ctx.saved = saved
+        ctx.n_params = len(params)
+        return rgb.view_as(rgb), gl_c.view_as(gl_c), gl_f.view_as(gl_f)
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_gl_c, d_gl_f):
+        sv = ctx.saved
+        model, rays, idx32, N, Sc, Sf, chunk, taps = (sv[k] for k in ("model", "rays", "idx32", "N", "Sc", "Sf", "chunk", "taps"))
+        dev = rays.device
+        lib = L.lib()
+        f32 = dict(dtype=torch.float32, device=dev)
+        d_rgb = torch.zeros(N, 3, **f32) if d_rgb is None else d_rgb.contiguous().float()
+        zc, raw_c = taps["z_coarse"], taps["raw_coarse"]
+        with torch.no_grad(), torch.cuda.device(dev):
+            def comp_bwd(z, raw):
+                d_raw = torch.empty_like(raw)
+                L.check(lib.snb_composite_backward(L.ptr(z), L.ptr(raw), None, z.shape[0], z.shape[1], L.ptr(d_rgb),
+                                                   L.ptr(d_raw), L.stream_handle()))
+                return d_raw
+            if Sf > 0:
+                zf, raw_f = taps["z_fine"], taps["raw_fine"]
+                z_all, order = torch.sort(torch.cat([zf, zc], -1), dim=-1, stable=True)               # rendering.py:421
+                raw_all = torch.gather(torch.cat([raw_f, raw_c], 1), 1, order.unsqueeze(-1).expand(-1, -1, 4)).contiguous()
+                d_all = comp_bwd(z_all.contiguous(), raw_all)
+                d_cat = torch.zeros_like(d_all).scatter_(1, order.unsqueeze(-1).expand(-1, -1, 4), d_all)
+                passes = [(zf, d_cat[:, :Sf].contiguous(), d_gl_f, sv["noise_f"]), (zc, d_cat[:, Sf:].contiguous(), d_gl_c, sv["noise_c"])]
+            else:
+                passes = [(zc, comp_bwd(zc, raw_c), d_gl_c, sv["noise_c"])]
+            fields = model._grad_params()
+            grads = [torch.zeros_like(p, dtype=torch.float32) if p.requires_grad else None for _, _, p in fields]
+            G = L.Weights()
+            for (name, i, _), g in zip(fields, grads):
+                if g is None:
+                    continue
+                if i is None:
+                    setattr(G, name, g.data_ptr())
+                else:
+                    getattr(G, name)[i] = g.data_ptr()
+            h = model.handle()
+            opts = model.route_opts()
+            nbytes = lib.snb_moe_backward_workspace_bytes(h, min(chunk, N * max(Sc, Sf)), opts.capacity_factor)
+            ws = L.Workspace.get(nbytes, dev, tag="backward")
+            o, d = rays[:, None, 0:3], rays[:, None, 3:6]
+            img = (idx32 if idx32 is not None else torch.zeros(N, dtype=torch.int32, device=dev)).float()
+            for z, d_raw, d_gl, noise in passes:
+                Sn = z.shape[1]
+                x = torch.cat([o + d * z.unsqueeze(-1), d.expand(N, Sn, 3), img.view(N, 1, 1).expand(N, Sn, 1)], -1).reshape(N * Sn, 7).contiguous()
+                d_out = d_raw.reshape(N * Sn, 4)
+                d_gl = None if d_gl is None else d_gl.contiguous().float()
+                for ci, i0 in enumerate(range(0, N * Sn, chunk)):
+                    rows = min(chunk, N * Sn - i0)
+                    L.check(lib.snb_moe_backward(h, L.ptr(x[i0:i0 + rows]), rows, L.ptr(noise[i0:i0 + rows]) if noise is not None else None,
+                                                 C.byref(opts), L.ptr(d_out[i0:i0 + rows]),
+                                                 L.ptr(d_gl[ci:ci + 1]) if d_gl is not None else None, C.byref(G), L.ptr(ws),
+                                                 ws.numel(), L.stream_handle()))
+        out = [None if g is None else g.to(p.dtype) for g, (_, _, p) in zip(grads, fields)]
+        return (None, None, None, None, *out)

@@ -636,3 +636,116 @@ def test_moe_layer_operator_vs_oracle(built_lib, cf, bpr, nobatch):
     y2_ref, _ = O.moe_layer(h, h, sd, "0", cfg, "fp32")
     d2 = (y2.cpu() - y2_ref).abs().amax(1)
     assert (d2 > 5e-5).float().mean() < 5e-3
+
+
+# ----------------------------------------------------------------------------- f1 backward
+def test_backward_parameter_gradients_vs_reference_golden(built_lib):
+    """loss.backward() through switch_nerf_b200.rendering.render_rays (composite^T + model-chunk backward
+    kernels, csrc/snb_backward.cu) reproduces the parameter gradients the UNMODIFIED reference produced for one
+    training-style step (tests/golden/grad_config1.npz, oracle/make_golden_grad.py: loss = mse(rgb_fine, target) +
+    moe_l_aux_wt * mean gate losses): same loss, all 32 gradients within grad_close() (1e-4 of the model's largest
+    gradient + 5 % of the tensor's own largest entry)."""
+    from oracle import make_golden_grad as G
+    from oracle import ref_shims as R
+    from switch_nerf_b200.nerf_moe import get_nerf_moe_inner
+    from switch_nerf_b200.rendering import render_rays
+    g = load_golden("grad_config1.npz")
+    c = G.CASE
+    sd, rays, idx, target = G.case_inputs(c)
+    hp = R.make_hparams(num_experts=c["E"], capacity_factor=c["cf"], bpr=c["bpr"], model_chunk_size=c["chunk"],
+                        coarse_samples=c["cs"], fine_samples=c["fs"])
+    model = get_nerf_moe_inner(hp, c["count"], 3)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    res, _ = render_rays(model, None, rays.cuda(), idx.cuda(), hp, None, None, True, True, False)
+    loss = G.training_loss(res, target.cuda(), c["wt"])
+    assert abs(float(loss) - float(g["loss"][0])) < 1e-5 * max(1.0, abs(float(g["loss"][0])))
+    loss.backward()
+    torch.cuda.synchronize()
+    scale = float(g["scale"][0])
+    names = [k[len("sample/"):] for k in g if k.startswith("sample/")]
+    params = dict(model.named_parameters())
+    assert len(names) == 32 and set(names) <= set(params)
+    worst = {}
+    for k in names:
+        assert params[k].grad is not None, k
+        mine = G.sample_of(params[k].grad.detach().float().cpu())
+        ref = torch.from_numpy(g["sample/" + k])
+        assert mine.shape == ref.shape, k
+        assert G.grad_close(mine, ref, scale), (k, float((mine - ref).abs().max()), float(ref.abs().max()), scale)
+        l1 = float(params[k].grad.double().abs().sum())
+        assert abs(l1 - g["stats/" + k][1]) <= 0.02 * g["stats/" + k][1] + 1e-4 * scale * params[k].numel(), (k, l1, g["stats/" + k][1])
+        worst[k] = float((mine - ref).abs().max()) / scale
+    print("worst |grad - reference| / scale:", max(worst.values()))
+
+
+def test_backward_model_chunk_vs_backward_plan(built_lib):
+    """snb_moe_backward on one chunk with drops (cf 0.5), BPR and an l_aux term vs oracle/backward_plan.py (which equals
+    autograd of the pinned forward restatement): every parameter gradient to fp32 accumulation accuracy."""
+    import ctypes as C
+    from oracle import backward_plan as B
+    from switch_nerf_b200 import _lib as L
+    from switch_nerf_b200 import synthetic as SY
+    sd = SY.synthetic_state_dict(num_experts=4, appearance_count=8, seed=21, gate_scale=3.0)
+    S = 1500
+    gen = torch.Generator().manual_seed(4)
+    x = torch.cat([torch.rand(S, 3, generator=gen) - 0.5, torch.nn.functional.normalize(torch.randn(S, 3, generator=gen), dim=1),
+                   torch.randint(0, 8, (S, 1), generator=gen).float()], 1)
+    d_out = torch.randn(S, 4, generator=gen)
+    for cf, bpr in ((0.5, True), (1.0, False)):
+        cfg = O.default_cfg(sd, cf, bpr)
+        ref = B.model_chunk_backward(x, sd, cfg, d_out, 0.37)
+        model, _ = make_model(sd, cf, bpr, False, "fp32")
+        fields = model._grad_params()
+        grads = [torch.zeros_like(p, dtype=torch.float32) for _, _, p in fields]
+        Gs = L.Weights()
+        for (name, i, _), gt in zip(fields, grads):
+            if i is None:
+                setattr(Gs, name, gt.data_ptr())
+            else:
+                getattr(Gs, name)[i] = gt.data_ptr()
+        lib, h, opts = L.lib(), model.handle(), model.route_opts()
+        nb = lib.snb_moe_backward_workspace_bytes(h, S, opts.capacity_factor)
+        ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        xd, dd, dl = x.cuda(), d_out.cuda(), torch.tensor([0.37], device="cuda")
+        L.check(lib.snb_moe_backward(h, L.ptr(xd), S, None, C.byref(opts), L.ptr(dd), L.ptr(dl), C.byref(Gs), L.ptr(ws), nb,
+                                     L.stream_handle()))
+        torch.cuda.synchronize()
+        named = {n: p for n, p in model.named_parameters()}
+        by_ptr = {p.data_ptr(): n for n, p in named.items()}
+        scale = max(float(v.abs().max()) for v in ref.values())
+        for (_, _, p), gt in zip(fields, grads):
+            n = by_ptr[p.data_ptr()]
+            err = float((gt.cpu() - ref[n]).abs().max())
+            assert err <= 2e-5 * scale + 2e-4 * float(ref[n].abs().max()), (cf, bpr, n, err, float(ref[n].abs().max()), scale)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_steps_reduce_loss(built_lib, precision):
+    """A Runner._training_step-style loop (runner.py:646-690, 1077-1123): forward through render_rays in training mode
+    (stratified perturb, sigma noise), loss = mse + moe_l_aux_wt * gate losses, backward, Adam step, re-packed weights --
+    the loss goes down.  bf16: the fused tcgen05 forward with the fp32 backward of the same function."""
+    from oracle import make_golden_grad as G
+    from oracle import ref_shims as R
+    from switch_nerf_b200.nerf_moe import get_nerf_moe_inner
+    from switch_nerf_b200.rendering import render_rays
+    c = G.CASE
+    sd, rays, idx, target = G.case_inputs(c)
+    hp = R.make_hparams(num_experts=c["E"], capacity_factor=c["cf"], bpr=c["bpr"], model_chunk_size=c["chunk"],
+                        coarse_samples=c["cs"], fine_samples=c["fs"], amp_bf16=(precision == "bf16"))
+    hp.use_sigma_noise, hp.sigma_noise_std, hp.perturb = True, 0.1, 1.0
+    model = get_nerf_moe_inner(hp, c["count"], 3)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=2e-3)
+    rays, idx, target = rays.cuda(), idx.cuda(), target.cuda()
+    losses = []
+    torch.manual_seed(0)
+    for _ in range(12):
+        opt.zero_grad(set_to_none=True)
+        res, _ = render_rays(model, None, rays, idx, hp, None, None, True, True, False, seed=7)
+        loss = G.training_loss(res, target, c["wt"])
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < 0.8 * losses[0], losses
