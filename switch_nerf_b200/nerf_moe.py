@@ -13,8 +13,7 @@ layer tags [0, 1, 2, xyz, sigma, color, moe_external_gate, gate_input_norm]; exp
 `torch.manual_seed` gives bit-identical initial weights.
 
 Scope: forward on the fused kernels; the backward for the parameters is attached by rendering.render_rays
-(csrc/snb_backward.cu, fp32 kernels).  The
-backward of the fused path is SURVEY.md 8f rank 1 ("next").
+(csrc/snb_backward.cu, fp32 kernels).
 """
 import ctypes as C
 import weakref
