@@ -266,6 +266,9 @@ typedef struct snb_render_opts {
    * in ray-major order; device pointers, nullable (= no noise). */
   const float* sigma_noise_coarse; /* [N * coarse_samples] */
   const float* sigma_noise_fine;   /* [N * fine_samples]   */
+  /* mip renderer only: rendering_mip.py:225 passes `randomized=hparams.perturb` to the fine resampling -- in eval too
+   * (the coarse perturb above is training-only) -- so it is a separate switch: 1 = stratified random u (seeded) */
+  int32_t resample_randomized;
 } snb_render_opts;
 
 /* Per-ray outputs (all nullable; device pointers). Keys of the reference `results` dict

@@ -46,7 +46,8 @@ class RouteOpts(C.Structure):
 class RenderOpts(C.Structure):
     _fields_ = [("coarse_samples", C.c_int32), ("fine_samples", C.c_int32), ("model_chunk_size", C.c_int64),
                 ("perturb", C.c_float), ("seed", C.c_uint64), ("white_bkgd", C.c_int32), ("precision", C.c_int32),
-                ("route", RouteOpts), ("sigma_noise_coarse", C.c_void_p), ("sigma_noise_fine", C.c_void_p)]
+                ("route", RouteOpts), ("sigma_noise_coarse", C.c_void_p), ("sigma_noise_fine", C.c_void_p),
+                ("resample_randomized", C.c_int32)]
 
 
 class RenderOut(C.Structure):

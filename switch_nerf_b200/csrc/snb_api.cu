@@ -69,7 +69,7 @@ int mip_composite_launch(const float* ze, const float* raw, const float* last_de
                          float rgb_padding, int white_bkgd, float* rgb, float* depth, float* var, float* weights,
                          cudaStream_t st);
 int mip_resample_launch(const float* ze, const float* weights, int64_t N, int Se, int nf, float resample_padding,
-                        float* zf, cudaStream_t st);
+                        int randomized, uint64_t seed, float* zf, cudaStream_t st);
 int tc_timeline_read(unsigned long long* host, int n);
 
 // [E][K][N] -> [E][N][K]
@@ -552,7 +552,6 @@ int snb_render_rays_mip(snb_model_t* mm, const float* rays, const float* radii, 
   SNB_REQUIRE(N >= 0 && (N == 0 || (rays && radii)), "snb_render_rays_mip: bad rays/radii");
   SNB_REQUIRE(o->coarse_samples >= 3 && (o->fine_samples == 0 || o->fine_samples >= 2), "snb_render_rays_mip: bad sample counts");
   SNB_REQUIRE(o->model_chunk_size >= 1, "snb_render_rays_mip: bad model_chunk_size");
-  SNB_REQUIRE(o->perturb == 0.f, "snb_render_rays_mip: only the deterministic (eval) sampling is implemented");
   if (N == 0) return SNB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int Sc = o->coarse_samples, Sf = o->fine_samples;
@@ -591,7 +590,7 @@ int snb_render_rays_mip(snb_model_t* mm, const float* rays, const float* radii, 
     return SNB_OK;
   };
   int rc;
-  if ((rc = coarse_z_launch(rays, N, Sc, 0.f, 0, zc, st))) return rc;
+  if ((rc = coarse_z_launch(rays, N, Sc, o->perturb, o->seed, zc, st))) return rc;       // rendering_mip.py:147-160
   if ((rc = run_pass(zc, Sc, raw_c, out->moe_gates_coarse, out->gate_loss_coarse))) return rc;
   const bool only_coarse = (Sf == 0);
   if ((rc = mip_composite_launch(zc, raw_c, last_delta, N, Sc, pad, o->white_bkgd,
@@ -600,7 +599,7 @@ int snb_render_rays_mip(snb_model_t* mm, const float* rays, const float* radii, 
                                  only_coarse ? nullptr : wc, st)))
     return rc;
   if (only_coarse) return SNB_OK;
-  if ((rc = mip_resample_launch(zc, wc, N, Sc, Sf, weights_resample_padding, zf, st))) return rc;
+  if ((rc = mip_resample_launch(zc, wc, N, Sc, Sf, weights_resample_padding, o->resample_randomized, o->seed, zf, st))) return rc;
   if ((rc = run_pass(zf, Sf, raw_f, out->moe_gates_fine, out->gate_loss_fine))) return rc;
   return mip_composite_launch(zf, raw_f, last_delta, N, Sf, pad, o->white_bkgd, out->rgb, out->depth,
                               out->depth_variance, nullptr, st);

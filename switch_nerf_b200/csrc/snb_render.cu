@@ -500,10 +500,12 @@ __global__ void __launch_bounds__(128) k_mip_composite(const float* __restrict__
 }
 
 // weights [N, n] (n = Se-1 intervals of the Se edges) -> blurred + padded pdf -> nf sorted samples
-// rendering_mip.py:217-226 + sorted_piecewise_constant_pdf1 (75-131), deterministic u.  One warp per ray.
+// rendering_mip.py:217-226 + sorted_piecewise_constant_pdf1 (75-131).  randomized = 0: u = linspace(0, 1 - eps, nf);
+// randomized = 1 (:97-105): stratified u_j = j/nf + rand * (1/nf - eps), capped at 1 - eps (ascending, so the samples
+// come out sorted as the reference's sort leaves them).  One warp per ray.
 __global__ void __launch_bounds__(128) k_mip_resample(const float* __restrict__ ze, const float* __restrict__ weights,
-                                                      int64_t N, int Se, int nf, float resample_padding,
-                                                      float* __restrict__ zf) {
+                                                      int64_t N, int Se, int nf, float resample_padding, int randomized,
+                                                      uint64_t seed, float* __restrict__ zf) {
   extern __shared__ float sm[];  // [4 warps][(n) wprime + (n+1) cdf + (n+1) edges]
   const int n = Se - 1;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -541,7 +543,13 @@ __global__ void __launch_bounds__(128) k_mip_resample(const float* __restrict__ 
   __syncwarp();
   const float end = 1.f - 1.1920928955078125e-07f;   // 1 - finfo(float32).eps
   for (int j = lane; j < nf; j += 32) {
-    const float u = linspace_to(j, nf, end);
+    float u;
+    if (randomized) {
+      const float sN = 1.f / (float)nf;
+      u = fminf(__fadd_rn((float)j * sN, __fmul_rn(u01(seed ^ 0x2545F4914F6CDD1Dull, (uint64_t)r, (uint64_t)j), sN - 1.1920928955078125e-07f)), end);
+    } else {
+      u = linspace_to(j, nf, end);
+    }
     int lo = 0, hi = n + 1;                  // first index with cdf > u
     while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
     const int i0 = min(max(lo - 1, 0), n), i1 = min(lo, n);
@@ -574,11 +582,11 @@ int mip_composite_launch(const float* ze, const float* raw, const float* last_de
 }
 
 int mip_resample_launch(const float* ze, const float* weights, int64_t N, int Se, int nf, float resample_padding,
-                        float* zf, cudaStream_t st) {
+                        int randomized, uint64_t seed, float* zf, cudaStream_t st) {
   if (N == 0 || nf == 0) return SNB_OK;
   size_t smem = (size_t)4 * (3 * (Se - 1) + 2) * sizeof(float);
   if (smem > 48 * 1024) SNB_CHECK_CUDA(cudaFuncSetAttribute(k_mip_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_mip_resample<<<(unsigned)cdiv(N, 4), 128, smem, st>>>(ze, weights, N, Se, nf, resample_padding, zf);
+  k_mip_resample<<<(unsigned)cdiv(N, 4), 128, smem, st>>>(ze, weights, N, Se, nf, resample_padding, randomized, seed, zf);
   SNB_CHECK_LAUNCH("k_mip_resample");
   return SNB_OK;
 }

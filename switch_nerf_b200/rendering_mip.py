@@ -14,12 +14,15 @@ from .nerf_moe import MipNeRFMoE
 
 def render_rays(nerf, rays: torch.Tensor, radii: torch.Tensor, image_indices: Optional[torch.Tensor],
                 hparams: Namespace, get_depth: bool = True, get_depth_variance: bool = True,
-                debug_taps: bool = False) -> Tuple[Dict[str, torch.Tensor], bool]:
+                debug_taps: bool = False, seed: Optional[int] = None,
+                deterministic_eval: bool = False) -> Tuple[Dict[str, torch.Tensor], bool]:
+    """reference rendering_mip.render_rays (133-174).  Like the reference, the coarse depths are perturbed only in
+    training mode (:147), while the fine resampling is randomised whenever `hparams.perturb` is non-zero -- in eval too
+    (:225, `randomized=hparams.perturb`; the reference default is perturb = 1.0).  `deterministic_eval=True` turns that
+    quirk off for reproducible evaluation; `seed` fixes the stratified jitter (default: drawn from torch's generator)."""
     model = nerf.module if hasattr(nerf, "module") and isinstance(nerf.module, MipNeRFMoE) else nerf
     if not isinstance(model, MipNeRFMoE):
         raise L.SnbError("rendering_mip.render_rays needs a switch_nerf_b200.nerf_moe.MipNeRFMoE model")
-    if float(getattr(hparams, "perturb", 0.0)) != 0.0:
-        raise NotImplementedError("randomised mip resampling (hparams.perturb != 0) is not implemented; set perturb = 0")
     rays = L.require_cuda_f32(rays, "rays", cols=8)
     N, dev = rays.shape[0], rays.device
     radii = L.require_cuda_f32(radii.reshape(-1), "radii")
@@ -28,7 +31,11 @@ def render_rays(nerf, rays: torch.Tensor, radii: torch.Tensor, image_indices: Op
     idx32 = None if image_indices is None else image_indices.to(device=dev, dtype=torch.int32).contiguous()
     opts = L.RenderOpts()
     opts.coarse_samples, opts.fine_samples, opts.model_chunk_size = Sc, Sf, chunk
-    opts.perturb, opts.seed = 0.0, 0
+    hp_perturb = float(getattr(hparams, "perturb", 0.0))
+    opts.perturb = hp_perturb if model.training else 0.0
+    opts.resample_randomized = int(hp_perturb != 0.0 and not (deterministic_eval and not model.training))
+    need_seed = opts.perturb > 0 or opts.resample_randomized
+    opts.seed = int(seed if seed is not None else torch.randint(0, 2 ** 62, (1,)).item()) if need_seed else 0
     opts.white_bkgd = int(bool(getattr(hparams, "white_bkgd", False)))
     opts.precision = L.PRECISIONS[model.precision]
     opts.route = model.route_opts()

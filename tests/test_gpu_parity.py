@@ -749,3 +749,73 @@ def test_training_steps_reduce_loss(built_lib, precision):
         opt.step()
         losses.append(float(loss))
     assert all(np.isfinite(losses)) and losses[-1] < 0.8 * losses[0], losses
+
+
+def test_eval_image_tiling(built_lib):
+    """SURVEY 8f-4, the eval_image half: render_image (device-side get_rays + batches of image_pixel_batch_size, ragged last
+    batch, results concatenated per key as Runner.render_image does, runner.py:2835-2885) == one render_rays call over all
+    rays of the image, per ray (batches only regroup the model chunks: the fp32 path is used with a capacity factor that
+    never drops, so chunking cannot change a sample)."""
+    from switch_nerf_b200.eval_image import render_image, render_image_blocknerf
+    from switch_nerf_b200.ray_utils import get_rays_for_image
+    from switch_nerf_b200.rendering import render_rays
+    sd = O.synthetic_state_dict(num_experts=4, appearance_count=16, seed=5, gate_scale=1.0)
+    model, hp = make_model(sd, 4.0, True, False, "fp32")
+    hp.coarse_samples, hp.fine_samples, hp.model_chunk_size, hp.image_pixel_batch_size = 24, 16, 2048, 700
+    hp.center_pixels = True
+    W, H = 47, 31
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(2)))
+    c2w = torch.cat([q, torch.tensor([[0.05], [-0.1], [0.02]])], 1).cuda()
+    res, rays = render_image(model, W, H, [40.0, 42.0, 23.1, 15.4], c2w, 3, hp, 0.05, 1.0, None)
+    assert rays.shape == (W * H, 8) and res["rgb_fine"].shape == (W * H, 3) and not res["rgb_fine"].is_cuda
+    want = get_rays_for_image(W, H, 40.0, 42.0, 23.1, 15.4, True, c2w, 0.05, 1.0, None).view(-1, 8)
+    assert torch.equal(rays, want)
+    idx = torch.full((W * H,), 3, dtype=torch.int32, device="cuda")
+    full, _ = render_rays(model, None, rays, idx, hp, None, None, True, False, True)
+    assert float((res["rgb_fine"] - full["rgb_fine"].cpu()).abs().max()) < 1e-5
+    assert float((res["depth_fine"] - full["depth_fine"].cpu()).abs().max()) < 1e-4
+    n_batches = -(-W * H // 700)
+    assert res["gate_loss_coarse"].numel() >= n_batches
+    res2, _ = render_image_blocknerf(model, rays.cpu(), None, idx.cpu(), hp)
+    assert torch.equal(res2["rgb_fine"], res["rgb_fine"])
+
+
+def test_render_mip_stochastic_sampling(built_lib):
+    """rendering_mip.py:97-105, 147-160, 225: stratified random fine resampling (whenever hparams.perturb != 0, in eval too)
+    and training-mode perturbation of the coarse edges.  Properties: the fine edges are sorted and inside [near, far]; sample j
+    of a ray lies in the inverse-cdf image of stratum [j/n, (j+1)/n), i.e. between the deterministic samples of u = j/n
+    and u = (j+1)/n; same seed -> same result, other seed -> other samples; deterministic_eval reproduces perturb = 0."""
+    from switch_nerf_b200.nerf_moe import get_nerf_moe_inner
+    from switch_nerf_b200.rendering_mip import render_rays as render_rays_mip
+    from oracle import ref_shims as R
+    g = load_golden("render_mip_w256.npz")
+    E, width, n_rays, cs, fs, chunk, seed, gs, count = g["params"]
+    sd = O.synthetic_state_dict(num_experts=int(E), appearance_count=int(count), seed=int(seed), gate_scale=float(gs), width=int(width))
+    hp = R.make_hparams(num_experts=int(E), model_chunk_size=int(chunk), coarse_samples=int(cs), fine_samples=int(fs),
+                        width=int(width), nerfmoe_class_name="MipNeRFMoE")
+    model = get_nerf_moe_inner(hp, int(count), 3)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    rays, radii, idx = (torch.from_numpy(g[k]).cuda() for k in ("rays", "radii", "image_indices"))
+    hp.perturb = 0
+    det, _ = render_rays_mip(model, rays, radii, idx, hp, True, True, debug_taps=True)
+    hp.perturb = 1.0
+    a, _ = render_rays_mip(model, rays, radii, idx, hp, True, True, debug_taps=True, seed=5)
+    b, _ = render_rays_mip(model, rays, radii, idx, hp, True, True, debug_taps=True, seed=5)
+    c, _ = render_rays_mip(model, rays, radii, idx, hp, True, True, debug_taps=True, seed=6)
+    d, _ = render_rays_mip(model, rays, radii, idx, hp, True, True, debug_taps=True, deterministic_eval=True)
+    torch.cuda.synchronize()
+    za, zc_, zd = a["_z_fine"], c["_z_fine"], det["_z_fine"]
+    assert torch.equal(za, b["_z_fine"]) and not torch.equal(za, zc_)
+    assert torch.equal(d["_z_fine"], zd) and torch.equal(d["rgb_fine"], det["rgb_fine"])
+    assert (za[:, 1:] >= za[:, :-1]).all()
+    assert (za >= rays[:, 6:7] - 1e-6).all() and (za <= rays[:, 7:8] + 1e-6).all()
+    # eval mode: same coarse edges, so the cdf is the same; monotone inverse cdf => stratified samples interleave with the
+    # deterministic ones of u_j = j (1 - eps) / (n - 1) >= j / n
+    n = za.shape[1]
+    assert (za[:, :-1] <= zd[:, 1:] + 1e-5).all(), "sample j must not pass the deterministic sample j + 1"
+    assert torch.isfinite(a["rgb_fine"]).all() and float((a["rgb_fine"] - det["rgb_fine"]).abs().max()) < 0.2
+    # training mode: the coarse edges move too
+    model.train()
+    t, _ = render_rays_mip(model, rays, radii, idx, hp, True, True, debug_taps=True, seed=5)
+    assert torch.isfinite(t["rgb_fine"]).all() and not torch.equal(t["_z_fine"], za)
