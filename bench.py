@@ -362,9 +362,11 @@ def main_mission_bay(args, rank, local_rank, world):
     samples_per_step = MB_RAYS * 2 * (MB_EDGES - 1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
 
+    @torch.no_grad()
     def step_resident():
         return render_rays_mip(model, rays_d, radii_d, idx_d, hp, True, True)[0]
 
+    @torch.no_grad()
     def step_e2e():
         res = render_rays_mip(model, rays_pin.to(device, non_blocking=True), radii_pin.to(device, non_blocking=True),
                               idx_pin.to(device, non_blocking=True), hp, True, True)[0]
@@ -478,6 +480,7 @@ def main_mission_bay(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+@torch.no_grad()
 def main_sweep_cf(args, local_rank):
     """BASELINE.json configs[4]: the routing-imbalance throughput curve on the current kernels (single GPU)."""
     from switch_nerf_b200 import synthetic as SY
@@ -571,9 +574,13 @@ def main():
     samples_per_step = N_RAYS * (COARSE + FINE)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)      # > 126 MB L2
 
+    # inference, as the reference's eval scripts run it (no autograd graph: with grad enabled render_rays also keeps the
+    # per-sample taps its backward needs)
+    @torch.no_grad()
     def step_resident():
         return render_rays(model, None, rays_d, idx_d, hp, None, None, True, True, False)[0]
 
+    @torch.no_grad()
     def step_e2e():
         r = rays_pin.to(device, non_blocking=True)
         i = idx_pin.to(device, non_blocking=True)
@@ -670,7 +677,8 @@ def main():
     parity_ref = None
     if rank == 0:
         model.args.moe_return_gates = True
-        res = render_rays(model, None, rays_d, idx_d, hp, None, None, True, True, False)[0]
+        with torch.no_grad():
+            res = render_rays(model, None, rays_d, idx_d, hp, None, None, True, True, False)[0]
         model.args.moe_return_gates = False
         parity_ref = parity_vs_reference_cuda(res) if args.precision == "bf16" else None
         cap = int(1.0 * ((CHUNK + EXPERTS - 1) // EXPERTS))
