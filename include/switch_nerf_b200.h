@@ -107,13 +107,37 @@ int snb_debug_timeline(uint64_t* host_out, int32_t n);
 /* ---- model object -----------------------------------------------------------------------
  * Concurrency: every entry point only enqueues on the caller's stream, but a model object owns the side streams /
  * events of its chunk pipeline and the zero-between-uses scratch of the routing kernel, so ONE caller stream may use a
- * given model at a time (serialise host threads that share a model; different models are independent). */
+ * given model at a time (serialise host threads that share a model; different models are independent).
+ * The only process-global state left is debug tooling: the launch counter, the phase-event pool of snb_profile_enable and
+ * the SNB_TIMELINE buffer -- not thread-safe, not meant for production. */
 /* Replaces models/nerf_moe.py:1004-1041 get_nerf_moe_inner + load_state_dict: copies/packs the
  * caller's fp32 weights into kernel-native layouts (fp32 [N,K] for the CUDA-core path; bf16
  * UMMA canonical K-major core-matrix tiles for the tcgen05 path).  Call again after an
  * optimizer step (snb_model_update) -- packing is one pass over ~16 MB. */
 int snb_model_create(const snb_model_desc* desc, const snb_weights* w, void* stream, snb_model_t** out);
 int snb_model_update(snb_model_t* m, const snb_weights* w, void* stream);
+
+/* Kernel-selection / pipeline knobs of a model object (A/B switches and the tuning found in profiles/).  A model starts
+ * with the defaults below, overridden once at creation by the SNB_* environment variables named in the comments (kept for
+ * the A/B scripts); snb_model_set_tuning changes them afterwards, and every forward call reads the model's copy -- no
+ * process-global state.  Fields <= -1 mean "default".  (gather_h needs the weights re-packed: call snb_model_update.) */
+typedef struct snb_tuning {
+  int32_t cta_group_front;  /* SNB_CG / SNB_CG_FRONT: 1 (default) or 2 = cta_group::2 CTA pairs for launch #1            */
+  int32_t cta_group_back;   /* SNB_CG / SNB_CG_BACK: the same for launch #2                                              */
+  int32_t ts;               /* SNB_TS: 1 (default) = hidden activations in tensor memory, 0 = shared-memory A operand     */
+  int32_t ts_front;         /* SNB_TS_FRONT: the same for launch #1 only                                                  */
+  int32_t wide;             /* SNB_WIDE: 1 = force the wide kernels at width 256 (always used for width 512 / mip)        */
+  int32_t route_full;       /* SNB_ROUTE_FULL: 1 = full-order routing (route_top1 + tile plan) instead of k_select        */
+  int32_t no_overlap;       /* SNB_NO_OVERLAP: 1 = routing on the caller's stream (no side stream / SM partition)         */
+  int32_t pipe_depth;       /* SNB_PIPE_DEPTH: launch #1 of how many chunks run ahead of launch #2 (default 2, EP 3)      */
+  int32_t route_sms;        /* SNB_ROUTE_SMS: SMs launch #1 leaves free for the routing kernels (default 8)               */
+  int32_t back_partition;   /* SNB_BACK_PART: 1 = launch #2 also leaves them free                                         */
+  int32_t no_ray_source;    /* SNB_NO_RAY_SOURCE: 1 = the render path materialises the [N*S,7] point tensor               */
+  int32_t gather_h;         /* SNB_GATHER_H: 1 = launch #2 gathers h from HBM instead of recomputing it (read when packing) */
+  int32_t front_ab;         /* SNB_FRONT_AB: debug bit mask for launch #1 (1 = no key histogram, 2 = no column sums)      */
+} snb_tuning;
+int snb_model_get_tuning(const snb_model_t* m, snb_tuning* out);
+int snb_model_set_tuning(snb_model_t* m, const snb_tuning* t);
 void snb_model_destroy(snb_model_t* m);
 
 /* Scratch bytes needed by snb_moe_forward / snb_render_rays for chunks of up to

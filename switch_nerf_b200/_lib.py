@@ -50,6 +50,12 @@ class RenderOpts(C.Structure):
                 ("resample_randomized", C.c_int32)]
 
 
+class Tuning(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "cta_group_front", "cta_group_back", "ts", "ts_front", "wide", "route_full", "no_overlap", "pipe_depth", "route_sms",
+        "back_partition", "no_ray_source", "gather_h", "front_ab")]
+
+
 class RenderOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "rgb", "depth", "depth_variance", "bg_lambda", "gate_loss_coarse", "gate_loss_fine",
@@ -81,6 +87,8 @@ _SIGNATURES = {
     "snb_route_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "snb_route_top1": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snb_model_get_tuning": (C.c_int, [C.c_void_p, C.POINTER(Tuning)]),
+    "snb_model_set_tuning": (C.c_int, [C.c_void_p, C.POINTER(Tuning)]),
     "snb_moe_backward_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_double]),
     "snb_moe_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(RouteOpts), C.c_void_p, C.c_void_p,
                                    C.POINTER(Weights), C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -188,6 +188,7 @@ int snb_model_create(const snb_model_desc* desc, const snb_weights* w, void* str
     return SNB_ECUDA;
   }
   Model* m = new (std::nothrow) Model();
+  if (m) tuning_from_env(&m->tune);
   SNB_REQUIRE(m, "out of host memory");
   m->d = *desc;
   m->xyz_in = 3 + 6 * desc->pos_xyz_freqs;
@@ -228,6 +229,25 @@ int snb_model_create(const snb_model_desc* desc, const snb_weights* w, void* str
 int snb_model_update(snb_model_t* mm, const snb_weights* w, void* stream) {
   SNB_REQUIRE(mm && w, "snb_model_update: NULL argument");
   return upload((Model*)mm, w, (cudaStream_t)stream);
+}
+
+int snb_model_get_tuning(const snb_model_t* mm, snb_tuning* out) {
+  SNB_REQUIRE(mm && out, "snb_model_get_tuning: NULL argument");
+  *out = ((const Model*)mm)->tune;
+  return SNB_OK;
+}
+
+int snb_model_set_tuning(snb_model_t* mm, const snb_tuning* t) {
+  Model* m = (Model*)mm;
+  SNB_REQUIRE(m && t, "snb_model_set_tuning: NULL argument");
+  SNB_REQUIRE((t->cta_group_front == 1 || t->cta_group_front == 2) && (t->cta_group_back == 1 || t->cta_group_back == 2),
+              "snb_model_set_tuning: cta_group must be 1 or 2");
+  SNB_REQUIRE(t->pipe_depth <= 3 && t->route_sms < m->sm_count / 2, "snb_model_set_tuning: pipe_depth <= 3, route_sms < SMs / 2");
+  const bool repack = (t->gather_h != 0) != (m->tune.gather_h != 0) || (t->wide != 0) != (m->tune.wide != 0);
+  SNB_REQUIRE(!repack || !m->tc_blob, "snb_model_set_tuning: gather_h / wide change the packed weight images: set them "
+                                      "through the environment (SNB_GATHER_H / SNB_WIDE) before the model is created");
+  m->tune = *t;
+  return SNB_OK;
 }
 
 void snb_model_destroy(snb_model_t* mm) {

@@ -71,6 +71,7 @@ struct Ep;   // expert-parallel group (snb_ep.cuh)
 // Device-side model storage (library-owned copies, see snb_model_create).
 struct Model {
   snb_model_desc d;
+  snb_tuning tune;   // per-model knobs (defaults <- SNB_* environment at creation; snb_model_set_tuning)
   int xyz_in;    // 3 + 6*pos_xyz_freqs
   int dir_in;    // 3 + 6*pos_dir_freqs
   int cat_in;    // width + dir_in + appearance_dim
@@ -138,6 +139,7 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
 // true when the kernels that will run for this model can take a RaySource (the TS kernels, all experts local)
 bool tc_ray_source_ok(const Model* m);
 bool tc_supported(const Model* m);
+void tuning_from_env(snb_tuning* t);
 void tc_release(Model* m);
 
 size_t route_workspace_bytes(int64_t S, int32_t E);

@@ -213,11 +213,27 @@ bool tc_supported(const Model* m) {
 }
 
 struct TcOwner { TcHost h; uint8_t* wblob; uint8_t* wblob_w; };
-static bool env_is(const char* name, int v) { const char* e = getenv(name); return e && atoi(e) == v; }
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+// defaults of a new model object; the SNB_* variables are read here once per model (A/B scripts), never on the call path
+void tuning_from_env(snb_tuning* t) {
+  const int cg = env_int("SNB_CG", 1);
+  t->cta_group_front = env_int("SNB_CG_FRONT", cg) == 2 ? 2 : 1;
+  t->cta_group_back = env_int("SNB_CG_BACK", cg) == 2 ? 2 : 1;
+  t->ts = env_int("SNB_TS", 1) != 0;
+  t->ts_front = t->ts && env_int("SNB_TS_FRONT", 1) != 0;
+  t->wide = env_int("SNB_WIDE", 0) != 0;
+  t->route_full = getenv("SNB_ROUTE_FULL") != nullptr;
+  t->no_overlap = getenv("SNB_NO_OVERLAP") != nullptr;
+  t->pipe_depth = env_int("SNB_PIPE_DEPTH", -1);
+  t->route_sms = env_int("SNB_ROUTE_SMS", -1);
+  t->back_partition = getenv("SNB_BACK_PART") != nullptr;
+  t->no_ray_source = getenv("SNB_NO_RAY_SOURCE") != nullptr;
+  t->gather_h = getenv("SNB_GATHER_H") != nullptr;
+  t->front_ab = env_int("SNB_FRONT_AB", 0);
+}
 // which kernel family evaluates a model: wide for width 512 and mip models (SNB_WIDE=1 forces it for A/B tests)
 static bool tc_use_wide(const Model* m) {
-  static const bool force = getenv("SNB_WIDE") && atoi(getenv("SNB_WIDE")) != 0;
-  return m->d.width != 256 || m->d.mip || force;
+  return m->d.width != 256 || m->d.mip || m->tune.wide;
 }
 
 void tc_release(Model* m) {
@@ -266,7 +282,7 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
     p.o_c0 = addf(MAX_E); p.o_c1 = addf(MAX_E);
     p.o_wsig = addf(MW); p.o_bsig = addf(1); p.o_wcol = addf((size_t)3 * H2); p.o_bcol = addf(3);
     p.o_b3x = addf((size_t)E * MW);
-    p.recompute_h = (getenv("SNB_GATHER_H") == nullptr && d.skip_layer >= 0) ? 1 : 0;
+    p.recompute_h = (!m->tune.gather_h && d.skip_layer >= 0) ? 1 : 0;
     p.mip = d.mip;
     p.E = E; p.skip_layer = d.skip_layer; p.pos_xyz_freqs = d.pos_xyz_freqs; p.pos_dir_freqs = d.pos_dir_freqs;
     p.appearance_dim = d.appearance_dim; p.appearance_count = d.appearance_count; p.hidden2 = H2; p.x_cols = m->x_cols;
@@ -1320,8 +1336,7 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
   c.lpart = ws.take<double>((size_t)SEL_MAX_E * SEL_PM_STRIDE);
   c.npm = 0;
   c.front_packed = false;
-  static const bool route_full = getenv("SNB_ROUTE_FULL") != nullptr;
-  c.select = !route_full && E <= SEL_MAX_E;
+  c.select = !m->tune.route_full && E <= SEL_MAX_E;
   c.rbytes = route_workspace_bytes(S, E);
   c.rws = ws.take<char>(c.rbytes);
   if (!ws.ok) { set_error("tc_forward: workspace too small"); return SNB_EWORKSPACE; }
@@ -1347,11 +1362,8 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_wide<2, 12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes<2>()));
     attr_done = true;
   }
-  static const int cg_env = getenv("SNB_CG") ? atoi(getenv("SNB_CG")) : 1;
-  static const int cg_front_env = getenv("SNB_CG_FRONT") ? atoi(getenv("SNB_CG_FRONT")) : cg_env;
-  static const int cg_back_env = getenv("SNB_CG_BACK") ? atoi(getenv("SNB_CG_BACK")) : cg_env;
-  c.cg = (cg_front_env == 2 && !c.wide) ? 2 : 1;
-  c.cg_back = (cg_back_env == 2 && !c.wide) ? 2 : 1;
+  c.cg = (m->tune.cta_group_front == 2 && !c.wide) ? 2 : 1;
+  c.cg_back = (m->tune.cta_group_back == 2 && !c.wide) ? 2 : 1;
   c.pe = profile_next();
   c.grid_cap = m->sm_count;
   return SNB_OK;
@@ -1384,14 +1396,12 @@ static int tc_front(Model* m, TcChunk& c, cudaStream_t st) {
     SNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_front<12, 2>, c.Pf, c.x, c.S, c.H, c.gates));
   } else {
     // SNB_TS_FRONT=0 / SNB_TS=0: shared-memory A operand (k_front)
-    static const bool ts_front = !(getenv("SNB_TS") && atoi(getenv("SNB_TS")) == 0) &&
-                                 !(getenv("SNB_TS_FRONT") && atoi(getenv("SNB_TS_FRONT")) == 0);
+    const bool ts_front = m->tune.ts != 0 && m->tune.ts_front != 0;
     if (ts_front && c.Pf.recompute_h && c.Pf.front[0].K16 <= TS_CAT_COLS) {
       // the [S,E] gates only leave the kernel when a caller taps them (or the full-order routing needs them)
       // the kernel keeps 16-bit row counters per CTA: a CTA must see fewer than 65536 rows (else k_pack_top1 does it)
       const bool pack = c.select && (int64_t)cdiv(n_front_tiles, grid1) * TILE < 65536;
-      static const int ab_env = getenv("SNB_FRONT_AB") ? atoi(getenv("SNB_FRONT_AB")) : 0;
-      c.Pf.ab = ab_env;
+      c.Pf.ab = m->tune.front_ab;
       float* gates_out = pack ? c.dbg_gates : c.gates;
       k_front_ts<12><<<grid1, THREADS, TSM_TOTAL, st>>>(c.Pf, c.x, c.S, gates_out, pack ? c.wsel : nullptr, c.hist0,
                                                          pack ? c.pm : nullptr, pack ? c.moe_idx : nullptr);
@@ -1472,7 +1482,7 @@ static int tc_back(Model* m, TcChunk& c, cudaStream_t st, bool finish_inline = t
   }
   if (c.pe) cudaEventRecord(c.pe->e[4], st);
   // launch #2 variants: SNB_TS=0 falls back to the shared-memory A operand (k_back); SNB_CG=2 runs CTA pairs
-  static const bool use_ts = !(getenv("SNB_TS") && atoi(getenv("SNB_TS")) == 0);
+  const bool use_ts = m->tune.ts != 0;
   const bool ts_ok = use_ts && c.Pb.recompute_h && c.Pb.back[1].K16 > MW && c.Pb.back[1].K16 - MW <= TS_CAT_COLS &&
                      c.Pb.front[0].K16 <= TS_CAT_COLS;
   if (c.wide) {
@@ -1505,8 +1515,8 @@ static int tc_back(Model* m, TcChunk& c, cudaStream_t st, bool finish_inline = t
 bool tc_ray_source_ok(const Model* m) {
   if (!m->tc_blob || m->ep || tc_use_wide(m)) return false;
   const TcParams& p = ((TcOwner*)m->tc_blob)->h.p;
-  static const bool ts_off = env_is("SNB_TS", 0) || env_is("SNB_TS_FRONT", 0) || env_is("SNB_CG", 2) ||
-                             env_is("SNB_CG_FRONT", 2) || env_is("SNB_CG_BACK", 2) || getenv("SNB_NO_RAY_SOURCE");
+  const snb_tuning& t = m->tune;
+  const bool ts_off = !t.ts || !t.ts_front || t.cta_group_front == 2 || t.cta_group_back == 2 || t.no_ray_source;
   return !ts_off && p.recompute_h && p.front[0].K16 <= TS_CAT_COLS && p.back[1].K16 > (uint32_t)MW &&
          p.back[1].K16 - MW <= TS_CAT_COLS;
 }
@@ -1543,15 +1553,14 @@ int tc_forward_chunks(Model* m, const float* x, int64_t B, int64_t chunk, const 
   }
   // tuning / A-B switches (read once): SNB_NO_OVERLAP routes on the caller's stream; SNB_PIPE_DEPTH = how many
   // launch #1 run ahead of launch #2 (1..3); SNB_ROUTE_SMS = SMs left free for the routing kernels
-  static const bool no_overlap = getenv("SNB_NO_OVERLAP") != nullptr;
+  const bool no_overlap = m->tune.no_overlap != 0;
   // defaults from the sweeps in profiles/: local experts depth 2 / 28 SMs (r1n: 12/20/28/36 SMs); expert-parallel
   // depth 3 / 36 SMs (r1q/r1r: the routing stage also scatters records to the peers and waits for theirs)
-  static const int depth_env = getenv("SNB_PIPE_DEPTH") ? atoi(getenv("SNB_PIPE_DEPTH")) : 0;
-  static const int route_env = getenv("SNB_ROUTE_SMS") ? atoi(getenv("SNB_ROUTE_SMS")) : -1;
-  static const bool back_full = getenv("SNB_BACK_PART") == nullptr;   // launch #2 keeps every SM (tile rounds!)
+  const int depth_env = m->tune.pipe_depth, route_env = m->tune.route_sms;
+  const bool back_full = !m->tune.back_partition;   // launch #2 keeps every SM (tile rounds!)
   // local experts + select routing: k_select is E CTAs of 1024 threads (one per SM); expert-parallel: the routing
   // stage also scatters records to the peers and waits for theirs (r1q/r1r)
-  static const bool route_full_env = getenv("SNB_ROUTE_FULL") != nullptr;
+  const bool route_full_env = m->tune.route_full != 0;
   const int sel_sms = 8;      // k_select: SEL_P = 8 CTAs of 1024 threads, one per SM
   // (r2t, N=2 expert-parallel: 8 / 16 / 36 SMs -> 729 / 726 / 682 M samples/s: the record scatter and the plan kernel are
   // short and follow k_select on the same SMs)

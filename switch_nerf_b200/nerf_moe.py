@@ -408,6 +408,20 @@ class NeRFMoE(nn.Module):
                 self._packed_versions = versions
         return self._handle
 
+    def tuning(self, **changes):
+        """Read (and optionally change) the kernel-selection / pipeline knobs of this model (snb_tuning: route_sms,
+        pipe_depth, ts, cta_group_*, route_full, no_overlap, ...): `model.tuning(route_sms=16)`; returns the current values."""
+        h = self.handle()
+        t = L.Tuning()
+        L.check(L.lib().snb_model_get_tuning(h, C.byref(t)))
+        if changes:
+            for k, v in changes.items():
+                if not hasattr(t, k):
+                    raise AttributeError(f"snb_tuning has no field {k!r}")
+                setattr(t, k, int(v))
+            L.check(L.lib().snb_model_set_tuning(h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in L.Tuning._fields_}
+
     def release(self):
         if self._handle is not None:
             L.lib().snb_model_destroy(self._handle)

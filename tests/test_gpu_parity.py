@@ -819,3 +819,30 @@ def test_render_mip_stochastic_sampling(built_lib):
     model.train()
     t, _ = render_rays_mip(model, rays, radii, idx, hp, True, True, debug_taps=True, seed=5)
     assert torch.isfinite(t["rgb_fine"]).all() and not torch.equal(t["_z_fine"], za)
+
+
+def test_model_tuning_struct(built_lib):
+    """snb_tuning: the kernel-selection knobs live on the model object (set through the ABI, read per call), not in
+    process-global state: switching routing / operand mode on a live model changes the kernels that run, the results agree,
+    and switching back reproduces the first result bit for bit."""
+    from switch_nerf_b200 import _lib as L
+    c = cuda_golden_case("e8_cf1_bpr")
+    model, _ = make_model(c["sd"], c["cf"], c["bpr"], False, "bf16")
+    x = c["x"].cuda()
+    t0 = model.tuning()
+    assert t0["ts"] == 1 and t0["cta_group_back"] == 1 and t0["route_full"] == 0 and t0["route_sms"] == -1
+    base = model(x)["outputs"].clone()
+    n0 = L.lib().snb_launch_count()
+    model(x)
+    n_sel = L.lib().snb_launch_count() - n0
+    model.tuning(route_full=1, ts=0)
+    n0 = L.lib().snb_launch_count()
+    alt = model(x)["outputs"].clone()
+    n_full = L.lib().snb_launch_count() - n0
+    assert n_full > n_sel                      # full-order routing = many kernels, k_select = one
+    d = (alt - base).abs()
+    assert float(d.mean()) < 3e-4 and float(d[:, :3].max()) <= 2 * 2.0 ** -8
+    assert model.tuning(route_full=0, ts=1)["ts"] == 1
+    assert torch.equal(model(x)["outputs"], base)
+    with pytest.raises(L.SnbError):
+        model.tuning(cta_group_back=3)
