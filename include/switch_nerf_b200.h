@@ -267,6 +267,48 @@ int snb_moe_backward(snb_model_t* m, const float* x, int64_t S, const float* sig
 int snb_composite_backward(const float* z, const float* raw, const float* last_delta, int64_t n_rays, int32_t n_samples,
                            const float* d_rgb, float* d_raw, void* stream);
 
+/* ---- f3: background NeRF + sphere parametrisation ------------------------------------------ */
+/* The background model of the reference: models/nerf.py:75-191 `NeRF` with xyz_dim = 4 (a point on the unit sphere +
+ * inverse distance), `layers` ReLU layers of `width` with the encoded input concatenated again at `skip_layer`,
+ * xyz_encoding_final, dir_a_encoding (width + dir + appearance -> width/2, ReLU), sigma / rgb heads.
+ * x [S, 8] = [pts(4), dir(3), image index]; out [S,4] = [sigmoid(rgb), sigma_activation(sigma (+noise))]. */
+typedef struct snb_bg_desc {
+  int32_t layers;           /* hparams.layers (8)                 */
+  int32_t skip_layer;       /* hparams.skip_layers[0] (4), -1 none */
+  int32_t width;            /* hparams.bg_layer_dim (256)          */
+  int32_t pos_xyz_freqs;    /* hparams.pos_xyz_dim (12)            */
+  int32_t pos_dir_freqs;    /* hparams.pos_dir_dim (4)             */
+  int32_t appearance_dim;   /* hparams.appearance_dim (48)         */
+  int32_t appearance_count;
+  int32_t shifted_softplus; /* sigma activation: 1 = softplus(x - 1) (models/nerf.py:58-72), 0 = ReLU */
+} snb_bg_desc;
+typedef struct snb_bg_weights {
+  const float* w[16];       /* xyz_encodings.{i}.0.weight [width, in_i]; in_0 = 4 + 8*freqs, in_skip = in_0 + width (encoded input first) */
+  const float* b[16];
+  const float* final_w; const float* final_b;    /* xyz_encoding_final   [width, width]            */
+  const float* dir_w; const float* dir_b;        /* dir_a_encoding.0     [width/2, width + dir + A] */
+  const float* sigma_w; const float* sigma_b;    /* sigma                [1, width]                */
+  const float* rgb_w; const float* rgb_b;        /* rgb                  [3, width/2]              */
+  const float* emb_a;                            /* embedding_a.weight   [count, A]                */
+} snb_bg_weights;
+typedef struct snb_bg_model snb_bg_model_t;
+int snb_bg_create(const snb_bg_desc* desc, const snb_bg_weights* w, void* stream, snb_bg_model_t** out);
+int snb_bg_update(snb_bg_model_t* m, const snb_bg_weights* w, void* stream);
+void snb_bg_destroy(snb_bg_model_t* m);
+size_t snb_bg_workspace_bytes(const snb_bg_model_t* m, int64_t S);
+int snb_bg_forward(snb_bg_model_t* m, const float* x, int64_t S, const float* sigma_noise, float* out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+/* rendering.py:497-518 `_intersect_sphere`: fg_far [N] = depth at which a ray leaves the (unit, after centre / radius)
+ * sphere; *bad (DEVICE int, nullable) is set to 1 if a ray's closest point to the centre lies outside the sphere (the
+ * reference raises 'Not all your cameras are bounded by the unit sphere'). */
+int snb_intersect_sphere(const float* rays, int64_t N, const float* sphere_center, const float* sphere_radius,
+                         float* fg_far, int32_t* bad, void* stream);
+/* rendering.py:521-570 `_depth2pts_outside` (include_xyz_real = False): for ray r and inverse depth z[r, j] in [0,1] the
+ * 4-D background point [p_sphere_rotated(3), z] and the conventional depth depth_real.  sphere_center / sphere_radius:
+ * DEVICE [3] each (nullable together). */
+int snb_depth2pts_outside(const float* rays, const float* sphere_center, const float* sphere_radius, const float* z,
+                          int64_t N, int32_t S, float* pts, float* depth_real, void* stream);
+
 /* ---- f2: ray generation ------------------------------------------------------------------- */
 /* Replaces ray_utils.get_ray_directions + get_rays (ray_utils.py:6-84) for one image: rays [H*W, 8] fp32 =
  * [origin(3), unit direction(3), near, far], pixel (row j, column i) at index j*W + i.
@@ -293,6 +335,10 @@ typedef struct snb_render_opts {
   /* mip renderer only: rendering_mip.py:225 passes `randomized=hparams.perturb` to the fine resampling -- in eval too
    * (the coarse perturb above is training-only) -- so it is a separate switch: 1 = stratified random u (seeded) */
   int32_t resample_randomized;
+  /* bg-NeRF rays (rendering.py:41-46, 215-216, 250-251): last_delta [N] holds the reference's raw value (fg_far for rays
+   * that continue into the background, 1e10 otherwise) and the composite of each level uses last_delta - max(z of that
+   * level) where last_delta < 1e10 */
+  int32_t last_delta_minus_zmax;
 } snb_render_opts;
 
 /* Per-ray outputs (all nullable; device pointers). Keys of the reference `results` dict

@@ -47,7 +47,18 @@ class RenderOpts(C.Structure):
     _fields_ = [("coarse_samples", C.c_int32), ("fine_samples", C.c_int32), ("model_chunk_size", C.c_int64),
                 ("perturb", C.c_float), ("seed", C.c_uint64), ("white_bkgd", C.c_int32), ("precision", C.c_int32),
                 ("route", RouteOpts), ("sigma_noise_coarse", C.c_void_p), ("sigma_noise_fine", C.c_void_p),
-                ("resample_randomized", C.c_int32)]
+                ("resample_randomized", C.c_int32), ("last_delta_minus_zmax", C.c_int32)]
+
+
+class BgDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("layers", "skip_layer", "width", "pos_xyz_freqs", "pos_dir_freqs", "appearance_dim",
+                                         "appearance_count", "shifted_softplus")]
+
+
+class BgWeights(C.Structure):
+    _fields_ = [("w", C.c_void_p * 16), ("b", C.c_void_p * 16), ("final_w", C.c_void_p), ("final_b", C.c_void_p),
+                ("dir_w", C.c_void_p), ("dir_b", C.c_void_p), ("sigma_w", C.c_void_p), ("sigma_b", C.c_void_p),
+                ("rgb_w", C.c_void_p), ("rgb_b", C.c_void_p), ("emb_a", C.c_void_p)]
 
 
 class Tuning(C.Structure):
@@ -87,6 +98,14 @@ _SIGNATURES = {
     "snb_route_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "snb_route_top1": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snb_bg_create": (C.c_int, [C.POINTER(BgDesc), C.POINTER(BgWeights), C.c_void_p, C.POINTER(C.c_void_p)]),
+    "snb_bg_update": (C.c_int, [C.c_void_p, C.POINTER(BgWeights), C.c_void_p]),
+    "snb_bg_destroy": (None, [C.c_void_p]),
+    "snb_bg_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
+    "snb_bg_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "snb_intersect_sphere": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snb_depth2pts_outside": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
     "snb_model_get_tuning": (C.c_int, [C.c_void_p, C.POINTER(Tuning)]),
     "snb_model_set_tuning": (C.c_int, [C.c_void_p, C.POINTER(Tuning)]),
     "snb_moe_backward_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_double]),

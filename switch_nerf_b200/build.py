@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsnb.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["snb_api.cu", "snb_route.cu", "snb_fp32.cu", "snb_render.cu", "snb_selftest.cu", "snb_tc.cu", "snb_ep.cu", "snb_backward.cu"]
+SOURCES = ["snb_api.cu", "snb_route.cu", "snb_fp32.cu", "snb_render.cu", "snb_selftest.cu", "snb_tc.cu", "snb_ep.cu", "snb_backward.cu", "snb_bg.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-cudart", "static", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

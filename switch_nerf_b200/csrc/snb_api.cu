@@ -58,6 +58,7 @@ int get_rays_launch(int W, int H, float fx, float fy, float cx, float cy, int ce
 int fill_x_launch(const float* rays, const int* image_indices, const float* z, int64_t N, int Sn, float* x,
                   cudaStream_t st);
 int zmid_launch(const float* z, int64_t N, int S, float* mid, cudaStream_t st);
+int last_delta_adj_launch(const float* last_delta, const float* z, int64_t N, int S, float* out, cudaStream_t st);
 int merge_composite_launch(const float* zf, const float* zc, const float* raw_f, const float* raw_c,
                            const float* last_delta, int64_t N, int Sf, int Sc, int presorted, int white_bkgd,
                            float* rgb, float* depth, float* var, float* lam, cudaStream_t st);
@@ -144,6 +145,15 @@ static int upload(Model* m, const snb_weights* w, cudaStream_t st) {
   return SNB_OK;
 }
 
+struct BgModel;
+int bg_create(const snb_bg_desc* d, const snb_bg_weights* w, cudaStream_t st, BgModel** out);
+int bg_update(BgModel* m, const snb_bg_weights* w, cudaStream_t st);
+void bg_destroy(BgModel* m);
+size_t bg_workspace_bytes(const BgModel* m, int64_t S);
+int bg_forward(BgModel* m, const float* x, int64_t S, const float* noise, float* out, Arena& ws, cudaStream_t st);
+int intersect_sphere_launch(const float* rays, int64_t N, const float* c, const float* rad, float* fg_far, int* bad, cudaStream_t st);
+int depth2pts_outside_launch(const float* rays, const float* c, const float* rad, const float* z, int64_t N, int S, float* pts,
+                             float* depth_real, cudaStream_t st);
 }  // namespace snb
 
 using namespace snb;
@@ -523,17 +533,30 @@ int snb_render_rays(snb_model_t* mm, const float* rays, const int32_t* image_ind
   int rc;
   if ((rc = coarse_z_launch(rays, N, Sc, o->perturb, o->seed, zc, st))) return rc;
   if ((rc = run_pass(zc, Sc, raw_c, out->moe_gates_coarse, out->gate_loss_coarse, o->sigma_noise_coarse))) return rc;
+  // bg-NeRF rays: last_delta - max(z) per level (rendering.py:215-216, 250-251); zmid / wc are free at those points
+  const bool adj = o->last_delta_minus_zmax && last_delta;
+  const float* ld_c = last_delta;
+  if (adj) {
+    float* t = (Sf == 0) ? wc : zmid;
+    if ((rc = last_delta_adj_launch(last_delta, zc, N, Sc, t, st))) return rc;
+    ld_c = t;
+  }
   if (Sf == 0) {
-    return composite_launch(zc, raw_c, last_delta, N, Sc, o->white_bkgd, out->rgb, out->depth, out->depth_variance,
+    return composite_launch(zc, raw_c, ld_c, N, Sc, o->white_bkgd, out->rgb, out->depth, out->depth_variance,
                             out->bg_lambda, nullptr, st);
   }
   // coarse weights -> pdf over the interior bins (rendering.py:237-241)
-  if ((rc = composite_launch(zc, raw_c, last_delta, N, Sc, 0, nullptr, nullptr, nullptr, nullptr, wc, st))) return rc;
+  if ((rc = composite_launch(zc, raw_c, ld_c, N, Sc, 0, nullptr, nullptr, nullptr, nullptr, wc, st))) return rc;
   if ((rc = zmid_launch(zc, N, Sc, zmid, st))) return rc;
   if ((rc = sample_pdf_launch(zmid, Sc - 1, wc, Sc, 1, nullptr, N, Sc - 2, Sf, o->seed, o->perturb == 0.f, zf, st))) return rc;
   if ((rc = run_pass(zf, Sf, raw_f, out->moe_gates_fine, out->gate_loss_fine, o->sigma_noise_fine))) return rc;
+  const float* ld_f = last_delta;
+  if (adj) {
+    if ((rc = last_delta_adj_launch(last_delta, zf, N, Sf, wc, st))) return rc;   // the max is over the fine samples only
+    ld_f = wc;
+  }
   // perturb == 0: z_fine comes from an ascending u through a monotone cdf, z_coarse is a linspace -> both sorted
-  return merge_composite_launch(zf, zc, raw_f, raw_c, last_delta, N, Sf, Sc, o->perturb == 0.f, o->white_bkgd, out->rgb, out->depth,
+  return merge_composite_launch(zf, zc, raw_f, raw_c, ld_f, N, Sf, Sc, o->perturb == 0.f, o->white_bkgd, out->rgb, out->depth,
                                 out->depth_variance, out->bg_lambda, st);
 }
 
@@ -634,6 +657,36 @@ int snb_umma_selftest(const void* a_bf16, const void* b_bf16, int32_t N, int32_t
 int snb_umma_microbench(int32_t N, int32_t a_in_tmem, int32_t flags, int32_t reps, uint64_t* out6, void* stream) {
   SNB_REQUIRE(out6, "snb_umma_microbench: NULL out");
   return umma_microbench(N, a_in_tmem, flags, reps, (unsigned long long*)out6, (cudaStream_t)stream);
+}
+
+// ---- f3: background NeRF + sphere parametrisation (snb_bg.cu) ----
+int snb_bg_create(const snb_bg_desc* desc, const snb_bg_weights* w, void* stream, snb_bg_model_t** out) {
+  return bg_create(desc, w, (cudaStream_t)stream, (BgModel**)out);
+}
+int snb_bg_update(snb_bg_model_t* m, const snb_bg_weights* w, void* stream) {
+  SNB_REQUIRE(m && w, "snb_bg_update: NULL argument");
+  return bg_update((BgModel*)m, w, (cudaStream_t)stream);
+}
+void snb_bg_destroy(snb_bg_model_t* m) { bg_destroy((BgModel*)m); }
+size_t snb_bg_workspace_bytes(const snb_bg_model_t* m, int64_t S) { return m ? bg_workspace_bytes((const BgModel*)m, S) : 0; }
+int snb_bg_forward(snb_bg_model_t* m, const float* x, int64_t S, const float* sigma_noise, float* out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  SNB_REQUIRE(m && S >= 0 && (S == 0 || (x && out)), "snb_bg_forward: bad argument");
+  SNB_REQUIRE(S == 0 || workspace, "snb_bg_forward: NULL workspace");
+  Arena a(workspace, workspace_bytes);
+  return bg_forward((BgModel*)m, x, S, sigma_noise, out, a, (cudaStream_t)stream);
+}
+int snb_intersect_sphere(const float* rays, int64_t N, const float* sphere_center, const float* sphere_radius, float* fg_far,
+                         int32_t* bad, void* stream) {
+  SNB_REQUIRE(N >= 0 && (N == 0 || (rays && fg_far)), "snb_intersect_sphere: bad argument");
+  SNB_REQUIRE((sphere_center == nullptr) == (sphere_radius == nullptr), "snb_intersect_sphere: centre and radius come together");
+  return intersect_sphere_launch(rays, N, sphere_center, sphere_radius, fg_far, bad, (cudaStream_t)stream);
+}
+int snb_depth2pts_outside(const float* rays, const float* sphere_center, const float* sphere_radius, const float* z, int64_t N,
+                          int32_t S, float* pts, float* depth_real, void* stream) {
+  SNB_REQUIRE(N >= 0 && S >= 0 && (N == 0 || S == 0 || (rays && z && pts && depth_real)), "snb_depth2pts_outside: bad argument");
+  SNB_REQUIRE((sphere_center == nullptr) == (sphere_radius == nullptr), "snb_depth2pts_outside: centre and radius come together");
+  return depth2pts_outside_launch(rays, sphere_center, sphere_radius, z, N, S, pts, depth_real, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -150,6 +150,12 @@ static int launch_linear(int act, const float* A, int lda, const float* W, const
   return SNB_OK;
 }
 
+// the same tiles for callers in other translation units (snb_bg.cu)
+int linear_launch(int act, const float* A, int lda, const float* W, const float* b, const float* R, int ldr, float* C,
+                  int ldc, int64_t rows, int N, int K, const float* noise, cudaStream_t st) {
+  return launch_linear(act, A, lda, W, b, R, ldr, C, ldc, rows, N, K, 1, nullptr, nullptr, noise, st);
+}
+
 // ------------------------------------------------------------------------------------------
 // k_ln_gate: gate_input = LayerNorm(g) (eps 1e-5, biased var); logits = wg @ gate_input;
 // gates = softmax(logits).  One warp per row.  (nerf_moe.py:372; tutel_moe_layer_nobatch.py:105-126)

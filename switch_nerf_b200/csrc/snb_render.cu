@@ -406,6 +406,29 @@ int zmid_launch(const float* z, int64_t N, int S, float* mid, cudaStream_t st) {
   return SNB_OK;
 }
 
+// rendering.py:215-216 / 250-251: rays that continue into the background model carry last_delta = fg_far; the composite
+// of a level uses last_delta - max(z of that level) for them (1e10 rays are left alone).  One warp per ray.
+__global__ void __launch_bounds__(128) k_last_delta_adj(const float* __restrict__ last_delta, const float* __restrict__ z,
+                                                        int64_t N, int S, float* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= N) return;
+  const int lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (int j = lane; j < S; j += 32) mx = fmaxf(mx, z[r * S + j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) {
+    const float ld = last_delta[r];
+    out[r] = (ld < 1e10f) ? (ld - mx) : ld;
+  }
+}
+int last_delta_adj_launch(const float* last_delta, const float* z, int64_t N, int S, float* out, cudaStream_t st) {
+  if (N == 0) return SNB_OK;
+  k_last_delta_adj<<<(unsigned)cdiv(N, 4), 128, 0, st>>>(last_delta, z, N, S, out);
+  SNB_CHECK_LAUNCH("k_last_delta_adj");
+  return SNB_OK;
+}
+
 int merge_composite_launch(const float* zf, const float* zc, const float* raw_f, const float* raw_c,
                            const float* last_delta, int64_t N, int Sf, int Sc, int presorted, int white_bkgd,
                            float* rgb, float* depth, float* var, float* lam, cudaStream_t st) {

@@ -161,3 +161,38 @@ def test_model_copies_do_not_share_the_c_handle_and_moe_layer_finds_its_owner():
     assert id(m2) in _OWNERS
     with pytest.raises(Exception):                     # no CPU path for the operator either
         m.layers["0"](torch.zeros(4, 256))
+
+
+def test_bg_nerf_mirror_layout_and_seed_parity():
+    """switch_nerf_b200.nerf.NeRF (background model, xyz_dim = 4): the reference's state_dict keys / shapes
+    (models/nerf.py:75-150) and, under the same seed, the weights the reference constructor draws -- pinned by the
+    checksum oracle/make_golden_bg.py stored from the unmodified reference."""
+    from torch import nn
+    from switch_nerf_b200.nerf import NeRF, ShiftedSoftplus
+    from tests.util import load_golden, sd_checksum
+    g = load_golden("bg_model_l8_w256_softplus.npz")
+    S_, layers, skip, width, softplus, seed, count = (int(v) for v in g["params"])
+    torch.manual_seed(seed)
+    bg = NeRF(12, 4, layers, [skip], width, 48, False, count, 3, 4, ShiftedSoftplus())
+    with torch.no_grad():
+        bg.sigma.bias += 1.5                                            # oracle.make_golden_bg.BG_SIGMA_BIAS
+    ck = float(g["sd_checksum"][0])
+    assert abs(sd_checksum(bg.state_dict()) - ck) < 1e-6 * ck
+    sd = bg.state_dict()
+    assert sd["xyz_encodings.0.0.weight"].shape == (256, 100)           # 4 + 4*12*2
+    assert sd["xyz_encodings.4.0.weight"].shape == (256, 356)           # skip: [encoded input | hidden]
+    assert sd["dir_a_encoding.0.weight"].shape == (128, 256 + 27 + 48)
+    assert sd["sigma.weight"].shape == (1, 256) and sd["rgb.weight"].shape == (3, 128)
+    assert sd["embedding_a.weight"].shape == (count, 48) and "xyz_encoding_final.bias" in sd
+    assert len(sd) == 2 * layers + 9
+    if HAVE_REF:
+        from oracle import ref_shims as R
+        R.install_shims()
+        from switch_nerf.models.nerf import NeRF as RefNeRF
+        torch.manual_seed(3)
+        ref = RefNeRF(12, 4, 8, [4], 64, 48, False, 5, 3, 4, nn.ReLU())
+        torch.manual_seed(3)
+        mine = NeRF(12, 4, 8, [4], 64, 48, False, 5, 3, 4, nn.ReLU())
+        a, b = ref.state_dict(), mine.state_dict()
+        assert list(a.keys()) == list(b.keys())
+        assert all(torch.equal(a[k], b[k]) for k in a)
