@@ -7,6 +7,8 @@ os.environ["SNB_TIMELINE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from switch_nerf_b200 import _lib as L, synthetic as O
+if os.environ.get("SNB_LIB"):
+    L.LIB_PATH = os.path.abspath(os.environ["SNB_LIB"])
 from switch_nerf_b200.configs import make_hparams
 from switch_nerf_b200.nerf_moe import get_nerf_moe_inner
 

@@ -153,7 +153,7 @@ using namespace ptx;
 __global__ void __launch_bounds__(192) k_umma_bench(int N, int ts, int flags, int reps, const uint8_t* __restrict__ src,
                                                     unsigned long long* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_mma, bar_full[4];
+  __shared__ uint64_t bar_mma, bar_full[4], bar_dummy, bar_set;
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int done;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -164,7 +164,10 @@ __global__ void __launch_bounds__(192) k_umma_bench(int N, int ts, int flags, in
   if (threadIdx.x == 0) {
     mbar_init(&bar_mma, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bar_full[i], 1);
+    mbar_init(&bar_dummy, 1);
+    mbar_init(&bar_set, 1);
     fence_mbar_init();
+    mbar_arrive(&bar_set);          // phase 0 of bar_set is complete from now on
     done = 0;
   }
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
@@ -177,11 +180,19 @@ __global__ void __launch_bounds__(192) k_umma_bench(int N, int ts, int flags, in
       const uint32_t idesc = umma_idesc_bf16(128, N);
       const unsigned long long t0 = clock64();
       for (int i = 0; i < reps; ++i) {
+        // flags: 0x200 tcgen05.commit after every 4th instruction (the ring-slot release of the fused kernels),
+        // 0x400 A operand columns at a stride of 16 (the in-place packed layout), 0x1000 a wait on an already
+        // completed mbarrier before every group of 4, 0x2000 B operand cycling through four 32 KB slots (needs copy size 2),
+        // 0x4000 the group's first instruction overwrites D (acc = 0)
         const uint32_t t = (uint32_t)(i & 3);
-        const uint64_t db = umma_smem_desc(smem_u32(sB) + 2u * t * 128u, 128u, 64u * 16u);
+        if ((flags & 0x1000) && t == 0) mbar_wait(&bar_set, 0);
+        const uint32_t bsrc = (flags & 0x2000) ? smem_u32(sL) + (uint32_t)((i >> 2) & 3) * 32768u : smem_u32(sB);
+        const uint64_t db = umma_smem_desc(bsrc + 2u * t * 128u, 128u, 64u * 16u);
         const uint32_t d = tmem_base + (uint32_t)((i >> 2) % (256 / N)) * (uint32_t)N;
-        if (ts) umma_bf16_ts(d, tmem_base + 256u + t * 8u, db, idesc, 1u);
-        else umma_bf16(d, umma_smem_desc(smem_u32(sA) + 2u * t * 128u, 128u, 64u * 16u), db, idesc, 1u);
+        const uint32_t acc = ((flags & 0x4000) && (i & 15) == 0) ? 0u : 1u;
+        if (ts) umma_bf16_ts(d, tmem_base + 256u + (uint32_t)((i >> 2) & 3) * ((flags & 0x400) ? 64u : 0u) + t * ((flags & 0x400) ? 16u : 8u), db, idesc, acc);
+        else umma_bf16(d, umma_smem_desc(smem_u32(sA) + 2u * t * 128u, 128u, 64u * 16u), db, idesc, acc);
+        if ((flags & 0x200) && t == 3) umma_commit(&bar_dummy);
       }
       umma_commit(&bar_mma);
       mbar_wait(&bar_mma, 0);

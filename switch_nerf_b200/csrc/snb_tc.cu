@@ -1354,8 +1354,8 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front_ts<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSM_TOTAL));
-    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_ts<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSM_TOTAL));
-    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_ts<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSM_TOTAL));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_ts<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSB_TOTAL));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_ts<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSB_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front_wide<1, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes<1>()));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_wide<1, 12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes<1>()));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front_wide<2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes<2>()));
@@ -1491,7 +1491,7 @@ static int tc_back(Model* m, TcChunk& c, cudaStream_t st, bool finish_inline = t
   } else if (c.cg_back == 2) {
     grid2 &= ~1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid2); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = ts_ok ? TSM_TOTAL : SM_TOTAL; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)grid2); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = ts_ok ? TSB_TOTAL : SM_TOTAL; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1499,7 +1499,7 @@ static int tc_back(Model* m, TcChunk& c, cudaStream_t st, bool finish_inline = t
     if (ts_ok) SNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_back_ts<4, 2>, c.Pb, c.tt, io));
     else SNB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_back<4, 2>, c.Pb, c.tt, io, (const __nv_bfloat16*)c.H));
   } else if (ts_ok) {
-    k_back_ts<4, 1><<<grid2, THREADS, TSM_TOTAL, st>>>(c.Pb, c.tt, io);
+    k_back_ts<4, 1><<<grid2, THREADS, TSB_TOTAL, st>>>(c.Pb, c.tt, io);
   } else {
     k_back<4, 1><<<grid2, THREADS, SM_TOTAL, st>>>(c.Pb, c.tt, io, c.H);
   }

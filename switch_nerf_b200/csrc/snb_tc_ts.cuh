@@ -24,11 +24,15 @@ static constexpr uint32_t TS_CAT_COLS = 96;                       // PE(xyz) / [
 static constexpr uint32_t TS_SBO = TS_CAT_COLS / 8 * 128;         // 1536 B between 8-row groups
 static constexpr uint32_t TS_ACAT_BYTES = TILE / 8 * TS_SBO;      // 24576
 static constexpr int TS_NST = 5;
+#ifndef TS_BACK_NST
+#define TS_BACK_NST 5
+#endif
+static constexpr int TS_NST_MAX = 6;
 
 struct __align__(16) TsCtl {
-  uint64_t full[2 * TS_NST];      // CTA pairs use 2*TS_NST half-size ring slots (each CTA streams half of a slice)
-  uint64_t empty[2 * TS_NST];
-  uint64_t peer_ok[2 * TS_NST];   // CTA pairs, leader only: the peer's half of the weight slice landed
+  uint64_t full[2 * TS_NST_MAX];      // CTA pairs use 2*NST half-size ring slots (each CTA streams half of a slice)
+  uint64_t empty[2 * TS_NST_MAX];
+  uint64_t peer_ok[2 * TS_NST_MAX];   // CTA pairs, leader only: the peer's half of the weight slice landed
   uint64_t acc_full[2];
   uint64_t a_ready[4];      // epilogue -> MMA: K-chunk of the next A operand packed into TMEM
   uint64_t s_ready[2][2];   // epilogue -> MMA: shared-memory K-chunk written, [cat block][chunk]
@@ -43,9 +47,20 @@ static constexpr size_t TSM_RED = TSM_VEC + SM_VEC_FLOATS * 4;
 static constexpr size_t TSM_CTL = TSM_RED + SM_RED_FLOATS * 4;
 static constexpr size_t TSM_TOTAL = TSM_CTL + sizeof(TsCtl) + 1024;
 static_assert(TSM_TOTAL <= 227 * 1024, "shared memory budget (TS kernel)");
+// launch #2 may use a deeper ring (TS_BACK_NST) -- timing diagnostic for now: with 6 slots the two cat blocks and the
+// reduction scratch alias (results are garbage, the schedule is that of a 6-slot ring)
+static constexpr bool TSB_DIAG = (TS_BACK_NST > 5);
+static constexpr uint32_t TSB_CAT_STRIDE = TSB_DIAG ? 0u : TS_ACAT_BYTES;
+static constexpr size_t TSB_RING = TSB_DIAG ? TS_ACAT_BYTES : 2 * TS_ACAT_BYTES;
+static constexpr size_t TSB_BIAS = TSB_RING + (size_t)TS_BACK_NST * STAGE_BYTES;
+static constexpr size_t TSB_VEC = TSB_DIAG ? TSB_BIAS : TSB_BIAS + 2 * 256 * 4;
+static constexpr size_t TSB_RED = TSB_DIAG ? TSB_BIAS : TSB_VEC + SM_VEC_FLOATS * 4;
+static constexpr size_t TSB_CTL = TSB_RED + SM_RED_FLOATS * 4;
+static constexpr size_t TSB_TOTAL = TSB_CTL + sizeof(TsCtl) + 1024;
+static_assert(TSB_TOTAL <= 227 * 1024, "shared memory budget (TS kernel, launch #2)");
 
 struct TsPipe {
-  uint32_t slice = 0;                  // weight slices produced / consumed
+  uint32_t stage = 0, phase = 0;       // ring position of the next weight slot to produce / consume
   uint32_t a_use[4] = {0, 0, 0, 0};
   uint32_t s_use[2][2] = {{0, 0}, {0, 0}};
   uint32_t acc_use[2] = {0, 0};
@@ -82,71 +97,112 @@ __device__ __forceinline__ uint32_t ts_round2(float a, float b, float& ra, float
 
 // ---- producer: the K-slices of one packed layer image (same images as k_back) ----
 // CG = 2 (CTA pair): each CTA streams its own half of the slice (output rows [rank*N/2, +N/2) are the contiguous half)
-template <int CG>
+// A ring slot holds as many consecutive 64-wide K-slices as fit in it (1 for N = 256, 2 for N = 128, 8 for the 32-wide
+// gate GEMM): the cost of a bulk copy hardly depends on its size (profiles/r3a_ring_experiments.md), so narrow layers
+// are fed by full-size copies too.  Segments of a layer start on a group boundary (K = 256 is 4 slices).
+__device__ __forceinline__ uint32_t ts_group(uint32_t N, int CG) {
+#ifdef TS_NO_GROUP
+  return 1u;
+#else
+  const uint32_t g = STAGE_BYTES / (N * 64u * 2u);
+  return (CG == 2 || g < 1u) ? 1u : g;
+#endif
+}
+template <int CG, int NST = TS_NST, bool BACK = false>
 __device__ __forceinline__ void ts_produce(const uint8_t* wsrc, uint32_t N, uint32_t K16, uint8_t* ring, TsCtl* ctl, TsPipe& pp,
                                            uint32_t rank) {
+  const uint32_t G = ts_group(N, CG);
   const uint32_t nsl = (K16 + 63) / 64;
-  for (uint32_t j = 0; j < nsl; ++j) {
-    const uint32_t klen = min(64u, K16 - 64u * j);
+  constexpr uint32_t NS = NST * CG, SB = STAGE_BYTES / CG;
+  for (uint32_t j = 0; j < nsl; j += G) {
+    const uint32_t klen = min(64u * G, K16 - 64u * j);
     const uint32_t bytes = N * klen * 2 / CG;
-    constexpr uint32_t NS = TS_NST * CG, SB = STAGE_BYTES / CG;
-    const uint32_t stage = pp.slice % NS, phase = (pp.slice / NS) & 1;
-    mbar_wait(&ctl->empty[stage], phase ^ 1);
+    const uint32_t stage = pp.stage;
+    mbar_wait(&ctl->empty[stage], pp.phase ^ 1);
+    if (++pp.stage == NS) { pp.stage = 0; pp.phase ^= 1; }
+#if defined(TS_DIAG_NOCOPY)      // timing diagnostic, launch #2 only: the weights "arrive" instantly (results are garbage)
+    if (BACK) { mbar_arrive(&ctl->full[stage]); continue; }
+#endif
     mbar_arrive_expect_tx(&ctl->full[stage], bytes);
     bulk_g2s(ring + (size_t)stage * SB, wsrc + (size_t)N * 64 * 2 * j + (size_t)rank * bytes, bytes, &ctl->full[stage]);
-    ++pp.slice;
   }
 }
 
 // ---- MMA issuer: one segment of a layer = consecutive K-slices whose A operand is all in TMEM (ts) or all in the
 // shared-memory cat block.  `a_tmem`: first column of the packed A operand; `cont`: accumulate onto an earlier segment.
+// Executed by ALL lanes of warp 1 with warp-uniform values; only the tcgen05.mma / tcgen05.commit themselves are
+// predicated on `leader` (one elected lane, the same for the whole kernel).  The issuing thread is what bounds the
+// tensor pipe here: written for lane 0 alone, every instruction carried a vector->uniform register waterfall
+// (ELECT + 4 x R2UR + BRA.U.ANY) and a slice cost ~830 clk of issue for 552 clk of tensor work
+// (profiles/r3g_issue_path.md).  Uniform control flow lets the descriptors live in uniform registers.
 // CG = 2: the leader CTA (rank 0) issues M = 256 instructions for the pair (each CTA's own TMEM / cat block supplies
 // its 128 rows of A, each CTA's ring slot half of B); the peer's warp 1 only forwards "my weight half landed".
-template <int CG>
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+template <int CG, int NST = TS_NST, uint32_t CAT_STRIDE = TS_ACAT_BYTES>
 __device__ __forceinline__ void ts_mma_seg(uint32_t N, uint32_t K, bool ts, uint32_t a_tmem, uint32_t acat_base,
                                            uint32_t ring_base, uint32_t d_tmem, TsCtl* ctl, TsPipe& pp, bool cont,
-                                           uint32_t rank, unsigned long long* tl, int* tn, uint32_t cb = 0) {
+                                           uint32_t rank, bool leader, unsigned long long* tl, int* tn, uint32_t cb = 0) {
   const uint32_t nsl = (K + 63) / 64;
   const uint32_t idesc = umma_idesc_bf16(TILE * CG, (int)N);
+  const uint32_t G = ts_group(N, CG);
+  constexpr uint32_t NS = NST * CG, SB = STAGE_BYTES / CG;
 #pragma unroll
   for (uint32_t j = 0; j < 4; ++j) {
     if (j >= nsl) break;
     const uint32_t klen = min(64u, K - 64u * j);
-    constexpr uint32_t NS = TS_NST * CG, SB = STAGE_BYTES / CG;
-    const uint32_t stage = pp.slice % NS, phase = (pp.slice / NS) & 1;
+    const uint32_t stage = pp.stage, phase = pp.phase;
+    const bool first = (j % G) == 0, last = ((j + 1) % G) == 0 || j + 1 == nsl;
+    if (last) { if (++pp.stage == NS) { pp.stage = 0; pp.phase ^= 1; } }
     if (CG == 2 && rank != 0) {
       mbar_wait(&ctl->full[stage], phase);
-      mbar_arrive_remote(mapa_shared(smem_u32(&ctl->peer_ok[stage]), 0));
-      ++pp.slice;
+      if (leader) mbar_arrive_remote(mapa_shared(smem_u32(&ctl->peer_ok[stage]), 0));
       continue;
     }
     if (ts) { mbar_wait(&ctl->a_ready[j], pp.a_use[j] & 1); ++pp.a_use[j]; }
     else if (j < 2) { mbar_wait(&ctl->s_ready[cb][j], pp.s_use[cb][j] & 1); ++pp.s_use[cb][j]; }
     if (tn) tl_mark(tl, 1, *tn, 100 + (int)j);
-    mbar_wait(&ctl->full[stage], phase);
-    if (CG == 2) mbar_wait(&ctl->peer_ok[stage], phase);
+    if (first) {
+      mbar_wait(&ctl->full[stage], phase);
+      if (CG == 2) mbar_wait(&ctl->peer_ok[stage], phase);
+    }
     if (tn) tl_mark(tl, 1, *tn, 110 + (int)j);
     tc_fence_after();
-    const uint32_t b_base = ring_base + stage * SB;
-    for (uint32_t t = 0; t < klen / 16; ++t) {
-      const uint64_t db = op_desc(b_base + (2u * t) * 128u, 128u, klen * 16u);
-      const uint32_t acc = (cont || (j | t)) ? 1u : 0u;
+    // descriptors of the slice: the start-address field counts 16-byte units, one K = 16 step is two 128-byte core
+    // matrices further (+16); addresses stay below 256 KB, so the 14-bit field never carries
+    const uint64_t db0 = op_desc(ring_base + stage * SB + (j % G) * (N * 128u), 128u, klen * 16u);
+    const uint64_t da0 = op_desc(acat_base + cb * CAT_STRIDE + (8u * j) * 128u, 128u, TS_SBO);
+    const uint32_t at0 = a_tmem + j * 64u;
+    const uint32_t acc0 = (cont || j) ? 1u : 0u;
+    auto issue = [&](uint32_t t) {
+      const uint32_t acc = t ? 1u : acc0;
       if (ts) {
-        if (CG == 2) umma_bf16_ts_pair(d_tmem, a_tmem + j * 64u + t * 16u, db, idesc, acc);
-        else umma_bf16_ts(d_tmem, a_tmem + j * 64u + t * 16u, db, idesc, acc);
+        if (CG == 2) umma_bf16_ts_pair(d_tmem, at0 + t * 16u, db0 + 16u * t, idesc, acc);
+        else umma_bf16_ts(d_tmem, at0 + t * 16u, db0 + 16u * t, idesc, acc);
       } else {
-        const uint64_t da = op_desc(acat_base + cb * TS_ACAT_BYTES + (8u * j + 2u * t) * 128u, 128u, TS_SBO);
-        if (CG == 2) umma_bf16_pair(d_tmem, da, db, idesc, acc);
-        else umma_bf16(d_tmem, da, db, idesc, acc);
+        if (CG == 2) umma_bf16_pair(d_tmem, da0 + 16u * t, db0 + 16u * t, idesc, acc);
+        else umma_bf16(d_tmem, da0 + 16u * t, db0 + 16u * t, idesc, acc);
+      }
+    };
+    if (leader) {
+      if (klen == 64u) {
+        issue(0); issue(1); issue(2); issue(3);
+      } else {
+        for (uint32_t t = 0; t < klen / 16; ++t) issue(t);
+      }
+      if (last) {
+        if (CG == 2) umma_commit_pair(&ctl->empty[stage], 3);    // frees the ring slot in BOTH CTAs
+        else umma_commit(&ctl->empty[stage]);
       }
     }
-    if (CG == 2) umma_commit_pair(&ctl->empty[stage], 3);    // frees the ring slot in BOTH CTAs
-    else umma_commit(&ctl->empty[stage]);
-    ++pp.slice;
   }
 }
 template <int CG>
-__device__ __forceinline__ void ts_commit_acc(TsCtl* ctl, uint32_t buf, uint32_t rank) {
+__device__ __forceinline__ void ts_commit_acc(TsCtl* ctl, uint32_t buf, uint32_t rank, bool leader) {
+  if (!leader) return;
   if (CG == 2) {
     if (rank == 0) umma_commit_pair(&ctl->acc_full[buf], 3);
   } else {
@@ -156,7 +212,11 @@ __device__ __forceinline__ void ts_commit_acc(TsCtl* ctl, uint32_t buf, uint32_t
 
 // ---- epilogue helpers ----
 __device__ __forceinline__ void ts_wait_acc(TsCtl* ctl, TsPipe& pp, int buf) {
+#ifdef TS_ACC_SPIN
+  mbar_wait(&ctl->acc_full[buf], pp.acc_use[buf] & 1);
+#else
   mbar_wait_backoff(&ctl->acc_full[buf], pp.acc_use[buf] & 1);
+#endif
   ++pp.acc_use[buf];
   tc_fence_after();
 }
@@ -214,12 +274,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
   const float* __restrict__ noise = io.noise;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int t_first0 = CG * ((int)blockIdx.x / CG), t_stride = (int)gridDim.x;   // pairs of tiles share the expert
-  TsCtl* ctl = reinterpret_cast<TsCtl*>(smem + TSM_CTL);
+  TsCtl* ctl = reinterpret_cast<TsCtl*>(smem + TSB_CTL);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2 * TS_NST; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); mbar_init(&ctl->peer_ok[i], 1); }
+    for (int i = 0; i < 2 * TS_NST_MAX; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); mbar_init(&ctl->peer_ok[i], 1); }
     mbar_init(&ctl->acc_full[0], 1);
     mbar_init(&ctl->acc_full[1], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS * CG);
@@ -230,9 +290,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
     if (CG == 2) tmem_alloc_pair<512>(&ctl->tmem_base);
     else tmem_alloc<512>(&ctl->tmem_base);
   }
-  float* sbias = reinterpret_cast<float*>(smem + TSM_BIAS);
-  float* svec = reinterpret_cast<float*>(smem + TSM_VEC);
-  float* sred = reinterpret_cast<float*>(smem + TSM_RED);
+  float* sbias = reinterpret_cast<float*>(smem + TSB_BIAS);
+  float* svec = reinterpret_cast<float*>(smem + TSB_VEC);
+  float* sred = reinterpret_cast<float*>(smem + TSB_RED);
   float *s_wsig = svec, *s_wcol = svec + 256;
   const int H2 = P.hidden2;
   for (int i = threadIdx.x; i < MW; i += THREADS) s_wsig[i] = P.fblob[P.o_wsig + i];
@@ -242,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
-  const uint32_t acat_base = smem_u32(smem + TSM_ACAT), ring_base = smem_u32(smem + TSM_RING);
+  const uint32_t acat_base = smem_u32(smem + TSM_ACAT), ring_base = smem_u32(smem + TSB_RING);
   const int n_tiles = *tt.n_tiles;
   const int NE = P.n_expert;
   const uint32_t K_xyz = P.front[0].K16, K_cat = P.back[1].K16 - MW;     // shared-memory operand widths (80, 80)
@@ -253,49 +313,52 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       for (int tb = t_first0; tb < n_tiles; tb += t_stride) {
         const int e = tt.tile_expert[tb + (int)rank];
         if (e >= 0) {
-          ts_produce<CG>(P.wblob + P.front[0].w_off, MW, K_xyz, smem + TSM_RING, ctl, pp, rank);
+          ts_produce<CG, TS_BACK_NST, true>(P.wblob + P.front[0].w_off, MW, K_xyz, smem + TSB_RING, ctl, pp, rank);
           for (int l = 0; l < NE; ++l) {
-            ts_produce<CG>(P.wblob + P.expert[l].w_off + (size_t)e * P.expert_w_stride, MW, MW, smem + TSM_RING, ctl, pp, rank);
-            if (l == P.skip_layer) ts_produce<CG>(P.wblob + P.front[0].w_off, MW, K_xyz, smem + TSM_RING, ctl, pp, rank);
+            ts_produce<CG, TS_BACK_NST, true>(P.wblob + P.expert[l].w_off + (size_t)e * P.expert_w_stride, MW, MW, smem + TSB_RING, ctl, pp, rank);
+            if (l == P.skip_layer) ts_produce<CG, TS_BACK_NST, true>(P.wblob + P.front[0].w_off, MW, K_xyz, smem + TSB_RING, ctl, pp, rank);
           }
         }
-        ts_produce<CG>(P.wblob + P.back[0].w_off, P.back[0].N, P.back[0].K16, smem + TSM_RING, ctl, pp, rank);
-        ts_produce<CG>(P.wblob + P.back[1].w_off, P.back[1].N, P.back[1].K16, smem + TSM_RING, ctl, pp, rank);
+        ts_produce<CG, TS_BACK_NST, true>(P.wblob + P.back[0].w_off, P.back[0].N, P.back[0].K16, smem + TSB_RING, ctl, pp, rank);
+        ts_produce<CG, TS_BACK_NST, true>(P.wblob + P.back[1].w_off, P.back[1].N, P.back[1].K16, smem + TSB_RING, ctl, pp, rank);
       }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t li = 0;
-      int tn = 0;
-      // layer li accumulates into buffer li & 1; a TMEM A operand sits in columns [0,128) of the other buffer
-      auto acc_of = [&](uint32_t l) { return tmem_base + (l & 1u) * 256u; };
-      auto a_of = [&](uint32_t l) { return tmem_base + ((l & 1u) ^ 1u) * 256u; };
-      uint32_t cb = 0;                 // cat block of this tile (alternates)
-      for (int tb = t_first0; tb < n_tiles; tb += t_stride, cb ^= 1u) {
-        const int e = tt.tile_expert[tb + (int)rank];
-        tl_mark(P.tl, 1, tn, 1);
-        if (e >= 0) {
-          ts_mma_seg<CG>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, false, rank, P.tl, &tn, cb);
-          ts_commit_acc<CG>(ctl, li & 1, rank);
-          tl_mark(P.tl, 1, tn, 120);
-          ++li;
-          for (int l = 0; l < NE; ++l, ++li) {
-            ts_mma_seg<CG>(MW, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, rank, P.tl, &tn);
-            if (l == P.skip_layer)
-              ts_mma_seg<CG>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, rank, P.tl, &tn, cb);
-            ts_commit_acc<CG>(ctl, li & 1, rank);
-            tl_mark(P.tl, 1, tn, 120);
-          }
+    // all 32 lanes run the issue loop on warp-uniform values (see ts_mma_seg); lane `leader` issues
+    const bool leader = elect_one();
+    unsigned long long* tlm = leader ? P.tl : nullptr;
+    uint32_t li = 0;
+    int tn = 0;
+    // layer li accumulates into buffer li & 1; a TMEM A operand sits in columns [0,128) of the other buffer
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    auto acc_of = [&](uint32_t l) { return tmem_u + (l & 1u) * 256u; };
+    auto a_of = [&](uint32_t l) { return tmem_u + ((l & 1u) ^ 1u) * 256u; };
+    uint32_t cb = 0;                 // cat block of this tile (alternates)
+    const int n_tiles_u = __shfl_sync(0xffffffffu, n_tiles, 0);
+    for (int tb = t_first0; tb < n_tiles_u; tb += t_stride, cb ^= 1u) {
+      const int e = __shfl_sync(0xffffffffu, tt.tile_expert[tb + (int)rank], 0);
+      tl_mark(tlm, 1, tn, 1);
+      if (e >= 0) {
+        ts_mma_seg<CG, TS_BACK_NST, TSB_CAT_STRIDE>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, false, rank, leader, tlm, &tn, cb);
+        ts_commit_acc<CG>(ctl, li & 1, rank, leader);
+        tl_mark(tlm, 1, tn, 120);
+        ++li;
+        for (int l = 0; l < NE; ++l, ++li) {
+          ts_mma_seg<CG, TS_BACK_NST, TSB_CAT_STRIDE>(MW, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, rank, leader, tlm, &tn);
+          if (l == P.skip_layer)
+            ts_mma_seg<CG, TS_BACK_NST, TSB_CAT_STRIDE>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, rank, leader, tlm, &tn, cb);
+          ts_commit_acc<CG>(ctl, li & 1, rank, leader);
+          tl_mark(tlm, 1, tn, 120);
         }
-        ts_mma_seg<CG>(P.back[0].N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, rank, P.tl, &tn);
-        ts_commit_acc<CG>(ctl, li & 1, rank);
-        tl_mark(P.tl, 1, tn, 120);
-        ++li;
-        ts_mma_seg<CG>(P.back[1].N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, rank, P.tl, &tn);
-        ts_mma_seg<CG>(P.back[1].N, K_cat, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, rank, P.tl, &tn, cb);
-        ts_commit_acc<CG>(ctl, li & 1, rank);
-        tl_mark(P.tl, 1, tn, 120);
-        ++li;
       }
+      ts_mma_seg<CG, TS_BACK_NST, TSB_CAT_STRIDE>(P.back[0].N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, rank, leader, tlm, &tn);
+      ts_commit_acc<CG>(ctl, li & 1, rank, leader);
+      tl_mark(tlm, 1, tn, 120);
+      ++li;
+      ts_mma_seg<CG, TS_BACK_NST, TSB_CAT_STRIDE>(P.back[1].N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, rank, leader, tlm, &tn);
+      ts_mma_seg<CG, TS_BACK_NST, TSB_CAT_STRIDE>(P.back[1].N, K_cat, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, true, rank, leader, tlm, &tn, cb);
+      ts_commit_acc<CG>(ctl, li & 1, rank, leader);
+      tl_mark(tlm, 1, tn, 120);
+      ++li;
     }
   } else {
     EpiCtx ec;
@@ -347,7 +410,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         pe_to_bf16<12>(pxyz, pe);
 #pragma unroll
         for (int i = NPE; i < NPAD; ++i) pe[i] = __float2bfloat16_rn(0.f);
-        ts_cat_store_row(acat_base + (uint32_t)blk * TS_ACAT_BYTES, row, pe, NPAD / 8);
+        ts_cat_store_row(acat_base + (uint32_t)blk * TSB_CAT_STRIDE, row, pe, NPAD / 8);
       }
       for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, blk, i, lane, remote_s);
     };
@@ -360,7 +423,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       const int e = cur.e, sidx = cur.sidx;
       const bool valid = sidx >= 0;
       const float g = cur.g;
-      const uint32_t acat_cur = acat_base + (uint32_t)cb * TS_ACAT_BYTES;
+      const uint32_t acat_cur = acat_base + (uint32_t)cb * TSB_CAT_STRIDE;
       tl_mark(tl, 0, tn, 1);
       // [PE(dir) | appearance | 0-pad] -> cat block (cs == 1 threads)
       auto write_cat = [&]() {
@@ -660,10 +723,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
                                                          int32_t* __restrict__ moe_idx) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   TsCtl* ctl = reinterpret_cast<TsCtl*>(smem + TSM_CTL);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2 * TS_NST; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); mbar_init(&ctl->peer_ok[i], 1); }
+    for (int i = 0; i < 2 * TS_NST_MAX; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); mbar_init(&ctl->peer_ok[i], 1); }
     mbar_init(&ctl->acc_full[0], 1);
     mbar_init(&ctl->acc_full[1], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&ctl->a_ready[i], EPI_WARPS);
@@ -700,27 +763,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_ts(TcParams P, const float
         ts_produce<1>(P.wblob + P.gate.w_off, GATE_N, MW, smem + TSM_RING, ctl, pp, 0);
       }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t li = 0;
-      int tn = 0;
-      auto acc_of = [&](uint32_t l) { return tmem_base + (l & 1u) * 256u; };
-      auto a_of = [&](uint32_t l) { return tmem_base + ((l & 1u) ^ 1u) * 256u; };
-      uint32_t cb = 0;
-      for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x, cb ^= 1u) {
-        tl_mark(P.tl, 1, tn, 1);
-        ts_mma_seg<1>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, false, 0, P.tl, &tn, cb);
-        ts_commit_acc<1>(ctl, li & 1, 0);
-        ++li;
-        for (int l = 1; l < NL; ++l, ++li) {
-          ts_mma_seg<1>(MW, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, 0, P.tl, &tn);
-          ts_commit_acc<1>(ctl, li & 1, 0);
-          tl_mark(P.tl, 1, tn, 120);
-        }
-        ts_mma_seg<1>(GATE_N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, 0, P.tl, &tn);
-        ts_commit_acc<1>(ctl, li & 1, 0);
-        tl_mark(P.tl, 1, tn, 120);
-        ++li;
+    const bool leader = elect_one();               // warp-uniform issue loop, see ts_mma_seg
+    unsigned long long* tlm = leader ? P.tl : nullptr;
+    uint32_t li = 0;
+    int tn = 0;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    auto acc_of = [&](uint32_t l) { return tmem_u + (l & 1u) * 256u; };
+    auto a_of = [&](uint32_t l) { return tmem_u + ((l & 1u) ^ 1u) * 256u; };
+    uint32_t cb = 0;
+    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x, cb ^= 1u) {
+      tl_mark(tlm, 1, tn, 1);
+      ts_mma_seg<1>(MW, K_xyz, false, 0, acat_base, ring_base, acc_of(li), ctl, pp, false, 0, leader, tlm, &tn, cb);
+      ts_commit_acc<1>(ctl, li & 1, 0, leader);
+      ++li;
+      for (int l = 1; l < NL; ++l, ++li) {
+        ts_mma_seg<1>(MW, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, 0, leader, tlm, &tn);
+        ts_commit_acc<1>(ctl, li & 1, 0, leader);
+        tl_mark(tlm, 1, tn, 120);
       }
+      ts_mma_seg<1>(GATE_N, MW, true, a_of(li), acat_base, ring_base, acc_of(li), ctl, pp, false, 0, leader, tlm, &tn);
+      ts_commit_acc<1>(ctl, li & 1, 0, leader);
+      tl_mark(tlm, 1, tn, 120);
+      ++li;
     }
   } else {
     EpiCtx ec;
