@@ -435,13 +435,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           if (valid) {
             float dvec[3] = {cur.d0, cur.d1, cur.d2};
             pe_to_bf16<FD>(dvec, cat);
+            // the embedding row in batches of 8 independent 16-byte loads (a rolled loop serialised 12 L2 round trips:
+            // ~4.7K clk on the critical path of the skip layer, profiles/r3g_issue_path.md)
             const float4* er = reinterpret_cast<const float4*>(P.emb_a + (int64_t)cur.ai * P.appearance_dim);
-            for (int i = 0; i < P.appearance_dim / 4; ++i) {
-              const float4 f = er[i];
-              cat[NDIR + 4 * i + 0] = __float2bfloat16_rn(f.x);
-              cat[NDIR + 4 * i + 1] = __float2bfloat16_rn(f.y);
-              cat[NDIR + 4 * i + 2] = __float2bfloat16_rn(f.z);
-              cat[NDIR + 4 * i + 3] = __float2bfloat16_rn(f.w);
+            const int n4 = P.appearance_dim / 4;
+            for (int i0 = 0; i0 < n4; i0 += 8) {
+              float4 f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = (i0 + i < n4) ? __ldg(er + i0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (i0 + i < n4) {
+                  cat[NDIR + 4 * (i0 + i) + 0] = __float2bfloat16_rn(f[i].x);
+                  cat[NDIR + 4 * (i0 + i) + 1] = __float2bfloat16_rn(f[i].y);
+                  cat[NDIR + 4 * (i0 + i) + 2] = __float2bfloat16_rn(f[i].z);
+                  cat[NDIR + 4 * (i0 + i) + 3] = __float2bfloat16_rn(f[i].w);
+                }
+              }
             }
           }
           ts_cat_store_row(acat_cur, row, cat, (int)K_cat / 8);
@@ -470,12 +480,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           tl_mark(tl, 0, tn, 10 + l);
           ts_wait_acc(ctl, pp, buf);
           tl_mark(tl, 0, tn, 20 + l);
-          if (skip_here) write_cat();          // every MMA of the skip layer has retired: the PE(xyz) block is free
           const uint32_t tb = tbuf_of(li);
           if (l < NE - 1) {
             ts_epi_hidden<true>(tb, sb, ec, ctl, tl, &tn);
             if (l + 1 == P.skip_layer) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, cb, i, lane, remote_s);
+            // every MMA of the skip layer has retired (acc_full above): the PE(xyz) block is free.  Filled AFTER the
+            // hand-off, under the next layer's MMAs
+            if (skip_here) write_cat();
           } else {
+            if (skip_here) write_cat();
             // last expert layer (no activation) -> combine: y = bf16(gate * bf16(out)) -> ReLU -> packed A; sigma head
             uint32_t v[2][16];
             tmem_ld16(tb + (uint32_t)(ec.cs * 16), v[0]);

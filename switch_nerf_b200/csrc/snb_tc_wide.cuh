@@ -50,7 +50,7 @@ constexpr size_t wide_smem_bytes() { return Wide<NH>::O_CTL + sizeof(WCtl) + 102
 static_assert(wide_smem_bytes<2>() <= 227 * 1024, "shared memory budget (wide kernel)");
 
 struct WPipe {
-  uint32_t slice = 0;
+  uint32_t stage = 0, phase = 0;       // ring position of the next weight slot to produce / consume
   uint32_t a_use[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint32_t s_use[2] = {0, 0};
   uint32_t acc_use[2] = {0, 0};
@@ -96,11 +96,11 @@ __device__ __forceinline__ void w_produce(const uint8_t* img, uint32_t Nh, uint3
   for (uint32_t j = 0; j < nsl; ++j) {
     const uint32_t klen = min((uint32_t)C::KS, K16 - C::KS * j);
     const uint32_t bytes = Nh * klen * 2;
-    const uint32_t stage = pp.slice % C::NST, phase = (pp.slice / C::NST) & 1;
-    mbar_wait(&ctl->empty[stage], phase ^ 1);
+    const uint32_t stage = pp.stage;
+    mbar_wait(&ctl->empty[stage], pp.phase ^ 1);
+    if (++pp.stage == (uint32_t)C::NST) { pp.stage = 0; pp.phase ^= 1; }
     mbar_arrive_expect_tx(&ctl->full[stage], bytes);
     bulk_g2s(ring + (size_t)stage * C::STAGE, img + (size_t)Nh * C::KS * 2 * j, bytes, &ctl->full[stage]);
-    ++pp.slice;
   }
 }
 template <int NH>
@@ -115,9 +115,11 @@ __device__ __forceinline__ void w_produce_layer(const uint8_t* wblob, const TcLa
 
 // ---- MMA issuer: a run of K16 input columns starting at A column a_col0 into accumulator d_tmem ----
 // wait: first pass over these A columns in this layer (half 0): wait for the chunk barriers
+// Executed by all lanes of warp 1 on warp-uniform values; the tcgen05.mma / tcgen05.commit are predicated on `leader`
+// (one elected lane): see ts_mma_seg in snb_tc_ts.cuh and profiles/r3g_issue_path.md.
 template <int NH>
 __device__ __forceinline__ void w_mma_run(uint32_t Nh, uint32_t K16, uint32_t a_col0, uint32_t a_base, uint32_t ring_base,
-                                          uint32_t d_tmem, bool first, bool wait, WCtl* ctl, WPipe& pp) {
+                                          uint32_t d_tmem, bool first, bool wait, WCtl* ctl, WPipe& pp, bool leader) {
   using C = Wide<NH>;
   const uint32_t nsl = (K16 + C::KS - 1) / C::KS;
   const uint32_t idesc = umma_idesc_bf16(TILE, (int)Nh);
@@ -135,30 +137,36 @@ __device__ __forceinline__ void w_mma_run(uint32_t Nh, uint32_t K16, uint32_t a_
         ++pp.s_use[c];
       }
     }
-    const uint32_t stage = pp.slice % C::NST, phase = (pp.slice / C::NST) & 1;
-    mbar_wait(&ctl->full[stage], phase);
+    const uint32_t stage = pp.stage;
+    mbar_wait(&ctl->full[stage], pp.phase);
+    if (++pp.stage == (uint32_t)C::NST) { pp.stage = 0; pp.phase ^= 1; }
     tc_fence_after();
-    const uint32_t b_base = ring_base + stage * C::STAGE;
-    for (uint32_t t = 0; t < klen / 16; ++t) {
-      const uint64_t da = op_desc(a_base + ((col + 16u * t) >> 3) * 128u, 128u, C::SBO);
-      const uint64_t db = op_desc(b_base + (2u * t) * 128u, 128u, klen * 16u);
-      umma_bf16(d_tmem, da, db, idesc, (first && j == 0 && t == 0) ? 0u : 1u);
+    // one K = 16 step = two 128-byte core matrices further in both operands: +16 in the descriptors' 16-byte address field
+    const uint64_t da0 = op_desc(a_base + (col >> 3) * 128u, 128u, C::SBO);
+    const uint64_t db0 = op_desc(ring_base + stage * C::STAGE, 128u, klen * 16u);
+    const uint32_t acc0 = (first && j == 0) ? 0u : 1u;
+    if (leader) {
+      if (klen == 32u) {
+        umma_bf16(d_tmem, da0, db0, idesc, acc0);
+        umma_bf16(d_tmem, da0 + 16u, db0 + 16u, idesc, 1u);
+      } else {
+        for (uint32_t t = 0; t < klen / 16; ++t) umma_bf16(d_tmem, da0 + 16u * t, db0 + 16u * t, idesc, t ? 1u : acc0);
+      }
+      umma_commit(&ctl->empty[stage]);
     }
-    umma_commit(&ctl->empty[stage]);
-    ++pp.slice;
   }
 }
 // one layer: every half (N = 256 or the whole narrow layer) over A columns [a_col0, a_col0 + K16) (+ a second run `seg2`
 // over the cat block: the skip term), accumulators of half h at TMEM columns [256h, ...)
 template <int NH>
 __device__ __forceinline__ void w_mma_layer(const TcLayer& L, uint32_t a_col0, uint32_t a_base, uint32_t ring_base,
-                                            uint32_t tmem_base, WCtl* ctl, WPipe& pp, const TcLayer* seg2 = nullptr) {
+                                            uint32_t tmem_base, WCtl* ctl, WPipe& pp, bool leader, const TcLayer* seg2 = nullptr) {
   using C = Wide<NH>;
   for (uint32_t h = 0; h * 256 < L.N; ++h) {
     const uint32_t Nh = min(256u, L.N - 256u * h);
-    w_mma_run<NH>(Nh, L.K16, a_col0, a_base, ring_base, tmem_base + 256u * h, true, h == 0, ctl, pp);
-    if (seg2) w_mma_run<NH>(Nh, seg2->K16, (uint32_t)C::W, a_base, ring_base, tmem_base + 256u * h, false, h == 0, ctl, pp);
-    umma_commit(&ctl->acc_full[h]);
+    w_mma_run<NH>(Nh, L.K16, a_col0, a_base, ring_base, tmem_base + 256u * h, true, h == 0, ctl, pp, leader);
+    if (seg2) w_mma_run<NH>(Nh, seg2->K16, (uint32_t)C::W, a_base, ring_base, tmem_base + 256u * h, false, h == 0, ctl, pp, leader);
+    if (leader) umma_commit(&ctl->acc_full[h]);
   }
 }
 
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_wide(TcParams P, TileTable 
   const float* __restrict__ noise = io.noise;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   WCtl* ctl = w_setup<NH>(smem, warp);
   float* sbias = reinterpret_cast<float*>(smem + C::O_BIAS);
   float* svec = reinterpret_cast<float*>(smem + C::O_VEC);
@@ -372,17 +380,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_wide(TcParams P, TileTable 
         w_produce_layer<NH>(P.wblob_w, P.back[1], 0, smem + C::O_RING, ctl, pp);
       }
   } else if (warp == 1) {
-    if (lane == 0)
-      for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
-        const int e = tt.tile_expert[t];
-        if (e >= 0) {
-          w_mma_layer<NH>(P.front[0], (uint32_t)C::W, a_base, ring_base, tmem_base, ctl, pp);
-          for (int l = 0; l < NE; ++l)
-            w_mma_layer<NH>(P.expert[l], 0u, a_base, ring_base, tmem_base, ctl, pp, l == P.skip_layer ? &P.front[0] : nullptr);
-        }
-        w_mma_layer<NH>(P.back[0], 0u, a_base, ring_base, tmem_base, ctl, pp);
-        w_mma_layer<NH>(P.back[1], 0u, a_base, ring_base, tmem_base, ctl, pp);
+    const bool leader = elect_one();               // warp-uniform issue loop, see w_mma_run
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int n_tiles_u = __shfl_sync(0xffffffffu, n_tiles, 0);
+    for (int t = (int)blockIdx.x; t < n_tiles_u; t += (int)gridDim.x) {
+      const int e = __shfl_sync(0xffffffffu, tt.tile_expert[t], 0);
+      if (e >= 0) {
+        w_mma_layer<NH>(P.front[0], (uint32_t)C::W, a_base, ring_base, tmem_u, ctl, pp, leader);
+        for (int l = 0; l < NE; ++l)
+          w_mma_layer<NH>(P.expert[l], 0u, a_base, ring_base, tmem_u, ctl, pp, leader, l == P.skip_layer ? &P.front[0] : nullptr);
       }
+      w_mma_layer<NH>(P.back[0], 0u, a_base, ring_base, tmem_u, ctl, pp, leader);
+      w_mma_layer<NH>(P.back[1], 0u, a_base, ring_base, tmem_u, ctl, pp, leader);
+    }
   } else {
     EpiCtx ec;
     ec.remote_a_ready = 0; ec.lane = lane; ec.q = warp & 3; ec.cs = (warp - 2) >> 2; ec.row = ec.q * 32 + lane;
@@ -556,7 +566,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_wide(TcParams P, const flo
   using C = Wide<NH>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   WCtl* ctl = w_setup<NH>(smem, warp);
   float* sbias = reinterpret_cast<float*>(smem + C::O_BIAS);
   float* sred = reinterpret_cast<float*>(smem + C::O_RED);
@@ -584,12 +594,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_front_wide(TcParams P, const flo
         w_produce_layer<NH>(P.wblob_w, P.gate, 0, smem + C::O_RING, ctl, pp);
       }
   } else if (warp == 1) {
-    if (lane == 0)
-      for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
-        w_mma_layer<NH>(P.front[0], (uint32_t)C::W, a_base, ring_base, tmem_base, ctl, pp);
-        for (int l = 1; l < NL; ++l) w_mma_layer<NH>(P.front[l], 0u, a_base, ring_base, tmem_base, ctl, pp);
-        w_mma_layer<NH>(P.gate, 0u, a_base, ring_base, tmem_base, ctl, pp);
-      }
+    const bool leader = elect_one();               // warp-uniform issue loop, see w_mma_run
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x) {
+      w_mma_layer<NH>(P.front[0], (uint32_t)C::W, a_base, ring_base, tmem_u, ctl, pp, leader);
+      for (int l = 1; l < NL; ++l) w_mma_layer<NH>(P.front[l], 0u, a_base, ring_base, tmem_u, ctl, pp, leader);
+      w_mma_layer<NH>(P.gate, 0u, a_base, ring_base, tmem_u, ctl, pp, leader);
+    }
   } else {
     EpiCtx ec;
     ec.remote_a_ready = 0; ec.lane = lane; ec.q = warp & 3; ec.cs = (warp - 2) >> 2; ec.row = ec.q * 32 + lane;
