@@ -103,6 +103,9 @@ struct TcParams {
   int recompute_h;          // 1: launch #2 recomputes h = xyz Linear(PE) per tile instead of gathering it from HBM
   int E, skip_layer, pos_xyz_freqs, pos_dir_freqs, appearance_dim, appearance_count, hidden2, x_cols;
   const float* emb_a;       // fp32 [count, A]
+  const __nv_bfloat16* emb_cat;   // bf16 [count, cat_cols]: the appearance row where launch #2's cat block wants it (columns
+                                  // [NDIR, NDIR + A), zeros elsewhere) -- 16-byte chunks copied as they are (TS kernels)
+  int32_t cat_cols;
   unsigned long long* tl;   // debug timeline (nullable): [role][TL_N] (tag<<48 | clock) marks of CTA 0
   int ab;                   // debug A/B switches (SNB_FRONT_AB): 1 = no level-0 histogram, 2 = no column sums
   // ray source (render passes on the TS kernels): the [S,7] rows [o + d z, d, image index] of rendering.py:357-362 are
@@ -135,6 +138,14 @@ __device__ __forceinline__ size_t packed_index(int n, int k, int N, int K16) {
   const int j = k / 64, kk = k % 64;
   const int klen = min(64, K16 - 64 * j);
   return (size_t)N * 64 * j + ((size_t)(n / 8) * (klen * 16) + (size_t)(kk / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2) / 2;
+}
+
+// embedding_a rows as launch #2's cat block holds them: [0 x ndir | bf16(row) | 0-pad] (cols columns per row)
+__global__ void k_pack_emb_cat(const float* __restrict__ emb, int count, int A, int ndir, int cols, __nv_bfloat16* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)count * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols) - ndir;
+  dst[i] = __float2bfloat16_rn((c >= 0 && c < A) ? emb[(int64_t)r * A + c] : 0.f);
 }
 
 __global__ void k_pack_layer(const float* __restrict__ w, int N, int K, int K16, __nv_bfloat16* __restrict__ dst) {
@@ -212,7 +223,7 @@ bool tc_supported(const Model* m) {
          (d.skip_layer >= 0 || (d.width == 256 && !d.mip));
 }
 
-struct TcOwner { TcHost h; uint8_t* wblob; uint8_t* wblob_w; };
+struct TcOwner { TcHost h; uint8_t* wblob; uint8_t* wblob_w; __nv_bfloat16* emb_cat; };
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 // defaults of a new model object; the SNB_* variables are read here once per model (A/B scripts), never on the call path
 void tuning_from_env(snb_tuning* t) {
@@ -242,6 +253,7 @@ void tc_release(Model* m) {
   if (own->wblob) cudaFree(own->wblob);
   if (own->wblob_w) cudaFree(own->wblob_w);
   if (own->h.fblob) cudaFree(own->h.fblob);
+  if (own->emb_cat) cudaFree(own->emb_cat);
   delete own;
   m->tc_blob = nullptr;
 }
@@ -294,6 +306,11 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
     p.wblob_w = own->wblob_w;
     p.fblob = own->h.fblob;
     p.emb_a = m->emb_a;
+    p.cat_cols = (int32_t)(p.back[1].K16 - (uint32_t)MW);
+    if (narrow && d.appearance_dim > 0 && p.cat_cols > 0) {
+      SNB_CHECK_CUDA(cudaMalloc((void**)&own->emb_cat, (size_t)d.appearance_count * p.cat_cols * sizeof(__nv_bfloat16)));
+      p.emb_cat = own->emb_cat;
+    }
     m->tc_blob = own;
     m->tc_bytes = wbytes;
   } else {
@@ -348,6 +365,11 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
   if (d.skip_layer >= 0) {
     k_sum_bias<<<(unsigned)cdiv((int64_t)E * MW, 256), 256, 0, st>>>(m->exp_b[d.skip_layer], m->xyz_b, E, MW, own->h.fblob + p.o_b3x);
     SNB_CHECK_LAUNCH("k_sum_bias");
+  }
+  if (own->emb_cat) {
+    k_pack_emb_cat<<<(unsigned)cdiv((int64_t)d.appearance_count * p.cat_cols, 256), 256, 0, st>>>(
+        m->emb_a, d.appearance_count, d.appearance_dim, m->dir_in, p.cat_cols, own->emb_cat);
+    SNB_CHECK_LAUNCH("k_pack_emb_cat");
   }
   (void)w;
   return SNB_OK;

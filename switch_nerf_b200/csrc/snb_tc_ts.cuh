@@ -373,31 +373,40 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
     int tn = 0;
     unsigned long long* tl = (warp == 2 && lane == 0) ? P.tl : nullptr;
     auto tbuf_of = [&](uint32_t l) { return tmem_base + ec.lane_base + (l & 1u) * 256u; };
-    struct RowIn { int e, sidx; float g, d0, d1, d2, x0, x1, x2; int ai; };
-    auto fetch_row = [&](int t) {
+    struct RowIn { int e, sidx; float g, d0, d1, d2, x0, x1, x2; int ai; int rows, row0; };
+    // A tile's rows arrive through a chain of dependent global loads (tile table -> sample index -> ray / depth / gate
+    // word, ~1K clk per level).  The three levels are issued in three different idle windows of the previous tile so that
+    // no epilogue warp ever waits for one of them in front of a hand-off.
+    auto fetch_meta = [&](int t) {
       RowIn r;
-      r.e = -1; r.sidx = -1; r.g = 0.f; r.d0 = r.d1 = r.d2 = 0.f; r.x0 = r.x1 = r.x2 = 0.f; r.ai = 0;
-      if (t < n_tiles) {
-        r.e = tt.tile_expert[t];
-        if (row < tt.tile_rows[t]) r.sidx = tt.row2sample[tt.tile_row0[t] + row];
-        if (r.sidx >= 0) {
-          const float* xr = x + (int64_t)r.sidx * io.x_stride;
-          if (r.e >= 0) r.g = io.wsel ? sel_gate(io.wsel[r.sidx]) : gate[(int64_t)r.sidx * io.g_stride];
-          if (P.ray_src) {
-            if (ec.cs == 0 && r.e >= 0) ray_row_xyz(P, r.sidx, r.x0, r.x1, r.x2);
-            if (ec.cs == 1) {
-              ray_row_dir(P, r.sidx, r.d0, r.d1, r.d2, r.ai);
-              r.ai = min(max(r.ai, 0), P.appearance_count - 1);
-            }
-          } else {
-            if (ec.cs == 0 && r.e >= 0) { r.x0 = xr[0]; r.x1 = xr[1]; r.x2 = xr[2]; }
-            if (ec.cs == 1) {
-              r.d0 = xr[P.x_cols - 4]; r.d1 = xr[P.x_cols - 3]; r.d2 = xr[P.x_cols - 2];
-              r.ai = min(max((int)xr[P.x_cols - 1], 0), P.appearance_count - 1);
-            }
-          }
+      r.e = -1; r.sidx = -1; r.g = 0.f; r.d0 = r.d1 = r.d2 = 0.f; r.x0 = r.x1 = r.x2 = 0.f; r.ai = 0; r.rows = 0; r.row0 = 0;
+      if (t < n_tiles) { r.e = tt.tile_expert[t]; r.rows = tt.tile_rows[t]; r.row0 = tt.tile_row0[t]; }
+      return r;
+    };
+    auto fetch_idx = [&](RowIn& r) {
+      if (row < r.rows) r.sidx = tt.row2sample[r.row0 + row];
+    };
+    auto fetch_data = [&](RowIn& r) {
+      if (r.sidx >= 0) {
+        const float* xr = x + (int64_t)r.sidx * io.x_stride;
+        if (r.e >= 0) r.g = io.wsel ? sel_gate(io.wsel[r.sidx]) : gate[(int64_t)r.sidx * io.g_stride];
+        // xyz: the cs == 0 thread of the row stages PE(xyz); direction + appearance index: all four threads of the row
+        // build a quarter of the [PE(dir) | appearance] block each (write_cat)
+        if (P.ray_src) {
+          if (ec.cs == 0 && r.e >= 0) ray_row_xyz(P, r.sidx, r.x0, r.x1, r.x2);
+          ray_row_dir(P, r.sidx, r.d0, r.d1, r.d2, r.ai);
+        } else {
+          if (ec.cs == 0 && r.e >= 0) { r.x0 = xr[0]; r.x1 = xr[1]; r.x2 = xr[2]; }
+          r.d0 = xr[P.x_cols - 4]; r.d1 = xr[P.x_cols - 3]; r.d2 = xr[P.x_cols - 2];
+          r.ai = (int)xr[P.x_cols - 1];
         }
+        r.ai = min(max(r.ai, 0), P.appearance_count - 1);
       }
+    };
+    auto fetch_row = [&](int t) {
+      RowIn r = fetch_meta(t);
+      fetch_idx(r);
+      fetch_data(r);
       return r;
     };
     const int n_sxyz = ((int)K_xyz + 63) / 64, n_scat = ((int)K_cat + 63) / 64;
@@ -417,6 +426,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
     RowIn nxt = fetch_row(t_first0 + (int)rank);
     if (nxt.e >= 0) stage_pe(nxt, 0);          // first tile of this CTA; later tiles are staged one tile ahead
     int cb = 0;
+    bool xyz_bias_ready = false;
+    const int cat_first = P.skip_layer > 0 ? P.skip_layer : 0;   // first layer after which the PE(xyz) block is free
     for (int tb = t_first0; tb < n_tiles; tb += t_stride, cb ^= 1) {
       const int t = tb + (int)rank;
       const RowIn cur = nxt;
@@ -425,52 +436,75 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       const float g = cur.g;
       const uint32_t acat_cur = acat_base + (uint32_t)cb * TSB_CAT_STRIDE;
       tl_mark(tl, 0, tn, 1);
-      // [PE(dir) | appearance | 0-pad] -> cat block (cs == 1 threads)
-      auto write_cat = [&]() {
-        if (ec.cs == 1) {
-          constexpr int NDIR = 3 + 6 * FD;
-          __align__(16) __nv_bfloat16 cat[TS_CAT_COLS];
+      // [PE(dir) | appearance | 0-pad] -> cat block: 16-byte chunk g (columns [8g, 8g + 8)) is built by the thread
+      // cs == g % 4 of the row, every index a compile-time constant (the first version filled a local array on 4 of the
+      // 16 warps: ~5K clk next to the skip layer, profiles/r3g_issue_path.md)
+      // In three parts (chunks g with g / 4 == part), one per layer after the skip layer: each part is one round of
+      // embedding loads (~1K clk of L2 latency) and fits under a layer's MMAs
+      auto write_cat = [&](int part) {
+        constexpr int NDIR = 3 + 6 * FD;
+        static_assert(NDIR <= 32, "PE(dir) lies in the first four chunks (part 0)");
+        float pe[NDIR];
 #pragma unroll
-          for (int i = 0; i < (int)TS_CAT_COLS; ++i) cat[i] = __float2bfloat16_rn(0.f);
-          if (valid) {
-            float dvec[3] = {cur.d0, cur.d1, cur.d2};
-            pe_to_bf16<FD>(dvec, cat);
-            // the embedding row in batches of 8 independent 16-byte loads (a rolled loop serialised 12 L2 round trips:
-            // ~4.7K clk on the critical path of the skip layer, profiles/r3g_issue_path.md)
-            const float4* er = reinterpret_cast<const float4*>(P.emb_a + (int64_t)cur.ai * P.appearance_dim);
-            const int n4 = P.appearance_dim / 4;
-            for (int i0 = 0; i0 < n4; i0 += 8) {
-              float4 f[8];
+        for (int i = 0; i < NDIR; ++i) pe[i] = 0.f;
+        if (part == 0) {
+          float sn[3], cs_[3];
+          const float dvec[3] = {cur.d0, cur.d1, cur.d2};
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = (i0 + i < n4) ? __ldg(er + i0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int a = 0; a < 3; ++a) { pe[a] = dvec[a]; sincosf(dvec[a], &sn[a], &cs_[a]); }
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (i0 + i < n4) {
-                  cat[NDIR + 4 * (i0 + i) + 0] = __float2bfloat16_rn(f[i].x);
-                  cat[NDIR + 4 * (i0 + i) + 1] = __float2bfloat16_rn(f[i].y);
-                  cat[NDIR + 4 * (i0 + i) + 2] = __float2bfloat16_rn(f[i].z);
-                  cat[NDIR + 4 * (i0 + i) + 3] = __float2bfloat16_rn(f[i].w);
-                }
-              }
+          for (int k = 0; k < FD; ++k) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {                      // same recurrence as pe_to_bf16
+              pe[3 + 6 * k + a] = sn[a];
+              pe[3 + 6 * k + 3 + a] = cs_[a];
+              const float s2 = 2.f * sn[a] * cs_[a];
+              const float c2 = 1.f - 2.f * sn[a] * sn[a];
+              sn[a] = s2;
+              cs_[a] = c2;
             }
           }
-          ts_cat_store_row(acat_cur, row, cat, (int)K_cat / 8);
+        }
+        // the appearance part comes from the pre-shifted bf16 table (snb_tc.cu: k_pack_emb_cat): one 16-byte load per
+        // chunk.  A gather of 128 random rows is bound by the L1 at about one lane-request per clock -- fp32 rows read with
+        // scalar loads cost 4K clk per tile, this layout 7 requests per row
+        const uint4* er = reinterpret_cast<const uint4*>(P.emb_cat + (int64_t)cur.ai * P.cat_cols);
+        const int n8 = (int)K_cat / 8;
+#pragma unroll
+        for (int g = 0; g < (int)TS_CAT_COLS / 8; ++g) {
+          if ((g >> 2) != part || (g & 3) != ec.cs || g >= n8) continue;
+          uint4 q = make_uint4(0u, 0u, 0u, 0u);
+          if (8 * g + 8 > NDIR && valid && P.emb_cat) q = __ldg(er + g);
+          if (8 * g < NDIR) {                                   // PE(dir) columns of this chunk (the table has zeros there)
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c0 = 8 * g + 2 * i, c1 = c0 + 1;
+              const uint32_t pp2 = pack2<false>(c0 < NDIR ? pe[c0 < NDIR ? c0 : 0] : 0.f, c1 < NDIR ? pe[c1 < NDIR ? c1 : 0] : 0.f);
+              w[i] = valid ? (w[i] | pp2) : 0u;
+            }
+            q = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          st_shared_v4(ts_cat_addr(acat_cur, row, g), q.x, q.y, q.z, q.w);
         }
       };
       float sig_acc = 0.f;
-      nxt = fetch_row(t + t_stride);
+      nxt = fetch_meta(t + t_stride);
       if (e >= 0) {
         // PE(xyz) of this tile was staged into block cb one tile ago (operand of the xyz layer and of the skip term)
         tl_mark(tl, 0, tn, 2);
         // ---- xyz layer (act none): h -> packed A ----
         {
           const int buf = (int)(li & 1);
-          epi_load_bias(P.fblob + P.front[0].b_off, MW, sbias, buf, ec.et);
+          // its bias was put into this slot during layer "2" of the previous tile (the tensor pipe ran this tile's xyz
+          // layer behind that layer's MMAs and has been idle since)
+          if (!xyz_bias_ready) epi_load_bias(P.fblob + P.front[0].b_off, MW, sbias, buf, ec.et);
           ts_wait_acc(ctl, pp, buf);
           ts_epi_hidden<false>(tbuf_of(li), sbias + buf * 256, ec, ctl, tl, &tn);
           if (P.skip_layer == 0) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, cb, i, lane, remote_s);
           ++li;
         }
+        fetch_idx(nxt);              // under the first expert layer's MMAs; fetch_data follows under the second layer's
         for (int l = 0; l < NE; ++l, ++li) {
           const int buf = (int)(li & 1);
           const bool skip_here = (l == P.skip_layer);
@@ -485,10 +519,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
             ts_epi_hidden<true>(tb, sb, ec, ctl, tl, &tn);
             if (l + 1 == P.skip_layer) for (int i = 0; i < n_sxyz; ++i) ts_signal_smem(ctl, cb, i, lane, remote_s);
             // every MMA of the skip layer has retired (acc_full above): the PE(xyz) block is free.  Filled AFTER the
-            // hand-off, under the next layer's MMAs
-            if (skip_here) write_cat();
+            // hand-off, under the following layers' MMAs
+            if (l >= cat_first && l < cat_first + 3) write_cat(l - cat_first);
+            if (l == 0) fetch_data(nxt);
           } else {
-            if (skip_here) write_cat();
+            if (l == 0) fetch_data(nxt);
+            for (int part = (l >= cat_first ? l - cat_first : 0); part < 3; ++part) write_cat(part);
             // last expert layer (no activation) -> combine: y = bf16(gate * bf16(out)) -> ReLU -> packed A; sigma head
             uint32_t v[2][16];
             tmem_ld16(tb + (uint32_t)(ec.cs * 16), v[0]);
@@ -515,12 +551,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         }
       } else {
         // dropped bucket: h = relu(0) = 0 -> zero A operand for layer "1" (it accumulates into B[li&1], reads B[~li&1])
+        fetch_idx(nxt);
+        fetch_data(nxt);
         const uint32_t ta = tbuf_of(li + 1);
         const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int c = 0; c < 4; ++c) tmem_st8(ta + (uint32_t)(c * 64 + ec.cs * 16), z);
         tmem_st_wait();
         for (int c = 0; c < 4; ++c) ts_signal(ctl, c, lane, ec.remote_a_ready);
-        write_cat();
+        for (int part = 0; part < 3; ++part) write_cat(part);
       }
       sred[(0 * 4 + ec.cs) * 128 + row] = sig_acc;
       // ---- layer "1" (act none) -> packed A; then release the cat chunks ----
@@ -540,6 +578,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       {
         const int buf = (int)(li & 1);
         epi_load_bias(P.fblob + P.back[1].b_off, H2, sbias, buf, ec.et);
+        // bias of the next tile's xyz layer -> the other slot (its last readers, layer "1", are past the barrier above)
+        xyz_bias_ready = nxt.e >= 0;
+        if (xyz_bias_ready) epi_load_bias(P.fblob + P.front[0].b_off, MW, sbias, buf ^ 1, ec.et);
         const float* sb = sbias + buf * 256;
         ts_wait_acc(ctl, pp, buf);
         const uint32_t tb = tbuf_of(li);
