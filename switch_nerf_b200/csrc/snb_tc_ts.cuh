@@ -565,10 +565,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
       {
         const int buf = (int)(li & 1);
         epi_load_bias(P.fblob + P.back[0].b_off, MW, sbias, buf, ec.et);
+        tl_mark(tl, 0, tn, 70);
         // the tensor pipe is busy with layer "1": stage the next tile's PE(xyz) into the other cat block now
         // (its last reader, layer "2" of the previous tile, retired before this tile started)
         if (nxt.e >= 0) stage_pe(nxt, cb ^ 1);
+        tl_mark(tl, 0, tn, 71);
         ts_wait_acc(ctl, pp, buf);
+        tl_mark(tl, 0, tn, 72);
         ts_epi_hidden<false>(tbuf_of(li), sbias + buf * 256, ec, ctl, tl, &tn);
         for (int i = 0; i < n_scat; ++i) ts_signal_smem(ctl, cb, i, lane, remote_s);
         tl_mark(tl, 0, tn, 50);
@@ -582,7 +585,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
         xyz_bias_ready = nxt.e >= 0;
         if (xyz_bias_ready) epi_load_bias(P.fblob + P.front[0].b_off, MW, sbias, buf ^ 1, ec.et);
         const float* sb = sbias + buf * 256;
+        tl_mark(tl, 0, tn, 73);
         ts_wait_acc(ctl, pp, buf);
+        tl_mark(tl, 0, tn, 74);
         const uint32_t tb = tbuf_of(li);
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
         for (int c = 0; c < H2 / 64; ++c) {
@@ -604,10 +609,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_ts(TcParams P, TileTable tt
           }
         }
         tc_fence_before();
+        tl_mark(tl, 0, tn, 75);
         sred[(1 * 4 + ec.cs) * 128 + row] = c0;
         sred[(2 * 4 + ec.cs) * 128 + row] = c1;
         sred[(3 * 4 + ec.cs) * 128 + row] = c2;
         epi_bar_sync();
+        tl_mark(tl, 0, tn, 76);
         if (ec.cs == 0 && valid) {
           auto rsum = [&](int v) { return sred[(v * 4 + 0) * 128 + row] + sred[(v * 4 + 1) * 128 + row] +
                                           sred[(v * 4 + 2) * 128 + row] + sred[(v * 4 + 3) * 128 + row]; };

@@ -233,8 +233,9 @@ def test_render_fp32_vs_reference_golden(built_lib, tag):
     sd = golden_sd(g)
     model, hp = make_model(sd, float(cf), bool(bpr), False, "fp32")
     hp.coarse_samples, hp.fine_samples, hp.model_chunk_size = int(cs), int(fs), int(chunk)
-    res, _ = render_rays(model, None, torch.from_numpy(g["rays"]).cuda(), torch.from_numpy(g["image_indices"]).cuda(),
-                         hp, None, None, True, True, False, debug_taps=True)
+    with torch.no_grad():       # in grad mode render_rays attaches the backward graph (results require grad)
+        res, _ = render_rays(model, None, torch.from_numpy(g["rays"]).cuda(), torch.from_numpy(g["image_indices"]).cuda(),
+                             hp, None, None, True, True, False, debug_taps=True)
     torch.cuda.synchronize()
     typ = "fine" if fs > 0 else "coarse"
     assert np.abs(res["_raw_coarse"].cpu().numpy() - g["raw_coarse"]).max() <= TOL
