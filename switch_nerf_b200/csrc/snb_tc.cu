@@ -307,7 +307,7 @@ int tc_pack_weights(Model* m, const snb_weights* w, cudaStream_t st) {
     p.fblob = own->h.fblob;
     p.emb_a = m->emb_a;
     p.cat_cols = (int32_t)(p.back[1].K16 - (uint32_t)MW);
-    if (narrow && d.appearance_dim > 0 && p.cat_cols > 0) {
+    if (d.appearance_dim > 0 && p.cat_cols > 0) {
       SNB_CHECK_CUDA(cudaMalloc((void**)&own->emb_cat, (size_t)d.appearance_count * p.cat_cols * sizeof(__nv_bfloat16)));
       p.emb_cat = own->emb_cat;
     }

@@ -433,25 +433,50 @@ __global__ void __launch_bounds__(THREADS, 1) k_back_wide(TcParams P, TileTable 
       const int e = cur.e, sidx = cur.sidx;
       const bool valid = sidx >= 0;
       nxt = fetch_row(t + (int)gridDim.x);
+      // [PE(dir) | appearance | 0-pad] -> cat block: the appearance part comes as 16-byte chunks from the pre-shifted bf16
+      // table (snb_tc.cu: k_pack_emb_cat; a gather of random fp32 rows through a local array cost ~5K clk per tile,
+      // profiles/r3g_issue_path.md), PE(dir) is merged into the chunks below column NDIR
       auto write_cat = [&]() {
         if (ec.cs == 1) {
           constexpr int NDIR = 3 + 6 * FD;
-          __align__(16) __nv_bfloat16 cat[C::CAT];
+          float pe[NDIR];
+          {
+            float sn[3], cs_[3];
+            const float dvec[3] = {cur.d0, cur.d1, cur.d2};
 #pragma unroll
-          for (int i = 0; i < C::CAT; ++i) cat[i] = __float2bfloat16_rn(0.f);
-          if (valid) {
-            float dvec[3] = {cur.d0, cur.d1, cur.d2};
-            pe_to_bf16<FD>(dvec, cat);
-            const float4* er = reinterpret_cast<const float4*>(P.emb_a + (int64_t)cur.ai * P.appearance_dim);
-            for (int i = 0; i < P.appearance_dim / 4; ++i) {
-              const float4 f = er[i];
-              cat[NDIR + 4 * i + 0] = __float2bfloat16_rn(f.x);
-              cat[NDIR + 4 * i + 1] = __float2bfloat16_rn(f.y);
-              cat[NDIR + 4 * i + 2] = __float2bfloat16_rn(f.z);
-              cat[NDIR + 4 * i + 3] = __float2bfloat16_rn(f.w);
+            for (int a = 0; a < 3; ++a) { pe[a] = dvec[a]; sincosf(dvec[a], &sn[a], &cs_[a]); }
+#pragma unroll
+            for (int k = 0; k < FD; ++k) {
+#pragma unroll
+              for (int a = 0; a < 3; ++a) {                      // same recurrence as pe_to_bf16
+                pe[3 + 6 * k + a] = sn[a];
+                pe[3 + 6 * k + 3 + a] = cs_[a];
+                const float s2 = 2.f * sn[a] * cs_[a];
+                const float c2 = 1.f - 2.f * sn[a] * sn[a];
+                sn[a] = s2;
+                cs_[a] = c2;
+              }
             }
           }
-          w_store_row<NH>(a_base, row, C::W / 8, cat, (int)K_cat / 8);
+          const uint4* er = reinterpret_cast<const uint4*>(P.emb_cat + (int64_t)cur.ai * P.cat_cols);
+          const int n8 = (int)K_cat / 8;
+#pragma unroll
+          for (int g = 0; g < C::CAT / 8; ++g) {
+            if (g >= n8) continue;
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (8 * g + 8 > NDIR && valid && P.emb_cat) q = __ldg(er + g);
+            if (8 * g < NDIR) {
+              uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int c0 = 8 * g + 2 * i, c1 = c0 + 1;
+                const uint32_t pp2 = pack2<false>(c0 < NDIR ? pe[c0 < NDIR ? c0 : 0] : 0.f, c1 < NDIR ? pe[c1 < NDIR ? c1 : 0] : 0.f);
+                w[i] = valid ? (w[i] | pp2) : 0u;
+              }
+              q = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            st_shared_v4(w_a_addr<NH>(a_base, row, C::W / 8 + g), q.x, q.y, q.z, q.w);
+          }
         }
       };
       float sig_acc = 0.f, dummy = 0.f;
