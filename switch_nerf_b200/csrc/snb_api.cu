@@ -2,6 +2,7 @@
 // carving and the host-side orchestration of render_rays.  No host synchronisation anywhere.
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -16,10 +17,14 @@ static thread_local char g_err[1024] = "";
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// process-wide measurement state (snb_profile_*): guarded, so that two host threads rendering with different models
+// do not corrupt the event pool (the header's single-stream-per-model rule covers everything model-owned)
+static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<PhaseEvents> g_prof_pool;
 static size_t g_prof_used = 0;
 PhaseEvents* profile_next() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   if (!g_prof_on) return nullptr;
   if (g_prof_pool.capacity() < 65536) g_prof_pool.reserve(65536);   // callers keep pointers: never reallocate
   if (g_prof_used >= g_prof_pool.size()) {
@@ -165,6 +170,7 @@ int snb_version(void) { return 100; }
 int64_t snb_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int snb_profile_enable(int32_t on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_on = on != 0;
   g_prof_used = 0;
   return SNB_OK;
@@ -175,6 +181,7 @@ int snb_debug_timeline(uint64_t* host_out, int32_t n) { return tc_timeline_read(
 int snb_profile_collect(double* out4) {
   SNB_REQUIRE(out4, "snb_profile_collect: NULL");
   SNB_CHECK_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   double f = 0, r = 0, b = 0;
   for (size_t i = 0; i < g_prof_used; ++i) {
     float t;

@@ -9,6 +9,7 @@
 //   radix passes  stable LSD radix sort of (key, sample) pairs, 9-bit digits, only for BPR
 //   k_loc         warp-ballot (match_any) rank inside a 256-sample block + scanned block offsets
 // No host round trip: capacity / counts / l_aux stay in device memory.
+#include <atomic>
 #include "snb_common.cuh"
 #include "snb_ep.cuh"
 #include "snb_select.cuh"
@@ -777,12 +778,12 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) k_select(SelectArgs a) {
 int route_select_launch(const SelectArgs& a, cudaStream_t st) {
   SNB_REQUIRE(a.E >= 1 && a.E <= SEL_MAX_E, "route_select: E=%d out of range [1,%d]", a.E, SEL_MAX_E);
   SNB_REQUIRE(a.S >= 1 && a.S < (1ll << 31), "route_select: S=%lld out of range", (long long)a.S);
-  static bool attr_done_dev[64] = {};
+  static std::atomic<bool> attr_done_dev[64];      // per device; setting the attribute twice is harmless
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!attr_done_dev[dev & 63]) {
+  if (!attr_done_dev[dev & 63].load(std::memory_order_acquire)) {
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
-    attr_done_dev[dev & 63] = true;
+    attr_done_dev[dev & 63].store(true, std::memory_order_release);
   }
   k_select<<<SEL_P, SEL_THREADS, sizeof(SelSmem), st>>>(a);
   SNB_CHECK_LAUNCH("k_select");

@@ -38,6 +38,8 @@
 // (tc_pack_weights) so a K-slice is ONE contiguous bulk copy.
 #include "snb_common.cuh"
 #include <stdlib.h>
+#include <atomic>
+#include <mutex>
 
 #include "snb_umma.cuh"
 #include "snb_ep.cuh"
@@ -1307,11 +1309,10 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
   {
     // debug only: SNB_TIMELINE=1 records clock marks of CTA 0 (front: slots [0,2*TL_N), back: [2*TL_N, 4*TL_N))
     static unsigned long long* tl_buf = nullptr;
-    static int tl_checked = 0;
-    if (!tl_checked) {
-      tl_checked = 1;
+    static std::once_flag tl_once;
+    std::call_once(tl_once, [] {
       if (getenv("SNB_TIMELINE")) { cudaMalloc((void**)&tl_buf, 5 * TL_N * 8); g_timeline = tl_buf; }
-    }
+    });
     if (tl_buf) {
       cudaMemsetAsync(tl_buf, 0, 5 * TL_N * 8, st);
       c.Pf.tl = tl_buf;
@@ -1366,11 +1367,11 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
   c.tt.seg_start = small + E + 1;
   c.tt.n_tiles = small + 2 * E + 4;
   c.tt.drop_counter = small + 2 * E + 5;
-  static bool attr_done_dev[64] = {};     // function attributes are per device
+  static std::atomic<bool> attr_done_dev[64];     // function attributes are per device; setting them twice is harmless
   int dev = 0;
   cudaGetDevice(&dev);
-  bool& attr_done = attr_done_dev[dev & 63];
-  if (!attr_done) {
+  std::atomic<bool>& attr_done = attr_done_dev[dev & 63];
+  if (!attr_done.load(std::memory_order_acquire)) {
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
@@ -1382,7 +1383,7 @@ static int tc_chunk_init(Model* m, TcChunk& c, const float* x, int64_t S, const 
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_wide<1, 12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes<1>()));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_front_wide<2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes<2>()));
     SNB_CHECK_CUDA(cudaFuncSetAttribute(k_back_wide<2, 12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes<2>()));
-    attr_done = true;
+    attr_done.store(true, std::memory_order_release);
   }
   c.cg = (m->tune.cta_group_front == 2 && !c.wide) ? 2 : 1;
   c.cg_back = (m->tune.cta_group_back == 2 && !c.wide) ? 2 : 1;

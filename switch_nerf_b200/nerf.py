@@ -99,6 +99,11 @@ class NeRF(nn.Module):
                 torch.cuda.current_stream().synchronize()
         return self._handle
 
+    def mark_dirty(self):
+        """Re-upload the weights at the next call (needed after writes through `param.data`, which do not bump
+        `Parameter._version`)."""
+        self._versions = None
+
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
         if h is not None:

@@ -408,6 +408,13 @@ class NeRFMoE(nn.Module):
                 self._packed_versions = versions
         return self._handle
 
+    def mark_dirty(self):
+        """Force a re-pack of the device copies at the next call.  `handle()` notices parameter changes through
+        `Parameter._version` (optimizer steps, `load_state_dict`, in-place ops on the parameter); writes through
+        `param.data` (`p.data.copy_()`, common in EMA / manual loading code) do not bump it -- call this after them.
+        With sharded experts the re-pack gathers the shards (a collective): call it on every rank."""
+        self._packed_versions = None
+
     def tuning(self, **changes):
         """Read (and optionally change) the kernel-selection / pipeline knobs of this model (snb_tuning: route_sms,
         pipe_depth, ts, cta_group_*, route_full, no_overlap, ...): `model.tuning(route_sms=16)`; returns the current values."""
