@@ -668,6 +668,10 @@ __device__ __forceinline__ void front_softmax_select(const TcParams& P, const fl
   // every one of the four threads of a row (cs = 0..3, different warps) holds all 32 accumulator columns, so
   // each computes the whole softmax of its row itself: no exchange rounds.  Thread cs stores gates
   // [4cs, 4cs+4) (debug tap only); thread 0 owns the routing word and the column sums.
+  // ... which only matters for the debug tap: without it the routing word, the histogram and the column sums all come
+  // from thread 0 of the row, and the other three warps of the lane quarter have nothing to do here (they used to
+  // compute 16 expf each: the softmax was issue-bound at ~2.6K clk per tile)
+  if (ec.cs != 0 && gates == nullptr) return;
   const float tsum = sred[0 * 128 + row] + sred[1 * 128 + row] + sred[2 * 128 + row] + sred[3 * 128 + row];
   const float tsq = sred[4 * 128 + row] + sred[5 * 128 + row] + sred[6 * 128 + row] + sred[7 * 128 + row];
   const float mean = tsum * inv_w;
@@ -686,9 +690,19 @@ __device__ __forceinline__ void front_softmax_select(const TcParams& P, const fl
   }
   float den = 0.f;
 #pragma unroll
-  for (int e = 0; e < MAX_E; ++e) {
+  for (int e = 0; e < MAX_E / 2; ++e) {
     lg[e] = (e < P.E) ? expf(lg[e] - mx) : 0.f;
     den += lg[e];
+  }
+  if (P.E > MAX_E / 2) {                       // uniform branch: 8 experts never evaluate the upper 8 exponentials
+#pragma unroll
+    for (int e = MAX_E / 2; e < MAX_E; ++e) {
+      lg[e] = (e < P.E) ? expf(lg[e] - mx) : 0.f;
+      den += lg[e];
+    }
+  } else {
+#pragma unroll
+    for (int e = MAX_E / 2; e < MAX_E; ++e) lg[e] = 0.f;
   }
   const float inv = 1.f / den;
 #pragma unroll

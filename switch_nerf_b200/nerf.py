@@ -105,12 +105,13 @@ class NeRF(nn.Module):
         self._versions = None
 
     def __del__(self):
-        h, self._handle = getattr(self, "_handle", None), None
-        if h is not None:
-            try:
+        try:                                     # may run during interpreter shutdown: nothing here is allowed to raise
+            h = self.__dict__.get("_handle")
+            self.__dict__["_handle"] = None
+            if h is not None:
                 L.lib().snb_bg_destroy(h)
-            except Exception:
-                pass
+        except Exception:
+            pass
 
     def forward(self, x: torch.Tensor, sigma_only: bool = False, sigma_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         if sigma_only:
