@@ -59,7 +59,11 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (true) {
+#ifdef SNB_BACKOFF_NS
+    __nanosleep(SNB_BACKOFF_NS);
+#else
     __nanosleep(40);
+#endif
     if (mbar_try_wait(bar, parity)) return;
     if ((++spins & 0xFFFFu) == 0) {
       uint64_t now;

@@ -8,6 +8,7 @@ import torch
 
 from oracle import switch_nerf_oracle as O
 from oracle.make_golden import ROUTE_CASES, make_gates, model_inputs
+from tests.util import sd_checksum
 from tests.util import (CUDA_MIP_GOLDENS, CUDA_MODEL_GOLDENS, bf16_contract_check, cuda_golden_case, golden_sd,
                         load_golden)
 
@@ -188,3 +189,73 @@ def test_backward_plan_composite_and_merge_equal_autograd():
     (drf, dsf), (drc, dsc) = B.merge_backward(order, Sf, d_rgbs, d_sig)
     for mine, ref in ((drf, raw_f.grad[..., :3]), (dsf * 30, raw_f.grad[..., 3]), (drc, raw_c.grad[..., :3]), (dsc * 30, raw_c.grad[..., 3])):
         assert float((mine - ref).abs().max()) <= 1e-10 * max(1.0, float(ref.abs().max()))
+
+
+# ----------------------------------------------------------------------------- row f3: background branch
+def _bg_sd(layers, skip, width, softplus, seed, count):
+    """Weights of the reference's bg model for a fixture: the mirror's constructor draws the same values under the same
+    seed (checked against the stored checksum)."""
+    from torch import nn
+    from switch_nerf_b200.nerf import NeRF, ShiftedSoftplus
+    torch.manual_seed(seed)
+    bg = NeRF(12, 4, layers, [skip], width, 48, False, count, 3, 4, ShiftedSoftplus() if softplus else nn.ReLU())
+    with torch.no_grad():
+        bg.sigma.bias += 1.5                       # oracle.make_golden_bg.BG_SIGMA_BIAS
+    return {k: v.detach() for k, v in bg.state_dict().items()}
+
+
+@pytest.mark.parametrize("tag", ["l8_w256_softplus", "l4_w64_relu"])
+def test_bg_oracle_model_pinned_to_reference(tag):
+    from oracle import bg_oracle as B
+    g = load_golden(f"bg_model_{tag}.npz")
+    S, layers, skip, width, softplus, seed, count = (int(v) for v in g["params"])
+    sd = _bg_sd(layers, skip, width, softplus, seed, count)
+    ck = float(g["sd_checksum"][0])
+    assert abs(sd_checksum(sd) - ck) < 1e-6 * ck
+    x = torch.from_numpy(g["x"])
+    out = B.bg_nerf_forward(x, sd, layers=layers, skip_layer=skip, shifted_softplus=bool(softplus))
+    out_n = B.bg_nerf_forward(x, sd, layers=layers, skip_layer=skip, shifted_softplus=bool(softplus),
+                              sigma_noise=torch.from_numpy(g["noise"]))
+    assert float((out - torch.from_numpy(g["out"])).abs().max()) <= 1e-6
+    assert float((out_n - torch.from_numpy(g["out_noise"])).abs().max()) <= 1e-6
+
+
+def test_bg_oracle_sphere_geometry_pinned_to_reference():
+    from oracle import bg_oracle as B
+    g = load_golden("bg_sphere_s24.npz")
+    rays, z = torch.from_numpy(g["rays"]), torch.from_numpy(g["z"])
+    for name, c, r in (("scaled", torch.from_numpy(g["center"]), torch.from_numpy(g["radius"])), ("unit", None, None)):
+        far = B.intersect_sphere(rays[:, 0:3], rays[:, 3:6], c, r)
+        pts, real = B.depth2pts_outside(rays[:, None, 0:3], rays[:, None, 3:6], z, c, r)
+        assert torch.equal(far, torch.from_numpy(g[f"fg_far_{name}"]))
+        assert torch.equal(pts, torch.from_numpy(g[f"pts_{name}"]))
+        assert torch.equal(real, torch.from_numpy(g[f"depth_real_{name}"]))
+    bad = rays[:1].clone()
+    bad[0, :3] = torch.tensor([5.0, 0.0, 0.0])
+    with pytest.raises(Exception, match="bounded by the unit sphere"):
+        B.intersect_sphere(bad[:, 0:3], bad[:, 3:6], None, None)
+
+
+@pytest.mark.parametrize("tag", ["fine", "coarse_only", "none_leave"])
+def test_bg_oracle_render_pinned_to_reference(tag):
+    """oracle.bg_oracle.render_rays_with_bg == the unmodified reference's render_rays(nerf, bg_nerf, ...) on every key."""
+    from oracle import bg_oracle as B
+    g = load_golden(f"bg_render_{tag}.npz")
+    E, n_rays, cs, fs, chunk, seed, gs, count, far = g["params"]
+    sd = O.synthetic_state_dict(num_experts=int(E), appearance_count=int(count), seed=int(seed), gate_scale=float(gs))
+    assert abs(sd_checksum(sd) - float(g["sd_checksum"][0])) < 1e-6 * float(g["sd_checksum"][0])
+    bg_sd = _bg_sd(8, 4, 256, True, int(seed) + 2, int(count))
+    assert abs(sd_checksum(bg_sd) - float(g["bg_checksum"][0])) < 1e-6 * float(g["bg_checksum"][0])
+    res = B.render_rays_with_bg(sd, O.default_cfg(sd, 1.0, True), bg_sd, dict(layers=8, skip_layer=4),
+                                torch.from_numpy(g["rays"]), torch.from_numpy(g["image_indices"]),
+                                torch.from_numpy(g["center"]), torch.from_numpy(g["radius"]),
+                                coarse_samples=int(cs), fine_samples=int(fs), model_chunk_size=int(chunk))
+    assert int(res["_present"]) == int(g["present"][0])
+    typ = "fine" if fs > 0 else "coarse"
+    keys = [k for k in g if k.endswith(f"_{typ}") or k.startswith("gate_loss")]
+    assert len(keys) >= 9
+    for k in keys:
+        a, b = res[k], torch.from_numpy(g[k])
+        # same torch CPU ops in the same order: equal up to the last bit of a differently associated sum
+        tol = 1e-6 * max(1.0, float(b.abs().max()))
+        assert a.shape == b.shape and float((a - b).abs().max()) <= tol, (k, float((a - b).abs().max()))
