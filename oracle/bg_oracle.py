@@ -41,41 +41,53 @@ def bg_nerf_forward(x: Tensor, sd: Dict[str, Tensor], *, layers: int, skip_layer
     return torch.cat([torch.sigmoid(rgb), sigma], -1)                                      # :191
 
 
+def _to_unit_sphere(origin: Tensor, direction: Tensor, center: Optional[Tensor], radius: Optional[Tensor]):
+    """rendering.py:499-501 / 529-531: the scene sphere becomes the unit sphere."""
+    if radius is None:
+        return origin, direction
+    return (origin - center) / radius, direction / radius
+
+
+def _closest_approach(origin: Tensor, direction: Tensor) -> Tensor:
+    """Ray parameter of the point closest to the sphere centre (rendering.py:508 / 534); negative behind the camera."""
+    return -torch.sum(direction * origin, dim=-1) / torch.sum(direction * direction, dim=-1)
+
+
 def intersect_sphere(rays_o: Tensor, rays_d: Tensor, center: Optional[Tensor], radius: Optional[Tensor]) -> Tensor:
-    """rendering.py:497-518: depth at which a ray leaves the unit sphere (after centre / radius)."""
-    if radius is not None:
-        rays_o = (rays_o - center) / radius
-        rays_d = rays_d / radius
-    d1 = -torch.sum(rays_d * rays_o, dim=-1) / torch.sum(rays_d * rays_d, dim=-1)
-    p = rays_o + d1.unsqueeze(-1) * rays_d
-    ray_d_cos = 1. / torch.norm(rays_d, dim=-1)
-    p_norm_sq = torch.sum(p * p, dim=-1)
-    if (p_norm_sq >= 1.).any():
+    """rendering.py:497-518: ray parameter at which a ray leaves the unit sphere (after centre / radius)."""
+    origin, direction = _to_unit_sphere(rays_o, rays_d, center, radius)
+    t_mid = _closest_approach(origin, direction)
+    closest = origin + t_mid.unsqueeze(-1) * direction
+    inv_len = 1. / torch.norm(direction, dim=-1)
+    dist_sq = torch.sum(closest * closest, dim=-1)
+    if (dist_sq >= 1.).any():                                    # :513-515, same message
         raise Exception('Not all your cameras are bounded by the unit sphere; please make sure the cameras are normalized properly!')
-    return d1 + torch.sqrt(1. - p_norm_sq) * ray_d_cos
+    half_chord = torch.sqrt(1. - dist_sq) * inv_len
+    return t_mid + half_chord
 
 
 def depth2pts_outside(rays_o: Tensor, rays_d: Tensor, depth: Tensor, center: Optional[Tensor], radius: Optional[Tensor]):
-    """rendering.py:521-570 with include_xyz_real = False.  rays_o / rays_d [N,1,3], depth [N,S] inverse distance."""
-    if radius is not None:
-        rays_o = (rays_o - center) / radius
-        rays_d = rays_d / radius
-    d1 = -torch.sum(rays_d * rays_o, dim=-1) / torch.sum(rays_d * rays_d, dim=-1)
-    p_mid = rays_o + d1.unsqueeze(-1) * rays_d
-    p_mid_norm = torch.norm(p_mid, dim=-1)
-    ray_d_cos = 1. / rays_d.norm(dim=-1)
-    d2 = torch.sqrt(1. - p_mid_norm * p_mid_norm) * ray_d_cos
-    p_sphere = rays_o + (d1 + d2).unsqueeze(-1) * rays_d
-    rot_axis = torch.cross(rays_o, p_sphere, dim=-1)
-    rot_axis = rot_axis / (torch.norm(rot_axis, dim=-1, keepdim=True) + 1e-8)
-    phi = torch.asin(p_mid_norm)
-    theta = torch.asin(p_mid_norm * depth)
-    rot_angle = (phi - theta).unsqueeze(-1)
-    p_new = p_sphere * torch.cos(rot_angle) + torch.cross(rot_axis, p_sphere, dim=-1) * torch.sin(rot_angle) + \
-        rot_axis * torch.sum(rot_axis * p_sphere, dim=-1, keepdim=True) * (1. - torch.cos(rot_angle))     # Rodrigues, :546-548
-    p_new = p_new / torch.norm(p_new, dim=-1, keepdim=True)
-    depth_real = 1. / (depth + 1e-8) * torch.cos(theta) + d1                                                # :552
-    return torch.cat((p_new, depth.unsqueeze(-1)), dim=-1), depth_real
+    """rendering.py:521-570 with include_xyz_real = False.  rays_o / rays_d [N,1,3]; depth [N,S] = inverse distance to the
+    sphere centre.  Returns the 4-D background points [point on the unit sphere, inverse distance] and the conventional
+    depth.  The point is the exit point of the ray rotated towards the ray direction by phi - theta about the axis
+    origin x exit (Rodrigues), phi = asin(|closest|), theta = asin(|closest| * depth)."""
+    origin, direction = _to_unit_sphere(rays_o, rays_d, center, radius)
+    t_mid = _closest_approach(origin, direction)
+    closest = origin + t_mid.unsqueeze(-1) * direction
+    dist = torch.norm(closest, dim=-1)
+    inv_len = 1. / direction.norm(dim=-1)
+    half_chord = torch.sqrt(1. - dist * dist) * inv_len                       # note: |closest| squared here, sum of squares in :512
+    exit_pt = origin + (t_mid + half_chord).unsqueeze(-1) * direction
+    axis = torch.cross(origin, exit_pt, dim=-1)
+    axis = axis / (torch.norm(axis, dim=-1, keepdim=True) + 1e-8)
+    theta = torch.asin(dist * depth)
+    angle = (torch.asin(dist) - theta).unsqueeze(-1)
+    cos_a, sin_a = torch.cos(angle), torch.sin(angle)
+    along = torch.sum(axis * exit_pt, dim=-1, keepdim=True)
+    rotated = exit_pt * cos_a + torch.cross(axis, exit_pt, dim=-1) * sin_a + axis * along * (1. - cos_a)   # :546-548
+    rotated = rotated / torch.norm(rotated, dim=-1, keepdim=True)
+    depth_real = 1. / (depth + 1e-8) * torch.cos(theta) + t_mid                                            # :552
+    return torch.cat((rotated, depth.unsqueeze(-1)), dim=-1), depth_real
 
 
 def _composite_flip(z_desc: Tensor, rgbs: Tensor, sigmas: Tensor, last_delta: Tensor):

@@ -39,3 +39,43 @@ def test_extract_critical_matches_route_top1_with_ties():
         (_, idx_s, loc_s, gates_s, cap), l_aux = extract_critical(gates, 1, 1.0, True, True)
     i2, l2, g2, c2, a2 = O.route_top1(gates, 1.0, True)
     assert torch.equal(i2, idx_s[0]) and torch.equal(l2, loc_s[0]) and c2 == cap and float(a2) == float(l_aux)
+
+
+@pytest.mark.parametrize("cs,fs,far,seed", [(24, 16, 1.0, 61), (20, 0, 2.5, 62)])
+def test_bg_branch_vs_live_reference(cs, fs, far, seed):
+    """oracle.bg_oracle (bg NeRF, sphere geometry, render_rays with bg_nerf) against the live reference on fresh seeds."""
+    from oracle import bg_oracle as B, ref_shims as R, switch_nerf_oracle as O
+    from oracle.make_golden_bg import bg_hparams, reference_bg
+    warnings.filterwarnings("ignore")
+    R.install_shims()
+    from switch_nerf import rendering
+    sd = O.synthetic_state_dict(num_experts=4, appearance_count=16, seed=seed, gate_scale=3.0)
+    hp = bg_hparams(R.make_hparams(num_experts=4, capacity_factor=1.0, bpr=True, model_chunk_size=1500, coarse_samples=cs,
+                                   fine_samples=fs), layers=6, skip=3, width=64)
+    m = R.build_reference_model(hp, appearance_count=16).eval()
+    m.load_state_dict(sd)
+    bg = reference_bg(hp, 16, seed + 2)
+    bg_sd = {k: v.detach() for k, v in bg.state_dict().items()}
+    rays, idx = O.synthetic_rays(80, 16, seed=seed + 1)
+    rays[:, 7] = far
+    c, r = torch.tensor([0.01, 0.02, -0.03]), torch.tensor([1.05, 0.95, 1.1])
+    with torch.no_grad(), R.stable_argsort():
+        ref, present = rendering.render_rays(m, bg, rays, idx, hp, c, r, True, True, True)
+    mine = B.render_rays_with_bg(sd, O.default_cfg(sd, 1.0, True), bg_sd, dict(layers=6, skip_layer=3), rays, idx, c, r,
+                                 coarse_samples=cs, fine_samples=fs, model_chunk_size=1500)
+    assert bool(present) == bool(int(mine["_present"])) and present
+    typ = "fine" if fs > 0 else "coarse"
+    for k in (f"rgb_{typ}", f"depth_{typ}", f"fg_rgb_{typ}", f"bg_rgb_{typ}", f"bg_depth_{typ}", f"bg_lambda_{typ}",
+              f"depth_variance_{typ}", "gate_loss_coarse"):
+        tol = 1e-6 * max(1.0, float(ref[k].abs().max()))
+        assert float((ref[k] - mine[k]).abs().max()) <= tol, k
+    # model and geometry alone, bit for bit
+    x = torch.cat([torch.nn.functional.normalize(torch.randn(500, 3), dim=-1), torch.rand(500, 1),
+                   torch.nn.functional.normalize(torch.randn(500, 3), dim=-1), torch.randint(0, 16, (500, 1)).float()], 1)
+    with torch.no_grad():
+        assert torch.equal(bg(x), B.bg_nerf_forward(x, bg_sd, layers=6, skip_layer=3))
+    z = torch.rand(80, 9)
+    p_ref, d_ref = rendering._depth2pts_outside(rays[:, None, 0:3], rays[:, None, 3:6], z, c, r, False, False)
+    p, d = B.depth2pts_outside(rays[:, None, 0:3], rays[:, None, 3:6], z, c, r)
+    assert torch.equal(p_ref, p) and torch.equal(d_ref, d)
+    assert torch.equal(rendering._intersect_sphere(rays[:, 0:3], rays[:, 3:6], c, r), B.intersect_sphere(rays[:, 0:3], rays[:, 3:6], c, r))
