@@ -196,3 +196,33 @@ def test_bg_nerf_mirror_layout_and_seed_parity():
         a, b = ref.state_dict(), mine.state_dict()
         assert list(a.keys()) == list(b.keys())
         assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_render_rays_rejects_foreign_models_before_touching_cuda():
+    """The renderer mirror refuses models it cannot hand to the library (no silent torch fallback)."""
+    from switch_nerf_b200._lib import SnbError
+    from switch_nerf_b200.rendering import render_rays
+    hp = make_hparams(num_experts=4)
+    m = get_nerf_moe_inner(hp, 16, 3)
+    rays = torch.zeros(4, 8)
+    with pytest.raises(SnbError):
+        render_rays(torch.nn.Linear(3, 3), None, rays, None, hp)
+    with pytest.raises(SnbError):
+        render_rays(m, torch.nn.Linear(3, 3), rays, None, hp)          # bg_nerf must be the NeRF mirror
+    with pytest.raises(SnbError):
+        render_rays(m, None, rays, None, hp)                            # CPU rays: no CPU path
+    hp.use_cascade = True
+    with pytest.raises(NotImplementedError):
+        render_rays(m, None, rays, None, hp)
+
+
+def test_mark_dirty_resets_the_packed_versions():
+    from switch_nerf_b200.nerf import NeRF, ShiftedSoftplus
+    m = get_nerf_moe_inner(make_hparams(num_experts=4), 16, 3)
+    m._packed_versions = ("x",)
+    m.mark_dirty()
+    assert m._packed_versions is None
+    bg = NeRF(12, 4, 4, [2], 64, 48, False, 8, 3, 4, ShiftedSoftplus())
+    bg._versions = ("x",)
+    bg.mark_dirty()
+    assert bg._versions is None
