@@ -57,6 +57,7 @@ class NeRF(nn.Module):
         self.rgb = nn.Linear(layer_dim // 2, 3)
         self._handle = None
         self._versions = None
+        self._device = None
 
     # ---- device model -------------------------------------------------------------------------
     def _weights(self):
@@ -80,8 +81,12 @@ class NeRF(nn.Module):
         dev = self.sigma.weight.device
         if dev.type != "cuda":
             raise L.SnbError("NeRF (background) runs on a CUDA device only (there is no CPU path)")
-        versions = tuple(p._version for p in self.parameters()) + (str(dev),)
+        versions = tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
         lib = L.lib()
+        if self._handle is not None and self._device != dev:      # the module moved to another GPU: new device copies
+            with torch.cuda.device(self._device):
+                lib.snb_bg_destroy(self._handle)
+            self._handle = None
         with torch.cuda.device(dev):
             if self._handle is None:
                 d = L.BgDesc(len(self.xyz_encodings), self.skip_layers[0] if self.skip_layers else -1, self.layer_dim,
@@ -90,7 +95,7 @@ class NeRF(nn.Module):
                 w, keep = self._weights()
                 h = C.c_void_p()
                 L.check(lib.snb_bg_create(C.byref(d), C.byref(w), L.stream_handle(), C.byref(h)))
-                self._handle, self._versions = h, versions
+                self._handle, self._versions, self._device = h, versions, dev
                 torch.cuda.current_stream().synchronize()
             elif versions != self._versions:
                 w, keep = self._weights()
